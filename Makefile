@@ -1,0 +1,28 @@
+# Builds libbluetangle_cuda.so (sm_100a) and the C oracle.  Used by __graft_entry__.build().
+NVCC      ?= nvcc
+PKG       := bluetangle.jl_b200
+CSRC      := $(wildcard $(PKG)/csrc/*.cu)
+OBJ       := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(CSRC))
+LIB       := $(PKG)/lib/libbluetangle_cuda.so
+NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+
+all: $(LIB) oracle
+
+$(LIB): $(OBJ)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) -shared -o $@ $(OBJ)
+
+build/%.o: $(PKG)/csrc/%.cu $(PKG)/csrc/bt_internal.cuh include/bluetangle_cuda.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+oracle: oracle/_build/libbt_oracle_c.so
+
+oracle/_build/libbt_oracle_c.so: oracle/strided_cpu.c
+	@mkdir -p oracle/_build
+	gcc -O3 -march=native -fopenmp -fPIC -shared -o $@ $< -lm
+
+clean:
+	rm -rf build $(LIB) oracle/_build
+
+.PHONY: all oracle clean

@@ -1,0 +1,272 @@
+// bt_dist.cu -- multi-GPU shards.  No reference analogue (the reference is single-threaded Julia); the closest
+// idea is its label-permutation helper relabel_swap (src/hilbert.jl:266-317).
+//
+// Layout: physical index = (rank << n_local) | local.  A logical->physical bit map is kept per handle.  Gates whose
+// non-diagonal targets are all local need no communication; diagonal gates and controls on rank bits are resolved
+// from the rank id (bt_gates.cu: localize).  Otherwise the qubits are re-mapped: every rank PULLS its new shard
+// straight out of its peers' HBM over NVLink (CUDA IPC / peer mappings) with an arbitrary bit permutation fused into
+// the same kernel -- exchange + local transposition in one pass, no pack/unpack buffers, no NCCL staging.
+#include "bt_internal.cuh"
+
+#define REMAP_KEEP 5        // the 5 lowest physical bits never move: every lane of a warp reads one contiguous 512 B run
+#define REMAP_TBITS 10      // permutation tables of 2^10 entries per 10-bit digit of the destination index
+#define REMAP_NT 4          // 4 digits cover 40 bits
+
+struct RemapParams {
+  const double2* src[16];
+  int n_local;
+  int rank;
+};
+
+// dst[i] = src_rank(P)[local(P)] with P = T0[d0] | T1[d1] | T2[d2] | T3[d3], d* = digits of ((rank << n_local) | i)
+__global__ void __launch_bounds__(256) k_remap_pull(double2* __restrict__ dst, uint64_t n, int64_t n_batch,
+                                                     const __grid_constant__ RemapParams P, const uint64_t* __restrict__ tables) {
+  __shared__ uint64_t T[REMAP_NT << REMAP_TBITS];
+  for (int i = threadIdx.x; i < (REMAP_NT << REMAP_TBITS); i += blockDim.x) T[i] = tables[i];
+  __syncthreads();
+  const uint64_t lmask = (1ull << P.n_local) - 1;
+  const uint64_t rank_hi = (uint64_t)P.rank << P.n_local;
+  const uint64_t total = n * (uint64_t)n_batch;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t dm = (1ull << REMAP_TBITS) - 1;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 independent 16-byte loads in flight per thread: NVLink round trips are ~2-4 us
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint64_t idx = i + u * stride;
+      uint64_t t = idx >> P.n_local;  // trajectory
+      uint64_t d = rank_hi | (idx & lmask);
+      uint64_t s = T[d & dm] | T[(1 << REMAP_TBITS) + ((d >> REMAP_TBITS) & dm)] | T[(2 << REMAP_TBITS) + ((d >> (2 * REMAP_TBITS)) & dm)] |
+                   T[(3 << REMAP_TBITS) + ((d >> (3 * REMAP_TBITS)) & dm)];
+      v[u] = P.src[s >> P.n_local][(t << P.n_local) | (s & lmask)];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
+  }
+  for (; i < total; i += stride) {
+    uint64_t t = i >> P.n_local;
+    uint64_t d = rank_hi | (i & lmask);
+    uint64_t s = T[d & dm] | T[(1 << REMAP_TBITS) + ((d >> REMAP_TBITS) & dm)] | T[(2 << REMAP_TBITS) + ((d >> (2 * REMAP_TBITS)) & dm)] |
+                 T[(3 << REMAP_TBITS) + ((d >> (3 * REMAP_TBITS)) & dm)];
+    dst[i] = P.src[s >> P.n_local][(t << P.n_local) | (s & lmask)];
+  }
+}
+
+extern "C" int bt_sv_create_shard(int n_qubits_total, int rank, int world, bt_sv** out) {
+  if (world < 1 || world > 16 || (world & (world - 1))) BT_FAIL(BT_ERR_ARG, "world must be a power of two <= 16");
+  if (rank < 0 || rank >= world) BT_FAIL(BT_ERR_ARG, "rank out of range");
+  int g = 0;
+  while ((1 << g) < world) ++g;
+  if (n_qubits_total - g < REMAP_KEEP + g) BT_FAIL(BT_ERR_ARG, "too few qubits (%d) for %d shards", n_qubits_total, world);
+  BT_TRY(bt_sv_create_internal(n_qubits_total, n_qubits_total - g, 1, world > 1, out));
+  bt_sv* s = *out;
+  s->rank = rank; s->world = world; s->g = g;
+  for (int r = 0; r < 16; ++r) { s->peer_amp[r] = nullptr; s->peer_alt[r] = nullptr; }
+  s->peer_amp[rank] = s->amp;
+  s->peer_alt[rank] = s->alt;
+  if (world == 1) s->peers_attached = true;
+  // |0..0> lives on rank 0 only
+  return bt_sv_set_basis(s, 0);
+}
+
+extern "C" int bt_sv_ipc_export(bt_sv* s, void* handles) {
+  BT_TRY(bt_check_sv(s));
+  if (!handles) BT_FAIL(BT_ERR_ARG, "null output");
+  if (!s->alt) BT_FAIL(BT_ERR_ARG, "not a shard handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= BT_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h0, h1;
+  BT_CUDA(cudaIpcGetMemHandle(&h0, s->amp));
+  BT_CUDA(cudaIpcGetMemHandle(&h1, s->alt));
+  memset(handles, 0, 2 * BT_IPC_HANDLE_BYTES);
+  memcpy(handles, &h0, sizeof(h0));
+  memcpy((char*)handles + BT_IPC_HANDLE_BYTES, &h1, sizeof(h1));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_ipc_attach(bt_sv* s, const void* all_handles) {
+  BT_TRY(bt_check_sv(s));
+  if (!all_handles) BT_FAIL(BT_ERR_ARG, "null handles");
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) continue;
+    cudaIpcMemHandle_t h0, h1;
+    memcpy(&h0, (const char*)all_handles + (size_t)r * 2 * BT_IPC_HANDLE_BYTES, sizeof(h0));
+    memcpy(&h1, (const char*)all_handles + (size_t)r * 2 * BT_IPC_HANDLE_BYTES + BT_IPC_HANDLE_BYTES, sizeof(h1));
+    void *p0 = nullptr, *p1 = nullptr;
+    BT_CUDA(cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess));
+    BT_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_amp[r] = (double2*)p0;
+    s->peer_alt[r] = (double2*)p1;
+  }
+  s->ipc_opened = true;
+  s->peers_attached = true;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_attach_local_peers(bt_sv** shards, int world) {
+  if (!shards || world < 1) BT_FAIL(BT_ERR_ARG, "invalid shard list");
+  for (int r = 0; r < world; ++r)
+    if (!shards[r] || shards[r]->world != world || shards[r]->rank != r) BT_FAIL(BT_ERR_ARG, "shard %d does not match (rank/world)", r);
+  for (int r = 0; r < world; ++r) {
+    bt_sv* s = shards[r];
+    BT_CUDA(cudaSetDevice(s->device));
+    for (int q = 0; q < world; ++q) {
+      if (shards[q]->device != s->device) {
+        int can = 0;
+        BT_CUDA(cudaDeviceCanAccessPeer(&can, s->device, shards[q]->device));
+        if (!can) BT_FAIL(BT_ERR_CUDA, "device %d cannot access device %d", s->device, shards[q]->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(shards[q]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) BT_CUDA(e);
+        cudaGetLastError();
+      }
+      s->peer_amp[q] = shards[q]->amp;
+      s->peer_alt[q] = shards[q]->alt;
+    }
+    s->peers_attached = true;
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_set_barrier(bt_sv* s, bt_barrier_fn fn, void* ctx) {
+  if (!s) BT_FAIL(BT_ERR_ARG, "null handle");
+  s->barrier = fn; s->barrier_ctx = ctx;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_set_allreduce(bt_sv* s, bt_allreduce_fn fn, void* ctx) {
+  if (!s) BT_FAIL(BT_ERR_ARG, "null handle");
+  s->allreduce = fn; s->allreduce_ctx = ctx;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_layout(const bt_sv* s, int* phys) {
+  if (!s || !phys) BT_FAIL(BT_ERR_ARG, "null argument");
+  for (int b = 0; b < s->n_qubits; ++b) phys[b] = s->phys_of_bit[b];
+  return BT_OK;
+}
+
+extern "C" int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* bytes_remote, float* ms_total) {
+  if (!s) BT_FAIL(BT_ERR_ARG, "null handle");
+  if (n_remaps) *n_remaps = s->n_remaps;
+  if (bytes_remote) *bytes_remote = s->remap_bytes;
+  if (ms_total) *ms_total = s->remap_ms;
+  return BT_OK;
+}
+
+// new_phys[lb] = physical bit position of logical bit lb after the remap (a permutation of 0..n-1)
+extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
+  BT_TRY(bt_check_sv(s));
+  if (!new_phys) BT_FAIL(BT_ERR_ARG, "null layout");
+  int n = s->n_qubits;
+  if (s->world == 1 && !s->alt) BT_TRY(bt_ensure_alt(s));
+  if (!s->peers_attached) BT_FAIL(BT_ERR_ARG, "shard peers are not attached (bt_sv_ipc_attach / bt_sv_attach_local_peers)");
+  // validate permutation; sigma[dst phys bit] = src phys bit
+  int sigma[64];
+  bool seen[64] = {false};
+  bool identity = true;
+  for (int lb = 0; lb < n; ++lb) {
+    int d = new_phys[lb];
+    if (d < 0 || d >= n || seen[d]) BT_FAIL(BT_ERR_ARG, "layout is not a permutation");
+    seen[d] = true;
+    sigma[d] = s->phys_of_bit[lb];
+    if (sigma[d] != d) identity = false;
+  }
+  if (identity) return BT_OK;
+  for (int d = 0; d < REMAP_KEEP; ++d)
+    if (sigma[d] != d) BT_FAIL(BT_ERR_ARG, "the %d lowest physical bits must stay in place (coalescing)", REMAP_KEEP);
+  // digit tables
+  std::vector<uint64_t> tab((size_t)REMAP_NT << REMAP_TBITS, 0);
+  for (int t = 0; t < REMAP_NT; ++t)
+    for (uint64_t v = 0; v < (1ull << REMAP_TBITS); ++v) {
+      uint64_t o = 0;
+      for (int j = 0; j < REMAP_TBITS; ++j) {
+        int d = t * REMAP_TBITS + j;
+        if (d < n && ((v >> j) & 1)) o |= 1ull << sigma[d];
+      }
+      tab[((size_t)t << REMAP_TBITS) + v] = o;
+    }
+  uint64_t* d_tab = nullptr;
+  BT_CUDA(cudaMallocAsync(&d_tab, tab.size() * sizeof(uint64_t), s->stream));
+  BT_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  // fraction of the new shard that comes from other ranks (for the NVLink traffic figure)
+  int moved_global = 0;
+  for (int d = s->n_local; d < n; ++d) if (sigma[d] < s->n_local) moved_global++;
+  // everyone's previous kernels must have finished writing `amp`
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  if (s->barrier) s->barrier(s->barrier_ctx);
+  RemapParams P;
+  for (int r = 0; r < 16; ++r) P.src[r] = (r < s->world) ? s->peer_amp[r] : nullptr;
+  P.n_local = s->n_local;
+  P.rank = s->rank;
+  cudaEvent_t e0 = s->ev0, e1 = s->ev1;
+  cudaEvent_t t0, t1;
+  BT_CUDA(cudaEventCreate(&t0));
+  BT_CUDA(cudaEventCreate(&t1));
+  (void)e0; (void)e1;
+  BT_CUDA(cudaEventRecord(t0, s->stream));
+  uint64_t nloc = 1ull << s->n_local;
+  unsigned grid = (unsigned)std::min<uint64_t>((s->len / 4 + 255) / 256 + 1, 148ull * 8);
+  k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
+  BT_CHECK_LAUNCH(s);
+  BT_CUDA(cudaEventRecord(t1, s->stream));
+  BT_CUDA(cudaFreeAsync(d_tab, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  BT_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  // nobody may overwrite the buffer others are still reading
+  if (s->barrier) s->barrier(s->barrier_ctx);
+  std::swap(s->amp, s->alt);
+  for (int r = 0; r < s->world; ++r) std::swap(s->peer_amp[r], s->peer_alt[r]);
+  for (int lb = 0; lb < n; ++lb) s->phys_of_bit[lb] = new_phys[lb];
+  s->n_remaps++;
+  s->remap_ms += ms;
+  // bytes pulled from other ranks: a fraction (1 - 2^-moved_global) of the shard
+  double frac = 1.0 - ldexp(1.0, -moved_global);
+  s->remap_bytes += (uint64_t)(frac * (double)s->len * 16.0);
+  return BT_OK;
+}
+
+// Make the given logical bits local.  Victims are the highest local physical positions not in `need`.
+int bt_prepare_local_bits(bt_sv* s, int n, const int* logical_bits) {
+  if (s->world == 1) return BT_OK;
+  int nq = s->n_qubits, nl = s->n_local;
+  std::vector<int> need_global;
+  bool is_needed[64] = {false};
+  for (int i = 0; i < n; ++i) {
+    is_needed[logical_bits[i]] = true;
+    if (s->phys_of_bit[logical_bits[i]] >= nl) need_global.push_back(logical_bits[i]);
+  }
+  if (need_global.empty()) return BT_OK;
+  int logical_at[64];
+  for (int lb = 0; lb < nq; ++lb) logical_at[s->phys_of_bit[lb]] = lb;
+  int new_phys[64];
+  for (int lb = 0; lb < nq; ++lb) new_phys[lb] = s->phys_of_bit[lb];
+  int pos = nl - 1;
+  for (size_t i = 0; i < need_global.size(); ++i) {
+    while (pos >= REMAP_KEEP && is_needed[logical_at[pos]]) --pos;
+    if (pos < REMAP_KEEP) BT_FAIL(BT_ERR_UNSUPPORTED, "cannot make all requested qubits local");
+    int victim = logical_at[pos];
+    int gl = need_global[i];
+    std::swap(new_phys[victim], new_phys[gl]);
+    --pos;
+  }
+  return bt_sv_remap(s, new_phys);
+}
+
+// Gate-level preparation: non-diagonal targets must be local (physical bits in g refer to the current layout).
+int bt_prepare_local(bt_sv* s, const GateDesc& g) {
+  if (s->world == 1) return BT_OK;
+  if (g.diag) return BT_OK;
+  int logical_at[64];
+  for (int lb = 0; lb < s->n_qubits; ++lb) logical_at[s->phys_of_bit[lb]] = lb;
+  int lbs[4], n = 0;
+  bool any_global = false;
+  for (int t = 0; t < g.k; ++t) {
+    lbs[n++] = logical_at[g.tb[t]];
+    if (g.tb[t] >= s->n_local) any_global = true;
+  }
+  if (!any_global) return BT_OK;
+  return bt_prepare_local_bits(s, n, lbs);
+}

@@ -1,0 +1,457 @@
+// bt_measure.cu -- Born measurement + collapse, Kraus trajectory step, inverse-CDF sampling.
+//
+// Replaces born_measure_Z (src/hilbert.jl:682-696), _reset_Z (:752-759), __calc_prob (src/struct.jl:9-29),
+// __QuantumChannel_new_apply (src/struct.jl:31-55), _weighted_sample (src/hilbert.jl:810-819) and sample
+// (src/ops.jl:46-62).  All decisions (outcome, Kraus index, normalisation factor) are taken on the device from
+// caller-supplied uniforms, per trajectory, so a batch of trajectories advances without host round trips.
+#include "bt_internal.cuh"
+
+int bt_reduce_rdm_at(const bt_sv* cs, int k, const int* tb, size_t res_off);
+int bt_prepare_local_bits(bt_sv* s, int n, const int* logical_bits);
+
+// ---- measurement ----------------------------------------------------------------------------------------------
+// res: n_batch x 4 packed 2x2 RDMs ([0] = p0, [3] = p1).  outcome = (u < p0) ? 0 : 1  (src/hilbert.jl:693)
+__global__ void k_decide_measure(const double* __restrict__ res, const double* __restrict__ u, int32_t* __restrict__ outcome,
+                                 double* __restrict__ scale, int64_t n_batch) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_batch) return;
+  double p0 = res[4 * t], p1 = res[4 * t + 3];
+  int ind = (u[t] < p0) ? 0 : 1;
+  outcome[t] = ind;
+  scale[2 * t] = 1.0 / sqrt(ind == 0 ? p0 : p1);  // normalize(P_ind * state): divide by the actual norm
+  scale[2 * t + 1] = p0;
+}
+
+// pair (i0 = bit clear, i1 = bit set): keep the measured half scaled, zero the other; reset moves |1> to |0>.
+__global__ void __launch_bounds__(256) k_collapse(double2* __restrict__ a, int n_local, int bit, uint64_t npairs,
+                                                   const int32_t* __restrict__ outcome, const double* __restrict__ scale, int reset) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const double2 zero = make_double2(0.0, 0.0);
+  for (; g < npairs; g += stride) {
+    uint64_t t = g >> (n_local - 1);
+    uint64_t i0 = ((g >> bit) << (bit + 1)) | (g & ((1ull << bit) - 1));
+    uint64_t i1 = i0 | (1ull << bit);
+    int ind = outcome[t];
+    double sc = scale[2 * t];
+    if (ind == 0) {
+      double2 x = a[i0];
+      a[i0] = make_double2(x.x * sc, x.y * sc);
+      a[i1] = zero;
+    } else {
+      double2 x = a[i1];
+      x = make_double2(x.x * sc, x.y * sc);
+      if (reset) { a[i0] = x; a[i1] = zero; }
+      else { a[i1] = x; a[i0] = zero; }
+    }
+  }
+}
+
+extern "C" int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* outcome, double* p0, int reset) {
+  BT_TRY(bt_check_sv(s));
+  if (!u) BT_FAIL(BT_ERR_ARG, "null uniforms");
+  if (qubit < 1 || qubit > s->n_qubits) BT_FAIL(BT_ERR_ARG, "N must be larger than qubit");
+  BT_TRY(bt_ensure_traj(s));
+  int lb = s->n_qubits - qubit;
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(s, 1, &lb));
+  int bit = s->phys_of_bit[lb];
+  BT_CUDA(cudaMemcpyAsync(s->d_u, u, s->n_batch * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  int tb[1] = {bit};
+  BT_TRY(bt_reduce_rdm(s, 1, tb));
+  if (s->world > 1) {
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 4));
+    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
+    s->allreduce(s->allreduce_ctx, s->h_res, (int)(s->n_batch * 4));
+    BT_CUDA(cudaMemcpyAsync(s->d_res, s->h_res, s->n_batch * 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  }
+  k_decide_measure<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(s->d_res, s->d_u, s->d_outcome, s->d_scale, s->n_batch);
+  BT_CHECK_LAUNCH(s);
+  uint64_t npairs = s->len >> 1;
+  unsigned grid = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 148ull * 32);
+  k_collapse<<<grid, 256, 0, s->stream>>>(s->amp, s->n_local, bit, npairs, s->d_outcome, s->d_scale, reset);
+  BT_CHECK_LAUNCH(s);
+  if (outcome || p0) {
+    if (outcome) BT_CUDA(cudaMemcpyAsync(outcome, s->d_outcome, s->n_batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (p0) {
+      BT_CUDA(cudaMemcpyAsync(s->h_res, s->d_scale, s->n_batch * 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+    if (p0) for (int64_t t = 0; t < s->n_batch; ++t) p0[t] = s->h_res[2 * t + 1];
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_outcomes(const bt_sv* s, int32_t* outcome) {
+  BT_TRY(bt_check_sv(s));
+  if (!outcome) BT_FAIL(BT_ERR_ARG, "null output");
+  if (!s->d_outcome) BT_FAIL(BT_ERR_ARG, "no measurement has been made on this handle");
+  BT_CUDA(cudaMemcpyAsync(outcome, s->d_outcome, s->n_batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+// ---- Kraus trajectory step ---------------------------------------------------------------------------------------
+// One block per trajectory.  rho (packed, D*D doubles) is the RDM in the reference's *probability* ordering;
+// `swap` != 0 means the operator is applied in the other ordering (2-qubit channel with qubit > target,
+// SURVEY App. A.5 #2): probabilities use rho as is, the normalisation uses the bit-swapped rho.
+// K: nK row-major DxD matrices.  mats out: row-major DxD (stride 64), scaled by 1/||K_ind psi||.
+template <int D>
+__device__ double kraus_weight(const double2* __restrict__ K, const double2* rho) {
+  // Re tr(K rho K') = sum_a sum_b sum_c Re( K[a][b] rho[b][c] conj(K[a][c]) )
+  double tot = 0.0;
+  for (int a = 0; a < D; ++a)
+    for (int b = 0; b < D; ++b) {
+      double2 kab = K[a * D + b];
+      if (kab.x == 0.0 && kab.y == 0.0) continue;
+      for (int c = 0; c < D; ++c) {
+        double2 kac = K[a * D + c];
+        double2 r = rho[b * D + c];
+        // kab * r
+        double xr = kab.x * r.x - kab.y * r.y, xi = kab.x * r.y + kab.y * r.x;
+        // * conj(kac), real part
+        tot += xr * kac.x + xi * kac.y;
+      }
+    }
+  return tot;
+}
+
+template <int D>
+__global__ void __launch_bounds__(64) k_decide_kraus(const double* __restrict__ res, const double* __restrict__ u,
+                                                      const double2* __restrict__ K, int nK, int swap,
+                                                      int32_t* __restrict__ chosen, double2* __restrict__ mats,
+                                                      double* __restrict__ probs_out, int32_t* __restrict__ err) {
+  __shared__ double2 rho[D * D];
+  __shared__ double2 rho_s[D * D];
+  __shared__ double probs[64];
+  __shared__ int s_ind;
+  __shared__ double s_scale;
+  const int64_t t = blockIdx.x;
+  const double* v = res + t * (D * D);
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    int a = i / D, b = i % D;
+    double2 r;
+    if (a == b) r = make_double2(v[a * D + a], 0.0);
+    else if (a < b) r = make_double2(v[a * D + b], v[b * D + a]);
+    else r = make_double2(v[b * D + a], -v[a * D + b]);
+    rho[i] = r;
+  }
+  __syncthreads();
+  if (D == 4) {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+      int a = i / D, b = i % D;
+      int a2 = ((a & 1) << 1) | (a >> 1), b2 = ((b & 1) << 1) | (b >> 1);
+      rho_s[i] = swap ? rho[a2 * D + b2] : rho[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) rho_s[i] = rho[i];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nK; k += blockDim.x) {
+    probs[k] = kraus_weight<D>(K + (size_t)k * D * D, rho);
+    if (probs_out) probs_out[t * nK + k] = probs[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ind = -1;
+    if (u) {
+      double rval = u[t], cum = 0.0;
+      for (int k = 0; k < nK; ++k) {  // src/hilbert.jl:814-817: first i with rval <= cumsum[i]
+        cum += probs[k];
+        if (rval <= cum) { ind = k; break; }
+      }
+      if (ind < 0) { atomicExch(err, 1); ind = nK - 1; }
+      double w = kraus_weight<D>(K + (size_t)ind * D * D, rho_s);
+      s_scale = 1.0 / sqrt(w);
+      chosen[t] = ind;
+    }
+    s_ind = ind;
+  }
+  __syncthreads();
+  if (u) {
+    const double2* Ks = K + (size_t)s_ind * D * D;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x)
+      mats[t * 64 + i] = make_double2(Ks[i].x * s_scale, Ks[i].y * s_scale);
+  }
+}
+
+static int kraus_common(bt_sv* s, int nq, int qubit, int target, const bt_c64* K, int nK, const double* u,
+                        int32_t* chosen, double* probs_host) {
+  if (!K) BT_FAIL(BT_ERR_ARG, "null Kraus operators");
+  if (nK < 1 || nK > 64) BT_FAIL(BT_ERR_ARG, "number of Kraus operators must be 1..64");
+  int N = s->n_qubits;
+  int D = 1 << nq;
+  int lb_apply[3], lb_prob[3];
+  int swap = 0;
+  if (nq == 1) {
+    if (qubit < 1 || qubit > N) BT_FAIL(BT_ERR_ARG, "N must be larger than qubit");
+    lb_apply[0] = lb_prob[0] = N - qubit;
+  } else if (nq == 2) {
+    if (qubit < 1 || target < 1 || qubit > N || target > N) BT_FAIL(BT_ERR_ARG, "N must be larger than qubits");
+    if (qubit == target) BT_FAIL(BT_ERR_ARG, "`qubit` and `target_qubit` must differ");
+    lb_apply[0] = N - target; lb_apply[1] = N - qubit;            // K indexed 2*b_qubit + b_target
+    int lo = std::min(qubit, target), hi = std::max(qubit, target);
+    lb_prob[0] = N - hi; lb_prob[1] = N - lo;                      // rho_A indexed 2*b_min + b_max
+    swap = qubit > target;
+  } else if (nq == 3) {
+    if (qubit < 1 || qubit + 2 > N) BT_FAIL(BT_ERR_ARG, "N must be larger than all three qubits");
+    for (int i = 0; i < 3; ++i) lb_apply[i] = lb_prob[i] = N - (qubit + 2 - i);
+  } else {
+    BT_FAIL(BT_ERR_ARG, "Noise models are available only for up to 3 qubits!");
+  }
+  BT_TRY(bt_ensure_traj(s));
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(s, nq, lb_apply));
+  int tb_apply[3], tb_prob[3];
+  for (int i = 0; i < nq; ++i) { tb_apply[i] = s->phys_of_bit[lb_apply[i]]; tb_prob[i] = s->phys_of_bit[lb_prob[i]]; }
+  // Kraus table -> device (row-major), staged through the scratch area behind d_mats' sibling buffer
+  std::vector<double2> hk((size_t)nK * D * D);
+  for (int k = 0; k < nK; ++k)
+    for (int r = 0; r < D; ++r)
+      for (int c = 0; c < D; ++c) {
+        const bt_c64& z = K[(size_t)k * D * D + r + c * D];
+        hk[(size_t)k * D * D + r * D + c] = make_double2(z.re, z.im);
+      }
+  double2* d_K = nullptr;
+  BT_CUDA(cudaMallocAsync(&d_K, hk.size() * sizeof(double2), s->stream));
+  BT_CUDA(cudaMemcpyAsync(d_K, hk.data(), hk.size() * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));  // hk is pageable host memory: finish the copy before it goes away
+  if (u) BT_CUDA(cudaMemcpyAsync(s->d_u, u, s->n_batch * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  BT_TRY(bt_reduce_rdm(s, nq, tb_prob));
+  if (s->world > 1) {
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * D * D));
+    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
+    s->allreduce(s->allreduce_ctx, s->h_res, (int)(s->n_batch * D * D));
+    BT_CUDA(cudaMemcpyAsync(s->d_res, s->h_res, s->n_batch * D * D * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  }
+  double* d_probs = nullptr;
+  if (probs_host) BT_CUDA(cudaMallocAsync(&d_probs, (size_t)s->n_batch * nK * sizeof(double), s->stream));
+  const double* du = u ? s->d_u : nullptr;
+  if (nq == 1) k_decide_kraus<2><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err);
+  else if (nq == 2) k_decide_kraus<4><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, swap, s->d_outcome, s->d_mats, d_probs, s->d_err);
+  else k_decide_kraus<8><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err);
+  BT_CHECK_LAUNCH(s);
+  BT_CUDA(cudaFreeAsync(d_K, s->stream));
+  if (u) BT_TRY(bt_launch_gate_devmat(s, nq, tb_apply, s->d_mats));
+  if (probs_host) {
+    BT_CUDA(cudaMemcpyAsync(probs_host, d_probs, (size_t)s->n_batch * nK * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    BT_CUDA(cudaFreeAsync(d_probs, s->stream));
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  if (chosen) {
+    BT_CUDA(cudaMemcpyAsync(chosen, s->d_outcome, s->n_batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    BT_CUDA(cudaMemcpyAsync(s->h_flag, s->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->h_flag[0]) {
+      BT_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int32_t), s->stream));
+      BT_FAIL(BT_ERR_SAMPLE, "_weighted_sample: uniform draw exceeds the cumulative Kraus probabilities (reference returns nothing)");
+    }
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_kraus(bt_sv* s, int nq, int qubit, int target, const bt_c64* K, int nK, const double* u, int32_t* chosen) {
+  BT_TRY(bt_check_sv(s));
+  if (!u) BT_FAIL(BT_ERR_ARG, "null uniforms");
+  return kraus_common(s, nq, qubit, target, K, nK, u, chosen, nullptr);
+}
+
+extern "C" int bt_sv_kraus_probs(const bt_sv* s, int nq, int qubit, int target, const bt_c64* K, int nK, double* probs) {
+  BT_TRY(bt_check_sv(s));
+  if (!probs) BT_FAIL(BT_ERR_ARG, "null output");
+  return kraus_common(const_cast<bt_sv*>(s), nq, qubit, target, K, nK, nullptr, nullptr, probs);
+}
+
+// ---- sampling ------------------------------------------------------------------------------------------------------
+// Two-level inverse CDF: (1) sums of p over blocks of 2^SB entries, (2) inclusive scan of the block sums,
+// (3) one warp per shot: binary search over the block prefix, then a warp scan inside the block.
+// p(i) = |a[i]|^2 for a state vector, Re a[i*(dim+1)] for the diagonal of a density matrix.
+#define SB 12
+
+__device__ __forceinline__ double prob_at(const double2* __restrict__ a, uint64_t i, uint64_t dm_stride) {
+  if (dm_stride) return a[i * dm_stride].x;
+  double2 x = a[i];
+  return x.x * x.x + x.y * x.y;
+}
+
+__global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum) {
+  // one CTA per block of 2^SB entries; fixed-order tree => reproducible
+  __shared__ double sm[8];
+  const uint64_t b0 = (uint64_t)blockIdx.x << SB;
+  double acc = 0.0;
+  for (uint64_t k = threadIdx.x; k < (1ull << SB); k += 256) {
+    uint64_t i = b0 + k;
+    if (i < n) acc += prob_at(a, i, dm_stride);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sm[w];
+    bsum[blockIdx.x] = s;
+  }
+}
+
+// single-CTA inclusive scan (sequential carry over tiles of 1024)
+__global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ x, uint64_t n) {
+  __shared__ double warp_tot[32];
+  __shared__ double carry_s;
+  if (threadIdx.x == 0) carry_s = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint64_t base = 0; base < n; base += 1024) {
+    uint64_t i = base + threadIdx.x;
+    double v = (i < n) ? x[i] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += y;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      double w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    double off = carry_s + (warp > 0 ? warp_tot[warp - 1] : 0.0);
+    v += off;
+    if (i < n) x[i] = v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = v;
+    __syncthreads();
+  }
+}
+
+// pre: prefix = inclusive scan of block sums (nb entries); total mass `lo..hi` window for sharded sampling:
+// a shot with target t (already scaled to the global total) is handled iff offset <= t' where t' = t - offset
+// falls in (.., local_total]; otherwise out = -1.
+__global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride,
+                                                 const double* __restrict__ prefix, uint64_t nb,
+                                                 const double* __restrict__ u, uint64_t shots, double total_global, double offset,
+                                                 int is_last_rank, int64_t* __restrict__ out) {
+  const uint64_t shot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (shot >= shots) return;
+  const double local_total = prefix[nb - 1];
+  double t = u[shot] * total_global - offset;
+  // ownership: first index with global cumsum >= target
+  bool mine = (offset == 0.0 ? true : t > 0.0) && (t <= local_total || is_last_rank);
+  if (offset == 0.0 && t <= 0.0) mine = true;  // u == 0 -> first entry with cumsum >= 0
+  if (!mine) { if (lane == 0) out[shot] = -1; return; }
+  // binary search: first block j with prefix[j] >= t
+  uint64_t lo = 0, hi = nb - 1;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (prefix[mid] >= t) hi = mid; else lo = mid + 1;
+  }
+  const uint64_t j = lo;
+  double carry = (j > 0) ? prefix[j - 1] : 0.0;
+  const uint64_t b0 = j << SB;
+  const uint64_t bend = (b0 + (1ull << SB) < n) ? b0 + (1ull << SB) : n;
+  int64_t found = -1;
+  int64_t last_nz = -1;
+  for (uint64_t base = b0; base < bend && found < 0; base += 32) {
+    uint64_t i = base + lane;
+    double p = (i < bend) ? prob_at(a, i, dm_stride) : 0.0;
+    double v = p;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += y;
+    }
+    double cum = carry + v;
+    unsigned hit = __ballot_sync(0xffffffffu, (i < bend) && (cum >= t));
+    unsigned nz = __ballot_sync(0xffffffffu, p != 0.0);
+    if (hit) found = (int64_t)(base + (__ffs(hit) - 1));
+    else {
+      if (nz) last_nz = (int64_t)(base + (31 - __clz(nz)));
+      carry = __shfl_sync(0xffffffffu, cum, 31);
+    }
+  }
+  if (found < 0) found = (last_nz >= 0) ? last_nz : (int64_t)(bend - 1);  // rounding fell off the end of the block
+  if (lane == 0) out[shot] = found;
+}
+
+static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_stride, const double* u, uint64_t shots, int64_t* out) {
+  if (!u || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (shots == 0) return BT_OK;
+  uint64_t nb = (n + (1ull << SB) - 1) >> SB;
+  double *d_prefix = nullptr, *d_u = nullptr;
+  int64_t* d_out = nullptr;
+  BT_CUDA(cudaMallocAsync(&d_prefix, nb * sizeof(double), s->stream));
+  BT_CUDA(cudaMallocAsync(&d_u, shots * sizeof(double), s->stream));
+  BT_CUDA(cudaMallocAsync(&d_out, shots * sizeof(int64_t), s->stream));
+  BT_CUDA(cudaMemcpyAsync(d_u, u, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_block_sums<<<(unsigned)nb, 256, 0, s->stream>>>(base, n, dm_stride, d_prefix);
+  BT_CHECK_LAUNCH(s);
+  k_scan_inclusive<<<1, 1024, 0, s->stream>>>(d_prefix, nb);
+  BT_CHECK_LAUNCH(s);
+  double total = 0.0, offset = 0.0;
+  int is_last = 1;
+  BT_CUDA(cudaMemcpyAsync(s->h_res, d_prefix + (nb - 1), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  total = s->h_res[0];
+  if (s->world > 1) {
+    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
+    // physical rank order is the order of the physical index; totals all-gathered through a sum
+    std::vector<double> tots(s->world, 0.0);
+    tots[s->rank] = total;
+    s->allreduce(s->allreduce_ctx, tots.data(), s->world);
+    total = 0.0;
+    for (int r = 0; r < s->world; ++r) { if (r == s->rank) offset = total; total += tots[r]; }
+    is_last = (s->rank == s->world - 1);
+  }
+  uint64_t threads = shots * 32;
+  k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots, total, offset, is_last, d_out);
+  BT_CHECK_LAUNCH(s);
+  BT_CUDA(cudaMemcpyAsync(out, d_out, shots * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaFreeAsync(d_prefix, s->stream));
+  BT_CUDA(cudaFreeAsync(d_u, s->stream));
+  BT_CUDA(cudaFreeAsync(d_out, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+// physical index -> logical index (identity unless a sharded state has been remapped)
+static inline int64_t phys_to_logical(const bt_sv* s, uint64_t phys) {
+  uint64_t out = 0;
+  for (int lb = 0; lb < s->n_qubits; ++lb)
+    if ((phys >> s->phys_of_bit[lb]) & 1) out |= 1ull << lb;
+  return (int64_t)out;
+}
+
+extern "C" int bt_sv_sample(const bt_sv* cs, const double* u, uint64_t shots, int64_t* out) {
+  BT_TRY(bt_check_sv(cs));
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  if (s->n_batch != 1) BT_FAIL(BT_ERR_ARG, "bt_sv_sample needs n_batch == 1 (use bt_sv_sample_batched)");
+  BT_TRY(sample_impl(s, s->amp, 1ull << s->n_local, 0, u, shots, out));
+  if (s->world > 1) {
+    std::vector<double> buf(shots);
+    for (uint64_t i = 0; i < shots; ++i) {
+      if (out[i] >= 0) buf[i] = (double)phys_to_logical(s, ((uint64_t)s->rank << s->n_local) | (uint64_t)out[i]);
+      else buf[i] = 0.0;
+    }
+    s->allreduce(s->allreduce_ctx, buf.data(), (int)shots);
+    for (uint64_t i = 0; i < shots; ++i) out[i] = (int64_t)buf[i];
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_sample_batched(const bt_sv* cs, const double* u, uint64_t shots_per_traj, int64_t* out) {
+  BT_TRY(bt_check_sv(cs));
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  if (s->world > 1) BT_FAIL(BT_ERR_UNSUPPORTED, "batched sampling of a sharded state");
+  for (int64_t t = 0; t < s->n_batch; ++t)
+    BT_TRY(sample_impl(s, s->amp + ((uint64_t)t << s->n_local), 1ull << s->n_local, 0, u + t * shots_per_traj, shots_per_traj, out + t * shots_per_traj));
+  return BT_OK;
+}
+
+int bt_sample_diag(bt_sv* v, int n, const double* u, uint64_t shots, int64_t* out) {
+  return sample_impl(v, v->amp, 1ull << n, (1ull << n) + 1, u, shots, out);
+}

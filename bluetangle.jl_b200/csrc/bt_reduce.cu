@@ -1,0 +1,647 @@
+// bt_reduce.cu -- read-only reductions over the amplitudes: reduced density matrices, norms, inner products,
+// per-bit probabilities and Pauli-string expectation values.
+//
+// Replaces partial_trace (src/linalg.jl:167-192 one qubit, :198-230 adjacent pair, :83-140 general via
+// state*state'), expect (src/func.jl:91-101) and correlation (:139-147).  One pass reads 16 B per amplitude;
+// per-thread accumulators -> warp shuffles -> shared memory -> one partial per block, then a second tiny
+// kernel adds the partials in a fixed order, so every result is bit-reproducible for a given shape.
+#include "bt_internal.cuh"
+
+static const int RB = 256;  // reduction block size
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ out) {
+  __shared__ double sm[(RB / 32) * NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[warp * NV + i] = x;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += RB) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < RB / 32; ++w) x += sm[w * NV + i];
+    out[i] = x;
+  }
+  __syncthreads();
+}
+
+// final stage: res[t][v] = sum_b part[(t*nblk + b)*nv + v]
+__global__ void k_sum_partials(const double* __restrict__ part, double* __restrict__ res, int nblk, int nv, int64_t n_batch) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_batch * nv) return;
+  int64_t t = i / nv;
+  int v = (int)(i % nv);
+  double x = 0.0;
+  for (int b = 0; b < nblk; ++b) x += part[((size_t)t * nblk + b) * nv + v];
+  res[i] = x;
+}
+
+struct RdmPlan {
+  int ni;
+  int ins[4];
+  uint64_t off[8];
+};
+
+__device__ __forceinline__ uint64_t rdm_expand(uint64_t g, const RdmPlan& p) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < p.ni) {
+      int b = p.ins[i];
+      g = ((g >> b) << (b + 1)) | (g & ((1ull << b) - 1));
+    }
+  return g;
+}
+
+// rho[a][b] = sum x_a conj(x_b).  Stored as D*D doubles: [a*D+a] = diag (real); for a<b: [a*D+b] = Re, [b*D+a] = Im of rho[a][b].
+template <int K>
+__global__ void __launch_bounds__(RB) k_rdm(const double2* __restrict__ a, int n_local, const __grid_constant__ RdmPlan P,
+                                             double* __restrict__ part, int nblk) {
+  constexpr int D = 1 << K;
+  const int64_t traj = blockIdx.y;
+  const uint64_t ngroups = 1ull << (n_local - K);
+  const double2* base = a + ((uint64_t)traj << n_local);
+  double acc[D * D];
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
+  for (uint64_t g = (uint64_t)blockIdx.x * RB + threadIdx.x; g < ngroups; g += (uint64_t)nblk * RB) {
+    uint64_t i0 = rdm_expand(g, P);
+    double2 x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = base[i0 + P.off[j]];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      acc[r * D + r] += x[r].x * x[r].x + x[r].y * x[r].y;
+#pragma unroll
+      for (int c = r + 1; c < D; ++c) {
+        // x_r * conj(x_c)
+        acc[r * D + c] += x[r].x * x[c].x + x[r].y * x[c].y;
+        acc[c * D + r] += x[r].y * x[c].x - x[r].x * x[c].y;
+      }
+    }
+  }
+  block_reduce_store<D * D>(acc, part + ((size_t)traj * nblk + blockIdx.x) * (D * D));
+}
+
+__global__ void __launch_bounds__(RB) k_norm2(const double2* __restrict__ a, int n_local, double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const uint64_t n = 1ull << n_local;
+  const double2* base = a + ((uint64_t)traj << n_local);
+  double acc[1] = {0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
+    double2 x = base[i];
+    acc[0] += x.x * x.x + x.y * x.y;
+  }
+  block_reduce_store<1>(acc, part + ((size_t)traj * nblk + blockIdx.x));
+}
+
+__global__ void __launch_bounds__(RB) k_inner(const double2* __restrict__ a, const double2* __restrict__ b, int n_local,
+                                               double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const uint64_t n = 1ull << n_local;
+  const double2* pa = a + ((uint64_t)traj << n_local);
+  const double2* pb = b + ((uint64_t)traj << n_local);
+  double acc[2] = {0.0, 0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
+    double2 x = pa[i], y = pb[i];
+    acc[0] += x.x * y.x + x.y * y.y;  // conj(x)*y
+    acc[1] += x.x * y.y - x.y * y.x;
+  }
+  block_reduce_store<2>(acc, part + ((size_t)traj * nblk + blockIdx.x) * 2);
+}
+
+// Per-bit probabilities in one pass: out[0] = sum p, out[1+b] = sum of p over amplitudes with bit b set.
+// A block walks contiguous chunks of 2^cb amplitudes; bits 0..7 are thread bits, 8..cb-1 iteration bits,
+// the rest chunk bits.
+#define BP_MAXBITS 40
+__global__ void __launch_bounds__(RB) k_bitprobs(const double2* __restrict__ a, int n_local, int cbits, double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const double2* base = a + ((uint64_t)traj << n_local);
+  const uint64_t chunk_len = 1ull << cbits;
+  const uint64_t nchunks = 1ull << (n_local - cbits);
+  const int iters = (int)((chunk_len + RB - 1) / RB);
+  const int nhi = n_local - cbits;
+  double tot = 0.0;
+  double it_acc[4] = {0, 0, 0, 0};
+  double hi[28];
+#pragma unroll
+  for (int b = 0; b < 28; ++b) hi[b] = 0.0;
+  for (uint64_t ch = blockIdx.x; ch < nchunks; ch += nblk) {
+    double ct = 0.0;
+    const double2* cp = base + ch * chunk_len;
+    for (int it = 0; it < iters; ++it) {
+      uint64_t k = (uint64_t)it * RB + threadIdx.x;
+      if (k < chunk_len) {
+        double2 x = cp[k];
+        double p = x.x * x.x + x.y * x.y;
+        ct += p;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((it >> j) & 1) it_acc[j] += p;
+      }
+    }
+    tot += ct;
+#pragma unroll
+    for (int b = 0; b < 28; ++b)
+      if (b < nhi && ((ch >> b) & 1)) hi[b] += ct;
+  }
+  // assemble per-thread vector: [tot, bits 0..n_local-1]
+  double* out = part + ((size_t)traj * nblk + blockIdx.x) * (BP_MAXBITS + 1);
+  __shared__ double sm[RB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = 0; v <= n_local; ++v) {
+    double x;
+    if (v == 0) x = tot;
+    else {
+      int b = v - 1;
+      if (b < 8 && b < cbits) x = ((threadIdx.x >> b) & 1) ? tot : 0.0;
+      else if (b < cbits) {
+        int j = b - 8;
+        x = (j == 0) ? it_acc[0] : (j == 1) ? it_acc[1] : (j == 2) ? it_acc[2] : it_acc[3];
+      } else {
+        int j = b - cbits;
+        x = 0.0;
+#pragma unroll
+        for (int q = 0; q < 28; ++q)
+          if (q == j) x = hi[q];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < RB / 32; ++w) s += sm[w];
+      out[v] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// <P> for a Pauli string: xm = X|Y positions, zm = Z|Y positions, ny = number of Y.
+// Pairs (i, i^xm) are visited once (i has the top bit of xm clear) so every amplitude is read exactly once.
+__global__ void __launch_bounds__(RB) k_pauli(const double2* __restrict__ a, int n_local, uint64_t xm, uint64_t zm, int ny, int topx,
+                                               double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const double2* base = a + ((uint64_t)traj << n_local);
+  double acc[1] = {0.0};
+  if (xm == 0) {
+    const uint64_t n = 1ull << n_local;
+    for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
+      double2 x = base[i];
+      double p = x.x * x.x + x.y * x.y;
+      acc[0] += (__popcll(i & zm) & 1) ? -p : p;
+    }
+  } else {
+    // (-i)^ny as a complex constant
+    double cr, ci;
+    switch (ny & 3) { case 0: cr = 1; ci = 0; break; case 1: cr = 0; ci = -1; break; case 2: cr = -1; ci = 0; break; default: cr = 0; ci = 1; }
+    const uint64_t n = 1ull << (n_local - 1);
+    for (uint64_t g = (uint64_t)blockIdx.x * RB + threadIdx.x; g < n; g += (uint64_t)nblk * RB) {
+      uint64_t i = ((g >> topx) << (topx + 1)) | (g & ((1ull << topx) - 1));
+      uint64_t j = i ^ xm;
+      double2 x = base[i], y = base[j];
+      // term_i = c * s_i * conj(x) * y ; term_j = c * s_j * conj(y) * x
+      double tr = x.x * y.x + x.y * y.y, ti = x.x * y.y - x.y * y.x;  // conj(x)*y
+      double si = (__popcll(i & zm) & 1) ? -1.0 : 1.0;
+      double sj = (__popcll(j & zm) & 1) ? -1.0 : 1.0;
+      // real part of c*(si*(tr + i ti) + sj*(tr - i ti))
+      double re = (si + sj) * tr, im = (si - sj) * ti;
+      acc[0] += cr * re - ci * im;
+    }
+  }
+  block_reduce_store<1>(acc, part + ((size_t)traj * nblk + blockIdx.x));
+}
+
+__global__ void k_abs2(const double2* __restrict__ a, double* __restrict__ p, uint64_t len) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < len; i += stride) {
+    double2 x = a[i];
+    p[i] = x.x * x.x + x.y * x.y;
+  }
+}
+
+__global__ void k_scale_by_norm(double2* __restrict__ a, int n_local, uint64_t len, const double* __restrict__ norm2) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < len; i += stride) {
+    double s = rsqrt(norm2[i >> n_local]);
+    // one Newton step is not needed for parity (<=1e-10) but keep full precision via 1/sqrt
+    s = 1.0 / sqrt(norm2[i >> n_local]);
+    double2 x = a[i];
+    a[i] = make_double2(x.x * s, x.y * s);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+static int pick_nblk(const bt_sv* s, uint64_t work_items_per_traj) {
+  uint64_t want = (work_items_per_traj + RB - 1) / RB;
+  uint64_t cap = std::max<uint64_t>(1, (148ull * 16) / (uint64_t)s->n_batch);
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, cap));
+}
+
+static int check_batch_grid(const bt_sv* s) {
+  if (s->n_batch > 65535) BT_FAIL(BT_ERR_UNSUPPORTED, "n_batch > 65535 not supported by the reduction kernels");
+  return BT_OK;
+}
+
+static int finish(const bt_sv* s, int nblk, int nv, size_t res_off) {
+  int64_t tot = s->n_batch * nv;
+  if (res_off + (size_t)tot > s->res_cap) BT_FAIL(BT_ERR_ARG, "internal: result buffer overflow");
+  k_sum_partials<<<(unsigned)((tot + 255) / 256), 256, 0, s->stream>>>(s->d_part, s->d_res + res_off, nblk, nv, s->n_batch);
+  BT_CHECK_LAUNCH(s);
+  return BT_OK;
+}
+
+int bt_reduce_rdm_at(const bt_sv* cs, int k, const int* tb, size_t res_off) {
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  if (k < 1 || k > 3) BT_FAIL(BT_ERR_ARG, "rdm arity %d unsupported", k);
+  if (s->n_local < k) BT_FAIL(BT_ERR_ARG, "state too small for a %d-qubit RDM", k);
+  RdmPlan P;
+  int sorted[4];
+  for (int i = 0; i < k; ++i) {
+    if (tb[i] < 0 || tb[i] >= s->n_local) BT_FAIL(BT_ERR_UNSUPPORTED, "reduced density matrix over a global qubit needs a remap first");
+    sorted[i] = tb[i];
+  }
+  std::sort(sorted, sorted + k);
+  for (int i = 0; i + 1 < k; ++i)
+    if (sorted[i] == sorted[i + 1]) BT_FAIL(BT_ERR_ARG, "repeated qubit");
+  P.ni = k;
+  for (int i = 0; i < 4; ++i) P.ins[i] = i < k ? sorted[i] : 0;
+  for (int j = 0; j < (1 << k); ++j) {
+    uint64_t o = 0;
+    for (int t = 0; t < k; ++t)
+      if ((j >> t) & 1) o |= 1ull << tb[t];
+    P.off[j] = o;
+  }
+  int D = 1 << k, nv = D * D;
+  int nblk = pick_nblk(s, 1ull << (s->n_local - k));
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * nv));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  if (k == 1) k_rdm<1><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+  else if (k == 2) k_rdm<2><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+  else k_rdm<3><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  return finish(s, nblk, nv, res_off);
+}
+
+int bt_reduce_rdm(const bt_sv* s, int k, const int* tb) { return bt_reduce_rdm_at(s, k, tb, 0); }
+
+int bt_reduce_norm2(const bt_sv* cs) {
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  int nblk = pick_nblk(s, 1ull << s->n_local);
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  k_norm2<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  return finish(s, nblk, 1, 0);
+}
+
+// unpack the packed D*D doubles of one trajectory into a column-major complex matrix (rho[a][b] at a + b*D)
+static void unpack_rdm(const double* v, int D, bt_c64* out) {
+  for (int a = 0; a < D; ++a) {
+    out[a + a * D].re = v[a * D + a];
+    out[a + a * D].im = 0.0;
+    for (int b = a + 1; b < D; ++b) {
+      double re = v[a * D + b], im = v[b * D + a];
+      out[a + b * D].re = re; out[a + b * D].im = im;     // rho[a][b]
+      out[b + a * D].re = re; out[b + a * D].im = -im;    // rho[b][a] = conj
+    }
+  }
+}
+
+static int allreduce_host(const bt_sv* s, double* buf, int n) {
+  if (s->world > 1) {
+    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback (bt_sv_set_allreduce) before calling reductions");
+    s->allreduce(s->allreduce_ctx, buf, n);
+  }
+  return BT_OK;
+}
+
+int bt_prepare_local_bits(bt_sv* s, int n, const int* logical_bits);  // bt_dist.cu
+
+extern "C" int bt_sv_rdm1(const bt_sv* s, int qubit, bt_c64* out) {
+  BT_TRY(bt_check_sv(s));
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output");
+  if (qubit < 1 || qubit > s->n_qubits) BT_FAIL(BT_ERR_ARG, "qubit %d out of range", qubit);
+  int lb = s->n_qubits - qubit;
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(const_cast<bt_sv*>(s), 1, &lb));
+  int tb[1] = {s->phys_of_bit[lb]};
+  BT_TRY(bt_reduce_rdm(s, 1, tb));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 4));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 4)));
+  for (int64_t t = 0; t < s->n_batch; ++t) unpack_rdm(s->h_res + t * 4, 2, out + t * 4);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_rdm2(const bt_sv* s, int qa, int qb, bt_c64* out) {
+  BT_TRY(bt_check_sv(s));
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output");
+  if (qa < 1 || qb < 1 || qa > s->n_qubits || qb > s->n_qubits || qa == qb) BT_FAIL(BT_ERR_ARG, "invalid qubit pair (%d,%d)", qa, qb);
+  int lo = std::min(qa, qb), hi = std::max(qa, qb);
+  // index = 2*b_min + b_max (src/linalg.jl:206, :83-86): matrix bit 1 <-> smaller label, bit 0 <-> larger label
+  int lbs[2] = {s->n_qubits - hi, s->n_qubits - lo};
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(const_cast<bt_sv*>(s), 2, lbs));
+  int tb[2] = {s->phys_of_bit[lbs[0]], s->phys_of_bit[lbs[1]]};
+  BT_TRY(bt_reduce_rdm(s, 2, tb));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 16));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 16)));
+  for (int64_t t = 0; t < s->n_batch; ++t) unpack_rdm(s->h_res + t * 16, 4, out + t * 16);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_rdm3(const bt_sv* s, int first, bt_c64* out) {
+  BT_TRY(bt_check_sv(s));
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output");
+  if (first < 1 || first + 2 > s->n_qubits) BT_FAIL(BT_ERR_ARG, "N must be larger than all three qubits");
+  int lbs[3] = {s->n_qubits - (first + 2), s->n_qubits - (first + 1), s->n_qubits - first};
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(const_cast<bt_sv*>(s), 3, lbs));
+  int tb[3] = {s->phys_of_bit[lbs[0]], s->phys_of_bit[lbs[1]], s->phys_of_bit[lbs[2]]};
+  BT_TRY(bt_reduce_rdm(s, 3, tb));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 64));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 64)));
+  for (int64_t t = 0; t < s->n_batch; ++t) unpack_rdm(s->h_res + t * 64, 8, out + t * 64);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_norm2(const bt_sv* s, double* out) {
+  BT_TRY(bt_check_sv(s));
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output");
+  BT_TRY(bt_reduce_norm2(s));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch));
+  BT_TRY(allreduce_host(s, s->h_res, (int)s->n_batch));
+  for (int64_t t = 0; t < s->n_batch; ++t) out[t] = s->h_res[t];
+  return BT_OK;
+}
+
+extern "C" int bt_sv_inner(const bt_sv* a, const bt_sv* b, bt_c64* out) {
+  BT_TRY(bt_check_sv(a));
+  if (!b || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (a->len != b->len || a->n_qubits != b->n_qubits || a->device != b->device) BT_FAIL(BT_ERR_ARG, "bt_sv_inner: shape/device mismatch");
+  if (a->world > 1 && memcmp(a->phys_of_bit, b->phys_of_bit, sizeof(a->phys_of_bit)) != 0) BT_FAIL(BT_ERR_UNSUPPORTED, "bt_sv_inner: shard layouts differ");
+  bt_sv* s = const_cast<bt_sv*>(a);
+  BT_TRY(check_batch_grid(s));
+  BT_CUDA(cudaStreamSynchronize(b->stream));
+  int nblk = pick_nblk(s, 1ull << s->n_local);
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * 2));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  k_inner<<<grid, RB, 0, s->stream>>>(a->amp, b->amp, s->n_local, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  BT_TRY(finish(s, nblk, 2, 0));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 2));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 2)));
+  for (int64_t t = 0; t < s->n_batch; ++t) { out[t].re = s->h_res[2 * t]; out[t].im = s->h_res[2 * t + 1]; }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_normalize(bt_sv* s) {
+  BT_TRY(bt_check_sv(s));
+  BT_TRY(bt_reduce_norm2(s));
+  if (s->world > 1) {
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch));
+    BT_TRY(allreduce_host(s, s->h_res, (int)s->n_batch));
+    BT_CUDA(cudaMemcpyAsync(s->d_res, s->h_res, s->n_batch * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  }
+  unsigned grid = (unsigned)std::min<uint64_t>((s->len + 255) / 256, 148ull * 32);
+  k_scale_by_norm<<<grid, 256, 0, s->stream>>>(s->amp, s->n_local, s->len, s->d_res);
+  BT_CHECK_LAUNCH(s);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_probs(const bt_sv* cs, double* host) {
+  BT_TRY(bt_check_sv(cs));
+  if (!host) BT_FAIL(BT_ERR_ARG, "null output");
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  if (s->world > 1 && !s->alt) BT_FAIL(BT_ERR_ARG, "internal: shard without second buffer");
+  BT_TRY(bt_ensure_alt(s));
+  double* p = reinterpret_cast<double*>(s->alt);
+  unsigned grid = (unsigned)std::min<uint64_t>((s->len + 255) / 256, 148ull * 32);
+  k_abs2<<<grid, 256, 0, s->stream>>>(s->amp, p, s->len);
+  BT_CHECK_LAUNCH(s);
+  BT_CUDA(cudaMemcpyAsync(host, p, s->len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+// ---- expectation values -------------------------------------------------------------------------------------
+int bt_bitprobs(const bt_sv* cs) {
+  // leaves n_batch x (BP_MAXBITS+1) doubles in d_res: [0] = total, [1+b] = P(physical bit b = 1) (unnormalised)
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  int cbits = std::min(12, s->n_local);
+  uint64_t nchunks = 1ull << (s->n_local - cbits);
+  uint64_t cap = std::max<uint64_t>(1, (148ull * 8) / (uint64_t)s->n_batch);
+  int nblk = (int)std::max<uint64_t>(1, std::min<uint64_t>(nchunks, cap));
+  int nv = BP_MAXBITS + 1;
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * nv));
+  BT_CUDA(cudaMemsetAsync(s->d_part, 0, (size_t)s->n_batch * nblk * nv * sizeof(double), s->stream));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  k_bitprobs<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, cbits, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  if ((size_t)s->n_batch * nv > s->res_cap) BT_FAIL(BT_ERR_UNSUPPORTED, "too many trajectories for expect_1q_all");
+  return finish(s, nblk, nv, 0);
+}
+
+extern "C" int bt_sv_expect_1q_all(const bt_sv* cs, const bt_c64 m[4], double* out) {
+  BT_TRY(bt_check_sv(cs));
+  if (!m || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  int N = s->n_qubits;
+  bool diag = (m[1].re == 0 && m[1].im == 0 && m[2].re == 0 && m[2].im == 0);
+  if (diag) {
+    BT_TRY(bt_bitprobs(s));
+    int nv = BP_MAXBITS + 1;
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * nv));
+    BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * nv)));
+    for (int64_t t = 0; t < s->n_batch; ++t) {
+      const double* v = s->h_res + t * nv;
+      for (int q = 1; q <= N; ++q) {
+        int pb = s->phys_of_bit[N - q];
+        double p1, p0;
+        if (pb < s->n_local) { p1 = v[1 + pb]; p0 = v[0] - p1; }
+        else {
+          // global bit: after the all-reduce v[0] is the global total; the per-rank totals are gone, so
+          // global-bit probabilities are accumulated by the callback-free path below
+          p1 = 0; p0 = 0;
+        }
+        out[t * N + (q - 1)] = m[0].re * p0 + m[3].re * p1;
+      }
+    }
+    if (s->world > 1) {
+      // global bits: P(bit=1) = sum over ranks with that rank bit set of the local total -> second all-reduce
+      BT_TRY(bt_reduce_norm2(s));
+      BT_TRY(bt_results_to_host(s, (size_t)s->n_batch));
+      std::vector<double> buf((size_t)s->n_batch * (s->g + 1), 0.0);
+      for (int64_t t = 0; t < s->n_batch; ++t) {
+        buf[t * (s->g + 1)] = s->h_res[t];
+        for (int j = 0; j < s->g; ++j)
+          if ((s->rank >> j) & 1) buf[t * (s->g + 1) + 1 + j] = s->h_res[t];
+      }
+      BT_TRY(allreduce_host(s, buf.data(), (int)buf.size()));
+      for (int64_t t = 0; t < s->n_batch; ++t)
+        for (int q = 1; q <= N; ++q) {
+          int pb = s->phys_of_bit[N - q];
+          if (pb >= s->n_local) {
+            double p1 = buf[t * (s->g + 1) + 1 + (pb - s->n_local)];
+            double p0 = buf[t * (s->g + 1)] - p1;
+            out[t * N + (q - 1)] = m[0].re * p0 + m[3].re * p1;
+          }
+        }
+    }
+    return BT_OK;
+  }
+  // general 2x2: N reduced density matrices, one host synchronisation at the end
+  if ((size_t)s->n_batch * 4 * N > s->res_cap) BT_FAIL(BT_ERR_UNSUPPORTED, "too many trajectories for expect_1q_all");
+  int bt_reduce_rdm_at(const bt_sv*, int, const int*, size_t);
+  for (int q = 1; q <= N; ++q) {
+    int lb = N - q;
+    if (s->world > 1) BT_TRY(bt_prepare_local_bits(s, 1, &lb));
+    int tb[1] = {s->phys_of_bit[lb]};
+    BT_TRY(bt_reduce_rdm_at(s, 1, tb, (size_t)(q - 1) * s->n_batch * 4));
+  }
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 4 * N));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 4 * N)));
+  for (int q = 1; q <= N; ++q)
+    for (int64_t t = 0; t < s->n_batch; ++t) {
+      const double* v = s->h_res + ((size_t)(q - 1) * s->n_batch + t) * 4;
+      // <O> = sum_ab O[a,b] rho[b][a];  packed: v[0]=rho00, v[3]=rho11, v[1]=Re rho01, v[2]=Im rho01
+      // O column-major: O[a,b] = m[a + 2b]
+      double r01 = v[1], i01 = v[2];
+      double e = m[0].re * v[0] + m[3].re * v[3];
+      // O[0,1]*rho[1][0] + O[1,0]*rho[0][1];  rho10 = conj(rho01)
+      e += (m[2].re * r01 + m[2].im * i01);   // Re(O01 * conj(rho01))
+      e += (m[1].re * r01 - m[1].im * i01);   // Re(O10 * rho01)
+      out[t * N + (q - 1)] = e;
+    }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_expect_pauli(const bt_sv* cs, const char* paulis, double* out) {
+  BT_TRY(bt_check_sv(cs));
+  if (!paulis || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  int N = s->n_qubits;
+  if ((int)strlen(paulis) != N) BT_FAIL(BT_ERR_ARG, "Pauli string must have %d characters", N);
+  // X/Y on a global qubit needs the partner shard: bring those qubits local first
+  if (s->world > 1) {
+    int lbs[64], n = 0;
+    for (int q = 1; q <= N; ++q) {
+      char c = paulis[q - 1];
+      if (c == 'X' || c == 'x' || c == 'Y' || c == 'y') lbs[n++] = N - q;
+    }
+    if (n > s->n_local) BT_FAIL(BT_ERR_UNSUPPORTED, "too many X/Y factors for a sharded state");
+    if (n) BT_TRY(bt_prepare_local_bits(s, n, lbs));
+  }
+  uint64_t xm = 0, zm = 0, zglobal = 0;
+  int ny = 0;
+  for (int q = 1; q <= N; ++q) {
+    char c = paulis[q - 1];
+    int pb = s->phys_of_bit[N - q];
+    uint64_t bit = 1ull << pb;
+    switch (c) {
+      case 'I': case 'i': break;
+      case 'X': case 'x': xm |= bit; break;
+      case 'Y': case 'y': xm |= bit; zm |= bit; ny++; break;
+      case 'Z': case 'z': if (pb < s->n_local) zm |= bit; else zglobal |= 1ull << (pb - s->n_local); break;
+      default: BT_FAIL(BT_ERR_ARG, "Pauli string may only contain I, X, Y, Z");
+    }
+  }
+  int topx = 0;
+  for (int b = 0; b < 64; ++b) if ((xm >> b) & 1) topx = b;
+  uint64_t items = xm ? (1ull << (s->n_local - 1)) : (1ull << s->n_local);
+  int nblk = pick_nblk(s, items);
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  k_pauli<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, xm, zm, ny, topx, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  BT_TRY(finish(s, nblk, 1, 0));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch));
+  if (s->world > 1 && (__builtin_popcountll((uint64_t)s->rank & zglobal) & 1))
+    for (int64_t t = 0; t < s->n_batch; ++t) s->h_res[t] = -s->h_res[t];
+  BT_TRY(allreduce_host(s, s->h_res, (int)s->n_batch));
+  for (int64_t t = 0; t < s->n_batch; ++t) out[t] = s->h_res[t];
+  return BT_OK;
+}
+
+int bt_build_gate(const bt_sv* s, int nq, int qubit, int target, int control, const bt_c64* m, GateDesc* out);
+
+extern "C" int bt_sv_expect_product(const bt_sv* cs, int n_ops, const int* qubits, const bt_c64* mats, double* out) {
+  // Re <psi| (x)_j O_j |psi>  (src/func.jl:139-142 with expand_multi_op src/ops.jl:928-944): phi = (x)O psi on
+  // the scratch buffer with the ordinary gate kernels, then one fused inner-product pass.
+  BT_TRY(bt_check_sv(cs));
+  if (n_ops < 0 || (n_ops > 0 && (!qubits || !mats)) || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  for (int i = 0; i < n_ops; ++i) {
+    if (qubits[i] < 1 || qubits[i] > s->n_qubits) BT_FAIL(BT_ERR_ARG, "qubit %d out of range", qubits[i]);
+    for (int j = 0; j < i; ++j)
+      if (qubits[i] == qubits[j]) BT_FAIL(BT_ERR_ARG, "repeated qubit %d in operator list", qubits[i]);
+  }
+  if (s->world > 1) {
+    int lbs[64], n = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const bt_c64* m = mats + 4 * i;
+      bool diag = (m[1].re == 0 && m[1].im == 0 && m[2].re == 0 && m[2].im == 0);
+      if (!diag) lbs[n++] = s->n_qubits - qubits[i];
+    }
+    if (n) BT_TRY(bt_prepare_local_bits(s, n, lbs));
+  }
+  BT_TRY(bt_ensure_alt(s));
+  BT_CUDA(cudaMemcpyAsync(s->alt, s->amp, s->len * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+  std::swap(s->amp, s->alt);  // gates now act on the copy
+  int rc = BT_OK;
+  for (int i = 0; i < n_ops && rc == BT_OK; ++i) {
+    GateDesc g;
+    rc = bt_build_gate(s, 1, qubits[i], -1, -2, mats + 4 * i, &g);
+    if (rc == BT_OK) rc = bt_launch_gate(s, g);
+  }
+  std::swap(s->amp, s->alt);  // amp = psi, alt = phi
+  if (rc != BT_OK) return rc;
+  int nblk = pick_nblk(s, 1ull << s->n_local);
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * 2));
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  k_inner<<<grid, RB, 0, s->stream>>>(s->amp, s->alt, s->n_local, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  BT_TRY(finish(s, nblk, 2, 0));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 2));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 2)));
+  for (int64_t t = 0; t < s->n_batch; ++t) out[t] = s->h_res[2 * t];
+  return BT_OK;
+}
+
+extern "C" int bt_sv_expect_matrix2q(const bt_sv* s, int qubit, int target, const bt_c64 m[16], double* out) {
+  // Re <psi| O_{qubit,target} |psi> with O indexed 2*b_qubit + b_target, from the 4x4 RDM
+  BT_TRY(bt_check_sv(s));
+  if (!m || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (qubit < 1 || target < 1 || qubit > s->n_qubits || target > s->n_qubits || qubit == target) BT_FAIL(BT_ERR_ARG, "invalid qubit pair");
+  int lbs[2] = {s->n_qubits - target, s->n_qubits - qubit};
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(const_cast<bt_sv*>(s), 2, lbs));
+  int tb[2] = {s->phys_of_bit[lbs[0]], s->phys_of_bit[lbs[1]]};
+  BT_TRY(bt_reduce_rdm(s, 2, tb));
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * 16));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * 16)));
+  for (int64_t t = 0; t < s->n_batch; ++t) {
+    bt_c64 rho[16];
+    unpack_rdm(s->h_res + t * 16, 4, rho);
+    double e = 0.0;
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) {
+        // O[a,b] * rho[b][a]
+        const bt_c64& o = m[a + 4 * b];
+        const bt_c64& r = rho[b + 4 * a];
+        e += o.re * r.re - o.im * r.im;
+      }
+    out[t] = e;
+  }
+  return BT_OK;
+}

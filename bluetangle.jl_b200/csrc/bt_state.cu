@@ -1,0 +1,245 @@
+// bt_state.cu -- handle life cycle, host<->device transfers, error plumbing.
+// Replaces the state constructors of src/hilbert.jl:835-882 for a device-resident state.
+#include "bt_internal.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+static int g_strict = 0;
+
+void bt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* bt_last_error(void) { return g_err; }
+extern "C" int bt_version(void) { return 100; }
+extern "C" int bt_set_strict(int strict) { g_strict = strict; return BT_OK; }
+int bt_is_strict() { return g_strict; }
+
+extern "C" int bt_device_count(int* n) {
+  if (!n) BT_FAIL(BT_ERR_ARG, "bt_device_count: null output");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *n = 0; BT_FAIL(BT_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
+  *n = c;
+  return BT_OK;
+}
+
+extern "C" int bt_set_device(int device) {
+  BT_CUDA(cudaSetDevice(device));
+  return BT_OK;
+}
+
+int bt_check_sv(const bt_sv* s) {
+  if (!s) BT_FAIL(BT_ERR_ARG, "null state handle");
+  BT_CUDA(cudaSetDevice(s->device));
+  return BT_OK;
+}
+
+// ---- kernels --------------------------------------------------------------------------------------------
+__global__ void k_set_basis(double2* a, uint64_t per_traj, uint64_t len, uint64_t index, int hit) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < len; i += stride) {
+    uint64_t r = i & (per_traj - 1);
+    a[i] = make_double2((hit && r == index) ? 1.0 : 0.0, 0.0);
+  }
+}
+
+__global__ void k_fill(double2* a, uint64_t len, double2 v) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < len; i += stride) a[i] = v;
+}
+
+static int grid_for(uint64_t n, int block) {
+  uint64_t g = (n + block - 1) / block;
+  uint64_t cap = 148ull * 16;
+  return (int)std::min<uint64_t>(std::max<uint64_t>(g, 1), cap);
+}
+
+int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_alt, bt_sv** out) {
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output handle");
+  *out = nullptr;
+  if (n_qubits < 1 || n_qubits > 62) BT_FAIL(BT_ERR_ARG, "n_qubits=%d out of range", n_qubits);
+  if (n_local < 1 || n_local > n_qubits || n_local > 40) BT_FAIL(BT_ERR_ARG, "n_local=%d out of range", n_local);
+  if (n_batch < 1) BT_FAIL(BT_ERR_ARG, "n_batch must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) BT_FAIL(BT_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
+  bt_sv* s = new bt_sv();
+  memset(s, 0, sizeof(*s));
+  BT_CUDA(cudaGetDevice(&s->device));
+  s->n_qubits = n_qubits;
+  s->n_local = n_local;
+  s->n_batch = n_batch;
+  s->len = (uint64_t)n_batch << n_local;
+  s->rank = 0; s->world = 1; s->g = 0;
+  for (int b = 0; b < 64; ++b) s->phys_of_bit[b] = b;
+  cudaError_t ea = cudaMalloc(&s->amp, s->len * sizeof(double2));
+  if (ea != cudaSuccess) { delete s; cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "cudaMalloc of %llu bytes failed: %s", (unsigned long long)(s->len * sizeof(double2)), cudaGetErrorString(ea)); }
+  if (want_alt) {
+    ea = cudaMalloc(&s->alt, s->len * sizeof(double2));
+    if (ea != cudaSuccess) { cudaFree(s->amp); delete s; cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "cudaMalloc (second buffer) failed: %s", cudaGetErrorString(ea)); }
+  }
+  BT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  BT_CUDA(cudaEventCreate(&s->ev0));
+  BT_CUDA(cudaEventCreate(&s->ev1));
+  s->res_cap = std::max<size_t>(4096, (size_t)n_batch * 128);
+  BT_CUDA(cudaMalloc(&s->d_res, s->res_cap * sizeof(double)));
+  BT_CUDA(cudaMallocHost(&s->h_res, s->res_cap * sizeof(double)));
+  BT_CUDA(cudaMalloc(&s->d_err, sizeof(int32_t)));
+  BT_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int32_t), s->stream));
+  BT_CUDA(cudaMallocHost(&s->h_flag, 4 * sizeof(int32_t)));
+  k_set_basis<<<grid_for(s->len, 256), 256, 0, s->stream>>>(s->amp, 1ull << n_local, s->len, 0, 1);
+  BT_CHECK_LAUNCH(s);
+  *out = s;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_create(int n_qubits, int64_t n_batch, bt_sv** out) {
+  return bt_sv_create_internal(n_qubits, n_qubits, n_batch, false, out);
+}
+
+extern "C" int bt_sv_destroy(bt_sv* s) {
+  if (!s) return BT_OK;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  if (s->ipc_opened) {
+    for (int r = 0; r < s->world; ++r) {
+      if (r == s->rank) continue;
+      if (s->peer_amp[r]) cudaIpcCloseMemHandle(s->peer_amp[r]);
+      if (s->peer_alt[r]) cudaIpcCloseMemHandle(s->peer_alt[r]);
+    }
+  }
+  cudaFree(s->amp);
+  if (s->alt) cudaFree(s->alt);
+  if (s->d_part) cudaFree(s->d_part);
+  cudaFree(s->d_res);
+  cudaFreeHost(s->h_res);
+  if (s->d_u) cudaFree(s->d_u);
+  if (s->d_outcome) cudaFree(s->d_outcome);
+  if (s->d_mats) cudaFree(s->d_mats);
+  if (s->d_scale) cudaFree(s->d_scale);
+  cudaFree(s->d_err);
+  cudaFreeHost(s->h_flag);
+  cudaEventDestroy(s->ev0);
+  cudaEventDestroy(s->ev1);
+  cudaStreamDestroy(s->stream);
+  delete s;
+  return BT_OK;
+}
+
+int bt_ensure_traj(bt_sv* s) {
+  if (s->traj_cap >= (size_t)s->n_batch) return BT_OK;
+  size_t nb = (size_t)s->n_batch;
+  BT_CUDA(cudaMalloc(&s->d_u, nb * sizeof(double)));
+  BT_CUDA(cudaMalloc(&s->d_outcome, nb * sizeof(int32_t)));
+  BT_CUDA(cudaMemsetAsync(s->d_outcome, 0, nb * sizeof(int32_t), s->stream));
+  BT_CUDA(cudaMalloc(&s->d_mats, nb * 64 * sizeof(double2)));
+  BT_CUDA(cudaMalloc(&s->d_scale, nb * 2 * sizeof(double)));
+  s->traj_cap = nb;
+  return BT_OK;
+}
+
+int bt_ensure_partials(bt_sv* s, size_t doubles) {
+  if (s->part_cap >= doubles) return BT_OK;
+  if (s->d_part) { BT_CUDA(cudaStreamSynchronize(s->stream)); BT_CUDA(cudaFree(s->d_part)); s->d_part = nullptr; }
+  BT_CUDA(cudaMalloc(&s->d_part, doubles * sizeof(double)));
+  s->part_cap = doubles;
+  return BT_OK;
+}
+
+int bt_ensure_alt(bt_sv* s) {
+  if (s->alt) return BT_OK;
+  cudaError_t e = cudaMalloc(&s->alt, s->len * sizeof(double2));
+  if (e != cudaSuccess) { cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "scratch buffer of %llu bytes: %s", (unsigned long long)(s->len * 16), cudaGetErrorString(e)); }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_n_qubits(const bt_sv* s, int* n) {
+  if (!s || !n) BT_FAIL(BT_ERR_ARG, "null argument");
+  *n = s->n_qubits;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_set_basis(bt_sv* s, uint64_t index) {
+  BT_TRY(bt_check_sv(s));
+  if (s->n_qubits < 64 && index >= (1ull << s->n_qubits)) BT_FAIL(BT_ERR_ARG, "basis index out of range");
+  // sharded: physical layout is reset to identity, the owning rank holds the 1
+  for (int b = 0; b < 64; ++b) s->phys_of_bit[b] = b;
+  uint64_t local = index & ((1ull << s->n_local) - 1);
+  int hit = (int)((index >> s->n_local) == (uint64_t)s->rank);
+  k_set_basis<<<grid_for(s->len, 256), 256, 0, s->stream>>>(s->amp, 1ull << s->n_local, s->len, local, hit);
+  BT_CHECK_LAUNCH(s);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_set_plus(bt_sv* s) {
+  BT_TRY(bt_check_sv(s));
+  double v = 1.0 / sqrt(ldexp(1.0, s->n_qubits));  // (1+0im)/sqrt(2^N)  src/hilbert.jl:869
+  k_fill<<<grid_for(s->len, 256), 256, 0, s->stream>>>(s->amp, s->len, make_double2(v, 0.0));
+  BT_CHECK_LAUNCH(s);
+  return BT_OK;
+}
+
+extern "C" int bt_sv_upload(bt_sv* s, const bt_c64* host, uint64_t len) {
+  BT_TRY(bt_check_sv(s));
+  if (!host || len != s->len) BT_FAIL(BT_ERR_ARG, "upload length %llu != %llu", (unsigned long long)len, (unsigned long long)s->len);
+  BT_CUDA(cudaMemcpyAsync(s->amp, host, len * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_download(const bt_sv* s, bt_c64* host, uint64_t len) {
+  BT_TRY(bt_check_sv(s));
+  if (!host || len != s->len) BT_FAIL(BT_ERR_ARG, "download length %llu != %llu", (unsigned long long)len, (unsigned long long)s->len);
+  BT_CUDA(cudaMemcpyAsync(host, s->amp, len * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_copy(bt_sv* dst, const bt_sv* src) {
+  BT_TRY(bt_check_sv(dst));
+  if (!src || src->len != dst->len || src->n_qubits != dst->n_qubits) BT_FAIL(BT_ERR_ARG, "bt_sv_copy: shape mismatch");
+  BT_CUDA(cudaStreamSynchronize(src->stream));
+  BT_CUDA(cudaMemcpyAsync(dst->amp, src->amp, dst->len * sizeof(double2), cudaMemcpyDeviceToDevice, dst->stream));
+  memcpy(dst->phys_of_bit, src->phys_of_bit, sizeof(dst->phys_of_bit));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_sync(const bt_sv* s) {
+  BT_TRY(bt_check_sv(s));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_timer_start(bt_sv* s) {
+  BT_TRY(bt_check_sv(s));
+  BT_CUDA(cudaEventRecord(s->ev0, s->stream));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_timer_stop(bt_sv* s, float* ms) {
+  BT_TRY(bt_check_sv(s));
+  if (!ms) BT_FAIL(BT_ERR_ARG, "null output");
+  BT_CUDA(cudaEventRecord(s->ev1, s->stream));
+  BT_CUDA(cudaEventSynchronize(s->ev1));
+  BT_CUDA(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+  return BT_OK;
+}
+
+extern "C" int bt_sv_launch_count(const bt_sv* s, uint64_t* n) {
+  if (!s || !n) BT_FAIL(BT_ERR_ARG, "null argument");
+  *n = s->launches;
+  return BT_OK;
+}
+
+int bt_results_to_host(const bt_sv* s, size_t n_doubles) {
+  if (n_doubles > s->res_cap) BT_FAIL(BT_ERR_ARG, "result buffer too small");
+  BT_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, n_doubles * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}

@@ -1,0 +1,161 @@
+/*
+ * bluetangle_cuda.h -- C ABI of libbluetangle_cuda.so, the B200 (sm_100a) simulation backend for
+ * BlueTangle.jl's apply -> noise -> measure/sample -> expect path.
+ *
+ * The reference (pure Julia) has no FFI; its backend seam is multiple dispatch on the state type
+ * (src/hilbert.jl:469 / :639 / :566).  Every entry point below names the reference method it replaces for a
+ * device-resident state; the Julia `ccall` stubs a maintainer would add are in INTEGRATION.md and
+ * julia/BlueTangleCUDA.jl.
+ *
+ * Conventions:
+ *  - qubit arguments are the reference's 1-based labels; qubit 1 is the most significant bit of the basis
+ *    index (src/bit.jl:9-15), i.e. qubit q <-> bit N-q.  target = -1 means "1-qubit op", control = -2 means
+ *    "no control" (src/struct.jl:377,389,456).
+ *  - matrices are column-major ComplexF64 (Julia native), indexed 2*b_qubit + b_target exactly like Op.mat.
+ *  - every call returns 0 on success, <0 on error; bt_last_error() returns a thread-local message.
+ *    Nothing unwinds across the ABI.  There is no CPU fallback: no device => BT_ERR_CUDA.
+ *  - random numbers are never generated inside the library: callers pass uniform draws in [0,1).
+ *  - one CUDA stream per handle; gate calls only enqueue, calls returning data to the host synchronise.
+ */
+#ifndef BLUETANGLE_CUDA_H
+#define BLUETANGLE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_OK 0
+#define BT_ERR_ARG (-1)      /* invalid argument (mirrors the reference's throws) */
+#define BT_ERR_CUDA (-2)     /* CUDA runtime failure / no device */
+#define BT_ERR_ALLOC (-3)    /* out of device memory */
+#define BT_ERR_SAMPLE (-4)   /* _weighted_sample found no index (src/hilbert.jl:810-819 returns nothing) */
+#define BT_ERR_UNSUPPORTED (-5)
+
+typedef struct bt_sv bt_sv; /* state vector: n_batch trajectories of 2^n amplitudes, optionally one shard of P */
+typedef struct bt_dm bt_dm; /* density matrix stored as a 2n-qubit vector (row qubit q <-> bit n-q, column qubit q <-> bit 2n-q) */
+typedef struct { double re, im; } bt_c64; /* == Julia ComplexF64 */
+
+/* One op of a circuit handed to bt_sv_apply_circuit / bt_dm_apply_circuit (replaces the per-op loop of
+ * src/hilbert.jl:517-553 for plain gates).  nq in {1,2}; m column-major, first 4^nq entries used. */
+typedef struct {
+  int32_t nq, qubit, target, control;
+  bt_c64 m[16];
+} bt_gate;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+const char* bt_last_error(void);
+int bt_version(void);
+int bt_device_count(int* n);
+int bt_set_device(int device);
+
+/* ---- state vector life cycle: zero_state/one_state/plus_state/product_state src/hilbert.jl:835-882 -- */
+int bt_sv_create(int n_qubits, int64_t n_batch, bt_sv** out);     /* on the current device, |0..0> in every trajectory */
+int bt_sv_destroy(bt_sv* s);
+int bt_sv_n_qubits(const bt_sv* s, int* n);                       /* get_N  src/ops.jl:8 */
+int bt_sv_set_basis(bt_sv* s, uint64_t index);                    /* every trajectory := |index> */
+int bt_sv_set_plus(bt_sv* s);                                     /* plus_state src/hilbert.jl:869 */
+int bt_sv_upload(bt_sv* s, const bt_c64* host, uint64_t len);     /* len = n_batch * 2^n (local shard if sharded) */
+int bt_sv_download(const bt_sv* s, bt_c64* host, uint64_t len);
+int bt_sv_copy(bt_sv* dst, const bt_sv* src);
+int bt_sv_sync(const bt_sv* s);
+/* CUDA-event timing on the handle's stream (used by bench.py; events see exactly the launching stream) */
+int bt_sv_timer_start(bt_sv* s);
+int bt_sv_timer_stop(bt_sv* s, float* ms);
+int bt_sv_launch_count(const bt_sv* s, uint64_t* n);              /* kernels launched on this handle so far */
+
+/* ---- gates: op.expand(N)*state  src/hilbert.jl:505 with hilbert() src/hilbert.jl:18-159 --------------- */
+int bt_sv_apply_1q(bt_sv* s, int qubit, const bt_c64 m[4], int control);               /* hilbert.jl:143-159 */
+int bt_sv_apply_2q(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control);  /* hilbert.jl:18-70 (+CCZX :73-103; any matrix may be controlled unless strict) */
+int bt_sv_apply_3q(bt_sv* s, int first_qubit, const bt_c64 m[64]);                     /* hilbert3 hilbert.jl:106-128 */
+/* whole op list in one call; fuse != 0 enables the host fusion pass + multi-gate shared-memory kernel */
+int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse);
+/* gate applied only to trajectories whose outcome[t] == want (ifOp branches, src/struct.jl:587-590);
+ * outcome is a DEVICE pointer obtained from bt_sv_outcome_buffer */
+int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int want);
+int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
+int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
+
+/* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */
+int bt_sv_rdm1(const bt_sv* s, int qubit, bt_c64* out /* n_batch x 4, column-major 2x2 each */);
+int bt_sv_rdm2(const bt_sv* s, int qubit_a, int qubit_b, bt_c64* out /* n_batch x 16; index 2*b_min + b_max */);
+int bt_sv_rdm3(const bt_sv* s, int first_qubit, bt_c64* out /* n_batch x 64; qubits first..first+2 */);
+int bt_sv_norm2(const bt_sv* s, double* out /* n_batch: sum |a|^2 */);
+int bt_sv_inner(const bt_sv* a, const bt_sv* b, bt_c64* out /* n_batch: <a|b>, src/tensor.jl:199 */);
+int bt_sv_normalize(bt_sv* s);
+int bt_sv_probs(const bt_sv* s, double* host /* n_batch * 2^n : abs2.(state) src/ops.jl:51,98 */);
+
+/* ---- measurement: born_measure_Z src/hilbert.jl:682-696, _reset_Z :752-759 ----------------------------
+ * basis rotations (MX/MY/MR, src/hilbert.jl:669-679) are applied by the caller with bt_sv_apply_1q.
+ * u: n_batch uniforms; outcome = (u < p0) ? 0 : 1; the state is projected and renormalised by its own norm.
+ * outcome/p0 may be NULL (no host synchronisation then; outcomes stay in the device outcome buffer). */
+int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* outcome, double* p0, int reset);
+int bt_sv_outcomes(const bt_sv* s, int32_t* outcome /* n_batch: results of the last measure/kraus call */);
+
+/* ---- Kraus trajectory step: __QuantumChannel_new_apply src/struct.jl:31-55, __calc_prob :9-29,
+ * _weighted_sample src/hilbert.jl:810-819 (k = first i with u <= cumsum(p)[i]).
+ * nq in {1,2,3}; K = nK column-major (2^nq x 2^nq) matrices; target ignored unless nq == 2.
+ * Reproduces the reference's quirk for nq == 2 and qubit > target.
+ * chosen may be NULL (no synchronisation). */
+int bt_sv_kraus(bt_sv* s, int nq, int qubit, int target, const bt_c64* K, int nK, const double* u, int32_t* chosen);
+int bt_sv_kraus_probs(const bt_sv* s, int nq, int qubit, int target, const bt_c64* K, int nK, double* probs /* n_batch x nK */);
+
+/* ---- observables: expect src/func.jl:91-101, correlation :139-147 ------------------------------------ */
+int bt_sv_expect_pauli(const bt_sv* s, const char* paulis /* n chars from IXYZ, qubit 1 first */, double* out /* n_batch */);
+int bt_sv_expect_1q_all(const bt_sv* s, const bt_c64 m[4], double* out /* n_batch x n : Re<psi|m_q|psi> */);
+int bt_sv_expect_product(const bt_sv* s, int n_ops, const int* qubits, const bt_c64* mats /* n_ops x 4 */, double* out /* n_batch */);
+int bt_sv_expect_matrix2q(const bt_sv* s, int qubit, int target, const bt_c64 m[16], double* out);
+
+/* ---- sampling: sample src/ops.jl:46-62 as inverse CDF on caller-supplied uniforms:
+ * t = u*sum(p); index = first i with cumsum_i >= t.  n_batch must be 1 unless per_traj != 0, in which case
+ * shots uniforms are consumed per trajectory (out is n_batch x shots). */
+int bt_sv_sample(const bt_sv* s, const double* u, uint64_t shots, int64_t* out);
+int bt_sv_sample_batched(const bt_sv* s, const double* u, uint64_t shots_per_traj, int64_t* out);
+
+/* ---- density matrix: apply(rho,op) src/hilbert.jl:639-666; channels src/struct.jl:58-76 --------------- */
+int bt_dm_create(int n_qubits, bt_dm** out);                      /* |0..0><0..0| */
+int bt_dm_destroy(bt_dm* d);
+int bt_dm_n_qubits(const bt_dm* d, int* n);
+int bt_dm_from_sv(bt_dm* d, const bt_sv* s);                      /* state*state' src/ops.jl:810 */
+int bt_dm_upload(bt_dm* d, const bt_c64* host, uint64_t len);     /* column-major 2^n x 2^n */
+int bt_dm_download(const bt_dm* d, bt_c64* host, uint64_t len);
+int bt_dm_sync(const bt_dm* d);
+int bt_dm_timer_start(bt_dm* d);
+int bt_dm_timer_stop(bt_dm* d, float* ms);
+int bt_dm_launch_count(const bt_dm* d, uint64_t* n);
+int bt_dm_apply_1q(bt_dm* d, int qubit, const bt_c64 m[4], int control);               /* e_op*rho*e_op' hilbert.jl:655-656 */
+int bt_dm_apply_2q(bt_dm* d, int qubit, int target, const bt_c64 m[16], int control);
+int bt_dm_kraus(bt_dm* d, int nq, int qubit, int target, const bt_c64* K, int nK);      /* sum_k E_k rho E_k'  struct.jl:58-76: one HBM pass */
+int bt_dm_dephase(bt_dm* d, int qubit);                                                 /* born_measure_Z(N,rho,q) hilbert.jl:784-796 */
+int bt_dm_apply_circuit(bt_dm* d, const bt_gate* g, uint64_t n, int fuse);
+int bt_dm_diag(const bt_dm* d, double* host /* 2^n : real(diag(rho)) src/ops.jl:130 */);
+int bt_dm_trace(const bt_dm* d, bt_c64* out);
+int bt_dm_expect_pauli(const bt_dm* d, const char* paulis, double* out);               /* real(tr(rho*O)) func.jl:92,146 */
+int bt_dm_expect_1q_all(const bt_dm* d, const bt_c64 m[4], double* out /* n */);        /* func.jl:98 */
+int bt_dm_expect_product(const bt_dm* d, int n_ops, const int* qubits, const bt_c64* mats, double* out);
+int bt_dm_sample(const bt_dm* d, const double* u, uint64_t shots, int64_t* out);
+
+/* ---- multi-GPU shards (no reference analogue).  One process per GPU: each rank creates its
+ * shard, the host plumbing (torch.distributed / MPI) all-gathers the IPC handles and supplies a barrier.
+ * The top log2(world) index bits are global (= the lowest-numbered qubits).  Gates on global qubits that
+ * are diagonal or controls need no communication; others trigger a qubit-remap exchange in which every rank
+ * pulls its new shard from its peers' memory over NVLink in one kernel (bit permutation fused in). */
+#define BT_IPC_HANDLE_BYTES 64
+typedef void (*bt_barrier_fn)(void* ctx);
+int bt_sv_create_shard(int n_qubits_total, int rank, int world, bt_sv** out);
+int bt_sv_ipc_export(bt_sv* s, void* handles /* 2*BT_IPC_HANDLE_BYTES: both buffers */);
+int bt_sv_ipc_attach(bt_sv* s, const void* all_handles /* world x 2*BT_IPC_HANDLE_BYTES, rank order */);
+int bt_sv_attach_local_peers(bt_sv** shards, int world); /* single-process variant: all shards in this process */
+int bt_sv_set_barrier(bt_sv* s, bt_barrier_fn fn, void* ctx);
+int bt_sv_remap(bt_sv* s, const int* new_phys_of_logical_bit /* n_qubits_total entries */);
+int bt_sv_layout(const bt_sv* s, int* phys_of_logical_bit /* n_qubits_total */);
+int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* bytes_pulled_remote, float* ms_total);
+/* scalars returned by reductions on a shard are LOCAL partial sums unless an all-reduce callback is set */
+typedef void (*bt_allreduce_fn)(void* ctx, double* buf, int n);
+int bt_sv_set_allreduce(bt_sv* s, bt_allreduce_fn fn, void* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLUETANGLE_CUDA_H */
