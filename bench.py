@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 backend (contract: see task prompt / DESIGN.md section "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the reference path's CPU port on the host cores
+
+N = 1: workload C2 of BASELINE.json configs[1] -- 28-qubit state vector, QFT(28) + 100 random layers (4,556 gates),
+       ComplexF64.  One step = reset to |0..0> + the whole circuit.
+N > 1: workload C5 -- (31 + log2 N)-qubit random circuit sharded over N ranks (torchrun, one rank per GPU); value is
+       reported in 28-qubit-equivalent gates/s (gates x local amplitudes / 2^28, summed over ranks) so that the
+       numbers at different N measure the same per-GPU work ("weak" scaling).
+metric: gates/s.  `value` is device-resident throughput (CUDA events on the launching stream); `e2e` goes through
+the public host API with host buffers (gate list in, expectation values and samples out).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def bench_single(args):
+    import __graft_entry__ as ge
+
+    bt = ge.load_package()
+    L = bt._lib
+    from importlib import import_module
+
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    N, depth = args.qubits, args.depth
+    specs = wl.c2_qft_layered(N, depth, 28)
+    ops = wl.to_ops(bt, specs)
+    arr = bt.pack_gates(ops)  # host buffer: what crosses the C ABI every step
+    ngates = len(arr)
+    s = bt.zero_state(N)
+    lib = s.lib
+
+    def step():
+        L.check(lib.bt_sv_set_basis(s.h, 0))
+        L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), ngates, 1))
+
+    for _ in range(args.warmup):
+        step()
+    s.sync()
+    clocks = ClockSampler(0)
+    clocks.start()
+    L.check(lib.bt_sv_profile_enable(s.h, 1))
+    n0 = s.launch_count()
+    ms = C.c_float()
+    L.check(lib.bt_sv_timer_start(s.h))
+    for _ in range(args.steps):
+        step()
+    L.check(lib.bt_sv_timer_stop(s.h, C.byref(ms)))
+    n1 = s.launch_count()
+    counts = (C.c_uint64 * 4)()
+    cms = (C.c_double * 4)()
+    L.check(lib.bt_sv_profile_read(s.h, counts, cms))
+    L.check(lib.bt_sv_profile_enable(s.h, 0))
+    clk = clocks.stop()
+    ms_per_step = ms.value / args.steps
+    value = ngates / (ms_per_step / 1e3)
+    norm = bt.norm2(s)
+
+    # roofline of the dominant kernel (fused tile kernel): algorithmic bytes = 32 B x 2^N per launch
+    peaks, peak_src = load_peaks()
+    cls_names = ["tile", "dense", "diag", "other"]
+    per_cls = {cls_names[i]: {"launches": int(counts[i]), "ms": float(cms[i])} for i in range(4)}
+    dom = max(range(4), key=lambda i: cms[i])
+    bytes_per_launch = 32.0 * (1 << N)
+    roof = None
+    if counts[dom] > 0:
+        avg_ms = cms[dom] / counts[dom]
+        ach = bytes_per_launch / (avg_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_tile (fused multi-gate pass)" if dom == 0 else cls_names[dom], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "share_of_step": cms[dom] / (ms.value), "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_spec": ach / 8000.0}
+        tfile = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(tfile):
+            try:
+                roof["traffic"] = json.load(open(tfile)).get("k_tile_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # unfused single-gate kernels on the same state: the per-gate HBM roofline the north star quotes
+    micro = {}
+    for name, fn in (("1q_dense_H_q14", lambda: L.check(lib.bt_sv_apply_1q(s.h, N // 2, L.ptr(L.cmat(bt.gate["H"], 2)), -2))),
+                     ("2q_dense_q3_q17", lambda: L.check(lib.bt_sv_apply_2q(s.h, 3, min(17, N), L.ptr(L.cmat(bt.gates("FSIM(0.3,0.2)"), 4)), -2)))):
+        for _ in range(3):
+            fn()
+        t = C.c_float()
+        L.check(lib.bt_sv_timer_start(s.h))
+        for _ in range(10):
+            fn()
+        L.check(lib.bt_sv_timer_stop(s.h, C.byref(t)))
+        micro[name] = {"ms": t.value / 10, "GBps": bytes_per_launch / (t.value / 10 / 1e3) / 1e9}
+
+    # end to end through the host API: gate list in (host), <Z_q> for every qubit and 4096 samples out (host)
+    us = np.random.Generator(np.random.PCG64(7)).random(4096)
+    e2e_t = []
+    ez = None
+    for _ in range(max(1, min(args.steps, 3))):
+        t0 = time.perf_counter()
+        st = s
+        L.check(lib.bt_sv_set_basis(st.h, 0))
+        L.check(lib.bt_sv_apply_circuit(st.h, L.ptr(arr), ngates, 1))
+        ez = bt.expect(st, "Z")
+        smp = bt.sample(st, 4096, uniforms=us)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_t))
+    e2e = {"value": ngates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes + us.nbytes), "d2h_bytes_per_step": int(ez.nbytes + smp.nbytes + 8),
+           "seconds_per_step": e2e_s, "api": "bt_sv_set_basis + bt_sv_apply_circuit(host gate list) + bt_sv_expect_1q_all + bt_sv_sample"}
+
+    cpu = cpu_baseline_port(N, specs, budget_s=args.cpu_budget) if not args.no_cpu else None
+    out = {"metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
+           "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers (H/RX/RY/RZ/T + CNOT/CZ/CP brickwork), {ngates} gates, seed 28",
+                      "fusion": "host fusion pass + shared-memory tile kernel", "l2": f"inputs larger than L2 ({(16 << N) / 2**30:.1f} GiB state)", "parallelism": "1 GPU"},
+           "clocks": clk, "e2e": e2e, "gpu_launches": int(n1 - n0), "roofline": roof, "kernels": per_cls, "unfused_gate_kernels": micro,
+           "cpu_baseline": cpu, "state_norm2": norm}
+    print(json.dumps(out))
+
+
+def cpu_baseline_port(N, specs, budget_s=15.0):
+    """The oracle's strided C port (oracle/strided_cpu.c, OpenMP over all host cores) timed on a bounded sample of the
+    same workload: consecutive gates of the layered section at the full size, until the time budget is used."""
+    from oracle import bt_oracle as O
+    from oracle import strided as S
+
+    try:
+        layered = specs[N * (N + 1) // 2:]  # skip the QFT prefix
+        sv = S.SV(N)
+        t0 = time.perf_counter()
+        n = 0
+        for name, q, t, c in layered:
+            sv.apply(O.Op(name, q, t, control=c))
+            n += 1
+            if time.perf_counter() - t0 > budget_s and n >= 4:
+                break
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "gates/s", "cores": S.num_threads(), "kind": "port",
+                "sample": f"first {n} gates of the layered section of the same circuit at {N} qubits, in-place strided C + OpenMP ({dt:.1f} s)"}
+    except MemoryError as e:
+        return {"value": None, "unit": "gates/s", "cores": 0, "kind": "port", "sample": f"not enough host memory: {e}"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def bench_sharded(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    bt = ge.load_package()
+    L = bt._lib
+    from importlib import import_module
+
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    D = import_module(ge.PKG_NAME + ".dist")
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = world.bit_length() - 1
+    n_local = args.shard_qubits
+    N = n_local + g
+    specs = wl.c5_random(N, args.c5_depth, 31)
+    arr = bt.pack_gates(wl.to_ops(bt, specs))
+    ngates = len(arr)
+    st = D.ShardedState(N)
+    lib = st.lib
+
+    def step():
+        L.check(lib.bt_sv_set_basis(st.h, 0))
+        L.check(lib.bt_sv_apply_circuit(st.h, L.ptr(arr), ngates, 1))
+
+    for _ in range(args.warmup):
+        step()
+    st.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    r0 = st.remap_stats()
+    n0 = st.launch_count()
+    ms = C.c_float()
+    L.check(lib.bt_sv_timer_start(st.h))
+    for _ in range(args.steps):
+        step()
+    L.check(lib.bt_sv_timer_stop(st.h, C.byref(ms)))
+    dist.barrier()
+    torch.cuda.synchronize()
+    n1 = st.launch_count()
+    r1 = st.remap_stats()
+    t = torch.tensor([ms.value], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ez = np.empty(N)
+    L.check(lib.bt_sv_expect_1q_all(st.h, L.ptr(L.cmat(bt.gate["Z"], 2)), L.pdouble(ez)))
+    nrm = np.empty(1)
+    L.check(lib.bt_sv_norm2(st.h, L.pdouble(nrm)))
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        ms_per_step = ms_max / args.steps
+        equiv = ngates * world * (2.0 ** (n_local - 28))
+        value = equiv / (ms_per_step / 1e3)
+        remaps = (r1[0] - r0[0]) / args.steps
+        rbytes = (r1[1] - r0[1]) / args.steps
+        rms = (r1[2] - r0[2]) / args.steps
+        out = {"metric": "gates/s", "value": value, "unit": "gates/s (28-qubit-equivalent: gates x shard amplitudes / 2^28, summed over ranks)", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
+               "config": {"workload": f"C5: {N}-qubit state vector random circuit (depth {args.c5_depth}: random 1q gate per qubit + CNOT/CZ brickwork, seed 31), {ngates} gates, "
+                                      f"2^{n_local} amplitudes per GPU", "parallelism": f"{world} shards, top {g} index bits global, qubit remap by peer-memory pull over NVLink",
+                          "l2": "inputs larger than L2"},
+               "circuit_gates_per_s": ngates / (ms_per_step / 1e3), "clocks": clk, "gpu_launches": int(n1 - n0),
+               "remap": {"per_step": remaps, "nvlink_bytes_per_rank_per_step": rbytes, "ms_per_step": rms, "GBps_per_rank": (rbytes / (rms / 1e3) / 1e9) if rms > 0 else None,
+                         "nvlink_peak_GBps": 900.0},
+               "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes), "d2h_bytes_per_step": int(ez.nbytes + 8),
+                       "note": "device-timed; the host API call (gate list in) is the timed call itself"},
+               "checksum": {"norm2": float(nrm[0]), "sum_expect_Z": float(np.sum(ez))}}
+        print(json.dumps(out))
+    dist.barrier()
+    del st
+    dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def bench_reference(args):
+    """Reference arm: the reference path's CPU port on the host cores (Julia itself is not installable here).  Value =
+    the oracle's strided C port (all host threads) on a bounded sample of the same 28-qubit circuit; the kron-chain
+    restatement of the reference ALGORITHM (2^N x 2^N sparse operator per gate) is timed beside it on what it can reach."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    from importlib import import_module
+
+    ge.load_package()
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    from oracle import bt_oracle as O
+    from oracle import strided as S
+
+    N, depth = args.qubits, args.depth
+    specs = wl.c2_qft_layered(N, depth, 28)
+    layered = specs[N * (N + 1) // 2:]
+    budget = max(4.0, args.cpu_budget)
+    sv = S.SV(N)
+    for name, q, t, c in layered[:2]:  # warm-up (page in 4 GiB)
+        sv.apply(O.Op(name, q, t, control=c))
+    vals = []
+    tot_g, tot_t = 0, 0.0
+    pos = 2
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            name, q, t, c = layered[pos % len(layered)]
+            sv.apply(O.Op(name, q, t, control=c))
+            pos += 1
+            n += 1
+            if time.perf_counter() - t0 > budget / max(1, args.steps) and n >= 2:
+                break
+        dt = time.perf_counter() - t0
+        vals.append(n / dt)
+        tot_g += n
+        tot_t += dt
+    value = tot_g / tot_t
+    # the reference ALGORITHM (kron chain + sparse mat-vec), on a size it can hold
+    nk = 16
+    ks = wl.layered(nk, 1, 28)[:12]
+    st = O.zero_state(nk)
+    t0 = time.perf_counter()
+    for name, q, t, c in ks:
+        st = O.Op(name, q, t, control=c).expand(nk) @ st
+    kdt = time.perf_counter() - t0
+    kron = {"qubits": nk, "gates_per_s": len(ks) / kdt, "gates_per_s_28q_equivalent": len(ks) / kdt * 2.0 ** (nk - 28),
+            "note": "restatement of hilbert()+SpMV (src/hilbert.jl:18-159,505) in scipy, single thread like the reference; cannot reach 28 qubits"}
+    out = {"impl": "reference", "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
+           "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers, bounded sample of the layered section", "parallelism": "host CPU"},
+           "cpu_baseline": {"value": value, "unit": "gates/s", "cores": S.num_threads(), "kind": "port",
+                            "sample": f"{tot_g} consecutive gates of the layered section at {N} qubits, in-place strided C + OpenMP ({tot_t:.1f} s)"},
+           "reference_algorithm": kron,
+           "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--qubits", type=int, default=28)
+    ap.add_argument("--depth", type=int, default=100)
+    ap.add_argument("--shard-qubits", type=int, default=31, help="local index bits per GPU for the sharded workload")
+    ap.add_argument("--c5-depth", type=int, default=20)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        if world == 1:
+            # launched without torchrun: re-exec under torch.distributed.run
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29533", __file__] + sys.argv[1:]
+            os.execv(sys.executable, cmd)
+        bench_sharded(args)
+    else:
+        bench_single(args)
+
+
+if __name__ == "__main__":
+    main()

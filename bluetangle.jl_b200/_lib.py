@@ -46,6 +46,7 @@ PROTOTYPES = {
     "bt_device_count": [C.POINTER(_i)],
     "bt_set_device": [_i],
     "bt_set_strict": [_i],
+    "bt_fusion_stats": [C.POINTER(_u64), C.POINTER(_u64)],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],
     "bt_sv_n_qubits": [_vp, C.POINTER(_i)],
@@ -58,6 +59,8 @@ PROTOTYPES = {
     "bt_sv_timer_start": [_vp],
     "bt_sv_timer_stop": [_vp, C.POINTER(C.c_float)],
     "bt_sv_launch_count": [_vp, C.POINTER(_u64)],
+    "bt_sv_profile_enable": [_vp, _i],
+    "bt_sv_profile_read": [_vp, C.POINTER(_u64), _pd],
     "bt_sv_apply_1q": [_vp, _i, _vp, _i],
     "bt_sv_apply_2q": [_vp, _i, _i, _vp, _i],
     "bt_sv_apply_3q": [_vp, _i, _vp],

@@ -141,9 +141,12 @@ extern "C" int bt_dm_apply_2q(bt_dm* d, int qubit, int target, const bt_c64 m[16
   GateDesc row;
   BT_TRY(build_row_gate(d, 2, qubit, target, control, m, &row));
   if (row.nc > 0 || row.diag || row.k < 2) return apply_two_sided(d, row);
-  // dense 2-qubit unitary: conj(U)(x)U is a product, so the row side and the column side are applied as two
-  // 4x4 updates (2 passes of 1 flop/B each) rather than one 16x16 block at the FP64 ridge.
-  return apply_two_sided(d, row);
+  // dense 2-qubit unitary: one pass with the 16x16 superoperator conj(U)(x)U.  Measured on B200 (profiles/):
+  // the 16x16 block (4 flop/B) still runs at the HBM roofline, so one pass beats two 4x4 passes.
+  std::vector<cplx> S(256, cplx(0, 0));
+  superop_add(4, row.m, S);
+  int rb[2] = {row.tb[0], row.tb[1]};
+  return apply_superop(d, 2, rb, S);
 }
 
 extern "C" int bt_dm_kraus(bt_dm* d, int nq, int qubit, int target, const bt_c64* K, int nK) {
@@ -172,39 +175,6 @@ extern "C" int bt_dm_kraus(bt_dm* d, int nq, int qubit, int target, const bt_c64
   }
   // K indexed 2*b_qubit + b_target: matrix bit 0 <-> target, bit 1 <-> qubit
   int rb[2] = {n - target, n - qubit};
-  // Product channels (every 2-qubit model of src/noise.jl:126 is E (x) E): S = S_q (x) S_t factorises into two
-  // 4x4 superoperators, applied as two cheap passes instead of one 16x16 block.
-  // S index: (c1 c0 r1 r0); factor A on (c1, r1) [qubit], B on (c0, r0) [target].
-  {
-    auto idx = [](int c1, int c0, int r1, int r0) { return ((c1 * 2 + c0) * 2 + r1) * 2 + r0; };
-    // find pivot
-    double best = 0; int pi = 0, pj = 0;
-    for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) { double a = std::abs(S[i * 16 + j]); if (a > best) { best = a; pi = i; pj = j; } }
-    int pc1 = (pi >> 3) & 1, pc0 = (pi >> 2) & 1, pr1 = (pi >> 1) & 1, pr0 = pi & 1;
-    int qc1 = (pj >> 3) & 1, qc0 = (pj >> 2) & 1, qr1 = (pj >> 1) & 1, qr0 = pj & 1;
-    cplx A[16], B[16];
-    cplx piv = S[pi * 16 + pj];
-    // A[(c1,r1),(c1',r1')] = S[(c1,pc0,r1,pr0),(c1',qc0,r1',qr0)] ; B[(c0,r0),(c0',r0')] = S[(pc1,c0,pr1,r0),(qc1,c0',qr1,r0')]/piv
-    for (int c1 = 0; c1 < 2; ++c1) for (int r1 = 0; r1 < 2; ++r1) for (int d1 = 0; d1 < 2; ++d1) for (int s1 = 0; s1 < 2; ++s1)
-      A[(c1 * 2 + r1) * 4 + (d1 * 2 + s1)] = S[idx(c1, pc0, r1, pr0) * 16 + idx(d1, qc0, s1, qr0)];
-    for (int c0 = 0; c0 < 2; ++c0) for (int r0 = 0; r0 < 2; ++r0) for (int d0 = 0; d0 < 2; ++d0) for (int s0 = 0; s0 < 2; ++s0)
-      B[(c0 * 2 + r0) * 4 + (d0 * 2 + s0)] = S[idx(pc1, c0, pr1, r0) * 16 + idx(qc1, d0, qr1, s0)] / piv;
-    double err = 0, nrm = 0;
-    for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) {
-      int c1 = (i >> 3) & 1, c0 = (i >> 2) & 1, r1 = (i >> 1) & 1, r0 = i & 1;
-      int d1 = (j >> 3) & 1, d0 = (j >> 2) & 1, s1 = (j >> 1) & 1, s0 = j & 1;
-      cplx p = A[(c1 * 2 + r1) * 4 + (d1 * 2 + s1)] * B[(c0 * 2 + r0) * 4 + (d0 * 2 + s0)];
-      err = std::max(err, std::abs(p - S[i * 16 + j]));
-      nrm = std::max(nrm, std::abs(S[i * 16 + j]));
-    }
-    if (best > 0 && err <= 4e-16 * nrm) {
-      // A, B are 4x4 superoperators with matrix bit 0 = row bit, bit 1 = column bit
-      std::vector<cplx> SA(A, A + 16), SB(B, B + 16);
-      int rbq[1] = {n - qubit}, rbt[1] = {n - target};
-      BT_TRY(apply_superop(d, 1, rbt, SB));
-      return apply_superop(d, 1, rbq, SA);
-    }
-  }
   return apply_superop(d, 2, rb, S);
 }
 

@@ -217,6 +217,7 @@ static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const
   uint64_t ngroups = (uint64_t)s->n_batch << gshift;
   uint64_t per_block = 256ull * U;
   unsigned grid = (unsigned)((ngroups + per_block - 1) / per_block);
+  bt_prof_begin(s, BT_CLS_DENSE);
   if (dmats) {
     k_dense<K, U, true, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, nullptr, 0);
   } else if (cond) {
@@ -224,6 +225,7 @@ static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const
   } else {
     k_dense<K, U, false, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0);
   }
+  bt_prof_end(s);
   BT_CHECK_LAUNCH(s);
   return BT_OK;
 }
@@ -237,10 +239,12 @@ static int launch_diag(bt_sv* s, const GateDesc& g, const int32_t* cond, int wan
   uint64_t ngroups = (uint64_t)s->n_batch << gshift;
   uint64_t per_block = 256ull * U;
   unsigned grid = (unsigned)((ngroups + per_block - 1) / per_block);
+  bt_prof_begin(s, BT_CLS_DIAG);
   if (cond)
     k_diag<K, U, true><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, cond, want);
   else
     k_diag<K, U, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, 0);
+  bt_prof_end(s);
   BT_CHECK_LAUNCH(s);
   return BT_OK;
 }

@@ -67,6 +67,11 @@ struct bt_sv {
   // timing / accounting
   cudaEvent_t ev0, ev1;
   mutable uint64_t launches;
+  // optional per-launch CUDA-event profile (bt_sv_profile_*): kernel class -> count / summed duration
+  bool prof_on;
+  std::vector<cudaEvent_t>* prof_ev;   // pairs (start, stop)
+  std::vector<int>* prof_cls;
+  size_t prof_used;
   // sharding
   int rank, world, g;        // g = log2(world)
   int phys_of_bit[64];       // logical bit -> physical bit (local bits 0..n_local-1, then rank bits)
@@ -119,6 +124,14 @@ int bt_ensure_alt(bt_sv* s);
 
 // fused multi-gate pass (bt_tile.cu)
 int bt_apply_fused(bt_sv* s, const std::vector<GateDesc>& gates);
+
+// kernel classes for the per-launch profile
+#define BT_CLS_TILE 0
+#define BT_CLS_DENSE 1
+#define BT_CLS_DIAG 2
+#define BT_CLS_OTHER 3
+void bt_prof_begin(bt_sv* s, int cls);
+void bt_prof_end(bt_sv* s);
 
 // helpers
 static inline cplx c64(const bt_c64& z) { return cplx(z.re, z.im); }

@@ -127,6 +127,7 @@ extern "C" int bt_sv_destroy(bt_sv* s) {
   cudaFreeHost(s->h_flag);
   cudaEventDestroy(s->ev0);
   cudaEventDestroy(s->ev1);
+  if (s->prof_ev) { for (cudaEvent_t e : *s->prof_ev) cudaEventDestroy(e); delete s->prof_ev; delete s->prof_cls; }
   cudaStreamDestroy(s->stream);
   delete s;
   return BT_OK;
@@ -241,5 +242,46 @@ int bt_results_to_host(const bt_sv* s, size_t n_doubles) {
   if (n_doubles > s->res_cap) BT_FAIL(BT_ERR_ARG, "result buffer too small");
   BT_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, n_doubles * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   BT_CUDA(cudaStreamSynchronize(s->stream));
+  return BT_OK;
+}
+
+// ---- per-launch profile -------------------------------------------------------------------------------------------
+void bt_prof_begin(bt_sv* s, int cls) {
+  if (!s->prof_on) return;
+  if (s->prof_used + 2 > s->prof_ev->size()) {
+    for (int i = 0; i < 512; ++i) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { s->prof_on = false; return; } s->prof_ev->push_back(e); }
+  }
+  cudaEventRecord((*s->prof_ev)[s->prof_used], s->stream);
+  s->prof_cls->push_back(cls);
+}
+void bt_prof_end(bt_sv* s) {
+  if (!s->prof_on) return;
+  cudaEventRecord((*s->prof_ev)[s->prof_used + 1], s->stream);
+  s->prof_used += 2;
+}
+
+extern "C" int bt_sv_profile_enable(bt_sv* s, int on) {
+  BT_TRY(bt_check_sv(s));
+  if (!s->prof_ev) { s->prof_ev = new std::vector<cudaEvent_t>(); s->prof_cls = new std::vector<int>(); }
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  s->prof_used = 0;
+  s->prof_cls->clear();
+  s->prof_on = on != 0;
+  return BT_OK;
+}
+
+// counts[4], ms[4]: launches and summed CUDA-event durations per kernel class since the last enable
+extern "C" int bt_sv_profile_read(bt_sv* s, uint64_t* counts, double* ms) {
+  BT_TRY(bt_check_sv(s));
+  if (!counts || !ms) BT_FAIL(BT_ERR_ARG, "null output");
+  for (int c = 0; c < 4; ++c) { counts[c] = 0; ms[c] = 0.0; }
+  if (!s->prof_ev) return BT_OK;
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
+    float t = 0.f;
+    BT_CUDA(cudaEventElapsedTime(&t, (*s->prof_ev)[i], (*s->prof_ev)[i + 1]));
+    int c = (*s->prof_cls)[i / 2];
+    counts[c]++; ms[c] += t;
+  }
   return BT_OK;
 }

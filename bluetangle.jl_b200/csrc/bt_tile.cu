@@ -1,6 +1,600 @@
-// bt_tile.cu -- placeholder: fused multi-gate pass (replaced by the shared-memory tile kernel).
+// bt_tile.cu -- host-side gate fusion + the multi-gate shared-memory tile kernel.
+//
+// No reference analogue: the reference applies one 2^N x 2^N sparse matrix per op (src/hilbert.jl:505); the
+// nearest ideas are the full-circuit product sa.sparse(circ) (src/struct.jl:877-888) and the duplicate-cancelling
+// optimize_simple (src/ops.jl:335-367).  Here:
+//   1. fusion: runs of 1- and 2-qubit gates are multiplied into dense 4x4 blocks on their qubit pair (a 1-qubit gate
+//      is absorbed by the block that last touched / first touches its qubit), then re-canonicalised (a lone CX comes
+//      back out as control + X, a CZ/CP chain as a diagonal);
+//   2. scheduling: blocks are packed greedily (dependency order preserved) into passes whose non-diagonal target
+//      bits fit a tile of T index bits (the low bits, for coalescing, plus chosen high bits); controls and
+//      diagonal factors on bits outside the tile ride along for free because they only depend on the tile's base index;
+//   3. each pass is ONE kernel: a CTA stages a 2^T-amplitude tile in shared memory with cp.async (XOR-swizzled
+//      16-byte slots), applies the pass's gates in place between __syncthreads, and writes the tile back: one HBM
+//      read + write for up to TILE_MAXG blocks.
+// HBM roofline per pass: 32 B per amplitude; FP64/shared-memory work per dense block ~ a quarter of that time on B200,
+// hence the default cap of blocks per pass (BT_FUSE_MAX_GATES) that keeps the kernel near the HBM bound.
 #include "bt_internal.cuh"
+#include <cuda_pipeline_primitives.h>
+#include <stdlib.h>
+
+#define TILE_MAXG 12
+#define TILE_LOWB 5     // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
+#define TILE_TMAX 12    // 2^12 amplitudes = 64 KB of shared memory per CTA
+#define TILE_THREADS 256
+
+struct TileGate {
+  int32_t kind;       // 0 dense, 1 diagonal
+  int32_t k;          // matrix index bits (<= 2)
+  int32_t tloc[2];    // tile-local position of matrix bit t, or -1 when the bit lies outside the tile (diagonal only)
+  int32_t text[2];    // physical position when outside the tile
+  int32_t ni;         // tile-local inserted positions (local targets + local controls), ascending
+  int32_t ins[6];
+  uint32_t lcmask;    // local controls, forced to 1
+  uint32_t niter;     // group-loop trip count = max(1, (2^T >> ni) / TILE_THREADS)
+  uint64_t ext_cmask; // controls outside the tile: all must be 1 in the tile's base index
+  uint32_t iter_sw[16]; // swizzled slot offset contributed by loop iteration i: sw(expand(i * TILE_THREADS))
+  double2 m[16];      // dense: row-major (1<<k)^2 ; diagonal: first 1<<k entries
+};
+
+struct TileParams {
+  int32_t T;            // tile bits
+  int32_t lowb;         // min(TILE_LOWB, T)
+  int32_t ngates;
+  int32_t pf_dist;      // L2 prefetch distance in tiles (0 = off)
+  uint32_t ntiles_lo, ntiles_hi;
+  int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
+  TileGate g[TILE_MAXG];
+};
+
+// XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
+__host__ __device__ __forceinline__ uint32_t sw(uint32_t c) { return c ^ ((c >> 3) & 7u); }
+
+__device__ __forceinline__ void cfma2(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 cmul2(double2 d, double2 x) { return make_double2(d.x * x.x - d.y * x.y, d.x * x.y + d.y * x.x); }
+
+__host__ __device__ __forceinline__ uint32_t expand32(uint32_t g, const TileGate& G) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < G.ni) {
+      int b = G.ins[i];
+      g = ((g >> b) << (b + 1)) | (g & ((1u << b) - 1u));
+    }
+  return g;
+}
+
+template <int GI, int NT>
+__device__ __forceinline__ void run_gate(const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+    const TileGate& G = P.g[GI];
+    if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
+    // local target bits and the fixed (external) part of the matrix index
+    int kl = 0;
+    uint32_t jext = 0;
+    uint32_t so[2] = {0u, 0u};
+    int tpos[2] = {0, 0};  // matrix bit of the i-th local target
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (t < G.k) {
+        if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
+        else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
+      }
+    const uint32_t ng = nloc >> G.ni;
+    const bool active = tid < ng;
+    const uint32_t niter = G.niter;
+    // slot of this thread's first group; further groups and the partner amplitudes are XOR offsets (sw is linear)
+    const uint32_t s0 = sw(expand32(tid, G) | G.lcmask);
+    if (G.kind == 0) {
+      if (G.k == 2) {
+        const double2* m = G.m;
+        const uint32_t o0 = so[0], o1 = so[1], o01 = so[0] ^ so[1];
+        if (active)
+          for (uint32_t it = 0; it < niter; ++it) {
+            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0, i2 = i0 ^ o1, i3 = i0 ^ o01;
+            double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+            double2 y0 = make_double2(0, 0), y1 = y0, y2 = y0, y3 = y0;
+            cfma2(y0, m[0], x0); cfma2(y0, m[1], x1); cfma2(y0, m[2], x2); cfma2(y0, m[3], x3);
+            cfma2(y1, m[4], x0); cfma2(y1, m[5], x1); cfma2(y1, m[6], x2); cfma2(y1, m[7], x3);
+            cfma2(y2, m[8], x0); cfma2(y2, m[9], x1); cfma2(y2, m[10], x2); cfma2(y2, m[11], x3);
+            cfma2(y3, m[12], x0); cfma2(y3, m[13], x1); cfma2(y3, m[14], x2); cfma2(y3, m[15], x3);
+            sm[i0] = y0; sm[i1] = y1; sm[i2] = y2; sm[i3] = y3;
+          }
+      } else {  // k == 1
+        const double2 m0 = G.m[0], m1 = G.m[1], m2 = G.m[2], m3 = G.m[3];
+        const uint32_t o0 = so[0];
+        if (active)
+          for (uint32_t it = 0; it < niter; ++it) {
+            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0;
+            double2 x0 = sm[i0], x1 = sm[i1];
+            double2 y0 = make_double2(0, 0), y1 = y0;
+            cfma2(y0, m0, x0); cfma2(y0, m1, x1);
+            cfma2(y1, m2, x0); cfma2(y1, m3, x1);
+            sm[i0] = y0; sm[i1] = y1;
+          }
+      }
+    } else {
+      // diagonal: entries with matrix index j; local bits enumerate, external bits fixed by the tile base
+      if (kl == 0) {
+        const double2 d = G.m[jext];
+        if (active && !(d.x == 1.0 && d.y == 0.0))
+          for (uint32_t it = 0; it < niter; ++it) {
+            const uint32_t i0 = s0 ^ G.iter_sw[it];
+            sm[i0] = cmul2(d, sm[i0]);
+          }
+      } else if (kl == 1) {
+        const double2 d0 = G.m[jext], d1 = G.m[jext | (1u << tpos[0])];
+        if (active)
+          for (uint32_t it = 0; it < niter; ++it) {
+            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0];
+            double2 x0 = sm[i0], x1 = sm[i1];
+            sm[i0] = cmul2(d0, x0);
+            sm[i1] = cmul2(d1, x1);
+          }
+      } else {
+        const double2 d0 = G.m[0], d1 = G.m[1u << tpos[0]], d2 = G.m[1u << tpos[1]], d3 = G.m[3];
+        if (active)
+          for (uint32_t it = 0; it < niter; ++it) {
+            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0], i2 = i0 ^ so[1], i3 = i1 ^ so[1];
+            double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+            sm[i0] = cmul2(d0, x0);
+            sm[i1] = cmul2(d1, x1);
+            sm[i2] = cmul2(d2, x2);
+            sm[i3] = cmul2(d3, x3);
+          }
+      }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void run_gate_slot(int gi, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+    switch (gi) {
+      case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
+      case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
+      case 2: run_gate<2, NT>(P, sm, base, tid, nloc); break;
+      case 3: run_gate<3, NT>(P, sm, base, tid, nloc); break;
+      case 4: run_gate<4, NT>(P, sm, base, tid, nloc); break;
+      case 5: run_gate<5, NT>(P, sm, base, tid, nloc); break;
+      case 6: run_gate<6, NT>(P, sm, base, tid, nloc); break;
+      case 7: run_gate<7, NT>(P, sm, base, tid, nloc); break;
+      case 8: run_gate<8, NT>(P, sm, base, tid, nloc); break;
+      case 9: run_gate<9, NT>(P, sm, base, tid, nloc); break;
+      case 10: run_gate<10, NT>(P, sm, base, tid, nloc); break;
+      default: run_gate<11, NT>(P, sm, base, tid, nloc); break;
+    }
+}
+
+
+// Persistent, double-buffered variant: one CTA of TILE_PTHREADS threads per SM walks tiles blockIdx.x, +gridDim.x, ...
+// While the gates of tile i run out of one 2^T buffer, tile i+1 streams into the other with cp.async, and the
+// finished tile drains with plain (fire-and-forget) stores: HBM traffic and FP64 work overlap inside one CTA.
+#define TILE_PTHREADS 1024
+__global__ void __launch_bounds__(TILE_PTHREADS, 1) k_tile_pers(double2* __restrict__ a, uint64_t ntiles, const __grid_constant__ TileParams P) {
+  constexpr int NT = TILE_PTHREADS;
+  extern __shared__ double2 smem[];
+  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
+  const int T = P.T, lowb = P.lowb;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nloc = 1u << T;
+  const uint32_t nhi = 1u << (T - lowb);
+  for (uint32_t h = tid; h < nhi; h += NT) {
+    uint64_t o = 0;
+    for (int j = lowb; j < T; ++j)
+      if ((h >> (j - lowb)) & 1u) o |= 1ull << P.tbits[j];
+    hi_off[h] = o;
+  }
+  __syncthreads();
+  const uint32_t lmask = (1u << lowb) - 1u;
+  auto tile_base = [&](uint64_t t) {
+    uint64_t base = t << lowb;
+    for (int j = lowb; j < T; ++j) {
+      int b = P.tbits[j];
+      base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
+    }
+    return base;
+  };
+  auto issue_load = [&](uint64_t base, double2* buf) {
+    for (uint32_t c = tid; c < nloc; c += NT) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
+    __pipeline_commit();
+  };
+  uint64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  int cur = 0;
+  uint64_t base = tile_base(tile);
+  issue_load(base, smem);
+  while (true) {
+    const uint64_t next = tile + gridDim.x;
+    const bool have_next = next < ntiles;
+    uint64_t nbase = 0;
+    if (have_next) {
+      nbase = tile_base(next);
+      issue_load(nbase, smem + ((size_t)(cur ^ 1) << T));
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    double2* sm = smem + ((size_t)cur << T);
+    for (int gi = 0; gi < P.ngates; ++gi) {
+      run_gate_slot<NT>(gi, P, sm, base, tid, nloc);
+      __syncthreads();
+    }
+    for (uint32_t c = tid; c < nloc; c += NT) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+    if (!have_next) break;
+    __syncthreads();  // everyone is done reading this buffer before the next prefetch overwrites it
+    tile = next; base = nbase; cur ^= 1;
+  }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_tile(double2* __restrict__ a, const __grid_constant__ TileParams P) {
+  extern __shared__ double2 sm[];
+  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
+  const int T = P.T, lowb = P.lowb;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nloc = 1u << T;
+  // base index of this tile: blockIdx with zeros inserted at every tile bit position
+  uint64_t base = (uint64_t)blockIdx.x << lowb;
+  for (int j = lowb; j < T; ++j) {
+    int b = P.tbits[j];
+    base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
+  }
+  const uint32_t nhi = 1u << (T - lowb);
+  for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
+    uint64_t o = 0;
+    for (int j = lowb; j < T; ++j)
+      if ((h >> (j - lowb)) & 1u) o |= 1ull << P.tbits[j];
+    hi_off[h] = o;
+  }
+  __syncthreads();
+  const uint32_t lmask = (1u << lowb) - 1u;
+  for (uint32_t c = tid; c < nloc; c += TILE_THREADS) {
+    const double2* src = a + (base + hi_off[c >> lowb] + (c & lmask));
+    __pipeline_memcpy_async(&sm[sw(c)], src, sizeof(double2));
+  }
+  __pipeline_commit();
+  // keep HBM streaming while this CTA computes: pull the tile a later CTA will need into L2 (one 2^lowb-amplitude
+  // run per thread), so that its load phase is an L2 hit instead of an HBM round trip
+  if (P.pf_dist > 0) {
+    const uint64_t ntiles = ((uint64_t)P.ntiles_hi << 32) | P.ntiles_lo;
+    const uint64_t pt = (uint64_t)blockIdx.x + (uint64_t)P.pf_dist;
+    if (pt < ntiles) {
+      uint64_t pbase = pt << lowb;
+      for (int j = lowb; j < T; ++j) {
+        int b = P.tbits[j];
+        pbase = ((pbase >> b) << (b + 1)) | (pbase & ((1ull << b) - 1ull));
+      }
+      for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
+        const double2* p = a + (pbase + hi_off[h]);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(sizeof(double2) << lowb)) : "memory");
+      }
+    }
+  }
+  __pipeline_wait_prior(0);
+  __syncthreads();
+
+  for (int gi = 0; gi < P.ngates; ++gi) {
+    // one code copy per gate slot: the slot index is a compile-time constant inside, so every matrix element is a
+    // constant-bank operand of its DFMA instead of a live register (keeps the kernel at 3 CTAs/SM)
+    run_gate_slot<TILE_THREADS>(gi, P, sm, base, tid, nloc);
+    __syncthreads();
+  }
+
+  for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+}
+
+// ---- host: fusion ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Block {
+  int nb;            // number of bits (1 or 2 for fusable blocks; >2 => opaque)
+  int bits[2];       // physical bits; matrix index bit t <-> bits[t]
+  cplx m[16];        // row-major dense (1<<nb)^2
+  bool opaque;       // not fusable (>= 3 bits): executed by the direct kernels
+  GateDesc desc;     // opaque: original; fusable: filled by finalize()
+  int ngates;        // original gates folded into this block
+  std::vector<int> touch;  // all physical bits the block touches (ordering)
+};
+
+// dense matrix of a canonical GateDesc over the ordered bit list `bits` (targets + controls), nb <= 2
+bool desc_to_dense(const GateDesc& g, int* nb, int* bits, cplx* m) {
+  int n = g.k + g.nc;
+  if (n > 2 || n == 0) return false;
+  *nb = n;
+  for (int i = 0; i < g.k; ++i) bits[i] = g.tb[i];
+  for (int i = 0; i < g.nc; ++i) bits[g.k + i] = g.cb[i];
+  int D = 1 << n, Dk = 1 << g.k;
+  uint32_t cm = ((1u << g.nc) - 1u) << g.k;
+  for (int r = 0; r < D; ++r)
+    for (int c = 0; c < D; ++c) {
+      cplx v;
+      bool rc = (r & cm) == cm, cc = (c & cm) == cm;
+      if (rc && cc) {
+        int rt = r & (Dk - 1), ct = c & (Dk - 1);
+        v = g.diag ? (rt == ct ? g.m[rt] : cplx(0, 0)) : g.m[rt * Dk + ct];
+      } else {
+        v = (r == c) ? cplx(1, 0) : cplx(0, 0);
+      }
+      m[r * D + c] = v;
+    }
+  return true;
+}
+
+void matmul(int D, const cplx* A, const cplx* B, cplx* Cout) {
+  cplx tmp[16];
+  for (int r = 0; r < D; ++r)
+    for (int c = 0; c < D; ++c) {
+      cplx s(0, 0);
+      for (int k = 0; k < D; ++k) s += A[r * D + k] * B[k * D + c];
+      tmp[r * D + c] = s;
+    }
+  for (int i = 0; i < D * D; ++i) Cout[i] = tmp[i];
+}
+
+// embed a 1-bit matrix u acting on matrix index bit `pos` of a 2-bit block
+void embed1(const cplx* u, int pos, cplx* out) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      int ro = (r >> (1 - pos)) & 1, co = (c >> (1 - pos)) & 1;  // the other bit
+      int rp = (r >> pos) & 1, cp = (c >> pos) & 1;
+      out[r * 4 + c] = (ro == co) ? u[rp * 2 + cp] : cplx(0, 0);
+    }
+}
+
+// reorder a 2-bit matrix given for bit order (b1,b0) into order (b0,b1)
+void swap_bits(cplx* m) {
+  static const int p[4] = {0, 2, 1, 3};
+  cplx t[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) t[r * 4 + c] = m[p[r] * 4 + p[c]];
+  for (int i = 0; i < 16; ++i) m[i] = t[i];
+}
+
+}  // namespace
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& blocks) {
+  std::vector<int> last(64, -1);  // last block index touching a physical bit
+  for (size_t gi = 0; gi < gates.size(); ++gi) {
+    const GateDesc& g = gates[gi];
+    int nb, bits[2];
+    cplx m[16];
+    if (g.k == 0 && g.nc == 0) {
+      // pure scalar (global factor) -- keep it: non-unitary scalars matter (Kraus), unit ones are skipped at launch
+      Block b; b.nb = 0; b.opaque = true; b.desc = g; b.ngates = 1;
+      blocks.push_back(b);
+      continue;
+    }
+    if (!desc_to_dense(g, &nb, bits, m)) {
+      Block b; b.nb = g.k + g.nc; b.opaque = true; b.desc = g; b.ngates = 1;
+      for (int i = 0; i < g.k; ++i) b.touch.push_back(g.tb[i]);
+      for (int i = 0; i < g.nc; ++i) b.touch.push_back(g.cb[i]);
+      blocks.push_back(b);
+      for (int t : b.touch) last[t] = (int)blocks.size() - 1;
+      continue;
+    }
+    if (nb == 1) {
+      int lb = last[bits[0]];
+      if (lb >= 0 && !blocks[lb].opaque) {
+        Block& B = blocks[lb];
+        if (B.nb == 1) { matmul(2, m, B.m, B.m); }
+        else {
+          cplx e[16];
+          embed1(m, B.bits[0] == bits[0] ? 0 : 1, e);
+          matmul(4, e, B.m, B.m);
+        }
+        B.ngates++;
+        continue;
+      }
+      Block b; b.nb = 1; b.bits[0] = bits[0]; b.opaque = false; b.ngates = 1;
+      for (int i = 0; i < 4; ++i) b.m[i] = m[i];
+      b.touch.push_back(bits[0]);
+      blocks.push_back(b);
+      last[bits[0]] = (int)blocks.size() - 1;
+      continue;
+    }
+    // nb == 2
+    int l0 = last[bits[0]], l1 = last[bits[1]];
+    if (l0 >= 0 && l0 == l1 && !blocks[l0].opaque && blocks[l0].nb == 2) {
+      Block& B = blocks[l0];
+      if (B.bits[0] != bits[0]) swap_bits(m);
+      matmul(4, m, B.m, B.m);
+      B.ngates++;
+      continue;
+    }
+    Block b; b.nb = 2; b.bits[0] = bits[0]; b.bits[1] = bits[1]; b.opaque = false; b.ngates = 1;
+    for (int i = 0; i < 16; ++i) b.m[i] = m[i];
+    // absorb pending pure 1-bit blocks that are the last thing on either bit
+    for (int t = 0; t < 2; ++t) {
+      int lb = last[bits[t]];
+      if (lb >= 0 && !blocks[lb].opaque && blocks[lb].nb == 1) {
+        cplx e[16];
+        embed1(blocks[lb].m, t, e);
+        matmul(4, b.m, e, b.m);
+        b.ngates += blocks[lb].ngates;
+        blocks[lb].nb = -1;  // tombstone
+      }
+    }
+    b.touch.push_back(bits[0]);
+    b.touch.push_back(bits[1]);
+    blocks.push_back(b);
+    last[bits[0]] = last[bits[1]] = (int)blocks.size() - 1;
+  }
+  // finalize
+  std::vector<Block> out;
+  out.reserve(blocks.size());
+  for (Block& b : blocks) {
+    if (b.nb == -1) continue;
+    if (!b.opaque) bt_canonicalize(b.nb, b.bits, b.m, 0, nullptr, &b.desc);
+    out.push_back(b);
+  }
+  blocks.swap(out);
+}
+
+static uint64_t g_fused_passes = 0, g_fused_blocks = 0;
+
+// bits of `d` that must be inside the tile: non-diagonal targets
+static void needed_bits(const GateDesc& d, std::vector<int>& out) {
+  out.clear();
+  if (!d.diag)
+    for (int i = 0; i < d.k; ++i) out.push_back(d.tb[i]);
+}
+
+static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass, const std::vector<int>& tile_bits_in) {
+  if (pass.size() == 1) return bt_launch_gate(s, pass[0]->desc);
+  int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TMAX));
+  int lowb = std::min(TILE_LOWB, T);
+  const bool persistent = env_int("BT_TILE_PERSISTENT", 0) != 0;
+  const uint32_t nthreads = persistent ? TILE_PTHREADS : TILE_THREADS;
+  // tile bits: low bits + requested + padding with the lowest free bits
+  bool in[64] = {false};
+  for (int j = 0; j < lowb; ++j) in[j] = true;
+  int cnt = lowb;
+  for (int b : tile_bits_in)
+    if (!in[b]) { in[b] = true; cnt++; }
+  for (int b = lowb; b < s->n_local && cnt < T; ++b)
+    if (!in[b]) { in[b] = true; cnt++; }
+  if (cnt != T) BT_FAIL(BT_ERR_ARG, "internal: tile has %d bits, expected %d", cnt, T);
+  TileParams P;
+  memset(&P, 0, sizeof(P));
+  P.T = T; P.lowb = lowb;
+  int local_pos[64];
+  for (int b = 0; b < 64; ++b) local_pos[b] = -1;
+  int j = 0;
+  for (int b = 0; b < s->n_local; ++b)
+    if (in[b]) { P.tbits[j] = b; local_pos[b] = j; j++; }
+  int ng = 0;
+  for (const Block* blk : pass) {
+    const GateDesc& d = blk->desc;
+    if (d.k > 2 || d.nc > 4) BT_FAIL(BT_ERR_ARG, "internal: gate not tileable");
+    if (d.diag) {
+      bool all_one = true;
+      for (int i = 0; i < (1 << d.k); ++i) if (d.m[i] != cplx(1, 0)) all_one = false;
+      if (all_one) continue;
+    }
+    TileGate& G = P.g[ng++];
+    G.kind = d.diag ? 1 : 0;
+    G.k = d.k;
+    G.lcmask = 0; G.ext_cmask = 0;
+    std::vector<int> ins;
+    for (int t = 0; t < d.k; ++t) {
+      int lp = local_pos[d.tb[t]];
+      G.tloc[t] = lp; G.text[t] = d.tb[t];
+      if (lp >= 0) ins.push_back(lp);
+      else if (!d.diag) BT_FAIL(BT_ERR_ARG, "internal: dense target outside the tile");
+    }
+    for (int c = 0; c < d.nc; ++c) {
+      int lp = local_pos[d.cb[c]];
+      if (lp >= 0) { G.lcmask |= 1u << lp; ins.push_back(lp); }
+      else G.ext_cmask |= 1ull << d.cb[c];
+    }
+    std::sort(ins.begin(), ins.end());
+    if (ins.size() > 6) BT_FAIL(BT_ERR_ARG, "internal: too many local bits in one gate");
+    G.ni = (int)ins.size();
+    for (size_t i = 0; i < ins.size(); ++i) G.ins[i] = ins[i];
+    int cntm = d.diag ? (1 << d.k) : (1 << (2 * d.k));
+    for (int i = 0; i < cntm; ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
+    uint32_t ngroups = (1u << T) >> G.ni;
+    G.niter = std::max<uint32_t>(1u, ngroups / nthreads);
+    if (G.niter > 16) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
+    for (uint32_t it = 0; it < G.niter; ++it) G.iter_sw[it] = sw(expand32(it * nthreads, G));
+  }
+  P.ngates = ng;
+  if (ng == 0) return BT_OK;
+  uint64_t ntiles = s->len >> T;
+  size_t smem = sizeof(double2) << T;
+  P.pf_dist = env_int("BT_TILE_PREFETCH", 0);  // measured on B200: no gain, off by default
+  if (lowb < 2) P.pf_dist = 0;  // bulk prefetch needs >= 16-byte multiples and alignment
+  P.ntiles_lo = (uint32_t)ntiles; P.ntiles_hi = (uint32_t)(ntiles >> 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_pers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
+    attr_set = true;
+  }
+  bt_prof_begin(s, BT_CLS_TILE);
+  if (persistent) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)nsm);
+    k_tile_pers<<<grid, TILE_PTHREADS, 2 * smem, s->stream>>>(s->amp, ntiles, P);
+  } else {
+    k_tile<<<(unsigned)ntiles, TILE_THREADS, smem, s->stream>>>(s->amp, P);
+  }
+  bt_prof_end(s);
+  BT_CHECK_LAUNCH(s);
+  g_fused_passes++;
+  g_fused_blocks += ng;
+  return BT_OK;
+}
+
 int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
-  for (size_t i = 0; i < gates.size(); ++i) BT_TRY(bt_launch_gate(s, gates[i]));
+  std::vector<Block> blocks;
+  fuse_blocks(gates, blocks);
+  const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TMAX));
+  const int lowb = std::min(TILE_LOWB, T);
+  const int maxg = std::max(1, std::min(TILE_MAXG, env_int("BT_FUSE_MAX_GATES", 8)));
+  const int window = env_int("BT_FUSE_WINDOW", 256);
+  const size_t n = blocks.size();
+  std::vector<char> done(n, 0);
+  size_t first = 0;
+  std::vector<int> need;
+  while (first < n) {
+    if (done[first]) { first++; continue; }
+    // opaque / scalar blocks run alone, in order
+    bool blocked[64] = {false};
+    bool in_tile[64] = {false};
+    for (int j = 0; j < lowb; ++j) in_tile[j] = true;
+    int tile_cnt = lowb;
+    std::vector<const Block*> pass;
+    std::vector<int> tile_bits;
+    double cost = 0.0;
+    int nblocked = 0;
+    size_t scanned = 0;
+    for (size_t i = first; i < n && scanned < (size_t)window && nblocked < s->n_local; ++i) {
+      if (done[i]) continue;
+      scanned++;
+      Block& b = blocks[i];
+      bool dep = false;
+      for (int t : b.touch) if (blocked[t]) dep = true;
+      bool ok = !dep;
+      if (ok && (b.opaque || b.desc.k > 2)) {
+        // runs through the direct kernels, alone: only as the first element of a pass
+        ok = pass.empty();
+        if (ok) {
+          pass.push_back(&b); done[i] = 1;
+          break;
+        }
+      }
+      if (ok) {
+        needed_bits(b.desc, need);
+        int extra = 0;
+        for (int t : need) if (!in_tile[t]) extra++;
+        double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
+        if (tile_cnt + extra > T || (int)pass.size() >= TILE_MAXG || (cost + c > (double)maxg && !pass.empty())) ok = false;
+        if (ok) {
+          for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
+          pass.push_back(&b); done[i] = 1; cost += c;
+          continue;
+        }
+      }
+      for (int t : b.touch) if (!blocked[t]) { blocked[t] = true; nblocked++; }
+      if (b.touch.empty()) break;  // a global scalar orders everything
+    }
+    if (pass.empty()) BT_FAIL(BT_ERR_ARG, "internal: fusion scheduler made no progress");
+    BT_TRY(launch_pass(s, pass, tile_bits));
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_fusion_stats(uint64_t* passes, uint64_t* blocks) {
+  if (passes) *passes = g_fused_passes;
+  if (blocks) *blocks = g_fused_blocks;
   return BT_OK;
 }

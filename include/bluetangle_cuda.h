@@ -64,6 +64,9 @@ int bt_sv_sync(const bt_sv* s);
 int bt_sv_timer_start(bt_sv* s);
 int bt_sv_timer_stop(bt_sv* s, float* ms);
 int bt_sv_launch_count(const bt_sv* s, uint64_t* n);              /* kernels launched on this handle so far */
+/* per-launch CUDA-event profile by kernel class {0: fused tile kernel, 1: dense gate, 2: diagonal gate, 3: other} */
+int bt_sv_profile_enable(bt_sv* s, int on);
+int bt_sv_profile_read(bt_sv* s, uint64_t counts[4], double ms[4]);
 
 /* ---- gates: op.expand(N)*state  src/hilbert.jl:505 with hilbert() src/hilbert.jl:18-159 --------------- */
 int bt_sv_apply_1q(bt_sv* s, int qubit, const bt_c64 m[4], int control);               /* hilbert.jl:143-159 */
@@ -75,6 +78,7 @@ int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse);
  * outcome is a DEVICE pointer obtained from bt_sv_outcome_buffer */
 int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int want);
 int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
+int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); /* cumulative: fused tile-kernel launches and blocks they carried */
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */

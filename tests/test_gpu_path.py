@@ -1,0 +1,390 @@
+"""GPU parity for the noise -> measure/sample -> expect part of the path, through the C ABI, against the oracle;
+includes the reference's own star tests (test/runtests.jl) restated for the device backend."""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rand_state(N, seed):
+    g = np.random.default_rng(seed)
+    v = g.normal(size=1 << N) + 1j * g.normal(size=1 << N)
+    return v / np.linalg.norm(v)
+
+
+def random_ops(mod, N, depth, seed, measure_prob=0.0):
+    """gates.jl:155-209 style generator (same structure, numpy RNG) producing ops for module ``mod``."""
+    g = np.random.default_rng(seed)
+    one = ["I", "X", "Y", "Z", "SX", "XSQRT", "H", "T", "S", "SD", "P", "U2", "U3"]
+    two = ["CX", "CNOT", "CY", "CZ", "CP", "RXX", "RYY", "RZZ", "RXY", "GIVENS", "FSIM", "SWAP", "ISWAP", "FSWAP", "SYC", "ECR"]
+    ops = []
+    for _ in range(depth):
+        c = 1
+        while c <= N:
+            pool = one if c == N else one + two
+            s = pool[g.integers(len(pool))]
+            p = [round(float(x) * np.pi, 2) for x in g.normal(size=3)]
+            if s in one:
+                if s == "P":
+                    ops.append(mod.Op(f"P({p[0]})", c))
+                elif s == "U2":
+                    ops.append(mod.Op(f"U2({p[0]},{p[1]})", c))
+                elif s == "U3":
+                    ops.append(mod.Op(f"U3({p[0]},{p[1]},{p[2]})", c))
+                else:
+                    ops.append(mod.Op(s, c))
+                c += 1
+            else:
+                if s == "FSIM":
+                    ops.append(mod.Op(f"FSIM({p[0]},{p[1]})", c, c + 1))
+                elif s in ("CP", "RXX", "RYY", "RZZ", "RXY", "GIVENS"):
+                    ops.append(mod.Op(f"{s}({p[0]})", c, c + 1))
+                else:
+                    ops.append(mod.Op(s, c, c + 1))
+                c += 2
+        for i in range(1, N + 1):
+            if g.random() < measure_prob:
+                ops.append(mod.Op(["MX", "MY", "MZ"][g.integers(3)], i))
+    return ops
+
+
+# ---- partial traces ------------------------------------------------------------------------------------------
+def test_partial_trace(bt, orc):
+    N = 7
+    v = rand_state(N, 3)
+    s = bt.CuState.from_numpy(v)
+    for q in range(1, N + 1):
+        assert np.max(np.abs(bt.partial_trace(s, q) - orc.partial_trace_1(v, q))) < TOL
+    for q in range(1, N):
+        assert np.max(np.abs(bt.partial_trace(s, q, q + 1) - orc.partial_trace_2adj(v, q, q + 1))) < TOL
+        assert np.max(np.abs(bt.partial_trace(s, q + 1, q) - orc.partial_trace_2adj(v, q + 1, q))) < TOL
+    for a, b in itertools.permutations(range(1, N + 1), 2):
+        assert np.max(np.abs(bt.partial_trace(s, [a, b]) - orc.partial_trace_general(v, [a, b]))) < TOL
+    for q in range(1, N - 1):
+        assert np.max(np.abs(bt.partial_trace(s, [q, q + 1, q + 2]) - orc.partial_trace_general(v, [q, q + 1, q + 2]))) < TOL
+
+
+def test_norm_inner_probs(bt, orc):
+    N = 9
+    a, b = rand_state(N, 1), rand_state(N, 2)
+    sa, sb = bt.CuState.from_numpy(a), bt.CuState.from_numpy(b * 0.5)
+    assert abs(bt.inner(sa, sb) - np.vdot(a, b * 0.5)) < TOL
+    assert abs(bt.fidelity(sa, sb) - abs(np.vdot(a, 0.5 * b)) ** 2) < TOL
+    assert abs(bt.norm2(sb) - 0.25) < TOL
+    bt.normalize(sb)
+    assert np.max(np.abs(sb.to_numpy() - b)) < TOL
+    assert np.max(np.abs(bt.prob(sa) - np.abs(a) ** 2)) < 1e-15
+
+
+# ---- measurement ---------------------------------------------------------------------------------------------
+def test_born_measure_all_bases_same_draws(bt, orc):
+    N = 6
+    for seed in range(30):
+        v = rand_state(N, seed)
+        q = 1 + seed % N
+        name = ["MZ", "MX", "MY", "MR"][seed % 4]
+        s = bt.CuState.from_numpy(v)
+        _, ind_d = bt.apply(s, bt.Op(name, q), rng=bt.Draws(seed), track_measurements=True)
+        ref, ind_o = orc.apply(v, orc.Op(name, q), draws=orc.Draws(seed), track_measurements=True)
+        assert ind_d == ind_o
+        assert np.max(np.abs(s.to_numpy() - ref)) < TOL
+
+
+def test_reference_mid_circuit_known_answers(bt):
+    """test/runtests.jl:195-231."""
+    ops_reset = [bt.Op("X", 1), bt.Op("RES", 1), bt.Op("MZ", 1)]
+    ops_ifop = [bt.Op("X", 1), bt.ifOp("MZ", 1, bt.Op("I", 1), bt.Op("X", 1))]
+    ops_mid = [bt.Op("X", 1), bt.Op("X", 2), bt.Op("CX", 2, 3), bt.Op("CX", 1, 2), bt.Op("X", 2), bt.Op("MZ", 2), bt.Op("RES", 2),
+               bt.Op("CX", 2, 3), bt.Op("CX", 1, 2), bt.Op("CX", 2, 3), bt.Op("X", 1)]
+    assert bt.run(ops_reset, 1)[0] == [0]
+    assert bt.run(ops_ifop, 1)[0] == [1]
+    assert bt.run(ops_mid, 1)[0] == [1]
+    _, m = bt.apply(ops_reset, bt.zero_state(1), track_measurements=True)
+    assert m == [0]
+    _, m = bt.apply(ops_ifop, bt.zero_state(1), track_measurements=True)
+    assert m == [1]
+    _, m = bt.apply(ops_mid, bt.zero_state(3), track_measurements=True)
+    assert m == [1]
+
+
+def test_reference_seed_locked_noisy_run(bt, orc):
+    """test/runtests.jl:233-259: the device backend as a third participant: identical mid-circuit outcomes and
+    states under the same draws."""
+    def ops(m):
+        return [m.Op("H", 1), m.Op("CX", 1, 2), m.Op("RY(0.37)", 1), m.Op("RZ(0.19)", 2), m.Op("MZ", 1), m.Op("X", 2), m.Op("MZ", 2)]
+    nm_d = bt.NoiseModel("depolarizing", 0.03)
+    nm_o = orc.NoiseModel.model("depolarizing", 0.03)
+    for seed in range(1, 41):
+        sd, mid_d = bt.apply(ops(bt), bt.zero_state(2), noise=nm_d, rng=bt.Draws(1000 + seed), track_measurements=True)
+        so, mid_o = orc.apply_ops(orc.zero_state(2), ops(orc), noise=nm_o, draws=orc.Draws(1000 + seed), track_measurements=True)
+        assert mid_d == mid_o
+        assert np.linalg.norm(sd.to_numpy() - so) < 1e-8
+
+
+def test_reference_seed_locked_opqc(bt, orc):
+    """test/runtests.jl:261-285."""
+    def ops(m, QC):
+        return [m.Op("H", 1), m.Op("CX", 1, 2), QC("depolarizing", 0.07, 1), QC("depolarizing", 0.04, 1, 2), m.Op("MZ", 1), m.Op("MZ", 2)]
+    for seed in range(1, 41):
+        sd, mid_d = bt.apply(ops(bt, bt.OpQC), bt.zero_state(2), rng=bt.Draws(2000 + seed), track_measurements=True)
+        so, mid_o = orc.apply_ops(orc.zero_state(2), ops(orc, orc.OpQC.model), draws=orc.Draws(2000 + seed), track_measurements=True)
+        assert mid_d == mid_o
+        assert np.linalg.norm(sd.to_numpy() - so) < 1e-8
+
+
+# ---- Kraus channels on state vectors -----------------------------------------------------------------------------
+MODELS = ["amplitude_damping", "phase_damping", "phase_flip", "bit_flip", "bit_phase_flip", "depolarizing", "depolarizing_amp", "rot_x", "rot_y", "rot_z", "rot_p", "rot_xyz", "MZ"]
+
+
+def test_kraus_probs_and_trajectory_step(bt, orc):
+    N = 5
+    k = 0
+    for model in MODELS:
+        if model == "rot_xyz":
+            continue  # not CPTP for generic p: the reference's validity check rejects it
+        for (q, t) in [(2, -1), (5, -1), (2, 3), (3, 2), (1, 4), (4, 1), (5, 3)]:
+            k += 1
+            v = rand_state(N, k)
+            p = 0.3
+            try:
+                od = bt.OpQC(model, p, q, t)
+            except ValueError:
+                with pytest.raises(ValueError):
+                    orc.OpQC.model(model, p, q, t)
+                continue
+            oo = orc.OpQC.model(model, p, q, t)
+            s = bt.CuState.from_numpy(v)
+            assert np.max(np.abs(od.prob(s) - np.array(oo.prob(v)))) < TOL, (model, q, t)
+            bt.apply(s, od, rng=bt.Draws(k))
+            ref = orc.apply(v, oo, draws=orc.Draws(k))
+            assert np.max(np.abs(s.to_numpy() - ref)) < TOL, (model, q, t)
+
+
+def test_reference_kraus_prob_relation(bt, orc):
+    """test/runtests.jl:19-35: tr(K pA K') == ||hilbert(N,K,q,t) psi||^2 == OpQC.prob."""
+    N = 6
+    v = rand_state(N, 11)
+    s = bt.CuState.from_numpy(v)
+    K = bt.noise_model("depolarizing", 0.5, two_qubit=True)
+    pA = bt.partial_trace(s, [2, 3])
+    probs = [np.real(np.trace(k @ pA @ k.conj().T)) for k in K]
+    probs2 = []
+    for k in K:
+        c = s.copy()
+        bt.apply(c, bt.Op("K", k, 2, 3))
+        probs2.append(bt.norm2(c))
+    probs3 = bt.OpQC("my quantum channel", K, 2, 3).prob(s)
+    assert np.allclose(probs, probs2, atol=1e-12) and np.allclose(probs, probs3, atol=1e-12)
+
+
+def test_kraus_3q(bt, orc):
+    N = 5
+    K1 = orc.noise_model("amplitude_damping", 0.3)
+    K3 = [np.kron(np.kron(a, b), c) for a in K1 for b in K1 for c in K1]
+    for first in (1, 2, 3):
+        v = rand_state(N, first)
+        s = bt.CuState.from_numpy(v)
+        bt.apply(s, bt.OpQC("ad3", K3, first), rng=bt.Draws(first))
+        ref = orc.apply(v, orc.OpQC("ad3", K3, first), draws=orc.Draws(first))
+        assert np.max(np.abs(s.to_numpy() - ref)) < TOL
+
+
+def test_weighted_sample_failure_is_loud(bt):
+    """src/hilbert.jl:810-819 returns nothing when the draw exceeds the last cumulative sum -> error, not a silent pick."""
+    import ctypes as C
+    s = bt.zero_state(2)
+    K = [0.5 * bt.gate["I"], 0.5 * bt.gate["X"]]  # not trace preserving on purpose: probabilities sum to 0.5
+    tab = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in K])
+    u = np.array([0.9])
+    chosen = np.zeros(1, dtype=np.int32)
+    rc = s.lib.bt_sv_kraus(s.h, 1, 1, -1, tab.ctypes.data_as(C.c_void_p), 2, u.ctypes.data_as(C.POINTER(C.c_double)), chosen.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == -4
+
+
+# ---- noisy trajectories vs oracle on a random circuit with measurements -------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_noisy_monitored_circuit_same_draws(bt, orc, seed):
+    N, depth = 5, 6
+    od = random_ops(bt, N, depth, seed, measure_prob=0.15)
+    oo = random_ops(orc, N, depth, seed, measure_prob=0.15)
+    nm_d, nm_o = bt.NoiseModel("amplitude_damping", 0.05), orc.NoiseModel.model("amplitude_damping", 0.05)
+    sd, mid_d = bt.apply(od, bt.zero_state(N), noise=nm_d, rng=bt.Draws(seed), track_measurements=True)
+    so, mid_o = orc.apply_ops(orc.zero_state(N), oo, noise=nm_o, draws=orc.Draws(seed), track_measurements=True)
+    assert mid_d == mid_o
+    assert np.max(np.abs(sd.to_numpy() - so)) < TOL
+
+
+# ---- circuits: gate by gate == circuit call (test/runtests.jl:54-73 model) -----------------------------------------
+def test_circuit_call_equals_sequential_and_oracle(bt, orc):
+    N, depth = 10, 50
+    od, oo = random_ops(bt, N, depth, 7), random_ops(orc, N, depth, 7)
+    v = rand_state(N, 5)
+    s1 = bt.CuState.from_numpy(v)
+    for o in od:
+        bt.apply(s1, o)
+    s2 = bt.CuState.from_numpy(v)
+    bt.apply(od, s2)
+    ref = orc.apply_ops(v, oo)
+    assert np.max(np.abs(s1.to_numpy() - ref)) < TOL
+    assert np.max(np.abs(s2.to_numpy() - ref)) < 1e-12 + TOL
+
+
+# ---- expectation values, correlations, sampling ----------------------------------------------------------------------
+def test_expect_and_correlation(bt, orc):
+    N = 6
+    v = rand_state(N, 21)
+    s = bt.CuState.from_numpy(v)
+    for name in ["Z", "X", "Y", "T", "H", "S", "P0", "SP", "RX(0.3)"]:
+        assert np.max(np.abs(bt.expect(s, name) - np.array(orc.expect(v, name)))) < TOL, name
+    for q in range(1, N + 1):
+        assert abs(bt.expect(s, bt.Op("H", q)) - orc.expect(v, orc.Op("H", q))) < TOL
+    assert abs(bt.expect(s, bt.Op("FSIM(0.2,0.3)", 2, 5)) - orc.expect(v, orc.Op("FSIM(0.2,0.3)", 2, 5))) < TOL
+    for ops_s, qs in [("Z,Z", [2, 4]), ("X,Y", [1, 6]), ("Y,Y,Z", [3, 1, 5]), ("T,Z", [2, 3]), ("X,H,SP", [6, 2, 4]), ("Y", [4])]:
+        assert abs(bt.correlation(s, ops_s, qs) - orc.correlation(v, ops_s, qs)) < TOL, ops_s
+    assert abs(bt.correlation(s, [1, 3]) - orc.correlation_z(v, [1, 3])) < TOL
+
+
+def test_sample_matches_inverse_cdf(bt, orc):
+    for N in (3, 11, 14):
+        v = rand_state(N, N)
+        s = bt.CuState.from_numpy(v)
+        us = np.random.default_rng(N).random(4096)
+        assert np.array_equal(bt.sample(s, 4096, uniforms=us), orc.sample(v, us))
+    # sparse state: only structurally non-zero entries are ever returned, sample_exact lists them ascending
+    v = np.zeros(1 << 10, dtype=complex)
+    v[[5, 77, 900]] = [0.6, 0.0 + 0.64j, 0.48]
+    s = bt.CuState.from_numpy(v)
+    us = np.concatenate([[0.0, 0.36, 0.3600001, 0.999999], np.random.default_rng(1).random(200)])
+    assert np.array_equal(bt.sample(s, len(us), uniforms=us), orc.sample(v, us))
+    a, b = bt.sample_exact(s)
+    assert list(a) == [5, 77, 900] and np.allclose(b, [0.36, 0.4096, 0.2304])
+    m = bt.measure(s)
+    assert abs(m.expect[0] - orc.sample_to_expectation(a, b, 10, [1])) < 1e-15
+
+
+# ---- density matrices ------------------------------------------------------------------------------------------------
+def test_dm_unitaries_match_oracle_and_sv(bt, orc):
+    """test/runtests.jl:89-107: state*state' == rho after the same ops."""
+    N, depth = 4, 20
+    od, oo = random_ops(bt, N, depth, 9), random_ops(orc, N, depth, 9)
+    rho = bt.CuRho(N)
+    st = bt.zero_state(N)
+    for o in od:
+        bt.apply(rho, o)
+        bt.apply(st, o)
+    ref = orc.to_rho(oo, N)
+    assert np.max(np.abs(rho.to_numpy() - ref)) < TOL
+    v = st.to_numpy()
+    assert np.max(np.abs(np.outer(v, v.conj()) - rho.to_numpy())) < TOL
+    assert np.max(np.abs(bt.CuRho.from_state(st).to_numpy() - rho.to_numpy())) < TOL
+    assert np.max(np.abs(bt.expect(rho, "T") - np.array(orc.expect(ref, "T")))) < TOL
+    assert np.max(np.abs(bt.expect(rho, "X") - np.array(orc.expect(ref, "X")))) < TOL
+
+
+def test_dm_controlled_and_nonadjacent(bt, orc):
+    N = 4
+    g = np.random.default_rng(0)
+    v = rand_state(N, 1)
+    rho0 = np.outer(v, v.conj())
+    cases = [("X", 3, -1, 1), ("H", 1, -1, 4), ("CX", 1, 3, -2), ("CZ", 4, 2, -2), ("FSIM(0.3,0.2)", 4, 1, -2), ("ECR", 2, 3, 4), ("RZZ(0.3)", 1, 4, -2), ("T", 2, -1, -2)]
+    for name, q, t, c in cases:
+        rho = bt.CuRho.from_numpy(rho0)
+        bt.apply(rho, bt.Op(name, q, t, control=c))
+        ref = orc.apply(rho0, orc.Op(name, q, t, control=c))
+        assert np.max(np.abs(rho.to_numpy() - ref)) < TOL, (name, q, t, c)
+
+
+def test_dm_channels_match_oracle(bt, orc):
+    N = 4
+    v = rand_state(N, 2)
+    rho0 = np.outer(v, v.conj())
+    for model in ["amplitude_damping", "phase_damping", "depolarizing", "bit_flip", "depolarizing_amp"]:
+        for (q, t) in [(1, -1), (4, -1), (2, 3), (3, 2), (1, 4), (4, 2)]:
+            rho = bt.CuRho.from_numpy(rho0)
+            bt.apply(rho, bt.OpQC(model, 0.2, q, t))
+            ref = orc.apply(rho0, orc.OpQC.model(model, 0.2, q, t))
+            assert np.max(np.abs(rho.to_numpy() - ref)) < TOL, (model, q, t)
+    # a non-product 2-qubit channel (correlated XX / ZZ errors) exercises the 16x16 superoperator kernel
+    K = [np.sqrt(0.7) * np.eye(4), np.sqrt(0.2) * np.kron(orc.GATE["X"], orc.GATE["X"]), np.sqrt(0.1) * np.kron(orc.GATE["Z"], orc.GATE["Z"])]
+    for (q, t) in [(1, 2), (4, 1), (3, 1)]:
+        rho = bt.CuRho.from_numpy(rho0)
+        bt.apply(rho, bt.OpQC("corr", K, q, t))
+        ref = orc.apply(rho0, orc.OpQC("corr", K, q, t))
+        assert np.max(np.abs(rho.to_numpy() - ref)) < TOL
+
+
+def test_reference_opqc_equals_noisemodel_on_dm(bt, orc):
+    """test/runtests.jl:136-166 (t1): OpQC after each op == NoiseModel on the density matrix."""
+    N, depth, p = 1, 20, 0.01
+    ops = random_ops(bt, N, depth, 4)
+    v = rand_state(N, 8)
+    rho1 = bt.CuRho.from_numpy(np.outer(v, v.conj()))
+    rho2 = bt.CuRho.from_numpy(np.outer(v, v.conj()))
+    nm = bt.NoiseModel("depolarizing", p)
+    for o in ops:
+        bt.apply(rho1, o)
+        bt.apply(rho1, bt.OpQC("depolarizing", p, o.qubit))
+        bt.apply(rho2, o, noise=nm)
+    assert np.linalg.norm(rho1.to_numpy() - rho2.to_numpy()) < 1e-12
+
+
+def test_dm_noisy_circuit_and_trajectory_average(bt, orc):
+    """test/runtests.jl:109-131: noisy DM == oracle; average of noisy trajectories approaches it."""
+    N, depth = 4, 8
+    od, oo = random_ops(bt, N, depth, 13), random_ops(orc, N, depth, 13)
+    nm_d, nm_o = bt.NoiseModel("depolarizing", 0.1), orc.NoiseModel.model("depolarizing", 0.1)
+    rho = bt.CuRho(N)
+    for o in od:
+        bt.apply(rho, o, noise=nm_d)
+    ref = orc.to_rho(oo, N, noise=nm_o)
+    assert np.max(np.abs(rho.to_numpy() - ref)) < TOL
+    exact = float(np.sum(bt.expect(rho, "T")))
+    T = 2000
+    st = bt.zero_state(N, T)
+    U = np.random.default_rng(0).random((T, len(od) + 8))
+    bt.apply(od, st, noise=nm_d, rng=bt.BatchDraws(U))
+    avg = float(np.mean(np.sum(bt.expect(st, "T"), axis=1)))
+    assert abs(avg - exact) < 0.1
+    assert abs(rho.to_numpy().trace() - 1) < 1e-12
+
+
+def test_dm_sample_diag_dephase_pauli(bt, orc):
+    N = 5
+    od, oo = random_ops(bt, N, 6, 3), random_ops(orc, N, 6, 3)
+    nm_d, nm_o = bt.NoiseModel("amplitude_damping", 0.1), orc.NoiseModel.model("amplitude_damping", 0.1)
+    rho = bt.CuRho(N)
+    for o in od:
+        bt.apply(rho, o, noise=nm_d)
+    ref = orc.to_rho(oo, N, noise=nm_o)
+    a, b = bt.sample_exact(rho)
+    ao, bo = orc.sample_exact(ref)
+    assert np.array_equal(a, ao) and np.max(np.abs(b - bo)) < TOL
+    for ops_s, qs in [("Z,Z", [2, 4]), ("X,Y", [1, 5]), ("T,X", [2, 3])]:
+        assert abs(bt.correlation(rho, ops_s, qs) - orc.correlation(ref, ops_s, qs)) < TOL
+    bt.born_measure_Z(rho, 2)
+    assert np.max(np.abs(rho.to_numpy() - orc.born_measure_Z_rho(N, ref, 2))) < TOL
+    with pytest.raises(RuntimeError):
+        bt.apply(rho, bt.Op("MZ", 1))  # src/hilbert.jl:772: unsupported in the reference, stays unsupported
+
+
+# ---- batched trajectories ------------------------------------------------------------------------------------------
+def test_batched_trajectories_equal_sequential_loop(bt, orc):
+    """SURVEY C4 in miniature: every trajectory of the batch equals the oracle's sequential shot fed the same draws."""
+    N, depth, T = 5, 6, 16
+    od = random_ops(bt, N, depth, 5, measure_prob=0.2)
+    oo = random_ops(orc, N, depth, 5, measure_prob=0.2)
+    od.insert(7, bt.ifOp("MZ", 2, "I", "X"))
+    oo.insert(7, orc.ifOp("MZ", 2, [orc.Op("I", 2)], [orc.Op("X", 2)]))
+    M = sum(1 for o in od if o.type == "🔬")
+    U = np.random.default_rng(3).random((T, M))
+    outs = bt.run(od, T, batch=bt.BatchDraws(U))
+    st = bt.zero_state(N, T)
+    bt.apply(od, st, rng=bt.BatchDraws(U))
+    got = st.to_numpy()
+    for t in range(T):
+        so, mid_o = orc.apply_ops(orc.zero_state(N), [o for o in oo], draws=orc.ListDraws(U[t]), track_measurements=True)
+        assert outs[t] == mid_o
+        assert np.max(np.abs(got[t] - so)) < TOL
