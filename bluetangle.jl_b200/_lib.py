@@ -111,6 +111,8 @@ PROTOTYPES = {
     "bt_sv_attach_local_peers": [C.POINTER(_vp), _i],
     "bt_sv_set_barrier": [_vp, BARRIER_FN, _vp],
     "bt_sv_remap": [_vp, C.POINTER(_i)],
+    "bt_group_apply_circuit": [C.POINTER(_vp), _i, _vp, _u64, _i],
+    "bt_plan_circuit_host": [_i, _i, _vp, _u64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i],
     "bt_sv_layout": [_vp, C.POINTER(_i)],
     "bt_sv_remap_stats": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(C.c_float)],
     "bt_sv_set_allreduce": [_vp, ALLREDUCE_FN, _vp],

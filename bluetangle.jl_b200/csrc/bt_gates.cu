@@ -252,7 +252,7 @@ static int launch_diag(bt_sv* s, const GateDesc& g, const int32_t* cond, int wan
 // Resolve bits that live on the rank index of a sharded state: a control on a global bit is a
 // rank-conditional skip, a diagonal target on a global bit selects one half of the diagonal.  Returns 1 when
 // nothing is left to do on this rank.
-static int localize(const bt_sv* s, GateDesc* g) {
+int bt_localize(const bt_sv* s, GateDesc* g) {
   int nl = s->n_local;
   // controls
   int nc2 = 0;
@@ -285,7 +285,7 @@ static int localize(const bt_sv* s, GateDesc* g) {
 int bt_launch_gate(bt_sv* s, const GateDesc& g_in, const int32_t* cond, int want) {
   GateDesc g = g_in;
   if (s->world > 1) {
-    int r = localize(s, &g);
+    int r = bt_localize(s, &g);
     if (r < 0) return r;
     if (r == 1) return BT_OK;
   }

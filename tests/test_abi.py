@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/bluetangle_cuda.h declares; no compute calls (CPU box)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "bluetangle_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"\b(bt_[a-z0-9_]+)\s*\(", txt))
+    names -= {"bt_barrier_fn", "bt_allreduce_fn"}
+    return sorted(names)
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    assert len(names) >= 60
+    for must in ["bt_sv_apply_1q", "bt_sv_apply_2q", "bt_sv_apply_circuit", "bt_sv_measure_z", "bt_sv_kraus", "bt_sv_sample", "bt_sv_expect_pauli",
+                 "bt_dm_apply_1q", "bt_dm_kraus", "bt_sv_create_shard", "bt_sv_remap", "bt_last_error"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(bt):
+    lib = bt._lib.load()
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_prototypes_cover_the_header(bt):
+    protos = set(bt._lib.PROTOTYPES) | {"bt_last_error"}
+    assert set(declared_symbols()) <= protos, sorted(set(declared_symbols()) - protos)
+
+
+def test_no_device_is_a_loud_error_not_a_fallback(bt):
+    """On a box without a GPU the product path must fail loudly (no CPU fallback)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bt._lib.BTError):
+        bt.zero_state(4)
+    assert b"no CPU fallback" in bt._lib.load().bt_last_error() or b"CUDA" in bt._lib.load().bt_last_error()
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, smoke() and bench.py's cpu_baseline / reference legs may touch oracle/ (checker, never product)."""
+    pkg = os.path.join(ROOT, "bluetangle.jl_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libbt_oracle|oracle/_build|oracle/_ref|bt_oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not pat.search(src), f

@@ -1,0 +1,104 @@
+"""Host-side logic of the front-end mirror that needs no device: tables, op constructors and their errors, packing,
+draw bookkeeping, workload generators.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import bt_oracle as O
+
+
+def test_gate_tables_match_the_oracle_restatement(bt):
+    for name, m in O.GATE.items():
+        assert np.array_equal(bt.gate[name], m), name
+    for expr in ["P(0.3)", "RX(.1pi)", "RY(0.5π)", "RZ(-pi/4)", "U1(0.2)", "U2(0.1,0.2)", "U3(0.1,0.2,0.3)", "CP(0.3)", "GIVENS(0.2)", "FSIM(0.1,0.2)", "SWAPA(0.3)",
+                 "RXX(0.4)", "RYY(0.5)", "RZZ(0.6)", "RXY(0.7)", "MZ", "MX", "MY", "RES"]:
+        assert np.allclose(bt.gates(expr), O.gates(expr), atol=0, rtol=0), expr
+    with pytest.raises(KeyError):
+        bt.gates("NOPE")
+
+
+def test_kraus_tables_match(bt):
+    for model in ["amplitude_damping", "phase_damping", "phase_flip", "bit_flip", "bit_phase_flip", "depolarizing", "depolarizing_amp", "rot_x", "rot_y", "rot_z", "rot_p", "rot_xyz", "MZ"]:
+        for two in (False, True):
+            a, b = bt.noise_model(model, 0.13, two), O.noise_model(model, 0.13, two)
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (model, two)
+    assert bt.is_valid_quantum_channel(bt.noise_model("depolarizing", 0.2))
+    assert not bt.is_valid_quantum_channel([0.5 * bt.gate["I"]])
+
+
+def test_op_constructors_mirror_reference_errors(bt):
+    o = bt.Op("CX", 2, 3)
+    assert (o.q, o.qubit, o.target_qubit, o.control, o.noisy, o.type) == (2, 2, 3, -2, True, "op")
+    assert bt.Op("RZ(0.3)", 1).type == "phase"
+    m = bt.Op("MX", 2)
+    assert m.type == "🔬" and m.noisy is False
+    with pytest.raises(ValueError):
+        bt.Op("MZ", 1, control=2)          # src/struct.jl:400-402
+    with pytest.raises(ValueError):
+        bt.Op("X", np.eye(4), 1)           # src/struct.jl:393-396
+    with pytest.raises(ValueError):
+        bt.Op("CX", 1, 1)                  # src/struct.jl:465
+    ccx = bt.Op("CCX", 1, 2, 3)            # src/struct.jl:436-449
+    assert (ccx.name, ccx.qubit, ccx.target_qubit, ccx.control) == ("CX", 1, 3, 2)
+    with pytest.raises(ValueError):
+        bt.Op("CCH", 1, 2, 3)
+    res = bt.Op("RES", 2)
+    assert isinstance(res, bt.OpQC) and res.name == "res" and res.q == 1
+    assert bt.Op(["RZ", 0.25], 3).name.startswith("RZ(")
+    with pytest.raises(ValueError):
+        bt.OpQC("bad", [0.5 * np.eye(2)], 1)
+    with pytest.raises(ValueError):
+        bt.OpQC("depolarizing", 0.1, 1, 2).__class__("x", bt.noise_model("depolarizing", 0.1), 1, 2)  # 1q Kraus with a target
+    with pytest.raises(ValueError):
+        bt.ifOp("H", 1)
+    nm = bt.NoiseModel("depolarizing", 0.1)
+    assert nm.q1.q == 1 and nm.q2.q == 2 and len(nm.q2.kraus) == 16
+
+
+def test_pack_gates_layout(bt):
+    ops = [bt.Op("H", 3), bt.Op("FSIM(0.1,0.2)", 2, 5), bt.Op("X", 4, control=1)]
+    arr = bt.pack_gates(ops)
+    assert arr.dtype.itemsize == 272
+    assert list(arr["nq"]) == [1, 2, 1] and list(arr["qubit"]) == [3, 2, 4] and list(arr["target"]) == [-1, 5, -1] and list(arr["control"]) == [-2, -2, 1]
+    assert np.allclose(arr[1]["m"].reshape(4, 4, order="F"), bt.gates("FSIM(0.1,0.2)"))
+    assert np.allclose(arr[0]["m"][:4].reshape(2, 2, order="F"), bt.gate["H"])
+
+
+def test_bit_helpers_and_postprocessing(bt):
+    assert bt.int2bin(2, 4) == [0, 0, 1, 0] and bt.bin2int([0, 0, 1, 0]) == 2
+    bitstr, probs = np.array([1, 4, 6]), np.array([0.36, 0.4096, 0.2304])
+    for qs in ([1], [2], [3], [1, 3]):
+        assert abs(bt._sample_to_expectation(bitstr, probs, 3, qs) - O.sample_to_expectation(bitstr, probs, 3, qs)) < 1e-15
+    for k in range(1, 5):
+        assert abs(bt.mag_moments(3, bitstr, probs, k) - O.mag_moments(3, bitstr, probs, k)) < 1e-12
+    v, p = bt.get_probs_from_sample([3, 1, 3, 3], 2)
+    assert list(v) == [1, 3] and np.allclose(p, [0.25, 0.75])
+
+
+def test_batch_draws_consume_per_trajectory(bt):
+    U = np.arange(12, dtype=float).reshape(3, 4)
+    d = bt.BatchDraws(U)
+    assert list(d.take()) == [0, 4, 8]
+    assert list(d.take(np.array([True, False, True]))) == [1, 5, 9]
+    assert list(d.cnt) == [2, 1, 2]
+    assert list(d.take()) == [2, 5, 10]
+
+
+def test_workload_generators_are_deterministic(bt):
+    import __graft_entry__ as ge
+    from importlib import import_module
+
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    c2 = wl.c2_qft_layered(28, 100, 28)
+    assert len(c2) == 4556 and c2 == wl.c2_qft_layered(28, 100, 28)
+    assert len(wl.qft(28)) == 406
+    c1 = wl.c1_brickwork()
+    assert len(c1) == 20 * 12 + 10 * 6 + 10 * 5
+    ops_d, ops_o = wl.to_ops(bt, c1), wl.to_ops(O, c1)
+    for a, b in zip(ops_d, ops_o):
+        assert np.array_equal(a.mat, b.mat) and (a.qubit, a.target_qubit, a.control) == (b.qubit, b.target_qubit, b.control)
+    c4, nm = wl.c4_monitored(8, 6, 20)
+    assert nm == sum(1 for s in c4 if s[0] == "MZ")
