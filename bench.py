@@ -225,7 +225,8 @@ def bench_sharded(args):
     D = import_module(ge.PKG_NAME + ".dist")
     rank, world, local = D.env_rank_world()
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = world.bit_length() - 1
     n_local = args.shard_qubits
     N = n_local + g
@@ -242,7 +243,8 @@ def bench_sharded(args):
     for _ in range(args.warmup):
         step()
     st.sync()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -250,16 +252,25 @@ def bench_sharded(args):
     r0 = st.remap_stats()
     n0 = st.launch_count()
     ms = C.c_float()
+    L.check(lib.bt_sv_profile_enable(st.h, 1))
+    t_host0 = time.perf_counter()
     L.check(lib.bt_sv_timer_start(st.h))
     for _ in range(args.steps):
         step()
     L.check(lib.bt_sv_timer_stop(st.h, C.byref(ms)))
-    dist.barrier()
+    t_host = time.perf_counter() - t_host0
+    counts = (C.c_uint64 * 4)()
+    cms = (C.c_double * 4)()
+    L.check(lib.bt_sv_profile_read(st.h, counts, cms))
+    L.check(lib.bt_sv_profile_enable(st.h, 0))
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     n1 = st.launch_count()
     r1 = st.remap_stats()
     t = torch.tensor([ms.value], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     ez = np.empty(N)
     L.check(lib.bt_sv_expect_1q_all(st.h, L.ptr(L.cmat(bt.gate["Z"], 2)), L.pdouble(ez)))
@@ -280,15 +291,19 @@ def bench_sharded(args):
                                       f"2^{n_local} amplitudes per GPU", "parallelism": f"{world} shards, top {g} index bits global, qubit remap by peer-memory pull over NVLink",
                           "l2": "inputs larger than L2"},
                "circuit_gates_per_s": ngates / (ms_per_step / 1e3), "clocks": clk, "gpu_launches": int(n1 - n0),
+               "kernels_rank0": {n: {"launches": int(counts[i]), "ms": float(cms[i])} for i, n in enumerate(["tile", "dense", "diag", "other"])},
+               "host_seconds_rank0": t_host,
                "remap": {"per_step": remaps, "nvlink_bytes_per_rank_per_step": rbytes, "ms_per_step": rms, "GBps_per_rank": (rbytes / (rms / 1e3) / 1e9) if rms > 0 else None,
                          "nvlink_peak_GBps": 900.0},
                "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes), "d2h_bytes_per_step": int(ez.nbytes + 8),
                        "note": "device-timed; the host API call (gate list in) is the timed call itself"},
                "checksum": {"norm2": float(nrm[0]), "sum_expect_Z": float(np.sum(ez))}}
         print(json.dumps(out))
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     del st
-    dist.destroy_process_group()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -364,13 +379,14 @@ def main():
     ap.add_argument("--c5-depth", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5"], help="auto: C2 (28q) on 1 GPU, C5 (31q per GPU, sharded) on N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 or args.gpus > 1:
-        if world == 1:
+    if world > 1 or args.gpus > 1 or args.workload == "c5":
+        if world == 1 and args.gpus > 1:
             # launched without torchrun: re-exec under torch.distributed.run
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29533", __file__] + sys.argv[1:]
             os.execv(sys.executable, cmd)

@@ -341,8 +341,11 @@ __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, u
   const double local_total = prefix[nb - 1];
   double t = u[shot] * total_global - offset;
   // ownership: first index with global cumsum >= target
-  bool mine = (offset == 0.0 ? true : t > 0.0) && (t <= local_total || is_last_rank);
-  if (offset == 0.0 && t <= 0.0) mine = true;  // u == 0 -> first entry with cumsum >= 0
+  const bool is_first_rank = (is_last_rank & 2) != 0;
+  const bool last = (is_last_rank & 1) != 0;
+  // rank r owns the shot iff offset_r < target <= offset_r + total_r; target <= 0 goes to the first rank (u == 0 ->
+  // first entry with cumsum >= 0), anything past the end (rounding) to the last
+  bool mine = (t > 0.0 || is_first_rank) && (t <= local_total || last);
   if (!mine) { if (lane == 0) out[shot] = -1; return; }
   // binary search: first block j with prefix[j] >= t
   uint64_t lo = 0, hi = nb - 1;
@@ -405,7 +408,10 @@ static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_st
     s->allreduce(s->allreduce_ctx, tots.data(), s->world);
     total = 0.0;
     for (int r = 0; r < s->world; ++r) { if (r == s->rank) offset = total; total += tots[r]; }
-    is_last = (s->rank == s->world - 1);
+    is_last = (s->rank == s->world - 1) ? 1 : 0;
+    if (s->rank == 0) is_last |= 2;
+  } else {
+    is_last = 3;
   }
   uint64_t threads = shots * 32;
   k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots, total, offset, is_last, d_out);
@@ -430,6 +436,12 @@ extern "C" int bt_sv_sample(const bt_sv* cs, const double* u, uint64_t shots, in
   BT_TRY(bt_check_sv(cs));
   bt_sv* s = const_cast<bt_sv*>(cs);
   if (s->n_batch != 1) BT_FAIL(BT_ERR_ARG, "bt_sv_sample needs n_batch == 1 (use bt_sv_sample_batched)");
+  if (s->world > 1) {
+    // the inverse CDF runs over LOGICAL basis indices: bring the shards back to the identity layout first
+    int ident[64];
+    for (int b = 0; b < 64; ++b) ident[b] = b;
+    BT_TRY(bt_sv_remap(s, ident));
+  }
   BT_TRY(sample_impl(s, s->amp, 1ull << s->n_local, 0, u, shots, out));
   if (s->world > 1) {
     std::vector<double> buf(shots);

@@ -57,8 +57,6 @@ def main():
             e1 = float(np.max(np.abs(full - r)))
             e2 = float(np.max(np.abs(ez - bt.expect(ref, "Z"))))
             e3 = abs(nrm[0] - bt.norm2(ref))
-            ps = ["I"] * N
-            e4 = abs(ex[0] - bt._lib.load() and 0)  # placeholder replaced below
             exr = np.empty(1)
             L.check(ref.lib.bt_sv_expect_pauli(ref.h, pauli, L.pdouble(exr)))
             e4 = abs(ex[0] - exr[0])
