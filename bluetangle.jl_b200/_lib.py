@@ -28,6 +28,10 @@ class bt_gate(C.Structure):
     _fields_ = [("nq", C.c_int32), ("qubit", C.c_int32), ("target", C.c_int32), ("control", C.c_int32), ("m", bt_c64 * 16)]
 
 
+class bt_dm_op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nq", C.c_int32), ("qubit", C.c_int32), ("target", C.c_int32), ("control", C.c_int32), ("nK", C.c_int32), ("mats", C.c_void_p)]
+
+
 GATE_DTYPE = np.dtype([("nq", "<i4"), ("qubit", "<i4"), ("target", "<i4"), ("control", "<i4"), ("m", "<c16", (16,))])
 assert GATE_DTYPE.itemsize == C.sizeof(bt_gate)
 
@@ -99,6 +103,7 @@ PROTOTYPES = {
     "bt_dm_kraus": [_vp, _i, _i, _i, _vp, _i],
     "bt_dm_dephase": [_vp, _i],
     "bt_dm_apply_circuit": [_vp, _vp, _u64, _i],
+    "bt_dm_apply_ops": [_vp, _vp, _u64, _i],
     "bt_dm_diag": [_vp, _pd],
     "bt_dm_trace": [_vp, _vp],
     "bt_dm_expect_pauli": [_vp, C.c_char_p, _pd],

@@ -178,6 +178,154 @@ extern "C" int bt_dm_kraus(bt_dm* d, int nq, int qubit, int target, const bt_c64
   return apply_superop(d, 2, rb, S);
 }
 
+// ---- op lists with superoperator fusion -----------------------------------------------------------------------------
+// to_rho's loop (src/ops.jl:813-841) applies gate, then noise channel(s), op by op: 2 sparse GEMMs per unitary and 2*nK per
+// channel.  Here consecutive unitaries and channels on the same qubit (pair) are multiplied on the host into ONE 4x4 /
+// 16x16 superoperator, so "gate + depolarizing + amplitude damping" costs one pass over rho instead of three.
+namespace {
+struct SBlock {
+  int nb;           // qubits: 1 or 2
+  int bits[2];      // row bits; superoperator index bits: [0..nb-1] row, [nb..2nb-1] column
+  std::vector<cplx> S;
+  bool dead;
+};
+
+void smatmul(int D, const std::vector<cplx>& A, const std::vector<cplx>& B, std::vector<cplx>& C) {
+  std::vector<cplx> T((size_t)D * D, cplx(0, 0));
+  for (int r = 0; r < D; ++r)
+    for (int k = 0; k < D; ++k) {
+      cplx a = A[(size_t)r * D + k];
+      if (a == cplx(0, 0)) continue;
+      for (int c = 0; c < D; ++c) T[(size_t)r * D + c] += a * B[(size_t)k * D + c];
+    }
+  C.swap(T);
+}
+
+// 4x4 superoperator (index: bit0 row, bit1 column) of the qubit at block position p -> 16x16 (r0 r1 c0 c1)
+void sembed1(const std::vector<cplx>& S1, int p, std::vector<cplx>& out) {
+  out.assign(256, cplx(0, 0));
+  int q = 1 - p;
+  for (int I = 0; I < 16; ++I)
+    for (int J = 0; J < 16; ++J) {
+      int rI[2] = {I & 1, (I >> 1) & 1}, cI[2] = {(I >> 2) & 1, (I >> 3) & 1};
+      int rJ[2] = {J & 1, (J >> 1) & 1}, cJ[2] = {(J >> 2) & 1, (J >> 3) & 1};
+      if (rI[q] != rJ[q] || cI[q] != cJ[q]) continue;
+      out[(size_t)I * 16 + J] = S1[(size_t)(rI[p] | (cI[p] << 1)) * 4 + (rJ[p] | (cJ[p] << 1))];
+    }
+}
+
+// swap the two qubits of a 16x16 superoperator: index bits 0<->1 and 2<->3
+void sswap(std::vector<cplx>& S) {
+  auto perm = [](int I) { return ((I & 1) << 1) | ((I >> 1) & 1) | (((I >> 2) & 1) << 3) | (((I >> 3) & 1) << 2); };
+  std::vector<cplx> T(256);
+  for (int I = 0; I < 16; ++I)
+    for (int J = 0; J < 16; ++J) T[(size_t)perm(I) * 16 + perm(J)] = S[(size_t)I * 16 + J];
+  S.swap(T);
+}
+}  // namespace
+
+extern "C" int bt_dm_apply_ops(bt_dm* d, const bt_dm_op* ops, uint64_t n, int fuse) {
+  BT_TRY(check_dm(d));
+  if (n && !ops) BT_FAIL(BT_ERR_ARG, "null op list");
+  const int N = d->n;
+  std::vector<SBlock> blocks;
+  int last[64];
+  for (int b = 0; b < 64; ++b) last[b] = -1;
+  auto flush = [&]() -> int {
+    for (SBlock& B : blocks) {
+      if (B.dead) continue;
+      BT_TRY(apply_superop(d, B.nb, B.bits, B.S));
+    }
+    blocks.clear();
+    for (int b = 0; b < 64; ++b) last[b] = -1;
+    return BT_OK;
+  };
+  for (uint64_t i = 0; i < n; ++i) {
+    const bt_dm_op& o = ops[i];
+    if (!o.mats) BT_FAIL(BT_ERR_ARG, "op %llu: null matrices", (unsigned long long)i);
+    int nq = o.nq;
+    if (nq != 1 && nq != 2) BT_FAIL(BT_ERR_ARG, "density-matrix ops act on 1 or 2 qubits");
+    if (o.qubit < 1 || o.qubit > N || (nq == 2 && (o.target < 1 || o.target > N))) BT_FAIL(BT_ERR_ARG, "N must be larger than qubits");
+    if (nq == 2 && o.qubit == o.target) BT_FAIL(BT_ERR_ARG, "`qubit` and `target_qubit` must differ");
+    bool controlled = (o.kind == 0 && o.control != -2);
+    if (!fuse || (controlled && nq == 2) || (o.kind == 1 && o.nK < 1)) {
+      BT_TRY(flush());
+      if (o.kind == 0) {
+        if (nq == 1) BT_TRY(bt_dm_apply_1q(d, o.qubit, o.mats, o.control));
+        else BT_TRY(bt_dm_apply_2q(d, o.qubit, o.target, o.mats, o.control));
+      } else {
+        BT_TRY(bt_dm_kraus(d, nq, o.qubit, o.target, o.mats, o.nK));
+      }
+      continue;
+    }
+    // superoperator of this op on its own bits
+    int nb = nq, bits[2];
+    std::vector<cplx> S;
+    if (controlled) {
+      // controlled 1-qubit unitary = dense 4x4 V on (bit0 = qubit, bit1 = control): P1 (x) U + P0 (x) I
+      if (o.control < 1 || o.control > N || o.control == o.qubit) BT_FAIL(BT_ERR_ARG, "invalid control qubit");
+      cplx U[4], V[16];
+      colmajor_to_rowmajor_c(o.mats, 2, U);
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          int rc = r >> 1, cc = c >> 1, rt = r & 1, ct = c & 1;
+          V[r * 4 + c] = (rc != cc) ? cplx(0, 0) : (rc == 1 ? U[rt * 2 + ct] : (rt == ct ? cplx(1, 0) : cplx(0, 0)));
+        }
+      nb = 2; bits[0] = N - o.qubit; bits[1] = N - o.control;
+      S.assign(256, cplx(0, 0));
+      superop_add(4, V, S);
+    } else {
+      int D = 1 << nq;
+      int cnt = (o.kind == 0) ? 1 : o.nK;
+      S.assign((size_t)D * D * D * D, cplx(0, 0));
+      for (int k = 0; k < cnt; ++k) {
+        cplx V[16];
+        colmajor_to_rowmajor_c(o.mats + (size_t)k * D * D, D, V);
+        superop_add(D, V, S);
+      }
+      if (nq == 1) bits[0] = N - o.qubit;
+      else { bits[0] = N - o.target; bits[1] = N - o.qubit; }  // matrix bit 0 <-> target, bit 1 <-> qubit
+    }
+    if (nb == 1) {
+      int lb = last[bits[0]];
+      if (lb >= 0) {
+        SBlock& B = blocks[lb];
+        if (B.nb == 1) smatmul(4, S, B.S, B.S);
+        else {
+          std::vector<cplx> E;
+          sembed1(S, B.bits[0] == bits[0] ? 0 : 1, E);
+          smatmul(16, E, B.S, B.S);
+        }
+        continue;
+      }
+      SBlock B; B.nb = 1; B.bits[0] = bits[0]; B.bits[1] = -1; B.S = S; B.dead = false;
+      blocks.push_back(B);
+      last[bits[0]] = (int)blocks.size() - 1;
+      continue;
+    }
+    int l0 = last[bits[0]], l1 = last[bits[1]];
+    if (l0 >= 0 && l0 == l1 && blocks[l0].nb == 2) {
+      SBlock& B = blocks[l0];
+      if (B.bits[0] != bits[0]) sswap(S);
+      smatmul(16, S, B.S, B.S);
+      continue;
+    }
+    SBlock B; B.nb = 2; B.bits[0] = bits[0]; B.bits[1] = bits[1]; B.S = S; B.dead = false;
+    for (int t = 0; t < 2; ++t) {
+      int lb = last[bits[t]];
+      if (lb >= 0 && blocks[lb].nb == 1 && !blocks[lb].dead) {
+        std::vector<cplx> E;
+        sembed1(blocks[lb].S, t, E);
+        smatmul(16, B.S, E, B.S);
+        blocks[lb].dead = true;
+      }
+    }
+    blocks.push_back(B);
+    last[bits[0]] = last[bits[1]] = (int)blocks.size() - 1;
+  }
+  return flush();
+}
+
 __global__ void k_dephase(double2* __restrict__ a, uint64_t len, int rbit, int cbit) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

@@ -586,6 +586,9 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
     else:
         x, op = b, a
     if isinstance(op, (list, tuple)) and not (isinstance(op, tuple) and op and isinstance(op[0], str)):
+        if isinstance(x, CuRho) and FUSE_DEFAULT and all(isinstance(o, (Op, OpQC)) and not getattr(o, "ismeasure", False) and getattr(o, "q", 1) <= 2 for o in op):
+            _dm_apply_ops(x, list(op), noise)
+            return (x, []) if track_measurements else x
         mids: List = []
         for o in _coalesce(op, x, noise):
             if isinstance(o, _GateRun):
@@ -619,6 +622,35 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
     if isinstance(noise, NoiseModel):
         apply_noise(x, op, noise, rng)
     return (x, mid) if track_measurements else x
+
+
+def _dm_apply_ops(rho: CuRho, ops, noise) -> None:
+    """apply(rho, op; noise) for a whole op list in one library call (bt_dm_apply_ops): unitaries, OpQC channels and the
+    NoiseModel channels of apply_noise (src/hilbert.jl:346-364) become one fused superoperator per qubit (pair)."""
+    entries, keep = [], []
+
+    def add(kind, nq, qubit, target, control, mats):
+        D = 1 << nq
+        tab = np.ascontiguousarray(np.stack([L.cmat(m, D).reshape(-1, order="F") for m in mats]))
+        keep.append(tab)
+        entries.append((kind, nq, qubit, target, control, len(mats), tab.ctypes.data))
+
+    for o in ops:
+        if isinstance(o, OpQC):
+            add(1, o.q, o.qubit, o.target_qubit, -2, o.kraus)
+        else:
+            add(0, o.q, o.qubit, o.target_qubit, o.control, [o.mat])
+        if isinstance(noise, NoiseModel) and getattr(o, "noisy", False) is True:
+            if o.q == 1 and o.control == -2:
+                add(1, 1, o.qubit, -1, -2, noise.q1.kraus)
+            elif o.q == 1:
+                add(1, 2, o.control, o.qubit, -2, noise.q2.kraus)
+            else:
+                add(1, 2, o.qubit, o.target_qubit, -2, noise.q2.kraus)
+    arr = (L.bt_dm_op * len(entries))()
+    for i, e in enumerate(entries):
+        arr[i].kind, arr[i].nq, arr[i].qubit, arr[i].target, arr[i].control, arr[i].nK, arr[i].mats = e
+    L.check(rho.lib.bt_dm_apply_ops(rho.h, C.cast(arr, C.c_void_p), len(entries), 1))
 
 
 class _GateRun:
@@ -943,9 +975,7 @@ def to_state(circuit: Circuit, rng=None, n_batch: int = 1) -> CuState:
 def to_rho(circuit: Circuit) -> CuRho:
     """src/ops.jl:806-844."""
     rho = CuRho(circuit.N)
-    nm = circuit.options.noise
-    for op in circuit.ops:
-        apply(rho, op, noise=nm)
+    apply(circuit.ops, rho, noise=circuit.options.noise)
     return rho
 
 

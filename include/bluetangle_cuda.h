@@ -133,6 +133,16 @@ int bt_dm_apply_2q(bt_dm* d, int qubit, int target, const bt_c64 m[16], int cont
 int bt_dm_kraus(bt_dm* d, int nq, int qubit, int target, const bt_c64* K, int nK);      /* sum_k E_k rho E_k'  struct.jl:58-76: one HBM pass */
 int bt_dm_dephase(bt_dm* d, int qubit);                                                 /* born_measure_Z(N,rho,q) hilbert.jl:784-796 */
 int bt_dm_apply_circuit(bt_dm* d, const bt_gate* g, uint64_t n, int fuse);
+/* mixed list of unitaries and Kraus channels (to_rho's loop src/ops.jl:813-841 incl. apply_noise); fuse != 0 multiplies
+ * consecutive ops on the same qubit (pair) into one 4x4 / 16x16 superoperator => one pass over rho for gate + noise */
+typedef struct {
+  int32_t kind;            /* 0 = unitary (1 matrix), 1 = Kraus channel (nK matrices) */
+  int32_t nq;              /* 1 or 2 */
+  int32_t qubit, target, control; /* target = -1 for nq == 1; control = -2 for none (kind 0 only) */
+  int32_t nK;
+  const bt_c64* mats;      /* column-major 2^nq x 2^nq each */
+} bt_dm_op;
+int bt_dm_apply_ops(bt_dm* d, const bt_dm_op* ops, uint64_t n, int fuse);
 int bt_dm_diag(const bt_dm* d, double* host /* 2^n : real(diag(rho)) src/ops.jl:130 */);
 int bt_dm_trace(const bt_dm* d, bt_c64* out);
 int bt_dm_expect_pauli(const bt_dm* d, const char* paulis, double* out);               /* real(tr(rho*O)) func.jl:92,146 */

@@ -1,0 +1,123 @@
+"""BASELINE.json configs at their full sizes on the GPU, checked through size-independent properties (round trips,
+norm / trace preservation, fused == unfused) and against the strided CPU oracle where it finishes in seconds."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def mods():
+    import __graft_entry__ as ge
+    from importlib import import_module
+
+    return import_module(ge.PKG_NAME + ".workloads")
+
+
+def test_c2_28q_qft_roundtrip_and_fused_equals_unfused(bt):
+    """configs[1]: QFT(28) of a basis state, then its exact inverse (adjoint gates, reversed): encode -> decode must
+    return the basis state; fused and unfused executions of the layered circuit must agree on <Z_q> and samples."""
+    wl = mods()
+    L = bt._lib
+    N = 28
+    x = 0x5A5A5A5 & ((1 << N) - 1)
+    fwd = wl.to_ops(bt, wl.qft(N))
+    inv = [bt.Op(o.name + "^-1", o.mat.conj().T, o.qubit, o.target_qubit) if o.q == 2 else bt.Op(o.name + "^-1", o.mat.conj().T, o.qubit) for o in reversed(fwd)]
+    s = bt.basis_state(N, x)
+    bt.apply(fwd, s)
+    ez = bt.expect(s, "Z")
+    assert np.max(np.abs(ez)) < 1e-9  # uniform modulus after the QFT
+    assert abs(bt.norm2(s) - 1) < 1e-9
+    bt.apply(inv, s)
+    us = np.random.default_rng(0).random(64)
+    assert np.all(bt.sample(s, 64, uniforms=us) == x)  # bit-exact basis index after the round trip
+    p = np.empty(1)
+    ex = bt.expect(s, "Z")
+    want = np.array([1.0 - 2.0 * ((x >> (N - q)) & 1) for q in range(1, N + 1)])
+    assert np.max(np.abs(ex - want)) < 1e-9
+    del s
+    # layered part: fused vs unfused
+    arr = bt.pack_gates(wl.to_ops(bt, wl.layered(N, 6, 28)))
+    a, b = bt.zero_state(N), bt.zero_state(N)
+    L.check(a.lib.bt_sv_apply_circuit(a.h, L.ptr(arr), len(arr), 1))
+    L.check(b.lib.bt_sv_apply_circuit(b.h, L.ptr(arr), len(arr), 0))
+    assert np.max(np.abs(bt.expect(a, "Z") - bt.expect(b, "Z"))) < 1e-10
+    assert abs(bt.inner(a, b) - bt.norm2(b)) < 1e-9  # <a|b> == <b|b>: same state
+    us = np.random.default_rng(1).random(512)
+    assert np.mean(bt.sample(a, 512, uniforms=us) == bt.sample(b, 512, uniforms=us)) > 0.99  # identical up to 1e-16 boundary effects
+
+
+def test_c3_14q_density_matrix_noise_after_every_gate(bt, orc):
+    """configs[2]: depolarizing + amplitude damping after every gate on a 14-qubit density matrix (4 GiB)."""
+    wl = mods()
+    N = 14
+
+    def build(n, depth):
+        ops = []
+        for e in wl.c3_noisy_dm(n, depth, 14):
+            if e[0] == "gate":
+                name, q, t, c = e[1]
+                ops.append(bt.Op(name, q, t, control=c))
+            else:
+                _, model, p, q, t = e
+                ops.append(bt.OpQC(model, p, q, t))
+        return ops
+
+    ops = build(N, 3)
+    fused = bt.CuRho(N)
+    bt.apply(ops, fused)
+    seq = bt.CuRho(N)
+    for o in ops:
+        bt.apply(seq, o)
+    tr = C.c_double * 2
+    t1 = bt._lib.bt_c64()
+    bt._lib.check(fused.lib.bt_dm_trace(fused.h, C.byref(t1)))
+    assert abs(t1.re - 1) < 1e-10 and abs(t1.im) < 1e-12          # channels are trace preserving
+    assert np.max(np.abs(bt.expect(fused, "Z") - bt.expect(seq, "Z"))) < 1e-10
+    assert np.max(np.abs(bt.expect(fused, "X") - bt.expect(seq, "X"))) < 1e-10
+    a, pa = bt.sample_exact(fused)
+    b, pb = bt.sample_exact(seq)
+    assert np.array_equal(a, b) and np.max(np.abs(pa - pb)) < 1e-12 and np.all(pa >= -1e-15)
+    assert fused.launch_count() * 2 < seq.launch_count()
+    # same generator at 9 qubits against the strided CPU oracle
+    from oracle import strided as S
+    n = 9
+    rho = bt.CuRho(n)
+    bt.apply(build(n, 4), rho)
+    dm = S.DM(n)
+    for e in wl.c3_noisy_dm(n, 4, 14):
+        if e[0] == "gate":
+            name, q, t, c = e[1]
+            dm.apply(orc.Op(name, q, t, control=c))
+        else:
+            _, model, p, q, t = e
+            dm.apply(orc.OpQC.model(model, p, q, t))
+    assert np.max(np.abs(rho.to_numpy() - dm.to_matrix())) < 1e-10
+
+
+def test_c4_20q_monitored_trajectories_batched(bt, orc):
+    """configs[3] per-GPU share: 512 trajectories of a 20-qubit monitored brickwork circuit as ONE batched state (8 GiB);
+    trajectory t consumes U[t, :]; spot-checked against the sequential CPU oracle fed the same draws."""
+    from oracle import strided as S
+
+    wl = mods()
+    N, T = 20, 512
+    specs, M = wl.c4_monitored(N, 20, 20)
+    ops = wl.to_ops(bt, specs)
+    U = np.random.Generator(np.random.PCG64(20)).random((T, M))
+    st = bt.zero_state(N, T)
+    _, mids = bt.apply(ops, st, rng=bt.BatchDraws(U), track_measurements=True)
+    out = np.stack([np.asarray(m) for m in mids], axis=1)
+    assert out.shape == (T, M)
+    nrm = bt.norm2(st)
+    assert np.max(np.abs(nrm - 1)) < 1e-9
+    assert 0.2 < out.mean() < 0.8
+    oops = wl.to_ops(orc, specs)
+    ez = bt.expect(st, "Z")
+    for t in (0, 1, 255, 511):
+        sv, mo = S.SV(N).apply_ops(oops, draws=orc.ListDraws(U[t]), track_measurements=True)
+        assert list(out[t]) == mo                       # identical outcomes under shared uniform draws
+        assert np.max(np.abs(ez[t] - sv.expect_z_all())) < 1e-10

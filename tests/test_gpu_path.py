@@ -388,3 +388,21 @@ def test_batched_trajectories_equal_sequential_loop(bt, orc):
         so, mid_o = orc.apply_ops(orc.zero_state(N), [o for o in oo], draws=orc.ListDraws(U[t]), track_measurements=True)
         assert outs[t] == mid_o
         assert np.max(np.abs(got[t] - so)) < TOL
+
+
+def test_dm_fused_op_list_equals_op_by_op(bt, orc):
+    """bt_dm_apply_ops (host-fused superoperators: gate + noise in one pass) == apply(rho, op; noise) op by op == oracle."""
+    N, depth = 5, 6
+    od, oo = random_ops(bt, N, depth, 21), random_ops(orc, N, depth, 21)
+    od += [bt.Op("X", 2, control=4), bt.OpQC("amplitude_damping", 0.2, 3), bt.OpQC("depolarizing", 0.1, 4, 1), bt.Op("CX", 5, 1), bt.Op("FSIM(0.3,0.1)", 2, 3, control=5)]
+    oo += [orc.Op("X", 2, control=4), orc.OpQC.model("amplitude_damping", 0.2, 3), orc.OpQC.model("depolarizing", 0.1, 4, 1), orc.Op("CX", 5, 1), orc.Op("FSIM(0.3,0.1)", 2, 3, control=5)]
+    for nm_d, nm_o in ((False, False), (bt.NoiseModel("amplitude_damping", 0.07), orc.NoiseModel.model("amplitude_damping", 0.07))):
+        fused = bt.CuRho(N)
+        bt.apply(od, fused, noise=nm_d)
+        seq = bt.CuRho(N)
+        for o in od:
+            bt.apply(seq, o, noise=nm_d)
+        ref = orc.to_rho(oo, N, noise=nm_o)
+        assert np.max(np.abs(seq.to_numpy() - ref)) < TOL
+        assert np.max(np.abs(fused.to_numpy() - ref)) < TOL
+        assert fused.launch_count() < seq.launch_count()
