@@ -131,7 +131,7 @@ def load(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("BLUETANGLE_CUDA_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise BTError(-2, f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
     lib = C.CDLL(p)

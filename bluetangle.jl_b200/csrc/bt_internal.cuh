@@ -64,6 +64,8 @@ struct bt_sv {
   int32_t* d_err;     // device error flag
   int32_t* h_flag;    // pinned
   size_t traj_cap;
+  // grow-only device scratch (sampling prefix sums, uniforms, results)
+  void* d_scratch; size_t scratch_cap;
   // timing / accounting
   cudaEvent_t ev0, ev1;
   mutable uint64_t launches;
@@ -121,6 +123,7 @@ int bt_results_to_host(const bt_sv* s, size_t n_doubles);
 int bt_ensure_traj(bt_sv* s);
 int bt_ensure_partials(bt_sv* s, size_t doubles);
 int bt_ensure_alt(bt_sv* s);
+int bt_ensure_scratch(bt_sv* s, size_t bytes);
 
 // fused multi-gate pass (bt_tile.cu)
 int bt_apply_fused(bt_sv* s, const std::vector<GateDesc>& gates);

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ 
   __shared__ double sm[8];
   const uint64_t b0 = (uint64_t)blockIdx.x << SB;
   double acc = 0.0;
+#pragma unroll 8
   for (uint64_t k = threadIdx.x; k < (1ull << SB); k += 256) {
     uint64_t i = b0 + k;
     if (i < n) acc += prob_at(a, i, dm_stride);
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, u
   const int lane = threadIdx.x & 31;
   if (shot >= shots) return;
   const double local_total = prefix[nb - 1];
-  double t = u[shot] * total_global - offset;
+  double t = u[shot] * (total_global < 0.0 ? local_total : total_global) - offset;
   // ownership: first index with global cumsum >= target
   const bool is_first_rank = (is_last_rank & 2) != 0;
   const bool last = (is_last_rank & 1) != 0;
@@ -385,41 +386,36 @@ static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_st
   if (!u || !out) BT_FAIL(BT_ERR_ARG, "null argument");
   if (shots == 0) return BT_OK;
   uint64_t nb = (n + (1ull << SB) - 1) >> SB;
-  double *d_prefix = nullptr, *d_u = nullptr;
-  int64_t* d_out = nullptr;
-  BT_CUDA(cudaMallocAsync(&d_prefix, nb * sizeof(double), s->stream));
-  BT_CUDA(cudaMallocAsync(&d_u, shots * sizeof(double), s->stream));
-  BT_CUDA(cudaMallocAsync(&d_out, shots * sizeof(int64_t), s->stream));
+  size_t off_u = ((nb * sizeof(double) + 255) / 256) * 256;
+  size_t off_o = off_u + ((shots * sizeof(double) + 255) / 256) * 256;
+  BT_TRY(bt_ensure_scratch(s, off_o + shots * sizeof(int64_t)));
+  double* d_prefix = (double*)s->d_scratch;
+  double* d_u = (double*)((char*)s->d_scratch + off_u);
+  int64_t* d_out = (int64_t*)((char*)s->d_scratch + off_o);
   BT_CUDA(cudaMemcpyAsync(d_u, u, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_block_sums<<<(unsigned)nb, 256, 0, s->stream>>>(base, n, dm_stride, d_prefix);
   BT_CHECK_LAUNCH(s);
   k_scan_inclusive<<<1, 1024, 0, s->stream>>>(d_prefix, nb);
   BT_CHECK_LAUNCH(s);
-  double total = 0.0, offset = 0.0;
-  int is_last = 1;
-  BT_CUDA(cudaMemcpyAsync(s->h_res, d_prefix + (nb - 1), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  BT_CUDA(cudaStreamSynchronize(s->stream));
-  total = s->h_res[0];
+  double total = -1.0, offset = 0.0;  // total < 0: the kernel uses the local total (unsharded: no host round trip)
+  int is_last = 3;
   if (s->world > 1) {
+    BT_CUDA(cudaMemcpyAsync(s->h_res, d_prefix + (nb - 1), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    BT_CUDA(cudaStreamSynchronize(s->stream));
     if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
     // physical rank order is the order of the physical index; totals all-gathered through a sum
     std::vector<double> tots(s->world, 0.0);
-    tots[s->rank] = total;
+    tots[s->rank] = s->h_res[0];
     s->allreduce(s->allreduce_ctx, tots.data(), s->world);
     total = 0.0;
     for (int r = 0; r < s->world; ++r) { if (r == s->rank) offset = total; total += tots[r]; }
     is_last = (s->rank == s->world - 1) ? 1 : 0;
     if (s->rank == 0) is_last |= 2;
-  } else {
-    is_last = 3;
   }
   uint64_t threads = shots * 32;
   k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots, total, offset, is_last, d_out);
   BT_CHECK_LAUNCH(s);
   BT_CUDA(cudaMemcpyAsync(out, d_out, shots * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
-  BT_CUDA(cudaFreeAsync(d_prefix, s->stream));
-  BT_CUDA(cudaFreeAsync(d_u, s->stream));
-  BT_CUDA(cudaFreeAsync(d_out, s->stream));
   BT_CUDA(cudaStreamSynchronize(s->stream));
   return BT_OK;
 }

@@ -30,15 +30,21 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
   __syncthreads();
 }
 
-// final stage: res[t][v] = sum_b part[(t*nblk + b)*nv + v]
-__global__ void k_sum_partials(const double* __restrict__ part, double* __restrict__ res, int nblk, int nv, int64_t n_batch) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_batch * nv) return;
-  int64_t t = i / nv;
-  int v = (int)(i % nv);
+// final stage: res[t][v] = sum_b part[(t*nblk + b)*nv + v]; one 128-thread block per (t, v), fixed-order tree
+__global__ void __launch_bounds__(128) k_sum_partials(const double* __restrict__ part, double* __restrict__ res, int nblk, int nv, int64_t n_batch) {
+  __shared__ double sm[128];
+  const int64_t i = blockIdx.x;
+  const int64_t t = i / nv;
+  const int v = (int)(i % nv);
   double x = 0.0;
-  for (int b = 0; b < nblk; ++b) x += part[((size_t)t * nblk + b) * nv + v];
-  res[i] = x;
+  for (int b = threadIdx.x; b < nblk; b += 128) x += part[((size_t)t * nblk + b) * nv + v];
+  sm[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) res[i] = sm[0];
 }
 
 struct RdmPlan {
@@ -68,6 +74,7 @@ __global__ void __launch_bounds__(RB) k_rdm(const double2* __restrict__ a, int n
   double acc[D * D];
 #pragma unroll
   for (int i = 0; i < D * D; ++i) acc[i] = 0.0;
+#pragma unroll 4
   for (uint64_t g = (uint64_t)blockIdx.x * RB + threadIdx.x; g < ngroups; g += (uint64_t)nblk * RB) {
     uint64_t i0 = rdm_expand(g, P);
     double2 x[D];
@@ -92,6 +99,7 @@ __global__ void __launch_bounds__(RB) k_norm2(const double2* __restrict__ a, int
   const uint64_t n = 1ull << n_local;
   const double2* base = a + ((uint64_t)traj << n_local);
   double acc[1] = {0.0};
+#pragma unroll 8
   for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
     double2 x = base[i];
     acc[0] += x.x * x.x + x.y * x.y;
@@ -106,6 +114,7 @@ __global__ void __launch_bounds__(RB) k_inner(const double2* __restrict__ a, con
   const double2* pa = a + ((uint64_t)traj << n_local);
   const double2* pb = b + ((uint64_t)traj << n_local);
   double acc[2] = {0.0, 0.0};
+#pragma unroll 4
   for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
     double2 x = pa[i], y = pb[i];
     acc[0] += x.x * y.x + x.y * y.y;  // conj(x)*y
@@ -115,45 +124,49 @@ __global__ void __launch_bounds__(RB) k_inner(const double2* __restrict__ a, con
 }
 
 // Per-bit probabilities in one pass: out[0] = sum p, out[1+b] = sum of p over amplitudes with bit b set.
-// A block walks contiguous chunks of 2^cb amplitudes; bits 0..7 are thread bits, 8..cb-1 iteration bits,
-// the rest chunk bits.
+// Block j of a trajectory owns the contiguous range of 2^(cbits+lcpb) amplitudes starting at j << (cbits+lcpb):
+// bits 0..7 are thread bits, 8..cbits-1 iteration bits, cbits..cbits+lcpb-1 chunk-in-block bits (per-thread
+// accumulators), and the remaining high bits are constant per block and resolved from the block index in the final stage.
 #define BP_MAXBITS 40
-__global__ void __launch_bounds__(RB) k_bitprobs(const double2* __restrict__ a, int n_local, int cbits, double* __restrict__ part, int nblk) {
+#define BP_MAXLC 10
+__global__ void __launch_bounds__(RB) k_bitprobs(const double2* __restrict__ a, int n_local, int cbits, int lcpb, double* __restrict__ part, int nblk) {
   const int64_t traj = blockIdx.y;
-  const double2* base = a + ((uint64_t)traj << n_local);
-  const uint64_t chunk_len = 1ull << cbits;
-  const uint64_t nchunks = 1ull << (n_local - cbits);
-  const int iters = (int)((chunk_len + RB - 1) / RB);
-  const int nhi = n_local - cbits;
+  const double2* base = a + ((uint64_t)traj << n_local) + ((uint64_t)blockIdx.x << (cbits + lcpb));
+  const uint32_t chunk_len = 1u << cbits;
+  const uint32_t cpb = 1u << lcpb;
+  const int iters = (int)((chunk_len + RB - 1) / RB);  // <= 16
   double tot = 0.0;
   double it_acc[4] = {0, 0, 0, 0};
-  double hi[28];
+  double hi[BP_MAXLC];
 #pragma unroll
-  for (int b = 0; b < 28; ++b) hi[b] = 0.0;
-  for (uint64_t ch = blockIdx.x; ch < nchunks; ch += nblk) {
+  for (int b = 0; b < BP_MAXLC; ++b) hi[b] = 0.0;
+  for (uint32_t ch = 0; ch < cpb; ++ch) {
+    const double2* cp = base + (uint64_t)ch * chunk_len;
+    double p[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      uint32_t k = (uint32_t)it * RB + threadIdx.x;
+      double2 x = (it < iters && k < chunk_len) ? cp[k] : make_double2(0.0, 0.0);
+      p[it] = x.x * x.x + x.y * x.y;
+    }
     double ct = 0.0;
-    const double2* cp = base + ch * chunk_len;
-    for (int it = 0; it < iters; ++it) {
-      uint64_t k = (uint64_t)it * RB + threadIdx.x;
-      if (k < chunk_len) {
-        double2 x = cp[k];
-        double p = x.x * x.x + x.y * x.y;
-        ct += p;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((it >> j) & 1) it_acc[j] += p;
-      }
+    for (int it = 0; it < 16; ++it) {
+      ct += p[it];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((it >> j) & 1) it_acc[j] += p[it];
     }
     tot += ct;
 #pragma unroll
-    for (int b = 0; b < 28; ++b)
-      if (b < nhi && ((ch >> b) & 1)) hi[b] += ct;
+    for (int b = 0; b < BP_MAXLC; ++b)
+      if (b < lcpb && ((ch >> b) & 1)) hi[b] += ct;
   }
-  // assemble per-thread vector: [tot, bits 0..n_local-1]
   double* out = part + ((size_t)traj * nblk + blockIdx.x) * (BP_MAXBITS + 1);
   __shared__ double sm[RB / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int v = 0; v <= n_local; ++v) {
+  const int nv = 1 + cbits + lcpb;
+  for (int v = 0; v < nv; ++v) {
     double x;
     if (v == 0) x = tot;
     else {
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(RB) k_bitprobs(const double2* __restrict__ a, 
         int j = b - cbits;
         x = 0.0;
 #pragma unroll
-        for (int q = 0; q < 28; ++q)
+        for (int q = 0; q < BP_MAXLC; ++q)
           if (q == j) x = hi[q];
       }
     }
@@ -184,6 +197,32 @@ __global__ void __launch_bounds__(RB) k_bitprobs(const double2* __restrict__ a, 
   }
 }
 
+// final stage for k_bitprobs: value v <= inblock bits: plain sum over blocks; higher bits: sum of block totals over the
+// blocks whose index has that bit set.  One 128-thread block per (t, v), fixed-order tree.
+__global__ void __launch_bounds__(128) k_bitprobs_final(const double* __restrict__ part, double* __restrict__ res, int nblk, int inblock_bits, int n_local) {
+  __shared__ double sm[128];
+  const int nvs = BP_MAXBITS + 1;
+  const int64_t t = blockIdx.x / nvs;
+  const int v = (int)(blockIdx.x % nvs);
+  double x = 0.0;
+  if (v <= n_local) {
+    if (v <= inblock_bits) {
+      for (int b = threadIdx.x; b < nblk; b += 128) x += part[((size_t)t * nblk + b) * nvs + v];
+    } else {
+      int hb = v - 1 - inblock_bits;  // bit of the block index
+      for (int b = threadIdx.x; b < nblk; b += 128)
+        if ((b >> hb) & 1) x += part[((size_t)t * nblk + b) * nvs];
+    }
+  }
+  sm[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) res[blockIdx.x] = sm[0];
+}
+
 // <P> for a Pauli string: xm = X|Y positions, zm = Z|Y positions, ny = number of Y.
 // Pairs (i, i^xm) are visited once (i has the top bit of xm clear) so every amplitude is read exactly once.
 __global__ void __launch_bounds__(RB) k_pauli(const double2* __restrict__ a, int n_local, uint64_t xm, uint64_t zm, int ny, int topx,
@@ -193,6 +232,7 @@ __global__ void __launch_bounds__(RB) k_pauli(const double2* __restrict__ a, int
   double acc[1] = {0.0};
   if (xm == 0) {
     const uint64_t n = 1ull << n_local;
+#pragma unroll 8
     for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
       double2 x = base[i];
       double p = x.x * x.x + x.y * x.y;
@@ -203,6 +243,7 @@ __global__ void __launch_bounds__(RB) k_pauli(const double2* __restrict__ a, int
     double cr, ci;
     switch (ny & 3) { case 0: cr = 1; ci = 0; break; case 1: cr = 0; ci = -1; break; case 2: cr = -1; ci = 0; break; default: cr = 0; ci = 1; }
     const uint64_t n = 1ull << (n_local - 1);
+#pragma unroll 4
     for (uint64_t g = (uint64_t)blockIdx.x * RB + threadIdx.x; g < n; g += (uint64_t)nblk * RB) {
       uint64_t i = ((g >> topx) << (topx + 1)) | (g & ((1ull << topx) - 1));
       uint64_t j = i ^ xm;
@@ -241,7 +282,7 @@ __global__ void k_scale_by_norm(double2* __restrict__ a, int n_local, uint64_t l
 // ---- host side --------------------------------------------------------------------------------------------
 static int pick_nblk(const bt_sv* s, uint64_t work_items_per_traj) {
   uint64_t want = (work_items_per_traj + RB - 1) / RB;
-  uint64_t cap = std::max<uint64_t>(1, (148ull * 16) / (uint64_t)s->n_batch);
+  uint64_t cap = std::max<uint64_t>(1, (148ull * 8) / (uint64_t)s->n_batch);
   return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, cap));
 }
 
@@ -253,7 +294,7 @@ static int check_batch_grid(const bt_sv* s) {
 static int finish(const bt_sv* s, int nblk, int nv, size_t res_off) {
   int64_t tot = s->n_batch * nv;
   if (res_off + (size_t)tot > s->res_cap) BT_FAIL(BT_ERR_ARG, "internal: result buffer overflow");
-  k_sum_partials<<<(unsigned)((tot + 255) / 256), 256, 0, s->stream>>>(s->d_part, s->d_res + res_off, nblk, nv, s->n_batch);
+  k_sum_partials<<<(unsigned)tot, 128, 0, s->stream>>>(s->d_part, s->d_res + res_off, nblk, nv, s->n_batch);
   BT_CHECK_LAUNCH(s);
   return BT_OK;
 }
@@ -436,17 +477,22 @@ int bt_bitprobs(const bt_sv* cs) {
   bt_sv* s = const_cast<bt_sv*>(cs);
   BT_TRY(check_batch_grid(s));
   int cbits = std::min(12, s->n_local);
-  uint64_t nchunks = 1ull << (s->n_local - cbits);
-  uint64_t cap = std::max<uint64_t>(1, (148ull * 8) / (uint64_t)s->n_batch);
-  int nblk = (int)std::max<uint64_t>(1, std::min<uint64_t>(nchunks, cap));
+  int nchunk_bits = s->n_local - cbits;
+  // blocks per trajectory: a power of two, about 8 CTAs per SM over the whole batch
+  int lblk = 0;
+  while (lblk < nchunk_bits && ((uint64_t)2 << lblk) * (uint64_t)s->n_batch <= 148ull * 8) ++lblk;
+  int lcpb = nchunk_bits - lblk;
+  while (lcpb > BP_MAXLC) { --lcpb; ++lblk; }
+  int nblk = 1 << lblk;
   int nv = BP_MAXBITS + 1;
   BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * nv));
-  BT_CUDA(cudaMemsetAsync(s->d_part, 0, (size_t)s->n_batch * nblk * nv * sizeof(double), s->stream));
   dim3 grid(nblk, (unsigned)s->n_batch);
-  k_bitprobs<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, cbits, s->d_part, nblk);
+  k_bitprobs<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, cbits, lcpb, s->d_part, nblk);
   BT_CHECK_LAUNCH(s);
   if ((size_t)s->n_batch * nv > s->res_cap) BT_FAIL(BT_ERR_UNSUPPORTED, "too many trajectories for expect_1q_all");
-  return finish(s, nblk, nv, 0);
+  k_bitprobs_final<<<(unsigned)(s->n_batch * nv), 128, 0, s->stream>>>(s->d_part, s->d_res, nblk, cbits + lcpb, s->n_local);
+  BT_CHECK_LAUNCH(s);
+  return BT_OK;
 }
 
 extern "C" int bt_sv_expect_1q_all(const bt_sv* cs, const bt_c64 m[4], double* out) {

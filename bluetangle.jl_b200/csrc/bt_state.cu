@@ -117,6 +117,7 @@ extern "C" int bt_sv_destroy(bt_sv* s) {
   cudaFree(s->amp);
   if (s->alt) cudaFree(s->alt);
   if (s->d_part) cudaFree(s->d_part);
+  if (s->d_scratch) cudaFree(s->d_scratch);
   cudaFree(s->d_res);
   cudaFreeHost(s->h_res);
   if (s->d_u) cudaFree(s->d_u);
@@ -150,6 +151,15 @@ int bt_ensure_partials(bt_sv* s, size_t doubles) {
   if (s->d_part) { BT_CUDA(cudaStreamSynchronize(s->stream)); BT_CUDA(cudaFree(s->d_part)); s->d_part = nullptr; }
   BT_CUDA(cudaMalloc(&s->d_part, doubles * sizeof(double)));
   s->part_cap = doubles;
+  return BT_OK;
+}
+
+int bt_ensure_scratch(bt_sv* s, size_t bytes) {
+  if (s->scratch_cap >= bytes) return BT_OK;
+  if (s->d_scratch) { BT_CUDA(cudaStreamSynchronize(s->stream)); BT_CUDA(cudaFree(s->d_scratch)); s->d_scratch = nullptr; s->scratch_cap = 0; }
+  size_t cap = std::max<size_t>(bytes, 1 << 20);
+  BT_CUDA(cudaMalloc(&s->d_scratch, cap));
+  s->scratch_cap = cap;
   return BT_OK;
 }
 

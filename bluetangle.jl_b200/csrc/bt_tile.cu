@@ -18,10 +18,20 @@
 #include <cuda_pipeline_primitives.h>
 #include <stdlib.h>
 
-#define TILE_MAXG 12
-#define TILE_LOWB 5     // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
-#define TILE_TMAX 12    // 2^12 amplitudes = 64 KB of shared memory per CTA
-#define TILE_THREADS 256
+#ifndef TILE_MAXG
+#define TILE_MAXG 8      // single-gate slots per pass
+#endif
+#ifndef TILE_MAXC
+#define TILE_MAXC 4      // register-cluster slots per pass
+#endif
+#define TILE_MAXITEMS (TILE_MAXG + TILE_MAXC)
+#define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
+#define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
+#define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
+#define TILE_THREADS 128 // 3 CTAs x 128 threads: up to 170 registers per thread for the 16-amplitude clusters
+#ifndef CL_SLOTS
+#define CL_SLOTS 5       // cluster pattern on positions (0,1),(2,3),(1,2),(0,1),(2,3)
+#endif
 
 struct TileGate {
   int32_t kind;       // 0 dense, 1 diagonal
@@ -33,18 +43,30 @@ struct TileGate {
   uint32_t lcmask;    // local controls, forced to 1
   uint32_t niter;     // group-loop trip count = max(1, (2^T >> ni) / TILE_THREADS)
   uint64_t ext_cmask; // controls outside the tile: all must be 1 in the tile's base index
-  uint32_t iter_sw[16]; // swizzled slot offset contributed by loop iteration i: sw(expand(i * TILE_THREADS))
+  uint32_t iter_sw[32]; // swizzled slot offset contributed by loop iteration i: sw(expand(i * TILE_THREADS))
   double2 m[16];      // dense: row-major (1<<k)^2 ; diagonal: first 1<<k entries
+};
+
+// A register-resident cluster: each thread holds the 16 amplitudes spanned by 4 tile bits (positions 0..3) and applies up
+// to five dense 4x4 blocks on position pairs (0,1),(2,3),(1,2),(0,1),(2,3) before writing back -- one shared-memory round
+// trip for e.g. the brickwork triple (a,b),(c,d),(b,c) instead of three.
+struct TileCluster {
+  int32_t lp[4];        // tile-local bit of cluster position p
+  int32_t ins[4];       // lp sorted ascending
+  uint32_t use;         // bit s set: pattern slot s carries a block
+  uint32_t niter;       // max(1, (2^T >> 4) / TILE_THREADS)
+  uint32_t iter_sw[8];
+  double2 m[CL_SLOTS][16];  // row-major 4x4, matrix bit 0 <-> lower position of the slot's pair
 };
 
 struct TileParams {
   int32_t T;            // tile bits
   int32_t lowb;         // min(TILE_LOWB, T)
-  int32_t ngates;
-  int32_t pf_dist;      // L2 prefetch distance in tiles (0 = off)
-  uint32_t ntiles_lo, ntiles_hi;
+  int32_t nitems;
   int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
+  uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];
+  TileCluster cl[TILE_MAXC];
 };
 
 // XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
@@ -58,11 +80,11 @@ __device__ __forceinline__ void cfma2(double2& acc, double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 cmul2(double2 d, double2 x) { return make_double2(d.x * x.x - d.y * x.y, d.x * x.y + d.y * x.x); }
 
-__host__ __device__ __forceinline__ uint32_t expand32(uint32_t g, const TileGate& G) {
+__host__ __device__ __forceinline__ uint32_t expand_ins(uint32_t g, const int32_t* ins, int ni) {
 #pragma unroll
   for (int i = 0; i < 6; ++i)
-    if (i < G.ni) {
-      int b = G.ins[i];
+    if (i < ni) {
+      int b = ins[i];
       g = ((g >> b) << (b + 1)) | (g & ((1u << b) - 1u));
     }
   return g;
@@ -70,162 +92,156 @@ __host__ __device__ __forceinline__ uint32_t expand32(uint32_t g, const TileGate
 
 template <int GI, int NT>
 __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
-    const TileGate& G = P.g[GI];
-    if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
-    // local target bits and the fixed (external) part of the matrix index
-    int kl = 0;
-    uint32_t jext = 0;
-    uint32_t so[2] = {0u, 0u};
-    int tpos[2] = {0, 0};  // matrix bit of the i-th local target
+  const TileGate& G = P.g[GI];
+  if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
+  // local target bits and the fixed (external) part of the matrix index
+  int kl = 0;
+  uint32_t jext = 0;
+  uint32_t so[2] = {0u, 0u};
+  int tpos[2] = {0, 0};  // matrix bit of the i-th local target
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (t < G.k) {
-        if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
-        else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
-      }
-    const uint32_t ng = nloc >> G.ni;
-    const bool active = tid < ng;
-    const uint32_t niter = G.niter;
-    // slot of this thread's first group; further groups and the partner amplitudes are XOR offsets (sw is linear)
-    const uint32_t s0 = sw(expand32(tid, G) | G.lcmask);
-    if (G.kind == 0) {
-      if (G.k == 2) {
-        const double2* m = G.m;
-        const uint32_t o0 = so[0], o1 = so[1], o01 = so[0] ^ so[1];
-        if (active)
-          for (uint32_t it = 0; it < niter; ++it) {
-            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0, i2 = i0 ^ o1, i3 = i0 ^ o01;
-            double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
-            double2 y0 = make_double2(0, 0), y1 = y0, y2 = y0, y3 = y0;
-            cfma2(y0, m[0], x0); cfma2(y0, m[1], x1); cfma2(y0, m[2], x2); cfma2(y0, m[3], x3);
-            cfma2(y1, m[4], x0); cfma2(y1, m[5], x1); cfma2(y1, m[6], x2); cfma2(y1, m[7], x3);
-            cfma2(y2, m[8], x0); cfma2(y2, m[9], x1); cfma2(y2, m[10], x2); cfma2(y2, m[11], x3);
-            cfma2(y3, m[12], x0); cfma2(y3, m[13], x1); cfma2(y3, m[14], x2); cfma2(y3, m[15], x3);
-            sm[i0] = y0; sm[i1] = y1; sm[i2] = y2; sm[i3] = y3;
-          }
-      } else {  // k == 1
-        const double2 m0 = G.m[0], m1 = G.m[1], m2 = G.m[2], m3 = G.m[3];
-        const uint32_t o0 = so[0];
-        if (active)
-          for (uint32_t it = 0; it < niter; ++it) {
-            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0;
-            double2 x0 = sm[i0], x1 = sm[i1];
-            double2 y0 = make_double2(0, 0), y1 = y0;
-            cfma2(y0, m0, x0); cfma2(y0, m1, x1);
-            cfma2(y1, m2, x0); cfma2(y1, m3, x1);
-            sm[i0] = y0; sm[i1] = y1;
-          }
-      }
+  for (int t = 0; t < 2; ++t)
+    if (t < G.k) {
+      if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
+      else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
+    }
+  const uint32_t ng = nloc >> G.ni;
+  const bool active = tid < ng;
+  const uint32_t niter = G.niter;
+  // slot of this thread's first group; further groups and the partner amplitudes are XOR offsets (sw is linear)
+  const uint32_t s0 = sw(expand_ins(tid, G.ins, G.ni) | G.lcmask);
+  if (G.kind == 0) {
+    if (G.k == 2) {
+      const double2* m = G.m;
+      const uint32_t o0 = so[0], o1 = so[1], o01 = so[0] ^ so[1];
+      if (active)
+        for (uint32_t it = 0; it < niter; ++it) {
+          const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0, i2 = i0 ^ o1, i3 = i0 ^ o01;
+          double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+          double2 y0 = make_double2(0, 0), y1 = y0, y2 = y0, y3 = y0;
+          cfma2(y0, m[0], x0); cfma2(y0, m[1], x1); cfma2(y0, m[2], x2); cfma2(y0, m[3], x3);
+          cfma2(y1, m[4], x0); cfma2(y1, m[5], x1); cfma2(y1, m[6], x2); cfma2(y1, m[7], x3);
+          cfma2(y2, m[8], x0); cfma2(y2, m[9], x1); cfma2(y2, m[10], x2); cfma2(y2, m[11], x3);
+          cfma2(y3, m[12], x0); cfma2(y3, m[13], x1); cfma2(y3, m[14], x2); cfma2(y3, m[15], x3);
+          sm[i0] = y0; sm[i1] = y1; sm[i2] = y2; sm[i3] = y3;
+        }
+    } else {  // k == 1
+      const double2 m0 = G.m[0], m1 = G.m[1], m2 = G.m[2], m3 = G.m[3];
+      const uint32_t o0 = so[0];
+      if (active)
+        for (uint32_t it = 0; it < niter; ++it) {
+          const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ o0;
+          double2 x0 = sm[i0], x1 = sm[i1];
+          double2 y0 = make_double2(0, 0), y1 = y0;
+          cfma2(y0, m0, x0); cfma2(y0, m1, x1);
+          cfma2(y1, m2, x0); cfma2(y1, m3, x1);
+          sm[i0] = y0; sm[i1] = y1;
+        }
+    }
+  } else {
+    // diagonal: entries with matrix index j; local bits enumerate, external bits fixed by the tile base
+    if (kl == 0) {
+      const double2 d = G.m[jext];
+      if (active && !(d.x == 1.0 && d.y == 0.0))
+        for (uint32_t it = 0; it < niter; ++it) {
+          const uint32_t i0 = s0 ^ G.iter_sw[it];
+          sm[i0] = cmul2(d, sm[i0]);
+        }
+    } else if (kl == 1) {
+      const double2 d0 = G.m[jext], d1 = G.m[jext | (1u << tpos[0])];
+      if (active)
+        for (uint32_t it = 0; it < niter; ++it) {
+          const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0];
+          double2 x0 = sm[i0], x1 = sm[i1];
+          sm[i0] = cmul2(d0, x0);
+          sm[i1] = cmul2(d1, x1);
+        }
     } else {
-      // diagonal: entries with matrix index j; local bits enumerate, external bits fixed by the tile base
-      if (kl == 0) {
-        const double2 d = G.m[jext];
-        if (active && !(d.x == 1.0 && d.y == 0.0))
-          for (uint32_t it = 0; it < niter; ++it) {
-            const uint32_t i0 = s0 ^ G.iter_sw[it];
-            sm[i0] = cmul2(d, sm[i0]);
-          }
-      } else if (kl == 1) {
-        const double2 d0 = G.m[jext], d1 = G.m[jext | (1u << tpos[0])];
-        if (active)
-          for (uint32_t it = 0; it < niter; ++it) {
-            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0];
-            double2 x0 = sm[i0], x1 = sm[i1];
-            sm[i0] = cmul2(d0, x0);
-            sm[i1] = cmul2(d1, x1);
-          }
-      } else {
-        const double2 d0 = G.m[0], d1 = G.m[1u << tpos[0]], d2 = G.m[1u << tpos[1]], d3 = G.m[3];
-        if (active)
-          for (uint32_t it = 0; it < niter; ++it) {
-            const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0], i2 = i0 ^ so[1], i3 = i1 ^ so[1];
-            double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
-            sm[i0] = cmul2(d0, x0);
-            sm[i1] = cmul2(d1, x1);
-            sm[i2] = cmul2(d2, x2);
-            sm[i3] = cmul2(d3, x3);
-          }
-      }
+      const double2 d0 = G.m[0], d1 = G.m[1u << tpos[0]], d2 = G.m[1u << tpos[1]], d3 = G.m[3];
+      if (active)
+        for (uint32_t it = 0; it < niter; ++it) {
+          const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0], i2 = i0 ^ so[1], i3 = i1 ^ so[1];
+          double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+          sm[i0] = cmul2(d0, x0);
+          sm[i1] = cmul2(d1, x1);
+          sm[i2] = cmul2(d2, x2);
+          sm[i3] = cmul2(d3, x3);
+        }
     }
-}
-
-template <int NT>
-__device__ __forceinline__ void run_gate_slot(int gi, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
-    switch (gi) {
-      case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
-      case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
-      case 2: run_gate<2, NT>(P, sm, base, tid, nloc); break;
-      case 3: run_gate<3, NT>(P, sm, base, tid, nloc); break;
-      case 4: run_gate<4, NT>(P, sm, base, tid, nloc); break;
-      case 5: run_gate<5, NT>(P, sm, base, tid, nloc); break;
-      case 6: run_gate<6, NT>(P, sm, base, tid, nloc); break;
-      case 7: run_gate<7, NT>(P, sm, base, tid, nloc); break;
-      case 8: run_gate<8, NT>(P, sm, base, tid, nloc); break;
-      case 9: run_gate<9, NT>(P, sm, base, tid, nloc); break;
-      case 10: run_gate<10, NT>(P, sm, base, tid, nloc); break;
-      default: run_gate<11, NT>(P, sm, base, tid, nloc); break;
-    }
-}
-
-
-// Persistent, double-buffered variant: one CTA of TILE_PTHREADS threads per SM walks tiles blockIdx.x, +gridDim.x, ...
-// While the gates of tile i run out of one 2^T buffer, tile i+1 streams into the other with cp.async, and the
-// finished tile drains with plain (fire-and-forget) stores: HBM traffic and FP64 work overlap inside one CTA.
-#define TILE_PTHREADS 1024
-__global__ void __launch_bounds__(TILE_PTHREADS, 1) k_tile_pers(double2* __restrict__ a, uint64_t ntiles, const __grid_constant__ TileParams P) {
-  constexpr int NT = TILE_PTHREADS;
-  extern __shared__ double2 smem[];
-  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
-  const int T = P.T, lowb = P.lowb;
-  const uint32_t tid = threadIdx.x;
-  const uint32_t nloc = 1u << T;
-  const uint32_t nhi = 1u << (T - lowb);
-  for (uint32_t h = tid; h < nhi; h += NT) {
-    uint64_t o = 0;
-    for (int j = lowb; j < T; ++j)
-      if ((h >> (j - lowb)) & 1u) o |= 1ull << P.tbits[j];
-    hi_off[h] = o;
   }
-  __syncthreads();
-  const uint32_t lmask = (1u << lowb) - 1u;
-  auto tile_base = [&](uint64_t t) {
-    uint64_t base = t << lowb;
-    for (int j = lowb; j < T; ++j) {
-      int b = P.tbits[j];
-      base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
-    }
-    return base;
-  };
-  auto issue_load = [&](uint64_t base, double2* buf) {
-    for (uint32_t c = tid; c < nloc; c += NT) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
-    __pipeline_commit();
-  };
-  uint64_t tile = blockIdx.x;
-  if (tile >= ntiles) return;
-  int cur = 0;
-  uint64_t base = tile_base(tile);
-  issue_load(base, smem);
-  while (true) {
-    const uint64_t next = tile + gridDim.x;
-    const bool have_next = next < ntiles;
-    uint64_t nbase = 0;
-    if (have_next) {
-      nbase = tile_base(next);
-      issue_load(nbase, smem + ((size_t)(cur ^ 1) << T));
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
-    double2* sm = smem + ((size_t)cur << T);
-    for (int gi = 0; gi < P.ngates; ++gi) {
-      run_gate_slot<NT>(gi, P, sm, base, tid, nloc);
-      __syncthreads();
-    }
-    for (uint32_t c = tid; c < nloc; c += NT) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
-    if (!have_next) break;
-    __syncthreads();  // everyone is done reading this buffer before the next prefetch overwrites it
-    tile = next; base = nbase; cur ^= 1;
+}
+
+// dense 4x4 on cluster positions PL < PH of the 16 register-resident amplitudes x[] (index bit p <-> position p)
+template <int PL, int PH>
+__device__ __forceinline__ void cl_apply(double2 (&x)[16], const double2* __restrict__ m) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    // enumerate the two positions other than PL, PH
+    int base = 0, rb = r;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (p != PL && p != PH) { base |= (rb & 1) << p; rb >>= 1; }
+    const int i0 = base, i1 = base | (1 << PL), i2 = base | (1 << PH), i3 = base | (1 << PL) | (1 << PH);
+    const double2 x0 = x[i0], x1 = x[i1], x2 = x[i2], x3 = x[i3];
+    double2 y0 = make_double2(0, 0), y1 = y0, y2 = y0, y3 = y0;
+    cfma2(y0, m[0], x0); cfma2(y0, m[1], x1); cfma2(y0, m[2], x2); cfma2(y0, m[3], x3);
+    cfma2(y1, m[4], x0); cfma2(y1, m[5], x1); cfma2(y1, m[6], x2); cfma2(y1, m[7], x3);
+    cfma2(y2, m[8], x0); cfma2(y2, m[9], x1); cfma2(y2, m[10], x2); cfma2(y2, m[11], x3);
+    cfma2(y3, m[12], x0); cfma2(y3, m[13], x1); cfma2(y3, m[14], x2); cfma2(y3, m[15], x3);
+    x[i0] = y0; x[i1] = y1; x[i2] = y2; x[i3] = y3;
+  }
+}
+
+template <int CI, int NT>
+__device__ __forceinline__ void run_cluster(const TileParams& P, double2* __restrict__ sm, uint32_t tid, uint32_t nloc) {
+  const TileCluster& Cl = P.cl[CI];
+  const uint32_t ng = nloc >> 4;
+  if (tid >= ng) return;
+  const uint32_t s0 = sw(expand_ins(tid, Cl.ins, 4));
+  const uint32_t o0 = sw(1u << Cl.lp[0]), o1 = sw(1u << Cl.lp[1]), o2 = sw(1u << Cl.lp[2]), o3 = sw(1u << Cl.lp[3]);
+  const uint32_t use = Cl.use;
+  for (uint32_t it = 0; it < Cl.niter; ++it) {
+    const uint32_t b = s0 ^ Cl.iter_sw[it];
+    double2 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)];
+    if (use & 1u) cl_apply<0, 1>(x, Cl.m[0]);
+    if (use & 2u) cl_apply<2, 3>(x, Cl.m[1]);
+    if (use & 4u) cl_apply<1, 2>(x, Cl.m[2]);
+#if CL_SLOTS > 3
+    if (use & 8u) cl_apply<0, 1>(x, Cl.m[3]);
+    if (use & 16u) cl_apply<2, 3>(x, Cl.m[4]);
+#endif
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)] = x[j];
+  }
+}
+
+// one code copy per slot: the slot index is a compile-time constant inside, so every matrix element is a uniform-register /
+// constant-bank operand of its DFMA instead of a live register.  (A single run-time-indexed copy was measured 20 % slower.)
+template <int NT>
+__device__ __forceinline__ void run_item(int item, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+  switch (item) {
+    case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
+    case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
+    case 2: run_gate<2, NT>(P, sm, base, tid, nloc); break;
+#if TILE_MAXG > 4
+    case 3: run_gate<3, NT>(P, sm, base, tid, nloc); break;
+    case 4: run_gate<4, NT>(P, sm, base, tid, nloc); break;
+    case 5: run_gate<5, NT>(P, sm, base, tid, nloc); break;
+    case 6: run_gate<6, NT>(P, sm, base, tid, nloc); break;
+    case 7: run_gate<7, NT>(P, sm, base, tid, nloc); break;
+#else
+    case 3: run_gate<3, NT>(P, sm, base, tid, nloc); break;
+#endif
+    case TILE_MAXG + 0: run_cluster<0, NT>(P, sm, tid, nloc); break;
+    case TILE_MAXG + 1: run_cluster<1, NT>(P, sm, tid, nloc); break;
+#if TILE_MAXC > 3
+    case TILE_MAXG + 2: run_cluster<2, NT>(P, sm, tid, nloc); break;
+    default: run_cluster<3, NT>(P, sm, tid, nloc); break;
+#else
+    default: run_cluster<2, NT>(P, sm, tid, nloc); break;
+#endif
   }
 }
 
@@ -255,34 +271,75 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_tile(double2* __restrict__ 
     __pipeline_memcpy_async(&sm[sw(c)], src, sizeof(double2));
   }
   __pipeline_commit();
-  // keep HBM streaming while this CTA computes: pull the tile a later CTA will need into L2 (one 2^lowb-amplitude
-  // run per thread), so that its load phase is an L2 hit instead of an HBM round trip
-  if (P.pf_dist > 0) {
-    const uint64_t ntiles = ((uint64_t)P.ntiles_hi << 32) | P.ntiles_lo;
-    const uint64_t pt = (uint64_t)blockIdx.x + (uint64_t)P.pf_dist;
-    if (pt < ntiles) {
-      uint64_t pbase = pt << lowb;
-      for (int j = lowb; j < T; ++j) {
-        int b = P.tbits[j];
-        pbase = ((pbase >> b) << (b + 1)) | (pbase & ((1ull << b) - 1ull));
-      }
-      for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
-        const double2* p = a + (pbase + hi_off[h]);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(sizeof(double2) << lowb)) : "memory");
-      }
-    }
-  }
   __pipeline_wait_prior(0);
   __syncthreads();
 
-  for (int gi = 0; gi < P.ngates; ++gi) {
-    // one code copy per gate slot: the slot index is a compile-time constant inside, so every matrix element is a
-    // constant-bank operand of its DFMA instead of a live register (keeps the kernel at 3 CTAs/SM)
-    run_gate_slot<TILE_THREADS>(gi, P, sm, base, tid, nloc);
+  for (int i = 0; i < P.nitems; ++i) {
+    run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
     __syncthreads();
   }
 
   for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+}
+
+// Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
+// 2^T buffer, tile i+1 streams into the other with cp.async, so each CTA keeps HBM requests in flight during its own
+// FP64 phase.  With T = 11 this is 2 x 32 KB per CTA: still 3 CTAs per SM.
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_tile_db(double2* __restrict__ a, uint64_t ntiles, int tiles_per_cta, const __grid_constant__ TileParams P) {
+  extern __shared__ double2 smem[];
+  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
+  const int T = P.T, lowb = P.lowb;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nloc = 1u << T;
+  const uint32_t nhi = 1u << (T - lowb);
+  for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
+    uint64_t o = 0;
+    for (int j = lowb; j < T; ++j)
+      if ((h >> (j - lowb)) & 1u) o |= 1ull << P.tbits[j];
+    hi_off[h] = o;
+  }
+  __syncthreads();
+  const uint32_t lmask = (1u << lowb) - 1u;
+  auto tile_base = [&](uint64_t t) {
+    uint64_t base = t << lowb;
+    for (int j = lowb; j < T; ++j) {
+      int b = P.tbits[j];
+      base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
+    }
+    return base;
+  };
+  auto issue_load = [&](uint64_t base, double2* buf) {
+    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
+    __pipeline_commit();
+  };
+  uint64_t tile = (uint64_t)blockIdx.x * (uint64_t)tiles_per_cta;
+  if (tile >= ntiles) return;
+  const uint64_t tend = (tile + (uint64_t)tiles_per_cta < ntiles) ? tile + (uint64_t)tiles_per_cta : ntiles;
+  int cur = 0;
+  uint64_t base = tile_base(tile);
+  issue_load(base, smem);
+  while (true) {
+    const uint64_t next = tile + 1;
+    const bool have_next = next < tend;
+    uint64_t nbase = 0;
+    if (have_next) {
+      nbase = tile_base(next);
+      issue_load(nbase, smem + ((size_t)(cur ^ 1) << T));
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    double2* sm = smem + ((size_t)cur << T);
+    for (int i = 0; i < P.nitems; ++i) {
+      run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
+      __syncthreads();
+    }
+    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+    if (!have_next) break;
+    __syncthreads();  // everyone is done reading this buffer before the next prefetch overwrites it
+    tile = next; base = nbase; cur ^= 1;
+  }
 }
 
 // ---- host: fusion ------------------------------------------------------------------------------------------------------
@@ -446,12 +503,46 @@ static void needed_bits(const GateDesc& d, std::vector<int>& out) {
     for (int i = 0; i < d.k; ++i) out.push_back(d.tb[i]);
 }
 
-static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass, const std::vector<int>& tile_bits_in) {
-  if (pass.size() == 1) return bt_launch_gate(s, pass[0]->desc);
-  int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TMAX));
+static inline bool cluster_eligible(const GateDesc& d) { return !d.diag && d.k == 2 && d.nc == 0; }
+
+static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, int T) {
+  G.kind = d.diag ? 1 : 0;
+  G.k = d.k;
+  G.lcmask = 0; G.ext_cmask = 0;
+  std::vector<int> ins;
+  for (int t = 0; t < d.k; ++t) {
+    int lp = local_pos[d.tb[t]];
+    G.tloc[t] = lp; G.text[t] = d.tb[t];
+    if (lp >= 0) ins.push_back(lp);
+    else if (!d.diag) BT_FAIL(BT_ERR_ARG, "internal: dense target outside the tile");
+  }
+  for (int c = 0; c < d.nc; ++c) {
+    int lp = local_pos[d.cb[c]];
+    if (lp >= 0) { G.lcmask |= 1u << lp; ins.push_back(lp); }
+    else G.ext_cmask |= 1ull << d.cb[c];
+  }
+  std::sort(ins.begin(), ins.end());
+  if (ins.size() > 6) BT_FAIL(BT_ERR_ARG, "internal: too many local bits in one gate");
+  G.ni = (int)ins.size();
+  for (size_t i = 0; i < ins.size(); ++i) G.ins[i] = ins[i];
+  int cntm = d.diag ? (1 << d.k) : (1 << (2 * d.k));
+  for (int i = 0; i < cntm; ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
+  uint32_t ngroups = (1u << T) >> G.ni;
+  G.niter = std::max<uint32_t>(1u, ngroups / TILE_THREADS);
+  if (G.niter > 32) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
+  for (uint32_t it = 0; it < G.niter; ++it) G.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, G.ins, G.ni));
+  return BT_OK;
+}
+
+static const int CL_PAIR[5][2] = {{0, 1}, {2, 3}, {1, 2}, {0, 1}, {2, 3}};
+
+static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
+  if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
+  int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   int lowb = std::min(TILE_LOWB, T);
-  const bool persistent = env_int("BT_TILE_PERSISTENT", 0) != 0;
-  const uint32_t nthreads = persistent ? TILE_PTHREADS : TILE_THREADS;
+  const int tiles_per_cta = std::max(1, env_int("BT_TILE_PER_CTA", 8));
+  const bool dbuf = env_int("BT_TILE_DB", 0) != 0 && (s->len >> T) >= 2 * (uint64_t)tiles_per_cta;
+  const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= 4;
   // tile bits: low bits + requested + padding with the lowest free bits
   bool in[64] = {false};
   for (int j = 0; j < lowb; ++j) in[j] = true;
@@ -469,8 +560,9 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass, const st
   int j = 0;
   for (int b = 0; b < s->n_local; ++b)
     if (in[b]) { P.tbits[j] = b; local_pos[b] = j; j++; }
-  int ng = 0;
-  for (const Block* blk : pass) {
+  // drop identity diagonals
+  std::vector<const Block*> pass;
+  for (const Block* blk : pass_in) {
     const GateDesc& d = blk->desc;
     if (d.k > 2 || d.nc > 4) BT_FAIL(BT_ERR_ARG, "internal: gate not tileable");
     if (d.diag) {
@@ -478,68 +570,152 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass, const st
       for (int i = 0; i < (1 << d.k); ++i) if (d.m[i] != cplx(1, 0)) all_one = false;
       if (all_one) continue;
     }
-    TileGate& G = P.g[ng++];
-    G.kind = d.diag ? 1 : 0;
-    G.k = d.k;
-    G.lcmask = 0; G.ext_cmask = 0;
-    std::vector<int> ins;
-    for (int t = 0; t < d.k; ++t) {
-      int lp = local_pos[d.tb[t]];
-      G.tloc[t] = lp; G.text[t] = d.tb[t];
-      if (lp >= 0) ins.push_back(lp);
-      else if (!d.diag) BT_FAIL(BT_ERR_ARG, "internal: dense target outside the tile");
-    }
-    for (int c = 0; c < d.nc; ++c) {
-      int lp = local_pos[d.cb[c]];
-      if (lp >= 0) { G.lcmask |= 1u << lp; ins.push_back(lp); }
-      else G.ext_cmask |= 1ull << d.cb[c];
-    }
-    std::sort(ins.begin(), ins.end());
-    if (ins.size() > 6) BT_FAIL(BT_ERR_ARG, "internal: too many local bits in one gate");
-    G.ni = (int)ins.size();
-    for (size_t i = 0; i < ins.size(); ++i) G.ins[i] = ins[i];
-    int cntm = d.diag ? (1 << d.k) : (1 << (2 * d.k));
-    for (int i = 0; i < cntm; ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
-    uint32_t ngroups = (1u << T) >> G.ni;
-    G.niter = std::max<uint32_t>(1u, ngroups / nthreads);
-    if (G.niter > 16) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
-    for (uint32_t it = 0; it < G.niter; ++it) G.iter_sw[it] = sw(expand32(it * nthreads, G));
+    pass.push_back(blk);
   }
-  P.ngates = ng;
-  if (ng == 0) return BT_OK;
+  const size_t n = pass.size();
+  std::vector<char> used(n, 0);
+  int ng = 0, nc = 0, nitems = 0;
   uint64_t ntiles = s->len >> T;
   size_t smem = sizeof(double2) << T;
-  P.pf_dist = env_int("BT_TILE_PREFETCH", 0);  // measured on B200: no gain, off by default
-  if (lowb < 2) P.pf_dist = 0;  // bulk prefetch needs >= 16-byte multiples and alignment
-  P.ntiles_lo = (uint32_t)ntiles; P.ntiles_hi = (uint32_t)(ntiles >> 32);
   static bool attr_set = false;
   if (!attr_set) {
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
-    BT_CUDA(cudaFuncSetAttribute(k_tile_pers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set = true;
   }
-  bt_prof_begin(s, BT_CLS_TILE);
-  if (persistent) {
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
-    unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)nsm);
-    k_tile_pers<<<grid, TILE_PTHREADS, 2 * smem, s->stream>>>(s->amp, ntiles, P);
-  } else {
-    k_tile<<<(unsigned)ntiles, TILE_THREADS, smem, s->stream>>>(s->amp, P);
+  auto flush = [&]() -> int {
+    if (nitems == 0) return BT_OK;
+    P.nitems = nitems;
+    bt_prof_begin(s, BT_CLS_TILE);
+    if (dbuf) {
+      uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
+      k_tile_db<<<(unsigned)nct, TILE_THREADS, 2 * smem, s->stream>>>(s->amp, ntiles, tiles_per_cta, P);
+    } else {
+      k_tile<<<(unsigned)ntiles, TILE_THREADS, smem, s->stream>>>(s->amp, P);
+    }
+    bt_prof_end(s);
+    BT_CHECK_LAUNCH(s);
+    g_fused_passes++;
+    ng = nc = nitems = 0;
+    return BT_OK;
+  };
+
+  struct Try {
+    int nm;
+    uint32_t use;
+    int bit_at_pos[4];
+    int slot_of_member[CL_SLOTS];
+    size_t member[CL_SLOTS];
+    bool swapped[CL_SLOTS];
+  };
+  // greedy cluster formation over the 5-slot pattern, seeded at (seed_slot, seed_flip); gates that cannot join keep their
+  // place (after the cluster), so a later gate may only be pulled in if it shares no bit with any skipped gate
+  auto try_cluster = [&](size_t i, int seed_slot, int seed_flip, Try& R) {
+    int pos_of_bit[64];
+    for (int b = 0; b < 64; ++b) pos_of_bit[b] = -1;
+    for (int p = 0; p < 4; ++p) R.bit_at_pos[p] = -1;
+    R.use = 0; R.nm = 0;
+    int last_slot_on_pos[4] = {-1, -1, -1, -1};
+    bool blocked[64] = {false};
+    for (size_t jj = i; jj < n && jj < i + 24 && R.nm < CL_SLOTS; ++jj) {
+      if (used[jj]) continue;
+      const Block* hb = pass[jj];
+      const GateDesc& h = hb->desc;
+      bool dep = false;
+      for (int t : hb->touch) if (blocked[t]) dep = true;
+      bool placed = false;
+      if (!dep && cluster_eligible(h)) {
+        int a = h.tb[0], b = h.tb[1];  // matrix bit 0 <-> a, bit 1 <-> b
+        for (int sl = (jj == i ? seed_slot : 0); sl < CL_SLOTS && !placed; ++sl) {
+          if (R.use & (1u << sl)) continue;
+          int p = CL_PAIR[sl][0], q = CL_PAIR[sl][1];
+          if (sl <= last_slot_on_pos[p] || sl <= last_slot_on_pos[q]) continue;  // after earlier blocks on these positions
+          for (int f = 0; f < 2 && !placed; ++f) {
+            int flip = (jj == i) ? (seed_flip ^ f) : f;
+            int pa = flip ? q : p, pb = flip ? p : q;  // a -> pa, b -> pb
+            bool oka = (pos_of_bit[a] == pa) || (pos_of_bit[a] == -1 && R.bit_at_pos[pa] == -1);
+            bool okb = (pos_of_bit[b] == pb) || (pos_of_bit[b] == -1 && R.bit_at_pos[pb] == -1);
+            if (!oka || !okb) continue;
+            pos_of_bit[a] = pa; R.bit_at_pos[pa] = a;
+            pos_of_bit[b] = pb; R.bit_at_pos[pb] = b;
+            R.use |= 1u << sl;
+            last_slot_on_pos[p] = sl; last_slot_on_pos[q] = sl;
+            R.slot_of_member[R.nm] = sl; R.member[R.nm] = jj; R.swapped[R.nm] = (pa > pb);
+            R.nm++;
+            placed = true;
+          }
+          if (jj == i && !placed) break;  // the seed is only tried at its seed slot
+        }
+      }
+      if (jj == i && !placed) return;
+      if (!placed)
+        for (int t : hb->touch) blocked[t] = true;
+    }
+  };
+
+  for (size_t i = 0; i < n; ++i) {
+    if (used[i]) continue;
+    const GateDesc& d0 = pass[i]->desc;
+    bool made_cluster = false;
+    if (use_clusters && cluster_eligible(d0)) {
+      Try best; best.nm = 0;
+      for (int seed_slot = 0; seed_slot <= 2; seed_slot += 2)
+        for (int seed_flip = 0; seed_flip < 2; ++seed_flip) {
+          Try R;
+          try_cluster(i, seed_slot, seed_flip, R);
+          if (R.nm > best.nm) best = R;
+        }
+      if (best.nm >= 2) {
+        if (nc >= TILE_MAXC) BT_TRY(flush());
+        TileCluster& Cl = P.cl[nc];
+        // unused positions take free tile bits from the top (keeps the low bits as lane bits)
+        bool taken[32] = {false};
+        for (int p = 0; p < 4; ++p) if (best.bit_at_pos[p] >= 0) taken[local_pos[best.bit_at_pos[p]]] = true;
+        int freeb = T - 1;
+        for (int p = 0; p < 4; ++p) {
+          if (best.bit_at_pos[p] >= 0) { Cl.lp[p] = local_pos[best.bit_at_pos[p]]; continue; }
+          while (freeb >= 0 && taken[freeb]) --freeb;
+          if (freeb < 0) BT_FAIL(BT_ERR_ARG, "internal: no free tile bit for a cluster");
+          Cl.lp[p] = freeb; taken[freeb] = true;
+        }
+        for (int p = 0; p < 4; ++p) Cl.ins[p] = Cl.lp[p];
+        std::sort(Cl.ins, Cl.ins + 4);
+        Cl.use = best.use;
+        uint32_t ngroups = (1u << T) >> 4;
+        Cl.niter = std::max<uint32_t>(1u, ngroups / TILE_THREADS);
+        if (Cl.niter > 8) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
+        for (uint32_t it = 0; it < Cl.niter; ++it) Cl.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, Cl.ins, 4));
+        for (int mI = 0; mI < best.nm; ++mI) {
+          const GateDesc& h = pass[best.member[mI]]->desc;
+          cplx mm[16];
+          for (int e = 0; e < 16; ++e) mm[e] = h.m[e];
+          if (best.swapped[mI]) swap_bits(mm);  // matrix bit 0 must be the lower cluster position
+          for (int e = 0; e < 16; ++e) Cl.m[best.slot_of_member[mI]][e] = make_double2(mm[e].real(), mm[e].imag());
+          used[best.member[mI]] = 1;
+        }
+        P.item[nitems++] = (uint8_t)(TILE_MAXG + nc);
+        nc++;
+        g_fused_blocks += best.nm;
+        made_cluster = true;
+      }
+    }
+    if (made_cluster) continue;
+    if (ng >= TILE_MAXG) BT_TRY(flush());
+    BT_TRY(fill_gate_slot(P.g[ng], d0, local_pos, T));
+    P.item[nitems++] = (uint8_t)ng;
+    ng++;
+    used[i] = 1;
+    g_fused_blocks++;
   }
-  bt_prof_end(s);
-  BT_CHECK_LAUNCH(s);
-  g_fused_passes++;
-  g_fused_blocks += ng;
-  return BT_OK;
+  return flush();
 }
 
 int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   std::vector<Block> blocks;
   fuse_blocks(gates, blocks);
-  const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TMAX));
+  const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   const int lowb = std::min(TILE_LOWB, T);
-  const int maxg = std::max(1, std::min(TILE_MAXG, env_int("BT_FUSE_MAX_GATES", 8)));
+  const int maxg = std::max(1, std::min(24, env_int("BT_FUSE_MAX_GATES", 8)));
   const int window = env_int("BT_FUSE_WINDOW", 256);
   const size_t n = blocks.size();
   std::vector<char> done(n, 0);
@@ -577,7 +753,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
         int extra = 0;
         for (int t : need) if (!in_tile[t]) extra++;
         double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
-        if (tile_cnt + extra > T || (int)pass.size() >= TILE_MAXG || (cost + c > (double)maxg && !pass.empty())) ok = false;
+        if (tile_cnt + extra > T || (int)pass.size() >= 24 || (cost + c > (double)maxg && !pass.empty())) ok = false;
         if (ok) {
           for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
           pass.push_back(&b); done[i] = 1; cost += c;

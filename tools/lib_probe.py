@@ -1,0 +1,19 @@
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as ge
+bt = ge.load_package(); L = bt._lib
+from importlib import import_module
+wl = import_module("bluetangle_jl_b200.workloads")
+N, depth = 28, 100
+specs = wl.c2_qft_layered(N, depth, 28)
+arr = bt.pack_gates(wl.to_ops(bt, specs))
+s = bt.zero_state(N); lib = s.lib
+for (tb, db, mg) in ((12, 0, 8), (12, 0, 10), (11, 1, 8)):
+    os.environ["BT_TILE_BITS"] = str(tb); os.environ["BT_TILE_DB"] = str(db); os.environ["BT_FUSE_MAX_GATES"] = str(mg)
+    L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1)); s.sync()
+    ms = C.c_float(); n0 = s.launch_count()
+    L.check(lib.bt_sv_timer_start(s.h))
+    L.check(lib.bt_sv_set_basis(s.h, 0)); L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1))
+    L.check(lib.bt_sv_timer_stop(s.h, C.byref(ms)))
+    print(f"{os.environ.get('BLUETANGLE_CUDA_LIB','default')[-22:]} T={tb} db={db} mg={mg}: launches={s.launch_count()-n0} ms={ms.value:.1f} gates/s={len(arr)/ms.value*1e3:.0f}")

@@ -101,7 +101,7 @@ def main():
         rows.append((f"DM 1q unitary qubit {q}", fulld, t))
     for (q, t_) in [(n - 1, n), (2, 9), (1, 2)]:
         t = timed_dm(lambda: L.check(dl.bt_dm_apply_2q(d.h, q, t_, L.ptr(U4), -2)))
-        rows.append((f"DM 2q unitary ({q},{t_}) [2 launches]", fulld, t))
+        rows.append((f"DM 2q unitary ({q},{t_}) (one 16x16 superoperator pass)", fulld, t))
     K1 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01)])
     K2 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01, True)])
     Kc = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in [np.sqrt(0.7) * np.eye(4), np.sqrt(0.2) * np.kron(bt.gate["X"], bt.gate["X"]), np.sqrt(0.1) * np.kron(bt.gate["Z"], bt.gate["Z"])]])
