@@ -577,11 +577,11 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   int ng = 0, nc = 0, nitems = 0;
   uint64_t ntiles = s->len >> T;
   size_t smem = sizeof(double2) << T;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
+  if (!attr_set[s->device & 63]) {
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
-    attr_set = true;
+    attr_set[s->device & 63] = true;
   }
   auto flush = [&]() -> int {
     if (nitems == 0) return BT_OK;
