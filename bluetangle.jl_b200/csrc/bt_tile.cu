@@ -28,9 +28,14 @@
 #define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
 #define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
 #define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
+#ifndef TILE_THREADS
 #define TILE_THREADS 128 // 3 CTAs x 128 threads: up to 170 registers per thread for the 16-amplitude clusters
+#endif
+#ifndef TILE_MINB
+#define TILE_MINB 3
+#endif
 #ifndef CL_SLOTS
-#define CL_SLOTS 5       // cluster pattern on positions (0,1),(2,3),(1,2),(0,1),(2,3)
+#define CL_SLOTS 3       // cluster pattern on positions (0,1),(2,3),(1,2) [5 = + (0,1),(2,3): measured 4 % slower, code size]
 #endif
 
 struct TileGate {
@@ -245,7 +250,7 @@ __device__ __forceinline__ void run_item(int item, const TileParams& P, double2*
   }
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_tile(double2* __restrict__ a, const __grid_constant__ TileParams P) {
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __restrict__ a, const __grid_constant__ TileParams P) {
   extern __shared__ double2 sm[];
   __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
   const int T = P.T, lowb = P.lowb;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_tile(double2* __restrict__ 
 // Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
 // 2^T buffer, tile i+1 streams into the other with cp.async, so each CTA keeps HBM requests in flight during its own
 // FP64 phase.  With T = 11 this is 2 x 32 KB per CTA: still 3 CTAs per SM.
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_tile_db(double2* __restrict__ a, uint64_t ntiles, int tiles_per_cta, const __grid_constant__ TileParams P) {
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __restrict__ a, uint64_t ntiles, int tiles_per_cta, const __grid_constant__ TileParams P) {
   extern __shared__ double2 smem[];
   __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
   const int T = P.T, lowb = P.lowb;
