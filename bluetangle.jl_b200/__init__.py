@@ -8,3 +8,4 @@ from . import _lib
 from .host import *  # noqa: F401,F403
 from .host import _born_measure, _reset_Z, _final_measurement, _sample_to_expectation  # noqa: F401
 from .gates import gate, gates, noise_model, is_valid_quantum_channel  # noqa: F401
+from .qasm import from_qasm  # noqa: F401,E402

@@ -1036,3 +1036,52 @@ def run(circuit_or_ops, number_of_experiment: int = 1, rng=None, backend="cuda",
         _, mids = apply(circuit.ops, st, noise=nm, rng=rng, track_measurements=True)
         out.append([int(m) for m in mids])
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# remaining members of the path's API surface
+# ----------------------------------------------------------------------------------------------------------
+def born_measure_Z2(state: CuState, qubit1: int, qubit2: int, rng=None):
+    """Two-qubit Born measurement, ``born_measure_Z(N, state, qubit1, qubit2)`` src/hilbert.jl:705-721: outcome index
+    1..4 over the projectors [P0P0, P1P0, P0P1, P1P1] on (qubit1, qubit2), drawn with _weighted_sample (:810-819),
+    state projected and normalised."""
+    P0, P1 = gate["P0"], gate["P1"]
+    # expand_multi_op("Pa,Pb",[qubit1,qubit2]): first name acts on qubit1; kron index = 2*b_qubit1 + b_qubit2
+    proj = [np.kron(P0, P0), np.kron(P1, P0), np.kron(P0, P1), np.kron(P1, P1)]
+    if qubit1 > qubit2:
+        # bt_sv_kraus reproduces the CHANNEL quirk for qubit > target; this function has no such quirk, so hand the
+        # pair over in ascending order with the projectors re-indexed
+        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=c128)
+        proj = [swap @ p @ swap for p in proj]
+        qa, qb = qubit2, qubit1
+    else:
+        qa, qb = qubit1, qubit2
+    chosen = _channel_apply(state, proj, 2, qa, qb, rng)
+    ind = chosen + 1
+    return state, (int(ind[0]) if state.n_batch == 1 else ind)
+
+
+def sample_bit(state: CuState, shots: int = 1, rng=None) -> List[List[int]]:
+    """src/tensor.jl:164-176 for a state vector: sampled bit strings (qubit 1 first)."""
+    return [int2bin(int(a), state.N) for a in sample(state, shots, rng)]
+
+
+def hamiltonian_expect(x: State, terms) -> float:
+    """<H> for H = sum_k c_k * (operator string on qubits): the Pauli-sum form of src/vqa.jl:36-67 evaluated term by term
+    with the fused Pauli-string reduction (each term reads the state once).  terms: iterable of (coef, "Z,Z", [q1, q2])."""
+    tot = 0.0
+    for coef, names, qubits in terms:
+        tot = tot + coef * correlation(x, names, qubits)
+    return tot
+
+
+def entanglement_entropy(state: CuState) -> float:
+    """src/func.jl:299-312: Schmidt spectrum across the cut between the first N - N/2 and the last N/2 qubits (Julia reshapes
+    column-major, so its rows are the LOW N/2 index bits).  The SVD runs on the host on a downloaded copy: a convenience for
+    small N ("next" row of SURVEY 8f), not part of the device hot path."""
+    N = state.N
+    part_a = N // 2
+    v = state.to_numpy().reshape(1 << (N - part_a), 1 << part_a)
+    spec = np.linalg.svd(v, compute_uv=False) ** 2
+    spec = spec[spec > 0]
+    return float(np.sum(-spec * np.log(spec)))

@@ -1088,3 +1088,21 @@ def final_measurement(state: np.ndarray, basis: str = "Z", draws: Optional[Draws
             raise ValueError("measurement_basis error!")
         state = hilbert1(N, m, q) @ state
     return state
+
+
+def born_measure_Z2(N: int, state: np.ndarray, qubit1: int, qubit2: int, draws: Draws) -> Tuple[np.ndarray, int]:
+    """src/hilbert.jl:705-721 (two-qubit Born measurement; returns the 1-based index like the reference)."""
+    slist = [expand_multi_op(names, [qubit1, qubit2], N) @ state for names in ("P0,P0", "P1,P0", "P0,P1", "P1,P1")]
+    probs = [abs(np.vdot(state, s)) for s in slist]
+    ind = weighted_sample(probs, draws)
+    return _normalize(slist[ind]), ind + 1
+
+
+def entanglement_entropy(psi: np.ndarray) -> float:
+    """src/func.jl:299-312 (Julia reshape is column-major: rows = low N/2 index bits)."""
+    N = get_N(psi)
+    part_a = N // 2
+    mat = psi.reshape((1 << part_a, 1 << (N - part_a)), order="F")
+    spec = np.linalg.svd(mat, compute_uv=False) ** 2
+    spec = spec[spec > 0]
+    return float(np.sum(-spec * np.log(spec)))

@@ -406,3 +406,43 @@ def test_dm_fused_op_list_equals_op_by_op(bt, orc):
         assert np.max(np.abs(seq.to_numpy() - ref)) < TOL
         assert np.max(np.abs(fused.to_numpy() - ref)) < TOL
         assert fused.launch_count() < seq.launch_count()
+
+
+def test_two_qubit_born_measurement_sample_bit_entropy_hamiltonian(bt, orc):
+    N = 5
+    for seed, (q1, q2) in enumerate([(1, 2), (4, 2), (5, 1), (3, 4)]):
+        v = rand_state(N, 40 + seed)
+        s = bt.CuState.from_numpy(v)
+        _, ind = bt.born_measure_Z2(s, q1, q2, rng=bt.Draws(seed))
+        ref, ind_o = orc.born_measure_Z2(N, v, q1, q2, orc.Draws(seed))
+        assert ind == ind_o
+        assert np.max(np.abs(s.to_numpy() - ref)) < TOL
+    v = rand_state(N, 50)
+    s = bt.CuState.from_numpy(v)
+    us = np.random.default_rng(0).random(20)
+    bits = bt.sample_bit(s, 20, rng=type("R", (), {"uniform": lambda self, it=iter(us): float(next(it))})())
+    assert bits == [orc.int2bin(int(a), N) for a in orc.sample(v, us)]
+    for n in (4, 5, 6):
+        w = rand_state(n, n)
+        assert abs(bt.entanglement_entropy(bt.CuState.from_numpy(w)) - orc.entanglement_entropy(w)) < 1e-12
+    terms = [(0.5, "Z,Z", [1, 2]), (-1.25, "X", [3]), (0.7, "X,Y,Z", [5, 1, 4])]
+    assert abs(bt.hamiltonian_expect(s, terms) - sum(c * orc.correlation(v, o, q) for c, o, q in terms)) < TOL
+
+
+def test_qasm_circuit_end_to_end(bt, orc):
+    text = """OPENQASM 2.0; qreg q[5];
+    h q[0]; cx q[0],q[3]; rz(0.3) q[1]; u3(0.1,0.2,0.3) q[2]; cu1(pi/4) q[4],q[0]; crz(0.5) q[0],q[2]; swap q[2],q[4];
+    rzz(0.3) q[0],q[3]; fsim(0.1,0.2) q[1],q[2]; ccx q[0],q[1],q[2]; cswap q[4],q[1],q[3]; sdg q[1]; sx q[4];"""
+    ops = bt.from_qasm(text)
+    st = bt.apply(ops, bt.zero_state(5))
+    ref = orc.zero_state(5)
+    for o in ops:
+        oo = orc.Op(o.name, o.qubit, o.target_qubit, control=o.control)
+        if o.q == 2 and o.control != -2 and abs(o.qubit - o.target_qubit) != 1 and o.name not in ("CX", "CZ"):
+            # controlled non-adjacent SWAP: the reference's expand throws (src/hilbert.jl:58-64); build it from its definition
+            import scipy.sparse as sp
+            P1, P0 = orc.hilbert1(5, orc.GATE["P1"], o.control), orc.hilbert1(5, orc.GATE["P0"], o.control)
+            ref = (P1 @ orc.hilbert2(5, oo.mat, o.qubit, o.target_qubit) + P0) @ ref
+        else:
+            ref = oo.expand(5) @ ref
+    assert np.max(np.abs(st.to_numpy() - ref)) < TOL

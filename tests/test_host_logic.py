@@ -102,3 +102,30 @@ def test_workload_generators_are_deterministic(bt):
         assert np.array_equal(a.mat, b.mat) and (a.qubit, a.target_qubit, a.control) == (b.qubit, b.target_qubit, b.control)
     c4, nm = wl.c4_monitored(8, 6, 20)
     assert nm == sum(1 for s in c4 if s[0] == "MZ")
+
+
+def test_qasm_front_door(bt):
+    text = """
+    OPENQASM 2.0; include "qelib1.inc";
+    qreg q[4]; creg c[4];
+    h q[0]; cx q[0],q[1]; // bell
+    rz(0.25*pi) q[2]; u3(0.1,0.2,0.3) q[3]; sdg q[1]; tdg q[2]; sx q[0];
+    cu1(pi/4) q[1],q[3]; crz(0.5) q[0],q[2]; swap q[2],q[3]; rzz(0.3) q[0],q[3]; fsim(0.1,0.2) q[1],q[2];
+    ccx q[0],q[1],q[2]; cswap q[0],q[1],q[2];
+    barrier q; reset q[3]; measure q[1] -> c[1];
+    """
+    ops = bt.from_qasm(text)
+    names = [(o.name, o.qubit, getattr(o, "target_qubit", -1), getattr(o, "control", -2)) for o in ops]
+    assert names[0] == ("H", 1, -1, -2)
+    assert names[1] == ("X", 2, -1, 1)                     # cx a,b -> Op("X", b; control=a)  (src/qasm.jl:373)
+    assert names[2][0].startswith("RZ(") and names[2][1] == 3
+    assert names[4][0] == "SD" and names[5][0] == "TD" and names[6][0] == "XSQRT"
+    assert names[7] == ("U1(pi/4)", 4, -1, 2)
+    assert names[9] == ("SWAP", 3, 4, -2)
+    assert names[12] == ("CX", 1, 3, 2)                    # ccx a,b,c -> Op("CCX", a, b, c) -> CX(a -> c) controlled by b
+    assert names[13] == ("SWAP", 2, 3, 1)                  # cswap a,b,c -> Op("CSWAP", b, a, c)
+    assert isinstance(ops[14], bt.OpQC) and ops[14].name == "res"
+    assert ops[15].type == "🔬"
+    assert np.allclose(ops[2].mat, bt.gates("RZ(0.25*pi)"))
+    with pytest.raises(ValueError):
+        bt.from_qasm("foo q[0];")
