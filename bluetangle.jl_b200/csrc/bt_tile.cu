@@ -34,6 +34,11 @@
 #ifndef TILE_MINB
 #define TILE_MINB 3
 #endif
+#ifndef CL_BITS
+#define CL_BITS 3        // cluster width: 3 tile bits = 8 amplitudes per thread, slots (0,1),(1,2),(0,1); 4 = 16 amplitudes,
+                         // slots (0,1),(2,3),(1,2), 168 registers: measured 4 % slower on C2
+#endif
+#define CL_AMPS (1 << CL_BITS)
 #ifndef CL_SLOTS
 #define CL_SLOTS 3       // cluster pattern on positions (0,1),(2,3),(1,2) [5 = + (0,1),(2,3): measured 4 % slower, code size]
 #endif
@@ -68,6 +73,8 @@ struct TileParams {
   int32_t T;            // tile bits
   int32_t lowb;         // min(TILE_LOWB, T)
   int32_t nitems;
+  int32_t stagger_ns;   // first-wave CTAs of SM slot r (= blockIdx / #SMs) start r * stagger_ns late: breaks the load/compute lockstep
+  int32_t n_sm;
   int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
   uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];
@@ -176,15 +183,15 @@ __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restric
   }
 }
 
-// dense 4x4 on cluster positions PL < PH of the 16 register-resident amplitudes x[] (index bit p <-> position p)
+// dense 4x4 on cluster positions PL < PH of the CL_AMPS register-resident amplitudes x[] (index bit p <-> position p)
 template <int PL, int PH>
-__device__ __forceinline__ void cl_apply(double2 (&x)[16], const double2* __restrict__ m) {
+__device__ __forceinline__ void cl_apply(double2 (&x)[CL_AMPS], const double2* __restrict__ m) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    // enumerate the two positions other than PL, PH
+  for (int r = 0; r < CL_AMPS / 4; ++r) {
+    // enumerate the positions other than PL, PH
     int base = 0, rb = r;
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < CL_BITS; ++p)
       if (p != PL && p != PH) { base |= (rb & 1) << p; rb >>= 1; }
     const int i0 = base, i1 = base | (1 << PL), i2 = base | (1 << PH), i3 = base | (1 << PL) | (1 << PH);
     const double2 x0 = x[i0], x1 = x[i1], x2 = x[i2], x3 = x[i3];
@@ -200,16 +207,19 @@ __device__ __forceinline__ void cl_apply(double2 (&x)[16], const double2* __rest
 template <int CI, int NT>
 __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __restrict__ sm, uint32_t tid, uint32_t nloc) {
   const TileCluster& Cl = P.cl[CI];
-  const uint32_t ng = nloc >> 4;
+  const uint32_t ng = nloc >> CL_BITS;
   if (tid >= ng) return;
-  const uint32_t s0 = sw(expand_ins(tid, Cl.ins, 4));
-  const uint32_t o0 = sw(1u << Cl.lp[0]), o1 = sw(1u << Cl.lp[1]), o2 = sw(1u << Cl.lp[2]), o3 = sw(1u << Cl.lp[3]);
+  const uint32_t s0 = sw(expand_ins(tid, Cl.ins, CL_BITS));
+  uint32_t o[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) o[p] = (p < CL_BITS) ? sw(1u << Cl.lp[p]) : 0u;
   const uint32_t use = Cl.use;
   for (uint32_t it = 0; it < Cl.niter; ++it) {
     const uint32_t b = s0 ^ Cl.iter_sw[it];
-    double2 x[16];
+    double2 x[CL_AMPS];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)];
+    for (int j = 0; j < CL_AMPS; ++j) x[j] = sm[b ^ ((j & 1) ? o[0] : 0u) ^ ((j & 2) ? o[1] : 0u) ^ ((j & 4) ? o[2] : 0u) ^ ((j & 8) ? o[3] : 0u)];
+#if CL_BITS == 4
     if (use & 1u) cl_apply<0, 1>(x, Cl.m[0]);
     if (use & 2u) cl_apply<2, 3>(x, Cl.m[1]);
     if (use & 4u) cl_apply<1, 2>(x, Cl.m[2]);
@@ -217,8 +227,13 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
     if (use & 8u) cl_apply<0, 1>(x, Cl.m[3]);
     if (use & 16u) cl_apply<2, 3>(x, Cl.m[4]);
 #endif
+#else
+    if (use & 1u) cl_apply<0, 1>(x, Cl.m[0]);
+    if (use & 2u) cl_apply<1, 2>(x, Cl.m[1]);
+    if (use & 4u) cl_apply<0, 1>(x, Cl.m[2]);
+#endif
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)] = x[j];
+    for (int j = 0; j < CL_AMPS; ++j) sm[b ^ ((j & 1) ? o[0] : 0u) ^ ((j & 2) ? o[1] : 0u) ^ ((j & 4) ? o[2] : 0u) ^ ((j & 8) ? o[3] : 0u)] = x[j];
   }
 }
 
@@ -256,6 +271,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __res
   const int T = P.T, lowb = P.lowb;
   const uint32_t tid = threadIdx.x;
   const uint32_t nloc = 1u << T;
+  if (P.stagger_ns > 0 && blockIdx.x < 3u * (uint32_t)P.n_sm) {
+    // all CTAs are identical, so the resident CTAs of an SM would load, compute and store in lockstep (HBM idle while
+    // FP64 runs and vice versa); a one-off offset per SM slot keeps their phases apart for the rest of the kernel
+    uint32_t r = blockIdx.x / (uint32_t)P.n_sm;
+    for (uint32_t w = 0; w < r; ++w) __nanosleep((unsigned)P.stagger_ns);
+  }
   // base index of this tile: blockIdx with zeros inserted at every tile bit position
   uint64_t base = (uint64_t)blockIdx.x << lowb;
   for (int j = lowb; j < T; ++j) {
@@ -271,20 +292,25 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __res
   }
   __syncthreads();
   const uint32_t lmask = (1u << lowb) - 1u;
-  for (uint32_t c = tid; c < nloc; c += TILE_THREADS) {
-    const double2* src = a + (base + hi_off[c >> lowb] + (c & lmask));
-    __pipeline_memcpy_async(&sm[sw(c)], src, sizeof(double2));
+  const int dbg = P.stagger_ns < 0 ? -P.stagger_ns : 0;  // measurement aid: 1 = no gates, 2 = no HBM traffic (results invalid)
+  if (dbg != 2) {
+    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) {
+      const double2* src = a + (base + hi_off[c >> lowb] + (c & lmask));
+      __pipeline_memcpy_async(&sm[sw(c)], src, sizeof(double2));
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
   }
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
   __syncthreads();
 
-  for (int i = 0; i < P.nitems; ++i) {
-    run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
-    __syncthreads();
-  }
+  if (dbg != 1)
+    for (int i = 0; i < P.nitems; ++i) {
+      run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
+      __syncthreads();
+    }
 
-  for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+  if (dbg != 2)
+    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
 }
 
 // Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
@@ -539,7 +565,13 @@ static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, 
   return BT_OK;
 }
 
+#if CL_BITS == 4
 static const int CL_PAIR[5][2] = {{0, 1}, {2, 3}, {1, 2}, {0, 1}, {2, 3}};
+static const int CL_SEED2 = 2;
+#else
+static const int CL_PAIR[5][2] = {{0, 1}, {1, 2}, {0, 1}, {0, 1}, {0, 1}};
+static const int CL_SEED2 = 1;
+#endif
 
 static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
   if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
@@ -547,7 +579,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   int lowb = std::min(TILE_LOWB, T);
   const int tiles_per_cta = std::max(1, env_int("BT_TILE_PER_CTA", 8));
   const bool dbuf = env_int("BT_TILE_DB", 0) != 0 && (s->len >> T) >= 2 * (uint64_t)tiles_per_cta;
-  const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= 4;
+  const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= CL_BITS;
   // tile bits: low bits + requested + padding with the lowest free bits
   bool in[64] = {false};
   for (int j = 0; j < lowb; ++j) in[j] = true;
@@ -588,9 +620,13 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set[s->device & 63] = true;
   }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
   auto flush = [&]() -> int {
     if (nitems == 0) return BT_OK;
-    P.nitems = nitems;
+      P.nitems = nitems;
+    P.stagger_ns = env_int("BT_TILE_STAGGER_NS", 0);
+    P.n_sm = nsm;
     bt_prof_begin(s, BT_CLS_TILE);
     if (dbuf) {
       uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
@@ -664,7 +700,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     bool made_cluster = false;
     if (use_clusters && cluster_eligible(d0)) {
       Try best; best.nm = 0;
-      for (int seed_slot = 0; seed_slot <= 2; seed_slot += 2)
+      for (int seed_slot = 0; seed_slot <= CL_SEED2; seed_slot += CL_SEED2)
         for (int seed_flip = 0; seed_flip < 2; ++seed_flip) {
           Try R;
           try_cluster(i, seed_slot, seed_flip, R);
@@ -675,21 +711,21 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         TileCluster& Cl = P.cl[nc];
         // unused positions take free tile bits from the top (keeps the low bits as lane bits)
         bool taken[32] = {false};
-        for (int p = 0; p < 4; ++p) if (best.bit_at_pos[p] >= 0) taken[local_pos[best.bit_at_pos[p]]] = true;
+        for (int p = 0; p < CL_BITS; ++p) if (best.bit_at_pos[p] >= 0) taken[local_pos[best.bit_at_pos[p]]] = true;
         int freeb = T - 1;
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < CL_BITS; ++p) {
           if (best.bit_at_pos[p] >= 0) { Cl.lp[p] = local_pos[best.bit_at_pos[p]]; continue; }
           while (freeb >= 0 && taken[freeb]) --freeb;
           if (freeb < 0) BT_FAIL(BT_ERR_ARG, "internal: no free tile bit for a cluster");
           Cl.lp[p] = freeb; taken[freeb] = true;
         }
-        for (int p = 0; p < 4; ++p) Cl.ins[p] = Cl.lp[p];
-        std::sort(Cl.ins, Cl.ins + 4);
+        for (int p = 0; p < CL_BITS; ++p) Cl.ins[p] = Cl.lp[p];
+        std::sort(Cl.ins, Cl.ins + CL_BITS);
         Cl.use = best.use;
-        uint32_t ngroups = (1u << T) >> 4;
+        uint32_t ngroups = (1u << T) >> CL_BITS;
         Cl.niter = std::max<uint32_t>(1u, ngroups / TILE_THREADS);
         if (Cl.niter > 8) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
-        for (uint32_t it = 0; it < Cl.niter; ++it) Cl.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, Cl.ins, 4));
+        for (uint32_t it = 0; it < Cl.niter; ++it) Cl.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, Cl.ins, CL_BITS));
         for (int mI = 0; mI < best.nm; ++mI) {
           const GateDesc& h = pass[best.member[mI]]->desc;
           cplx mm[16];
@@ -720,7 +756,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   fuse_blocks(gates, blocks);
   const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   const int lowb = std::min(TILE_LOWB, T);
-  const int maxg = std::max(1, std::min(24, env_int("BT_FUSE_MAX_GATES", 8)));
+  const int maxg = std::max(1, std::min(24, env_int("BT_FUSE_MAX_GATES", 10)));
   const int window = env_int("BT_FUSE_WINDOW", 256);
   const size_t n = blocks.size();
   std::vector<char> done(n, 0);
