@@ -51,6 +51,7 @@ PROTOTYPES = {
     "bt_set_device": [_i],
     "bt_set_strict": [_i],
     "bt_fusion_stats": [C.POINTER(_u64), C.POINTER(_u64)],
+    "bt_fusion_flops": [_pd],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],
     "bt_sv_n_qubits": [_vp, C.POINTER(_i)],

@@ -526,6 +526,7 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
 }
 
 static uint64_t g_fused_passes = 0, g_fused_blocks = 0;
+static double g_fused_flops = 0.0;  // FP64 flops issued by the fused passes (FMA = 2)
 
 // bits of `d` that must be inside the tile: non-diagonal targets
 static void needed_bits(const GateDesc& d, std::vector<int>& out) {
@@ -737,6 +738,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         P.item[nitems++] = (uint8_t)(TILE_MAXG + nc);
         nc++;
         g_fused_blocks += best.nm;
+        g_fused_flops += 32.0 * (double)best.nm * (double)s->len;
         made_cluster = true;
       }
     }
@@ -747,6 +749,10 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     ng++;
     used[i] = 1;
     g_fused_blocks++;
+    {
+      double touched = ldexp((double)s->len, -d0.nc);
+      g_fused_flops += touched * (d0.diag ? 6.0 : (d0.k == 2 ? 32.0 : 16.0));
+    }
   }
   return flush();
 }
@@ -807,6 +813,12 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
     if (pass.empty()) BT_FAIL(BT_ERR_ARG, "internal: fusion scheduler made no progress");
     BT_TRY(launch_pass(s, pass, tile_bits));
   }
+  return BT_OK;
+}
+
+extern "C" int bt_fusion_flops(double* flops) {
+  if (!flops) BT_FAIL(BT_ERR_ARG, "null output");
+  *flops = g_fused_flops;
   return BT_OK;
 }
 

@@ -78,7 +78,9 @@ int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse);
  * outcome is a DEVICE pointer obtained from bt_sv_outcome_buffer */
 int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int want);
 int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
-int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); /* cumulative: fused tile-kernel launches and blocks they carried */
+int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); 
+int bt_fusion_flops(double* flops); /* cumulative FP64 flops issued by the fused passes (FMA = 2 flops) */
+ /* cumulative: fused tile-kernel launches and blocks they carried */
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */
