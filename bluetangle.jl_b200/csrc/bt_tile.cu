@@ -17,6 +17,7 @@
 #include "bt_internal.cuh"
 #include <cuda_pipeline_primitives.h>
 #include <stdlib.h>
+#include <atomic>
 
 #ifndef TILE_MAXG
 #define TILE_MAXG 8      // single-gate slots per pass
@@ -39,6 +40,9 @@
                          // slots (0,1),(2,3),(1,2), 168 registers: measured 4 % slower on C2
 #endif
 #define CL_AMPS (1 << CL_BITS)
+#ifndef CL_PIPE
+#define CL_PIPE 0         // 1 = software-pipeline two cluster groups per thread (measured: no gain, 166 registers)
+#endif
 #ifndef CL_SLOTS
 #define CL_SLOTS 3       // cluster pattern on positions (0,1),(2,3),(1,2) [5 = + (0,1),(2,3): measured 4 % slower, code size]
 #endif
@@ -214,11 +218,39 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
 #pragma unroll
   for (int p = 0; p < 4; ++p) o[p] = (p < CL_BITS) ? sw(1u << Cl.lp[p]) : 0u;
   const uint32_t use = Cl.use;
-  for (uint32_t it = 0; it < Cl.niter; ++it) {
+  uint32_t off[CL_AMPS];
+#pragma unroll
+  for (int j = 0; j < CL_AMPS; ++j) off[j] = ((j & 1) ? o[0] : 0u) ^ ((j & 2) ? o[1] : 0u) ^ ((j & 4) ? o[2] : 0u) ^ ((j & 8) ? o[3] : 0u);
+  uint32_t it = 0;
+#if CL_PIPE
+  // two cluster groups in flight per thread: the shared-memory loads of one overlap the DFMA chains of the other
+  for (; it + 1 < Cl.niter; it += 2) {
+    const uint32_t ba = s0 ^ Cl.iter_sw[it], bb = s0 ^ Cl.iter_sw[it + 1];
+    double2 xa[CL_AMPS], xb[CL_AMPS];
+#pragma unroll
+    for (int j = 0; j < CL_AMPS; ++j) xa[j] = sm[ba ^ off[j]];
+#pragma unroll
+    for (int j = 0; j < CL_AMPS; ++j) xb[j] = sm[bb ^ off[j]];
+#if CL_BITS == 4
+    if (use & 1u) { cl_apply<0, 1>(xa, Cl.m[0]); cl_apply<0, 1>(xb, Cl.m[0]); }
+    if (use & 2u) { cl_apply<2, 3>(xa, Cl.m[1]); cl_apply<2, 3>(xb, Cl.m[1]); }
+    if (use & 4u) { cl_apply<1, 2>(xa, Cl.m[2]); cl_apply<1, 2>(xb, Cl.m[2]); }
+#else
+    if (use & 1u) { cl_apply<0, 1>(xa, Cl.m[0]); cl_apply<0, 1>(xb, Cl.m[0]); }
+    if (use & 2u) { cl_apply<1, 2>(xa, Cl.m[1]); cl_apply<1, 2>(xb, Cl.m[1]); }
+    if (use & 4u) { cl_apply<0, 1>(xa, Cl.m[2]); cl_apply<0, 1>(xb, Cl.m[2]); }
+#endif
+#pragma unroll
+    for (int j = 0; j < CL_AMPS; ++j) sm[ba ^ off[j]] = xa[j];
+#pragma unroll
+    for (int j = 0; j < CL_AMPS; ++j) sm[bb ^ off[j]] = xb[j];
+  }
+#endif
+  for (; it < Cl.niter; ++it) {
     const uint32_t b = s0 ^ Cl.iter_sw[it];
     double2 x[CL_AMPS];
 #pragma unroll
-    for (int j = 0; j < CL_AMPS; ++j) x[j] = sm[b ^ ((j & 1) ? o[0] : 0u) ^ ((j & 2) ? o[1] : 0u) ^ ((j & 4) ? o[2] : 0u) ^ ((j & 8) ? o[3] : 0u)];
+    for (int j = 0; j < CL_AMPS; ++j) x[j] = sm[b ^ off[j]];
 #if CL_BITS == 4
     if (use & 1u) cl_apply<0, 1>(x, Cl.m[0]);
     if (use & 2u) cl_apply<2, 3>(x, Cl.m[1]);
@@ -233,7 +265,7 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
     if (use & 4u) cl_apply<0, 1>(x, Cl.m[2]);
 #endif
 #pragma unroll
-    for (int j = 0; j < CL_AMPS; ++j) sm[b ^ ((j & 1) ? o[0] : 0u) ^ ((j & 2) ? o[1] : 0u) ^ ((j & 4) ? o[2] : 0u) ^ ((j & 8) ? o[3] : 0u)] = x[j];
+    for (int j = 0; j < CL_AMPS; ++j) sm[b ^ off[j]] = x[j];
   }
 }
 
@@ -525,8 +557,8 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
   blocks.swap(out);
 }
 
-static uint64_t g_fused_passes = 0, g_fused_blocks = 0;
-static double g_fused_flops = 0.0;  // FP64 flops issued by the fused passes (FMA = 2)
+static std::atomic<uint64_t> g_fused_passes{0}, g_fused_blocks{0};
+static std::atomic<double> g_fused_flops{0.0};  // FP64 flops issued by the fused passes (FMA = 2)
 
 // bits of `d` that must be inside the tile: non-diagonal targets
 static void needed_bits(const GateDesc& d, std::vector<int>& out) {
@@ -738,7 +770,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         P.item[nitems++] = (uint8_t)(TILE_MAXG + nc);
         nc++;
         g_fused_blocks += best.nm;
-        g_fused_flops += 32.0 * (double)best.nm * (double)s->len;
+        g_fused_flops.store(g_fused_flops.load() + 32.0 * (double)best.nm * (double)s->len);
         made_cluster = true;
       }
     }
@@ -751,7 +783,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     g_fused_blocks++;
     {
       double touched = ldexp((double)s->len, -d0.nc);
-      g_fused_flops += touched * (d0.diag ? 6.0 : (d0.k == 2 ? 32.0 : 16.0));
+      g_fused_flops.store(g_fused_flops.load() + touched * (d0.diag ? 6.0 : (d0.k == 2 ? 32.0 : 16.0)));
     }
   }
   return flush();
@@ -818,12 +850,12 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
 
 extern "C" int bt_fusion_flops(double* flops) {
   if (!flops) BT_FAIL(BT_ERR_ARG, "null output");
-  *flops = g_fused_flops;
+  *flops = g_fused_flops.load();
   return BT_OK;
 }
 
 extern "C" int bt_fusion_stats(uint64_t* passes, uint64_t* blocks) {
-  if (passes) *passes = g_fused_passes;
-  if (blocks) *blocks = g_fused_blocks;
+  if (passes) *passes = g_fused_passes.load();
+  if (blocks) *blocks = g_fused_blocks.load();
   return BT_OK;
 }

@@ -75,7 +75,7 @@ int bt_sv_apply_3q(bt_sv* s, int first_qubit, const bt_c64 m[64]);              
 /* whole op list in one call; fuse != 0 enables the host fusion pass + multi-gate shared-memory kernel */
 int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse);
 /* gate applied only to trajectories whose outcome[t] == want (ifOp branches, src/struct.jl:587-590);
- * outcome is a DEVICE pointer obtained from bt_sv_outcome_buffer */
+ * the outcomes are the handle's device-side record of the last bt_sv_measure_z call) */
 int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int want);
 int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
 int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); 
