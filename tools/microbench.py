@@ -79,6 +79,16 @@ def main():
     so = np.empty(4096, dtype=np.int64)
     t = timed(s, lambda: L.check(lib.bt_sv_sample(s.h, L.pdouble(us), 4096, so.ctypes.data_as(C.POINTER(C.c_int64)))))
     rows.append(("sample 4096 shots (read only)", full / 2, t))
+    # state-vector Kraus trajectory step: RDM read (16 B/amp) + decision + scaled-Kraus apply (32 B/amp)
+    K1s = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01)])
+    K2s = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01, True)])
+    ua = np.array([0.5])
+    for q in [N, N // 2, 1]:
+        t = timed(s, lambda: L.check(lib.bt_sv_kraus(s.h, 1, q, -1, L.ptr(K1s), 4, L.pdouble(ua), None)))
+        rows.append((f"SV 1q depolarizing Kraus step qubit {q} (rdm 16 + apply 32 B/amp)", 48.0 * (1 << N), t))
+    for (q, t_) in [(N - 1, N), (3, 17)]:
+        t = timed(s, lambda: L.check(lib.bt_sv_kraus(s.h, 2, q, t_, L.ptr(K2s), 16, L.pdouble(ua), None)))
+        rows.append((f"SV 2q depolarizing Kraus step ({q},{t_}) (rdm 16 + apply 32 B/amp)", 48.0 * (1 << N), t))
     del s
     # density matrix
     n = N // 2
@@ -113,10 +123,10 @@ def main():
         rows.append((f"DM 2q depolarizing (16 Kraus, product) ({q},{t_})", fulld, t))
         t = timed_dm(lambda: L.check(dl.bt_dm_kraus(d.h, 2, q, t_, L.ptr(Kc), 3)))
         rows.append((f"DM 2q correlated channel (16x16) ({q},{t_})", fulld, t))
-    print(f"{'kernel':62s} {'ms':>9s} {'GB/s':>9s} {'of measured':>11s} {'of 8TB/s':>9s}")
+    print(f"{'kernel':72s} {'ms':>9s} {'GB/s':>9s} {'of measured':>11s} {'of 8TB/s':>9s}")
     for name, byts, ms in rows:
         gbs = byts / ms / 1e6
-        print(f"{name:62s} {ms:9.4f} {gbs:9.1f} {gbs/peak:11.3f} {gbs/8000:9.3f}")
+        print(f"{name:72s} {ms:9.4f} {gbs:9.1f} {gbs/peak:11.3f} {gbs/8000:9.3f}")
 
 
 if __name__ == "__main__":
