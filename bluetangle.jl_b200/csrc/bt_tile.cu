@@ -53,7 +53,7 @@ struct TileGate {
   int32_t tloc[2];    // tile-local position of matrix bit t, or -1 when the bit lies outside the tile (diagonal only)
   int32_t text[2];    // physical position when outside the tile
   int32_t ni;         // tile-local inserted positions (local targets + local controls), ascending
-  int32_t ins[6];
+  uint32_t bit_sw[8];  // swizzled slot contribution of thread-index bit k (host picks which free tile bit each thread bit walks)
   uint32_t lcmask;    // local controls, forced to 1
   uint32_t niter;     // group-loop trip count = max(1, (2^T >> ni) / TILE_THREADS)
   uint64_t ext_cmask; // controls outside the tile: all must be 1 in the tile's base index
@@ -66,7 +66,7 @@ struct TileGate {
 // trip for e.g. the brickwork triple (a,b),(c,d),(b,c) instead of three.
 struct TileCluster {
   int32_t lp[4];        // tile-local bit of cluster position p
-  int32_t ins[4];       // lp sorted ascending
+  uint32_t bit_sw[8];   // as in TileGate
   uint32_t use;         // bit s set: pattern slot s carries a block
   uint32_t niter;       // max(1, (2^T >> 4) / TILE_THREADS)
   uint32_t iter_sw[8];
@@ -86,7 +86,9 @@ struct TileParams {
 };
 
 // XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
-__host__ __device__ __forceinline__ uint32_t sw(uint32_t c) { return c ^ ((c >> 3) & 7u); }
+// (slot index bits 0..2 select the 16-byte bank group; they become the XOR of ALL 3-bit digits of the tile index, so a run
+// of 8 lanes is conflict-free whenever the three index bits it varies have distinct residues mod 3)
+__host__ __device__ __forceinline__ uint32_t sw(uint32_t c) { return c ^ ((c >> 3) & 7u) ^ ((c >> 6) & 7u) ^ ((c >> 9) & 7u); }
 
 __device__ __forceinline__ void cfma2(double2& acc, double2 a, double2 b) {
   acc.x = fma(a.x, b.x, acc.x);
@@ -96,14 +98,12 @@ __device__ __forceinline__ void cfma2(double2& acc, double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 cmul2(double2 d, double2 x) { return make_double2(d.x * x.x - d.y * x.y, d.x * x.y + d.y * x.x); }
 
-__host__ __device__ __forceinline__ uint32_t expand_ins(uint32_t g, const int32_t* ins, int ni) {
+__device__ __forceinline__ uint32_t thread_slot(const uint32_t* bit_sw, uint32_t tid) {
+  uint32_t r = 0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (i < ni) {
-      int b = ins[i];
-      g = ((g >> b) << (b + 1)) | (g & ((1u << b) - 1u));
-    }
-  return g;
+  for (int k = 0; k < 8; ++k)
+    if ((tid >> k) & 1u) r ^= bit_sw[k];
+  return r;
 }
 
 template <int GI, int NT>
@@ -125,7 +125,7 @@ __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restric
   const bool active = tid < ng;
   const uint32_t niter = G.niter;
   // slot of this thread's first group; further groups and the partner amplitudes are XOR offsets (sw is linear)
-  const uint32_t s0 = sw(expand_ins(tid, G.ins, G.ni) | G.lcmask);
+  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ sw(G.lcmask);
   if (G.kind == 0) {
     if (G.k == 2) {
       const double2* m = G.m;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
   const TileCluster& Cl = P.cl[CI];
   const uint32_t ng = nloc >> CL_BITS;
   if (tid >= ng) return;
-  const uint32_t s0 = sw(expand_ins(tid, Cl.ins, CL_BITS));
+  const uint32_t s0 = thread_slot(Cl.bit_sw, tid);
   uint32_t o[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) o[p] = (p < CL_BITS) ? sw(1u << Cl.lp[p]) : 0u;
@@ -567,6 +567,35 @@ static void needed_bits(const GateDesc& d, std::vector<int>& out) {
     for (int i = 0; i < d.k; ++i) out.push_back(d.tb[i]);
 }
 
+// Group enumeration for an item whose fixed tile positions are `fixed` (targets + local controls): group-index bit k walks
+// free tile position order[k].  The first three are chosen with distinct residues mod 3 so that 8 consecutive lanes hit 8
+// distinct bank groups under sw(); thread bits come first, loop-iteration bits after.
+static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bit_sw, uint32_t* iter_sw, int iter_cap, uint32_t* niter_out) {
+  int order[TILE_TMAX], n = 0;
+  bool used[TILE_TMAX] = {false};
+  bool res_taken[3] = {false, false, false};
+  for (int round = 0; round < 3; ++round)
+    for (int p = 0; p < T; ++p)
+      if (!((fixed_mask >> p) & 1u) && !used[p] && !res_taken[p % 3]) { order[n++] = p; used[p] = true; res_taken[p % 3] = true; break; }
+  for (int p = 0; p < T; ++p)
+    if (!((fixed_mask >> p) & 1u) && !used[p]) { order[n++] = p; used[p] = true; }
+  if (n != T - nfixed) return -1;
+  int tbits = 0;
+  while ((1 << tbits) < TILE_THREADS) ++tbits;
+  for (int k = 0; k < 8; ++k) bit_sw[k] = (k < n && k < tbits) ? sw(1u << order[k]) : 0u;
+  uint32_t ngroups = 1u << n;
+  uint32_t niter = ngroups > (uint32_t)TILE_THREADS ? ngroups / TILE_THREADS : 1u;
+  if ((int)niter > iter_cap) return -1;
+  for (uint32_t it = 0; it < niter; ++it) {
+    uint32_t c = 0;
+    for (int k = tbits; k < n; ++k)
+      if ((it >> (k - tbits)) & 1u) c |= 1u << order[k];
+    iter_sw[it] = sw(c);
+  }
+  *niter_out = niter;
+  return 0;
+}
+
 static inline bool cluster_eligible(const GateDesc& d) { return !d.diag && d.k == 2 && d.nc == 0; }
 
 static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, int T) {
@@ -585,16 +614,13 @@ static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, 
     if (lp >= 0) { G.lcmask |= 1u << lp; ins.push_back(lp); }
     else G.ext_cmask |= 1ull << d.cb[c];
   }
-  std::sort(ins.begin(), ins.end());
   if (ins.size() > 6) BT_FAIL(BT_ERR_ARG, "internal: too many local bits in one gate");
   G.ni = (int)ins.size();
-  for (size_t i = 0; i < ins.size(); ++i) G.ins[i] = ins[i];
+  uint32_t fixed = 0;
+  for (int lp : ins) fixed |= 1u << lp;
   int cntm = d.diag ? (1 << d.k) : (1 << (2 * d.k));
   for (int i = 0; i < cntm; ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
-  uint32_t ngroups = (1u << T) >> G.ni;
-  G.niter = std::max<uint32_t>(1u, ngroups / TILE_THREADS);
-  if (G.niter > 32) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
-  for (uint32_t it = 0; it < G.niter; ++it) G.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, G.ins, G.ni));
+  if (build_group_walk(T, fixed, G.ni, G.bit_sw, G.iter_sw, 32, &G.niter) != 0) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
   return BT_OK;
 }
 
@@ -752,13 +778,10 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
           if (freeb < 0) BT_FAIL(BT_ERR_ARG, "internal: no free tile bit for a cluster");
           Cl.lp[p] = freeb; taken[freeb] = true;
         }
-        for (int p = 0; p < CL_BITS; ++p) Cl.ins[p] = Cl.lp[p];
-        std::sort(Cl.ins, Cl.ins + CL_BITS);
+        uint32_t fixed = 0;
+        for (int p = 0; p < CL_BITS; ++p) fixed |= 1u << Cl.lp[p];
         Cl.use = best.use;
-        uint32_t ngroups = (1u << T) >> CL_BITS;
-        Cl.niter = std::max<uint32_t>(1u, ngroups / TILE_THREADS);
-        if (Cl.niter > 8) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
-        for (uint32_t it = 0; it < Cl.niter; ++it) Cl.iter_sw[it] = sw(expand_ins(it * TILE_THREADS, Cl.ins, CL_BITS));
+        if (build_group_walk(T, fixed, CL_BITS, Cl.bit_sw, Cl.iter_sw, 8, &Cl.niter) != 0) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
         for (int mI = 0; mI < best.nm; ++mI) {
           const GateDesc& h = pass[best.member[mI]]->desc;
           cplx mm[16];
