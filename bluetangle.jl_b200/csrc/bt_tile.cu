@@ -25,7 +25,9 @@
 #ifndef TILE_MAXC
 #define TILE_MAXC 4      // register-cluster slots per pass
 #endif
-#define TILE_MAXITEMS (TILE_MAXG + TILE_MAXC)
+#define TILE_MAXD 32     // diagonal-gate slots per pass (one run-time-indexed code copy: they carry <= 4 matrix entries)
+#define TILE_DBASE 16    // item ids >= TILE_DBASE are diagonal slots
+#define TILE_MAXITEMS (TILE_MAXG + TILE_MAXC + TILE_MAXD)
 #define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
 #define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
 #define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
@@ -61,6 +63,20 @@ struct TileGate {
   double2 m[16];      // dense: row-major (1<<k)^2 ; diagonal: first 1<<k entries
 };
 
+// Diagonal gate (k <= 2 targets, any of them possibly outside the tile, plus controls): cheap, so it gets many slots.
+struct TileDiag {
+  int32_t k;
+  int32_t ni;
+  int32_t tloc[2];
+  int32_t text[2];
+  uint32_t lcmask;
+  uint32_t niter;
+  uint64_t ext_cmask;
+  uint32_t bit_sw[8];
+  uint32_t iter_sw[16];
+  double2 m[4];
+};
+
 // A register-resident cluster: each thread holds the 16 amplitudes spanned by 4 tile bits (positions 0..3) and applies up
 // to five dense 4x4 blocks on position pairs (0,1),(2,3),(1,2),(0,1),(2,3) before writing back -- one shared-memory round
 // trip for e.g. the brickwork triple (a,b),(c,d),(b,c) instead of three.
@@ -83,6 +99,7 @@ struct TileParams {
   uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];
   TileCluster cl[TILE_MAXC];
+  TileDiag d[TILE_MAXD];
 };
 
 // XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
@@ -187,6 +204,51 @@ __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restric
   }
 }
 
+template <int NT>
+__device__ __noinline__ void run_diag(const TileDiag& G, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+  if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
+  int kl = 0;
+  uint32_t jext = 0;
+  uint32_t so[2] = {0u, 0u};
+  int tpos[2] = {0, 0};
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+    if (t < G.k) {
+      if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
+      else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
+    }
+  const uint32_t ng = nloc >> G.ni;
+  if (tid >= ng) return;
+  const uint32_t niter = G.niter;
+  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ sw(G.lcmask);
+  if (kl == 0) {
+    const double2 d = G.m[jext];
+    if (!(d.x == 1.0 && d.y == 0.0))
+      for (uint32_t it = 0; it < niter; ++it) {
+        const uint32_t i0 = s0 ^ G.iter_sw[it];
+        sm[i0] = cmul2(d, sm[i0]);
+      }
+  } else if (kl == 1) {
+    const double2 d0 = G.m[jext], d1 = G.m[jext | (1u << tpos[0])];
+    for (uint32_t it = 0; it < niter; ++it) {
+      const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0];
+      double2 x0 = sm[i0], x1 = sm[i1];
+      sm[i0] = cmul2(d0, x0);
+      sm[i1] = cmul2(d1, x1);
+    }
+  } else {
+    const double2 d0 = G.m[0], d1 = G.m[1u << tpos[0]], d2 = G.m[1u << tpos[1]], d3 = G.m[3];
+    for (uint32_t it = 0; it < niter; ++it) {
+      const uint32_t i0 = s0 ^ G.iter_sw[it], i1 = i0 ^ so[0], i2 = i0 ^ so[1], i3 = i1 ^ so[1];
+      double2 x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+      sm[i0] = cmul2(d0, x0);
+      sm[i1] = cmul2(d1, x1);
+      sm[i2] = cmul2(d2, x2);
+      sm[i3] = cmul2(d3, x3);
+    }
+  }
+}
+
 // dense 4x4 on cluster positions PL < PH of the CL_AMPS register-resident amplitudes x[] (index bit p <-> position p)
 template <int PL, int PH>
 __device__ __forceinline__ void cl_apply(double2 (&x)[CL_AMPS], const double2* __restrict__ m) {
@@ -273,6 +335,7 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
 // constant-bank operand of its DFMA instead of a live register.  (A single run-time-indexed copy was measured 20 % slower.)
 template <int NT>
 __device__ __forceinline__ void run_item(int item, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+  if (item >= TILE_DBASE) { run_diag<NT>(P.d[item - TILE_DBASE], sm, base, tid, nloc); return; }
   switch (item) {
     case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
     case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
@@ -624,6 +687,30 @@ static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, 
   return BT_OK;
 }
 
+// diagonal gate -> run-time-indexed slot; returns 1 if it does not fit a TileDiag (then it takes a specialised gate slot)
+static int fill_diag_slot(TileDiag& G, const GateDesc& d, const int* local_pos, int T) {
+  if (!d.diag || d.k > 2) return 1;
+  G.k = d.k;
+  G.lcmask = 0; G.ext_cmask = 0;
+  uint32_t fixed = 0;
+  int ni = 0;
+  for (int t = 0; t < 2; ++t) { G.tloc[t] = -1; G.text[t] = 0; }
+  for (int t = 0; t < d.k; ++t) {
+    int lp = local_pos[d.tb[t]];
+    G.tloc[t] = lp; G.text[t] = d.tb[t];
+    if (lp >= 0) { fixed |= 1u << lp; ni++; }
+  }
+  for (int c = 0; c < d.nc; ++c) {
+    int lp = local_pos[d.cb[c]];
+    if (lp >= 0) { G.lcmask |= 1u << lp; fixed |= 1u << lp; ni++; }
+    else G.ext_cmask |= 1ull << d.cb[c];
+  }
+  G.ni = ni;
+  for (int i = 0; i < (1 << d.k); ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
+  if (build_group_walk(T, fixed, ni, G.bit_sw, G.iter_sw, 16, &G.niter) != 0) return 1;
+  return 0;
+}
+
 #if CL_BITS == 4
 static const int CL_PAIR[5][2] = {{0, 1}, {2, 3}, {1, 2}, {0, 1}, {2, 3}};
 static const int CL_SEED2 = 2;
@@ -670,7 +757,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   }
   const size_t n = pass.size();
   std::vector<char> used(n, 0);
-  int ng = 0, nc = 0, nitems = 0;
+  int ng = 0, nc = 0, nd = 0, nitems = 0;
   uint64_t ntiles = s->len >> T;
   size_t smem = sizeof(double2) << T;
   static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
@@ -696,7 +783,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     bt_prof_end(s);
     BT_CHECK_LAUNCH(s);
     g_fused_passes++;
-    ng = nc = nitems = 0;
+    ng = nc = nd = nitems = 0;
     return BT_OK;
   };
 
@@ -798,6 +885,17 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       }
     }
     if (made_cluster) continue;
+    if (d0.diag && d0.k <= 2) {
+      if (nd >= TILE_MAXD) BT_TRY(flush());
+      if (fill_diag_slot(P.d[nd], d0, local_pos, T) == 0) {
+        P.item[nitems++] = (uint8_t)(TILE_DBASE + nd);
+        nd++;
+        used[i] = 1;
+        g_fused_blocks++;
+        g_fused_flops.store(g_fused_flops.load() + ldexp((double)s->len, -d0.nc) * 6.0);
+        continue;
+      }
+    }
     if (ng >= TILE_MAXG) BT_TRY(flush());
     BT_TRY(fill_gate_slot(P.g[ng], d0, local_pos, T));
     P.item[nitems++] = (uint8_t)ng;
@@ -817,7 +915,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   fuse_blocks(gates, blocks);
   const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   const int lowb = std::min(TILE_LOWB, T);
-  const int maxg = std::max(1, std::min(24, env_int("BT_FUSE_MAX_GATES", 10)));
+  const int maxg = std::max(1, std::min(40, env_int("BT_FUSE_MAX_GATES", 10)));
   const int window = env_int("BT_FUSE_WINDOW", 256);
   const size_t n = blocks.size();
   std::vector<char> done(n, 0);
@@ -855,7 +953,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
         int extra = 0;
         for (int t : need) if (!in_tile[t]) extra++;
         double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
-        if (tile_cnt + extra > T || (int)pass.size() >= 24 || (cost + c > (double)maxg && !pass.empty())) ok = false;
+        if (tile_cnt + extra > T || (int)pass.size() >= 44 || (cost + c > (double)maxg && !pass.empty())) ok = false;
         if (ok) {
           for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
           pass.push_back(&b); done[i] = 1; cost += c;
