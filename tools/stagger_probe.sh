@@ -1,1 +1,1 @@
-for ns in 0 -1 -2; do BT_TILE_STAGGER_NS=$ns PROBE_CFGS="12,0,8" python tools/lib_probe.py | sed "s/^/dbg=$ns /"; done
+for lp in 0 1; do BT_TILE_LOOP=$lp PROBE_CFGS="12,0,10" python tools/lib_probe.py | sed "s/^/loop=$lp /"; done
