@@ -236,8 +236,12 @@ def bench_sharded(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = world.bit_length() - 1
-    n_local = args.shard_qubits
-    N = n_local + g
+    if args.total_qubits > 0:  # strong scaling: fixed total size
+        N = args.total_qubits
+        n_local = N - g
+    else:                      # weak scaling: fixed shard size
+        n_local = args.shard_qubits
+        N = n_local + g
     specs = wl.c5_random(N, args.c5_depth, 31)
     arr = bt.pack_gates(wl.to_ops(bt, specs))
     ngates = len(arr)
@@ -293,7 +297,7 @@ def bench_sharded(args):
         rbytes = (r1[1] - r0[1]) / args.steps
         rms = (r1[2] - r0[2]) / args.steps
         out = {"metric": "gates/s", "value": value, "unit": "gates/s (28-qubit-equivalent: gates x shard amplitudes / 2^28, summed over ranks)", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total_qubits > 0 else "weak", "vs_baseline": None,
                "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
                "config": {"workload": f"C5: {N}-qubit state vector random circuit (depth {args.c5_depth}: random 1q gate per qubit + CNOT/CZ brickwork, seed 31), {ngates} gates, "
                                       f"2^{n_local} amplitudes per GPU", "parallelism": f"{world} shards, top {g} index bits global, qubit remap by peer-memory pull over NVLink",
@@ -384,6 +388,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=28)
     ap.add_argument("--depth", type=int, default=100)
     ap.add_argument("--shard-qubits", type=int, default=31, help="local index bits per GPU for the sharded workload")
+    ap.add_argument("--total-qubits", type=int, default=0, help="> 0: strong scaling of the sharded workload at this total size")
     ap.add_argument("--c5-depth", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
