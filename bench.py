@@ -233,6 +233,7 @@ def bench_sharded(args):
     D = import_module(ge.PKG_NAME + ".dist")
     rank, world, local = D.env_rank_world()
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = world.bit_length() - 1
