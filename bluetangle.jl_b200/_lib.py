@@ -54,6 +54,7 @@ PROTOTYPES = {
     "bt_fusion_flops": [_pd],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],
+    "bt_pool_release": [],
     "bt_sv_n_qubits": [_vp, C.POINTER(_i)],
     "bt_sv_set_basis": [_vp, _u64],
     "bt_sv_set_plus": [_vp],

@@ -60,6 +60,38 @@ static int grid_for(uint64_t n, int block) {
   return (int)std::min<uint64_t>(std::max<uint64_t>(g, 1), cap);
 }
 
+// ---- handle pool -------------------------------------------------------------------------------------------------
+// The reference's shot loops (src/ops.jl:619-630, :671-676) create a fresh zero_state per shot.  Creating a handle costs a
+// stream, events, pinned staging and several cudaMallocs (hundreds of microseconds), which dominates small circuits, so
+// destroyed unsharded handles of up to 64 MiB are parked here and re-used by the next create of the same shape.
+#include <mutex>
+static std::mutex g_pool_mu;
+static std::vector<bt_sv*> g_pool;
+static const size_t POOL_MAX_HANDLES = 16;
+static const uint64_t POOL_MAX_LEN = 1ull << 22;
+
+static bt_sv* pool_take(int n_qubits, int n_local, int64_t n_batch, int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (size_t i = 0; i < g_pool.size(); ++i) {
+    bt_sv* s = g_pool[i];
+    if (s->n_qubits == n_qubits && s->n_local == n_local && s->n_batch == n_batch && s->device == device) {
+      g_pool.erase(g_pool.begin() + i);
+      return s;
+    }
+  }
+  return nullptr;
+}
+
+static void really_destroy(bt_sv* s);
+
+static bool pool_put(bt_sv* s) {
+  if (s->world != 1 || s->is_dm || s->alt || s->len > POOL_MAX_LEN || s->prof_ev) return false;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool.size() >= POOL_MAX_HANDLES) return false;
+  g_pool.push_back(s);
+  return true;
+}
+
 int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_alt, bt_sv** out) {
   if (!out) BT_FAIL(BT_ERR_ARG, "null output handle");
   *out = nullptr;
@@ -69,6 +101,18 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) BT_FAIL(BT_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
+  if (!want_alt && n_local == n_qubits) {
+    int dev = 0;
+    BT_CUDA(cudaGetDevice(&dev));
+    if (bt_sv* r = pool_take(n_qubits, n_local, n_batch, dev)) {
+      r->launches = 0;
+      for (int b = 0; b < 64; ++b) r->phys_of_bit[b] = b;
+      k_set_basis<<<grid_for(r->len, 256), 256, 0, r->stream>>>(r->amp, 1ull << n_local, r->len, 0, 1);
+      BT_CHECK_LAUNCH(r);
+      *out = r;
+      return BT_OK;
+    }
+  }
   bt_sv* s = new bt_sv();
   memset(s, 0, sizeof(*s));
   BT_CUDA(cudaGetDevice(&s->device));
@@ -107,6 +151,19 @@ extern "C" int bt_sv_destroy(bt_sv* s) {
   if (!s) return BT_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
+  if (pool_put(s)) return BT_OK;
+  really_destroy(s);
+  return BT_OK;
+}
+
+extern "C" int bt_pool_release(void) {
+  std::vector<bt_sv*> v;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); v.swap(g_pool); }
+  for (bt_sv* s : v) { cudaSetDevice(s->device); really_destroy(s); }
+  return BT_OK;
+}
+
+static void really_destroy(bt_sv* s) {
   if (s->ipc_opened) {
     for (int r = 0; r < s->world; ++r) {
       if (r == s->rank) continue;
@@ -131,7 +188,6 @@ extern "C" int bt_sv_destroy(bt_sv* s) {
   if (s->prof_ev) { for (cudaEvent_t e : *s->prof_ev) cudaEventDestroy(e); delete s->prof_ev; delete s->prof_cls; }
   cudaStreamDestroy(s->stream);
   delete s;
-  return BT_OK;
 }
 
 int bt_ensure_traj(bt_sv* s) {

@@ -53,6 +53,7 @@ int bt_set_device(int device);
 /* ---- state vector life cycle: zero_state/one_state/plus_state/product_state src/hilbert.jl:835-882 -- */
 int bt_sv_create(int n_qubits, int64_t n_batch, bt_sv** out);     /* on the current device, |0..0> in every trajectory */
 int bt_sv_destroy(bt_sv* s);
+int bt_pool_release(void);                                       /* free the handles bt_sv_destroy parked for re-use (small unsharded states) */
 int bt_sv_n_qubits(const bt_sv* s, int* n);                       /* get_N  src/ops.jl:8 */
 int bt_sv_set_basis(bt_sv* s, uint64_t index);                    /* every trajectory := |index> */
 int bt_sv_set_plus(bt_sv* s);                                     /* plus_state src/hilbert.jl:869 */

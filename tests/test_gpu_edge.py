@@ -125,3 +125,18 @@ def test_three_qubit_and_kraus_ops_inside_op_lists(bt, orc):
             bt.apply(s2, od[5])           # ... unless strict mode asks for the reference's behaviour
     finally:
         bt._lib.check(s2.lib.bt_set_strict(0))
+
+
+def test_handle_pool_reuse_is_clean(bt):
+    """destroyed small handles are parked and re-used (per-shot loops create a zero_state per shot, src/ops.jl:619-630)"""
+    s = bt.plus_state(7)
+    bt.apply(s, bt.Op("MZ", 2), rng=bt.Draws(1))
+    del s
+    t = bt.zero_state(7)
+    want = np.zeros(128, dtype=complex); want[0] = 1
+    assert np.array_equal(t.to_numpy(), want) and t.launch_count() <= 1
+    u = bt.zero_state(7, 3)  # other shape: not the parked handle
+    assert u.to_numpy().shape == (3, 128)
+    del t, u
+    bt._lib.check(bt._lib.load().bt_pool_release())
+    assert np.array_equal(bt.zero_state(7).to_numpy(), want)
