@@ -76,6 +76,7 @@ PROTOTYPES = {
     "bt_sv_rdm1": [_vp, _i, _vp],
     "bt_sv_rdm2": [_vp, _i, _i, _vp],
     "bt_sv_rdm3": [_vp, _i, _vp],
+    "bt_sv_rdm": [_vp, _i, C.POINTER(_i), _vp],
     "bt_sv_norm2": [_vp, _pd],
     "bt_sv_inner": [_vp, _vp, _vp],
     "bt_sv_normalize": [_vp],

@@ -412,6 +412,33 @@ extern "C" int bt_sv_rdm3(const bt_sv* s, int first, bt_c64* out) {
   return BT_OK;
 }
 
+// general form of partial_trace(state, keep_qubits) (src/linalg.jl:83-86) for up to three arbitrary qubits: the kept
+// qubits are ordered by ascending label (first = most significant index bit of the reduced matrix), whatever order they are
+// listed in -- exactly what setdiff(1:N, keep) + the tensor reshape of the reference produce.
+extern "C" int bt_sv_rdm(const bt_sv* s, int k, const int* qubits, bt_c64* out) {
+  BT_TRY(bt_check_sv(s));
+  if (!qubits || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (k < 1 || k > 3) BT_FAIL(BT_ERR_UNSUPPORTED, "device partial_trace keeps 1, 2 or 3 qubits");
+  int q[3];
+  for (int i = 0; i < k; ++i) {
+    q[i] = qubits[i];
+    if (q[i] < 1 || q[i] > s->n_qubits) BT_FAIL(BT_ERR_ARG, "qubit %d out of range", q[i]);
+  }
+  std::sort(q, q + k);
+  for (int i = 0; i + 1 < k; ++i) if (q[i] == q[i + 1]) BT_FAIL(BT_ERR_ARG, "repeated qubit %d", q[i]);
+  int lbs[3];
+  for (int t = 0; t < k; ++t) lbs[t] = s->n_qubits - q[k - 1 - t];  // matrix bit 0 <-> largest label
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(const_cast<bt_sv*>(s), k, lbs));
+  int tb[3];
+  for (int t = 0; t < k; ++t) tb[t] = s->phys_of_bit[lbs[t]];
+  BT_TRY(bt_reduce_rdm(s, k, tb));
+  int D = 1 << k;
+  BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * D * D));
+  BT_TRY(allreduce_host(s, s->h_res, (int)(s->n_batch * D * D)));
+  for (int64_t t = 0; t < s->n_batch; ++t) unpack_rdm(s->h_res + t * D * D, D, out + t * D * D);
+  return BT_OK;
+}
+
 extern "C" int bt_sv_norm2(const bt_sv* s, double* out) {
   BT_TRY(bt_check_sv(s));
   if (!out) BT_FAIL(BT_ERR_ARG, "null output");

@@ -721,12 +721,13 @@ def partial_trace(state: CuState, *keep) -> np.ndarray:
         out = np.empty((state.n_batch, 4, 4), dtype=c128)
         L.check(lib.bt_sv_rdm2(state.h, qs[0], qs[1], L.ptr(out)))
         out = out.transpose(0, 2, 1)
-    elif len(qs) == 3 and qs[1] == qs[0] + 1 and qs[2] == qs[0] + 2:
+    elif len(qs) == 3 and general:
         out = np.empty((state.n_batch, 8, 8), dtype=c128)
-        L.check(lib.bt_sv_rdm3(state.h, qs[0], L.ptr(out)))
+        arr = (C.c_int * 3)(*qs)
+        L.check(lib.bt_sv_rdm(state.h, 3, arr, L.ptr(out)))
         out = out.transpose(0, 2, 1)
     else:
-        raise NotImplementedError("device partial_trace keeps 1, 2 or 3 consecutive qubits")
+        raise NotImplementedError("device partial_trace keeps up to 3 qubits (the reference's general path is O(4^N))")
     return out[0] if state.n_batch == 1 else out
 
 

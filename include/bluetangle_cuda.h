@@ -88,6 +88,7 @@ int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates 
 int bt_sv_rdm1(const bt_sv* s, int qubit, bt_c64* out /* n_batch x 4, column-major 2x2 each */);
 int bt_sv_rdm2(const bt_sv* s, int qubit_a, int qubit_b, bt_c64* out /* n_batch x 16; index 2*b_min + b_max */);
 int bt_sv_rdm3(const bt_sv* s, int first_qubit, bt_c64* out /* n_batch x 64; qubits first..first+2 */);
+int bt_sv_rdm(const bt_sv* s, int k, const int* qubits, bt_c64* out /* n_batch x 4^k */); /* partial_trace(state, keep) linalg.jl:83-86, k <= 3 arbitrary qubits, ascending-label order */
 int bt_sv_norm2(const bt_sv* s, double* out /* n_batch: sum |a|^2 */);
 int bt_sv_inner(const bt_sv* a, const bt_sv* b, bt_c64* out /* n_batch: <a|b>, src/tensor.jl:199 */);
 int bt_sv_normalize(bt_sv* s);

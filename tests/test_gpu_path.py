@@ -65,6 +65,8 @@ def test_partial_trace(bt, orc):
         assert np.max(np.abs(bt.partial_trace(s, [a, b]) - orc.partial_trace_general(v, [a, b]))) < TOL
     for q in range(1, N - 1):
         assert np.max(np.abs(bt.partial_trace(s, [q, q + 1, q + 2]) - orc.partial_trace_general(v, [q, q + 1, q + 2]))) < TOL
+    for trip in [(1, 3, 6), (7, 2, 4), (5, 6, 1)]:
+        assert np.max(np.abs(bt.partial_trace(s, list(trip)) - orc.partial_trace_general(v, list(trip)))) < TOL
 
 
 def test_norm_inner_probs(bt, orc):
