@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __
   const uint32_t tid = threadIdx.x;
   const uint32_t nloc = 1u << T;
   const uint32_t nhi = 1u << (T - lowb);
+  const int dbg = P.stagger_ns < 0 ? -P.stagger_ns : 0;  // measurement aid: 1 = no gates, 2 = no HBM traffic (results invalid)
   for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
     uint64_t o = 0;
     for (int j = lowb; j < T; ++j)
@@ -435,7 +436,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __
     return base;
   };
   auto issue_load = [&](uint64_t base, double2* buf) {
-    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
+    if (dbg != 2)
+      for (uint32_t c = tid; c < nloc; c += TILE_THREADS) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
     __pipeline_commit();
   };
   uint64_t tile = (uint64_t)blockIdx.x * (uint64_t)tiles_per_cta;
@@ -457,11 +459,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __
     }
     __syncthreads();
     double2* sm = smem + ((size_t)cur << T);
-    for (int i = 0; i < P.nitems; ++i) {
-      run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
-      __syncthreads();
-    }
-    for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+    if (dbg != 1)
+      for (int i = 0; i < P.nitems; ++i) {
+        run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
+        __syncthreads();
+      }
+    if (dbg != 2)
+      for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
     if (!have_next) break;
     __syncthreads();  // everyone is done reading this buffer before the next prefetch overwrites it
     tile = next; base = nbase; cur ^= 1;
