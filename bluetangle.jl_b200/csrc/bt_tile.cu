@@ -16,6 +16,7 @@
 // hence the default cap of blocks per pass (BT_FUSE_MAX_GATES) that keeps the kernel near the HBM bound.
 #include "bt_internal.cuh"
 #include <cuda_pipeline_primitives.h>
+#include <cuda.h>   // CUtensorMap (driver types only; the encode function is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <atomic>
 
@@ -95,6 +96,9 @@ struct TileParams {
   int32_t nitems;
   int32_t stagger_ns;   // first-wave CTAs of SM slot r (= blockIdx / #SMs) start r * stagger_ns late: breaks the load/compute lockstep
   int32_t n_sm;
+  int32_t swz_mode;     // 0: TMA-compatible 128-B swizzle, 1: all-digit swizzle
+  int32_t tma_coord_shift[5];  // tensor-copy variant: coordinate k of a tile = (base >> shift[k]) & mask[k]
+  uint32_t tma_coord_mask[5];
   int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
   uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];
@@ -106,6 +110,9 @@ struct TileParams {
 // (slot index bits 0..2 select the 16-byte bank group; they become the XOR of ALL 3-bit digits of the tile index, so a run
 // of 8 lanes is conflict-free whenever the three index bits it varies have distinct residues mod 3)
 __host__ __device__ __forceinline__ uint32_t sw(uint32_t c) { return c ^ ((c >> 3) & 7u) ^ ((c >> 6) & 7u) ^ ((c >> 9) & 7u); }
+// mode 0: bank group = digit0 ^ digit1 only -- exactly the TMA hardware swizzle CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk index
+// XOR 128-byte row index mod 8), used by the tensor-copy variant of the kernel; mode 1: all digits (cp.async variant)
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t c, int mode) { return mode ? sw(c) : (c ^ ((c >> 3) & 7u)); }
 
 __device__ __forceinline__ void cfma2(double2& acc, double2 a, double2 b) {
   acc.x = fma(a.x, b.x, acc.x);
@@ -126,6 +133,7 @@ __device__ __forceinline__ uint32_t thread_slot(const uint32_t* bit_sw, uint32_t
 template <int GI, int NT>
 __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
   const TileGate& G = P.g[GI];
+  const int P_swz = P.swz_mode;
   if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
   // local target bits and the fixed (external) part of the matrix index
   int kl = 0;
@@ -135,14 +143,14 @@ __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restric
 #pragma unroll
   for (int t = 0; t < 2; ++t)
     if (t < G.k) {
-      if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
+      if (G.tloc[t] >= 0) { so[kl] = swz(1u << G.tloc[t], P_swz); tpos[kl] = t; kl++; }
       else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
     }
   const uint32_t ng = nloc >> G.ni;
   const bool active = tid < ng;
   const uint32_t niter = G.niter;
   // slot of this thread's first group; further groups and the partner amplitudes are XOR offsets (sw is linear)
-  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ sw(G.lcmask);
+  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ swz(G.lcmask, P_swz);
   if (G.kind == 0) {
     if (G.k == 2) {
       const double2* m = G.m;
@@ -205,7 +213,7 @@ __device__ __forceinline__ void run_gate(const TileParams& P, double2* __restric
 }
 
 template <int NT>
-__device__ __noinline__ void run_diag(const TileDiag& G, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+__device__ __noinline__ void run_diag(const TileDiag& G, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc, int P_swz) {
   if ((base & G.ext_cmask) != G.ext_cmask) return;  // uniform per CTA
   int kl = 0;
   uint32_t jext = 0;
@@ -214,13 +222,13 @@ __device__ __noinline__ void run_diag(const TileDiag& G, double2* __restrict__ s
 #pragma unroll
   for (int t = 0; t < 2; ++t)
     if (t < G.k) {
-      if (G.tloc[t] >= 0) { so[kl] = sw(1u << G.tloc[t]); tpos[kl] = t; kl++; }
+      if (G.tloc[t] >= 0) { so[kl] = swz(1u << G.tloc[t], P_swz); tpos[kl] = t; kl++; }
       else if ((base >> G.text[t]) & 1ull) jext |= 1u << t;
     }
   const uint32_t ng = nloc >> G.ni;
   if (tid >= ng) return;
   const uint32_t niter = G.niter;
-  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ sw(G.lcmask);
+  const uint32_t s0 = thread_slot(G.bit_sw, tid) ^ swz(G.lcmask, P_swz);
   if (kl == 0) {
     const double2 d = G.m[jext];
     if (!(d.x == 1.0 && d.y == 0.0))
@@ -273,12 +281,13 @@ __device__ __forceinline__ void cl_apply(double2 (&x)[CL_AMPS], const double2* _
 template <int CI, int NT>
 __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __restrict__ sm, uint32_t tid, uint32_t nloc) {
   const TileCluster& Cl = P.cl[CI];
+  const int P_swz = P.swz_mode;
   const uint32_t ng = nloc >> CL_BITS;
   if (tid >= ng) return;
   const uint32_t s0 = thread_slot(Cl.bit_sw, tid);
   uint32_t o[4];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) o[p] = (p < CL_BITS) ? sw(1u << Cl.lp[p]) : 0u;
+  for (int p = 0; p < 4; ++p) o[p] = (p < CL_BITS) ? swz(1u << Cl.lp[p], P_swz) : 0u;
   const uint32_t use = Cl.use;
   uint32_t off[CL_AMPS];
 #pragma unroll
@@ -335,7 +344,7 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
 // constant-bank operand of its DFMA instead of a live register.  (A single run-time-indexed copy was measured 20 % slower.)
 template <int NT>
 __device__ __forceinline__ void run_item(int item, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
-  if (item >= TILE_DBASE) { run_diag<NT>(P.d[item - TILE_DBASE], sm, base, tid, nloc); return; }
+  if (item >= TILE_DBASE) { run_diag<NT>(P.d[item - TILE_DBASE], sm, base, tid, nloc, P.swz_mode); return; }
   switch (item) {
     case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
     case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
@@ -406,6 +415,72 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __res
 
   if (dbg != 2)
     for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
+}
+
+// ---- tensor-copy (TMA) variant ------------------------------------------------------------------------------------------
+// The tile moves between HBM and shared memory with ONE cp.async.bulk.tensor each way instead of 32 cp.async + 32 LDS/STG per
+// thread.  The tile's bit set {0..4} + runs of consecutive higher bits is described as a <= 5-D box of a tensor map over the state:
+// dim 0 = bits 0..2 (128 B, hardware 128-B swizzle == swz mode 0), dim k = the index bits from the start of run k up to the next
+// run, box = the run.  This takes the global traffic off the LSU / L1TEX data pipe that the gates' shared-memory round trips need.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned tile (required by the 128-B swizzle), then the mbarrier
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  double2* sm = reinterpret_cast<double2*>(smem_raw + pad);
+  const int T = P.T, lowb = P.lowb;
+  const uint32_t nloc = 1u << T;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + pad + ((size_t)sizeof(double2) << T));
+  const uint32_t tid = threadIdx.x;
+  uint64_t base = (uint64_t)blockIdx.x << lowb;
+  for (int j = lowb; j < T; ++j) {
+    int b = P.tbits[j];
+    base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
+  }
+  int32_t c1 = (int32_t)((base >> P.tma_coord_shift[1]) & P.tma_coord_mask[1]);
+  int32_t c2 = (int32_t)((base >> P.tma_coord_shift[2]) & P.tma_coord_mask[2]);
+  int32_t c3 = (int32_t)((base >> P.tma_coord_shift[3]) & P.tma_coord_mask[3]);
+  int32_t c4 = (int32_t)((base >> P.tma_coord_shift[4]) & P.tma_coord_mask[4]);
+  const uint32_t mb = smem_u32(mbar), dst = smem_u32(sm);
+  const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(sizeof(double2) << T)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+        "l"(tm), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mb)
+        : "memory");
+  }
+  // wait for the tile (phase 0); bounded spin so that a descriptor mistake traps instead of hanging the GPU
+  {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+      if (spin > (1u << 22)) __trap();
+    }
+  }
+
+  for (int i = 0; i < P.nitems; ++i) {
+    run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
+    __syncthreads();
+  }
+
+  // generic-proxy writes -> visible to the async proxy, then one bulk tensor store
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2),
+                 "r"(c3), "r"(c4), "r"(dst)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until it has been read
+  }
 }
 
 // Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
@@ -637,19 +712,20 @@ static void needed_bits(const GateDesc& d, std::vector<int>& out) {
 // Group enumeration for an item whose fixed tile positions are `fixed` (targets + local controls): group-index bit k walks
 // free tile position order[k].  The first three are chosen with distinct residues mod 3 so that 8 consecutive lanes hit 8
 // distinct bank groups under sw(); thread bits come first, loop-iteration bits after.
-static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bit_sw, uint32_t* iter_sw, int iter_cap, uint32_t* niter_out) {
+static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bit_sw, uint32_t* iter_sw, int iter_cap, uint32_t* niter_out, int mode) {
   int order[TILE_TMAX], n = 0;
   bool used[TILE_TMAX] = {false};
   bool res_taken[3] = {false, false, false};
+  const int plim = mode ? T : std::min(T, 6);  // mode 0: only positions below 6 reach the bank-group bits
   for (int round = 0; round < 3; ++round)
-    for (int p = 0; p < T; ++p)
+    for (int p = 0; p < plim; ++p)
       if (!((fixed_mask >> p) & 1u) && !used[p] && !res_taken[p % 3]) { order[n++] = p; used[p] = true; res_taken[p % 3] = true; break; }
   for (int p = 0; p < T; ++p)
     if (!((fixed_mask >> p) & 1u) && !used[p]) { order[n++] = p; used[p] = true; }
   if (n != T - nfixed) return -1;
   int tbits = 0;
   while ((1 << tbits) < TILE_THREADS) ++tbits;
-  for (int k = 0; k < 8; ++k) bit_sw[k] = (k < n && k < tbits) ? sw(1u << order[k]) : 0u;
+  for (int k = 0; k < 8; ++k) bit_sw[k] = (k < n && k < tbits) ? swz(1u << order[k], mode) : 0u;
   uint32_t ngroups = 1u << n;
   uint32_t niter = ngroups > (uint32_t)TILE_THREADS ? ngroups / TILE_THREADS : 1u;
   if ((int)niter > iter_cap) return -1;
@@ -657,7 +733,7 @@ static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bi
     uint32_t c = 0;
     for (int k = tbits; k < n; ++k)
       if ((it >> (k - tbits)) & 1u) c |= 1u << order[k];
-    iter_sw[it] = sw(c);
+    iter_sw[it] = swz(c, mode);
   }
   *niter_out = niter;
   return 0;
@@ -665,7 +741,7 @@ static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bi
 
 static inline bool cluster_eligible(const GateDesc& d) { return !d.diag && d.k == 2 && d.nc == 0; }
 
-static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, int T) {
+static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, int T, int mode) {
   G.kind = d.diag ? 1 : 0;
   G.k = d.k;
   G.lcmask = 0; G.ext_cmask = 0;
@@ -687,12 +763,12 @@ static int fill_gate_slot(TileGate& G, const GateDesc& d, const int* local_pos, 
   for (int lp : ins) fixed |= 1u << lp;
   int cntm = d.diag ? (1 << d.k) : (1 << (2 * d.k));
   for (int i = 0; i < cntm; ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
-  if (build_group_walk(T, fixed, G.ni, G.bit_sw, G.iter_sw, 32, &G.niter) != 0) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
+  if (build_group_walk(T, fixed, G.ni, G.bit_sw, G.iter_sw, 32, &G.niter, mode) != 0) BT_FAIL(BT_ERR_ARG, "internal: tile gate loop too long");
   return BT_OK;
 }
 
 // diagonal gate -> run-time-indexed slot; returns 1 if it does not fit a TileDiag (then it takes a specialised gate slot)
-static int fill_diag_slot(TileDiag& G, const GateDesc& d, const int* local_pos, int T) {
+static int fill_diag_slot(TileDiag& G, const GateDesc& d, const int* local_pos, int T, int mode) {
   if (!d.diag || d.k > 2) return 1;
   G.k = d.k;
   G.lcmask = 0; G.ext_cmask = 0;
@@ -711,7 +787,7 @@ static int fill_diag_slot(TileDiag& G, const GateDesc& d, const int* local_pos, 
   }
   G.ni = ni;
   for (int i = 0; i < (1 << d.k); ++i) G.m[i] = make_double2(d.m[i].real(), d.m[i].imag());
-  if (build_group_walk(T, fixed, ni, G.bit_sw, G.iter_sw, 16, &G.niter) != 0) return 1;
+  if (build_group_walk(T, fixed, ni, G.bit_sw, G.iter_sw, 16, &G.niter, mode) != 0) return 1;
   return 0;
 }
 
@@ -722,6 +798,67 @@ static const int CL_SEED2 = 2;
 static const int CL_PAIR[5][2] = {{0, 1}, {1, 2}, {0, 1}, {0, 1}, {0, 1}};
 static const int CL_SEED2 = 1;
 #endif
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+    else cudaGetLastError();
+  }
+  return fn;
+}
+
+// Describe the tile {in[b]} as a box of a <= 5-D tensor over the local amplitudes.  Returns false when the bit set needs more
+// than four runs (the cp.async kernel handles those).
+static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, TileParams& P) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc || T < 8) return false;
+  for (int b = 0; b < 5; ++b) if (!in[b]) return false;
+  int total_bits = 0;
+  while ((1ull << total_bits) < s->len) ++total_bits;
+  if ((1ull << total_bits) != s->len) return false;  // ragged batches stay on the cp.async path
+  // runs of consecutive tile bits from bit 3 up, each at most 8 bits long
+  int run_start[8], run_len[8], nr = 0;
+  for (int b = 3; b < s->n_local;) {
+    if (!in[b]) { ++b; continue; }
+    int e = b;
+    while (e < s->n_local && in[e] && e - b < 8) ++e;
+    if (nr >= 4) return false;
+    run_start[nr] = b; run_len[nr] = e - b; nr++;
+    b = e;
+  }
+  if (nr == 0 || run_start[0] != 3) return false;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  gdim[0] = 16; box[0] = 16;  // 8 amplitudes = 16 doubles = 128 B
+  for (int k = 0; k < 5; ++k) { P.tma_coord_shift[k] = 0; P.tma_coord_mask[k] = 0; }
+  for (int k = 1; k <= 4; ++k) {
+    if (k <= nr) {
+      int st = run_start[k - 1];
+      int en = (k < nr) ? run_start[k] : total_bits;
+      if (en - st > 32) return false;
+      gdim[k] = 1ull << (en - st);
+      gstride[k - 1] = (cuuint64_t)16 << st;
+      box[k] = 1u << run_len[k - 1];
+      P.tma_coord_shift[k] = st;
+      P.tma_coord_mask[k] = (en - st >= 32) ? 0xffffffffu : ((1u << (en - st)) - 1u);
+      if (gdim[k] > (1ull << 31)) return false;  // coordinates are signed 32-bit
+    } else {
+      gdim[k] = 1; box[k] = 1;
+      gstride[k - 1] = (cuuint64_t)16 << total_bits;  // never stepped
+    }
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)s->amp, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
   if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
@@ -742,6 +879,9 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   TileParams P;
   memset(&P, 0, sizeof(P));
   P.T = T; P.lowb = lowb;
+  alignas(64) CUtensorMap tmap;
+  const bool use_tma = env_int("BT_TILE_TMA", 1) != 0 && !dbuf && build_tensor_map(s, in, T, &tmap, P);
+  P.swz_mode = use_tma ? 0 : 1;
   int local_pos[64];
   for (int b = 0; b < 64; ++b) local_pos[b] = -1;
   int j = 0;
@@ -767,6 +907,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
   if (!attr_set[s->device & 63]) {
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set[s->device & 63] = true;
   }
@@ -778,7 +919,9 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     P.stagger_ns = env_int("BT_TILE_STAGGER_NS", 0);
     P.n_sm = nsm;
     bt_prof_begin(s, BT_CLS_TILE);
-    if (dbuf) {
+    if (use_tma) {
+      k_tile_tma<<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
+    } else if (dbuf) {
       uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
       k_tile_db<<<(unsigned)nct, TILE_THREADS, 2 * smem, s->stream>>>(s->amp, ntiles, tiles_per_cta, P);
     } else {
@@ -872,7 +1015,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         uint32_t fixed = 0;
         for (int p = 0; p < CL_BITS; ++p) fixed |= 1u << Cl.lp[p];
         Cl.use = best.use;
-        if (build_group_walk(T, fixed, CL_BITS, Cl.bit_sw, Cl.iter_sw, 8, &Cl.niter) != 0) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
+        if (build_group_walk(T, fixed, CL_BITS, Cl.bit_sw, Cl.iter_sw, 8, &Cl.niter, P.swz_mode) != 0) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
         for (int mI = 0; mI < best.nm; ++mI) {
           const GateDesc& h = pass[best.member[mI]]->desc;
           cplx mm[16];
@@ -891,7 +1034,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     if (made_cluster) continue;
     if (d0.diag && d0.k <= 2) {
       if (nd >= TILE_MAXD) BT_TRY(flush());
-      if (fill_diag_slot(P.d[nd], d0, local_pos, T) == 0) {
+      if (fill_diag_slot(P.d[nd], d0, local_pos, T, P.swz_mode) == 0) {
         P.item[nitems++] = (uint8_t)(TILE_DBASE + nd);
         nd++;
         used[i] = 1;
@@ -901,7 +1044,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       }
     }
     if (ng >= TILE_MAXG) BT_TRY(flush());
-    BT_TRY(fill_gate_slot(P.g[ng], d0, local_pos, T));
+    BT_TRY(fill_gate_slot(P.g[ng], d0, local_pos, T, P.swz_mode));
     P.item[nitems++] = (uint8_t)ng;
     ng++;
     used[i] = 1;
