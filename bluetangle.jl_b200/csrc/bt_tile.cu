@@ -19,6 +19,7 @@
 #include <cuda.h>   // CUtensorMap (driver types only; the encode function is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <atomic>
+#include <algorithm>
 
 #ifndef TILE_MAXG
 #define TILE_MAXG 8      // single-gate slots per pass
@@ -28,7 +29,13 @@
 #endif
 #define TILE_MAXD 32     // diagonal-gate slots per pass (one run-time-indexed code copy: they carry <= 4 matrix entries)
 #define TILE_DBASE 16    // item ids >= TILE_DBASE are diagonal slots
-#define TILE_MAXITEMS (TILE_MAXG + TILE_MAXC + TILE_MAXD)
+#define TILE_PBASE 48    // item ids >= TILE_PBASE are register programs
+#define TILE_MAXP 8      // register programs per pass
+#define TILE_MAXITEMS (TILE_PBASE + TILE_MAXP)
+#define PROG_BITS 4      // a register program holds the 2^4 amplitudes spanned by 4 tile bits in each thread
+#define PROG_AMPS (1 << PROG_BITS)
+#define PROG_MAXOPS 40
+#define PROG_MAXCOEF 160 // doubles
 #define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
 #define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
 #define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
@@ -90,6 +97,28 @@ struct TileCluster {
   double2 m[CL_SLOTS][16];  // row-major 4x4, matrix bit 0 <-> lower position of the slot's pair
 };
 
+// A register program: each thread loads the 16 amplitudes spanned by 4 tile bits (positions 0..3) and runs a list of
+// STRUCTURED micro-ops on them before writing back -- one shared-memory round trip for e.g. two brickwork layers on 4 qubits.
+// The micro-ops keep the gates' structure instead of multiplying it away into dense 4x4 blocks (16 FP64 ops / amplitude):
+//   U1_GEN  general 2x2                        8 ops / amplitude      U1_DIAG  diag(d0, d1)        4
+//   U1_REAL real 2x2 (H, RY, X, Z ...)         4                      U1_PHASE diag(1, d)          2
+//   U1_RXL  real diagonal, imaginary off-diag  4 (RX, Y ...)          CX       register moves      0
+//   CPHASE  phase on |11> (CZ, CP)             1
+// op word: site | (first coefficient << 8); the site fixes kind and cluster positions so that register indices are static.
+enum { PK_GEN = 0, PK_REAL = 1, PK_RXL = 2, PK_DIAG = 3, PK_PHASE = 4, PK_CX = 5, PK_CPHASE = 6 };
+#define PROG_SITE_U1(kind, p) ((kind) * 4 + (p))                 // 0..19
+#define PROG_SITE_CX(pc, pt) (20 + (pc) * 4 + (pt))              // 20..35 (pc != pt)
+#define PROG_SITE_CPHASE(pa, pb) (36 + (pa) * 4 + (pb))          // 36..51 (pa < pb)
+struct TileProg {
+  int32_t lp[PROG_BITS];  // tile-local bit of cluster position p
+  uint32_t bit_sw[8];
+  uint32_t niter;
+  uint32_t nops;
+  uint32_t iter_sw[8];
+  uint16_t op[PROG_MAXOPS];
+  double coef[PROG_MAXCOEF];
+};
+
 struct TileParams {
   int32_t T;            // tile bits
   int32_t lowb;         // min(TILE_LOWB, T)
@@ -104,7 +133,10 @@ struct TileParams {
   TileGate g[TILE_MAXG];
   TileCluster cl[TILE_MAXC];
   TileDiag d[TILE_MAXD];
+  TileProg pr[TILE_MAXP];
 };
+
+static_assert(sizeof(TileParams) + 128 <= 32764, "kernel parameters (tensor map + TileParams) must fit the 32 KB parameter space");
 
 // XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
 // (slot index bits 0..2 select the 16-byte bank group; they become the XOR of ALL 3-bit digits of the tile index, so a run
@@ -340,10 +372,150 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
   }
 }
 
+// ---- register programs ------------------------------------------------------------------------------------------------
+// In-place primitives written as PTX with tied operands: every micro-op leaves amplitude j in the registers it found it in,
+// so the run-time op loop carries x[] without the ~64 register moves per op that the compiler's phi resolution otherwise adds.
+// (a, b) <- (c0 a + c1 b, c2 a + c3 b)
+__device__ __forceinline__ void ip_real(double& a, double& b, double c0, double c1, double c2, double c3) {
+  asm("{\n\t.reg .f64 t;\n\tmul.f64 t, %0, %4;\n\tmul.f64 %0, %0, %2;\n\tfma.rn.f64 %0, %1, %3, %0;\n\tfma.rn.f64 %1, %1, %5, t;\n\t}"
+      : "+d"(a), "+d"(b)
+      : "d"(c0), "d"(c1), "d"(c2), "d"(c3));
+}
+// (x + i y) <- (dr + i di)(x + i y); ndi = -di
+__device__ __forceinline__ void ip_cmul(double& x, double& y, double dr, double di, double ndi) {
+  asm("{\n\t.reg .f64 t;\n\tmul.f64 t, %0, %3;\n\tmul.f64 %0, %0, %2;\n\tfma.rn.f64 %0, %1, %4, %0;\n\tfma.rn.f64 %1, %1, %2, t;\n\t}"
+      : "+d"(x), "+d"(y)
+      : "d"(dr), "d"(di), "d"(ndi));
+}
+// general complex 2x2 on the pair (a, b); c = re/im of m00, m01, m10, m11; n = -im of the same
+__device__ __forceinline__ void ip_gen(double2& a, double2& b, const double (&c)[8], const double (&n)[4]) {
+  asm("{\n\t.reg .f64 t1, t2, u;\n\t"
+      "mul.f64 t1, %0, %8;\n\tfma.rn.f64 t1, %1, %14, t1;\n\tfma.rn.f64 t1, %2, %10, t1;\n\tfma.rn.f64 t1, %3, %15, t1;\n\t"
+      "mul.f64 t2, %1, %8;\n\tfma.rn.f64 t2, %0, %9, t2;\n\tfma.rn.f64 t2, %3, %10, t2;\n\tfma.rn.f64 t2, %2, %11, t2;\n\t"
+      "mul.f64 u, %0, %4;\n\tfma.rn.f64 u, %1, %12, u;\n\tfma.rn.f64 u, %2, %6, u;\n\tfma.rn.f64 u, %3, %13, u;\n\t"
+      "mul.f64 %1, %1, %4;\n\tfma.rn.f64 %1, %0, %5, %1;\n\tfma.rn.f64 %1, %3, %6, %1;\n\tfma.rn.f64 %1, %2, %7, %1;\n\t"
+      "mov.f64 %0, u;\n\tmov.f64 %2, t1;\n\tmov.f64 %3, t2;\n\t}"
+      : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y)
+      : "d"(c[0]), "d"(c[1]), "d"(c[2]), "d"(c[3]), "d"(c[4]), "d"(c[5]), "d"(c[6]), "d"(c[7]), "d"(n[0]), "d"(n[1]), "d"(n[2]), "d"(n[3]));
+}
+
+// in-place exchange (XOR swap: a register-renaming swap would make the op loop shuffle all 64 data registers every iteration)
+__device__ __forceinline__ void ip_swap(double& a, double& b) {
+  asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, %0;\n\tmov.b64 q, %1;\n\txor.b64 p, p, q;\n\txor.b64 q, q, p;\n\txor.b64 p, p, q;\n\tmov.b64 %0, p;\n\tmov.b64 %1, q;\n\t}"
+      : "+d"(a), "+d"(b));
+}
+
+template <int KIND, int PQ>
+__device__ __forceinline__ void prog_u1(double2 (&x)[PROG_AMPS], const double* __restrict__ cc) {
+  if (KIND == PK_GEN) {  // cc = re/im of m00, m01, m10, m11
+    const double c[8] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], cc[7]};
+    const double n[4] = {-cc[1], -cc[3], -cc[5], -cc[7]};
+#pragma unroll
+    for (int r = 0; r < PROG_AMPS / 2; ++r) {
+      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
+      ip_gen(x[i0], x[i1], c, n);
+    }
+  } else if (KIND == PK_REAL) {  // cc = m00, m01, m10, m11 (real)
+    const double c0 = cc[0], c1 = cc[1], c2 = cc[2], c3 = cc[3];
+#pragma unroll
+    for (int r = 0; r < PROG_AMPS / 2; ++r) {
+      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
+      ip_real(x[i0].x, x[i1].x, c0, c1, c2, c3);
+      ip_real(x[i0].y, x[i1].y, c0, c1, c2, c3);
+    }
+  } else if (KIND == PK_RXL) {  // cc = m00, Im m01, Im m10, m11: a' = m00 a + i s01 b, b' = i s10 a + m11 b
+    const double c0 = cc[0], s01 = cc[1], s10 = cc[2], c3 = cc[3], ns01 = -s01, ns10 = -s10;
+#pragma unroll
+    for (int r = 0; r < PROG_AMPS / 2; ++r) {
+      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
+      ip_real(x[i0].x, x[i1].y, c0, ns01, s10, c3);
+      ip_real(x[i0].y, x[i1].x, c0, s01, ns10, c3);
+    }
+  } else if (KIND == PK_DIAG) {  // cc = re/im of d0, d1
+    const double d0r = cc[0], d0i = cc[1], d1r = cc[2], d1i = cc[3], nd0i = -d0i, nd1i = -d1i;
+#pragma unroll
+    for (int r = 0; r < PROG_AMPS / 2; ++r) {
+      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
+      ip_cmul(x[i0].x, x[i0].y, d0r, d0i, nd0i);
+      ip_cmul(x[i1].x, x[i1].y, d1r, d1i, nd1i);
+    }
+  } else {  // PK_PHASE: cc = re/im of d
+    const double dr = cc[0], di = cc[1], ndi = -di;
+#pragma unroll
+    for (int r = 0; r < PROG_AMPS / 2; ++r) {
+      const int i1 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)) | (1 << PQ);
+      ip_cmul(x[i1].x, x[i1].y, dr, di, ndi);
+    }
+  }
+}
+
+template <int PC, int PT>
+__device__ __forceinline__ void prog_cx(double2 (&x)[PROG_AMPS]) {
+#pragma unroll
+  for (int i = 0; i < PROG_AMPS; ++i)
+    if (((i >> PC) & 1) && !((i >> PT) & 1)) {
+      ip_swap(x[i].x, x[i | (1 << PT)].x);
+      ip_swap(x[i].y, x[i | (1 << PT)].y);
+    }
+}
+
+template <int PA, int PB>
+__device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const double* __restrict__ c) {
+#pragma unroll
+  for (int i = 0; i < PROG_AMPS; ++i)
+    if (((i >> PA) & 1) && ((i >> PB) & 1)) ip_cmul(x[i].x, x[i].y, c[0], c[1], -c[1]);
+}
+
+#define PROG_CASE_U1(kind)                                                   \
+  case PROG_SITE_U1(kind, 0): prog_u1<kind, 0>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 1): prog_u1<kind, 1>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 2): prog_u1<kind, 2>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 3): prog_u1<kind, 3>(x, c); break;
+#define PROG_CASE_CX(a, b) case PROG_SITE_CX(a, b): prog_cx<a, b>(x); break;
+#define PROG_CASE_CP(a, b) case PROG_SITE_CPHASE(a, b): prog_cphase<a, b>(x, c); break;
+
+template <int NT>
+__device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* __restrict__ sm, uint32_t tid, uint32_t nloc) {
+  const TileProg& G = P.pr[pi];
+  const int P_swz = P.swz_mode;
+  const uint32_t ng = nloc >> PROG_BITS;
+  if (tid >= ng) return;
+  const uint32_t s0 = thread_slot(G.bit_sw, tid);
+  const uint32_t o0 = swz(1u << G.lp[0], P_swz), o1 = swz(1u << G.lp[1], P_swz), o2 = swz(1u << G.lp[2], P_swz), o3 = swz(1u << G.lp[3], P_swz);
+  const uint32_t nops = G.nops;
+  for (uint32_t it = 0; it < G.niter; ++it) {
+    const uint32_t b = s0 ^ G.iter_sw[it];
+    double2 x[PROG_AMPS];
+#pragma unroll
+    for (int j = 0; j < PROG_AMPS; ++j) x[j] = sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)];
+    for (uint32_t k = 0; k < nops; ++k) {
+      const uint32_t op = G.op[k];
+      const double* __restrict__ c = G.coef + (op >> 8);
+      switch (op & 0xffu) {
+        PROG_CASE_U1(PK_GEN)
+        PROG_CASE_U1(PK_REAL)
+        PROG_CASE_U1(PK_RXL)
+        PROG_CASE_U1(PK_DIAG)
+        PROG_CASE_U1(PK_PHASE)
+        PROG_CASE_CX(0, 1) PROG_CASE_CX(0, 2) PROG_CASE_CX(0, 3)
+        PROG_CASE_CX(1, 0) PROG_CASE_CX(1, 2) PROG_CASE_CX(1, 3)
+        PROG_CASE_CX(2, 0) PROG_CASE_CX(2, 1) PROG_CASE_CX(2, 3)
+        PROG_CASE_CX(3, 0) PROG_CASE_CX(3, 1) PROG_CASE_CX(3, 2)
+        PROG_CASE_CP(0, 1) PROG_CASE_CP(0, 2) PROG_CASE_CP(0, 3)
+        PROG_CASE_CP(1, 2) PROG_CASE_CP(1, 3) PROG_CASE_CP(2, 3)
+        default: break;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PROG_AMPS; ++j) sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)] = x[j];
+  }
+}
+
 // one code copy per slot: the slot index is a compile-time constant inside, so every matrix element is a uniform-register /
 // constant-bank operand of its DFMA instead of a live register.  (A single run-time-indexed copy was measured 20 % slower.)
 template <int NT>
 __device__ __forceinline__ void run_item(int item, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
+  if (item >= TILE_PBASE) { run_prog<NT>(P, item - TILE_PBASE, sm, tid, nloc); return; }
   if (item >= TILE_DBASE) { run_diag<NT>(P.d[item - TILE_DBASE], sm, base, tid, nloc, P.swz_mode); return; }
   switch (item) {
     case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
@@ -550,7 +722,123 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __
 // ---- host: fusion ------------------------------------------------------------------------------------------------------
 namespace {
 
+// structured micro-op (see TileProg): the gate as written, before it is multiplied into a dense block
+struct MOp {
+  int kind;          // PK_*
+  int b[2];          // physical bits: U1 -> b[0]; CX -> control b[0], target b[1]; CPHASE -> the pair
+  int ncoef;
+  double c[8];
+  double cost;       // FP64 instructions per amplitude
+  double flops;      // FP64 flops per amplitude (FMA = 2)
+};
+
+static void mop_finish(MOp& o) {
+  static const int ncoef[7] = {8, 4, 4, 4, 2, 0, 2};
+  static const double cost[7] = {8, 4, 4, 4, 2, 0.5, 1};
+  static const double flops[7] = {14, 6, 6, 6, 3, 0, 1.5};
+  o.ncoef = ncoef[o.kind]; o.cost = cost[o.kind]; o.flops = flops[o.kind];
+}
+
+// classify a 2x2 (row-major) on physical bit `bit`; returns false for the identity (nothing to do)
+static bool mop_from_2x2(const cplx* m, int bit, MOp& o) {
+  o.b[0] = bit; o.b[1] = -1;
+  const cplx z(0, 0);
+  if (m[1] == z && m[2] == z) {
+    if (m[0] == cplx(1, 0)) {
+      if (m[3] == cplx(1, 0)) return false;
+      o.kind = PK_PHASE; o.c[0] = m[3].real(); o.c[1] = m[3].imag();
+    } else {
+      o.kind = PK_DIAG; o.c[0] = m[0].real(); o.c[1] = m[0].imag(); o.c[2] = m[3].real(); o.c[3] = m[3].imag();
+    }
+  } else if (m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0) {
+    o.kind = PK_REAL; for (int i = 0; i < 4; ++i) o.c[i] = m[i].real();
+  } else if (m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0) {
+    o.kind = PK_RXL; o.c[0] = m[0].real(); o.c[1] = m[1].imag(); o.c[2] = m[2].imag(); o.c[3] = m[3].real();
+  } else {
+    o.kind = PK_GEN; for (int i = 0; i < 4; ++i) { o.c[2 * i] = m[i].real(); o.c[2 * i + 1] = m[i].imag(); }
+  }
+  mop_finish(o);
+  return true;
+}
+
+static void mop_to_2x2(const MOp& o, cplx* m) {
+  const cplx z(0, 0);
+  switch (o.kind) {
+    case PK_GEN: for (int i = 0; i < 4; ++i) m[i] = cplx(o.c[2 * i], o.c[2 * i + 1]); break;
+    case PK_REAL: for (int i = 0; i < 4; ++i) m[i] = cplx(o.c[i], 0); break;
+    case PK_RXL: m[0] = cplx(o.c[0], 0); m[1] = cplx(0, o.c[1]); m[2] = cplx(0, o.c[2]); m[3] = cplx(o.c[3], 0); break;
+    case PK_DIAG: m[0] = cplx(o.c[0], o.c[1]); m[1] = z; m[2] = z; m[3] = cplx(o.c[2], o.c[3]); break;
+    default: m[0] = cplx(1, 0); m[1] = z; m[2] = z; m[3] = cplx(o.c[0], o.c[1]); break;  // PK_PHASE
+  }
+}
+
+// structured form of one canonical gate; `none` = identity.  false: no structured form (the block goes dense).
+static bool mop_classify(const GateDesc& g, MOp& o, bool* none) {
+  *none = false;
+  if (g.k == 1 && g.nc == 0) {
+    cplx m[4];
+    if (g.diag) { m[0] = g.m[0]; m[1] = m[2] = cplx(0, 0); m[3] = g.m[1]; }
+    else for (int i = 0; i < 4; ++i) m[i] = g.m[i];
+    if (!mop_from_2x2(m, g.tb[0], o)) *none = true;
+    return true;
+  }
+  if (g.k == 0 && g.nc == 1) {
+    cplx m[4] = {cplx(1, 0), cplx(0, 0), cplx(0, 0), g.m[0]};
+    if (!mop_from_2x2(m, g.cb[0], o)) *none = true;
+    return true;
+  }
+  if (g.k == 0 && g.nc == 2) {
+    if (g.m[0] == cplx(1, 0)) { *none = true; return true; }
+    o.kind = PK_CPHASE; o.b[0] = g.cb[0]; o.b[1] = g.cb[1]; o.c[0] = g.m[0].real(); o.c[1] = g.m[0].imag();
+    mop_finish(o);
+    return true;
+  }
+  if (g.k == 1 && g.nc == 1 && !g.diag && g.m[0] == cplx(0, 0) && g.m[3] == cplx(0, 0) && g.m[1] == cplx(1, 0) && g.m[2] == cplx(1, 0)) {
+    o.kind = PK_CX; o.b[0] = g.cb[0]; o.b[1] = g.tb[0];
+    mop_finish(o);
+    return true;
+  }
+  return false;
+}
+
+static void matmul2(const cplx* A, const cplx* B, cplx* C) {
+  cplx t[4] = {A[0] * B[0] + A[1] * B[2], A[0] * B[1] + A[1] * B[3], A[2] * B[0] + A[3] * B[2], A[2] * B[1] + A[3] * B[3]};
+  for (int i = 0; i < 4; ++i) C[i] = t[i];
+}
+
+// append `o` to a block's micro-op list, merging it into the last op on its bit(s) when that keeps the structure
+static void mop_append(std::vector<MOp>& prog, const MOp& o) {
+  const bool one = o.kind <= PK_PHASE;
+  for (int i = (int)prog.size() - 1; i >= 0; --i) {
+    MOp& q = prog[i];
+    const bool q_one = q.kind <= PK_PHASE;
+    bool touches = false;
+    for (int a = 0; a < (one ? 1 : 2); ++a)
+      for (int b = 0; b < (q_one ? 1 : 2); ++b)
+        if (o.b[a] == q.b[b]) touches = true;
+    if (!touches) continue;
+    if (one && q_one) {
+      cplx A[4], B[4], C[4];
+      mop_to_2x2(o, A); mop_to_2x2(q, B);
+      matmul2(A, B, C);
+      MOp r;
+      if (mop_from_2x2(C, o.b[0], r)) q = r; else prog.erase(prog.begin() + i);
+      return;
+    }
+    if (o.kind == PK_CPHASE && q.kind == PK_CPHASE && ((o.b[0] == q.b[0] && o.b[1] == q.b[1]) || (o.b[0] == q.b[1] && o.b[1] == q.b[0]))) {
+      cplx d = cplx(o.c[0], o.c[1]) * cplx(q.c[0], q.c[1]);
+      q.c[0] = d.real(); q.c[1] = d.imag();
+      return;
+    }
+    break;
+  }
+  prog.push_back(o);
+}
+
 struct Block {
+  std::vector<MOp> prog;  // structured form (valid when sok)
+  bool sok = false;       // the structured form exists and is cheaper than the dense block
+  double scost = 0.0, sflops = 0.0;
   int nb;            // number of bits (1 or 2 for fusable blocks; >2 => opaque)
   int bits[2];       // physical bits; matrix index bit t <-> bits[t]
   cplx m[16];        // row-major dense (1<<nb)^2
@@ -623,6 +911,7 @@ static int env_int(const char* name, int dflt) {
 
 static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& blocks) {
   std::vector<int> last(64, -1);  // last block index touching a physical bit
+  const bool use_prog = env_int("BT_TILE_PROGS", 1) != 0;
   for (size_t gi = 0; gi < gates.size(); ++gi) {
     const GateDesc& g = gates[gi];
     int nb, bits[2];
@@ -641,6 +930,9 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
       for (int t : b.touch) last[t] = (int)blocks.size() - 1;
       continue;
     }
+    MOp mop;
+    bool mnone = false;
+    const bool mok = mop_classify(g, mop, &mnone);
     if (nb == 1) {
       int lb = last[bits[0]];
       if (lb >= 0 && !blocks[lb].opaque) {
@@ -652,9 +944,12 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
           matmul(4, e, B.m, B.m);
         }
         B.ngates++;
+        if (B.sok && mok) { if (!mnone) mop_append(B.prog, mop); } else B.sok = false;
         continue;
       }
       Block b; b.nb = 1; b.bits[0] = bits[0]; b.opaque = false; b.ngates = 1;
+      b.sok = mok;
+      if (mok && !mnone) b.prog.push_back(mop);
       for (int i = 0; i < 4; ++i) b.m[i] = m[i];
       b.touch.push_back(bits[0]);
       blocks.push_back(b);
@@ -668,9 +963,12 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
       if (B.bits[0] != bits[0]) swap_bits(m);
       matmul(4, m, B.m, B.m);
       B.ngates++;
+      if (B.sok && mok) { if (!mnone) mop_append(B.prog, mop); } else B.sok = false;
       continue;
     }
     Block b; b.nb = 2; b.bits[0] = bits[0]; b.bits[1] = bits[1]; b.opaque = false; b.ngates = 1;
+    b.sok = mok;
+    if (mok && !mnone) b.prog.push_back(mop);
     for (int i = 0; i < 16; ++i) b.m[i] = m[i];
     // absorb pending pure 1-bit blocks that are the last thing on either bit
     for (int t = 0; t < 2; ++t) {
@@ -680,6 +978,8 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
         embed1(blocks[lb].m, t, e);
         matmul(4, b.m, e, b.m);
         b.ngates += blocks[lb].ngates;
+        if (b.sok && blocks[lb].sok) b.prog.insert(b.prog.begin(), blocks[lb].prog.begin(), blocks[lb].prog.end());
+        else b.sok = false;
         blocks[lb].nb = -1;  // tombstone
       }
     }
@@ -693,7 +993,14 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
   out.reserve(blocks.size());
   for (Block& b : blocks) {
     if (b.nb == -1) continue;
-    if (!b.opaque) bt_canonicalize(b.nb, b.bits, b.m, 0, nullptr, &b.desc);
+    if (!b.opaque) {
+      bt_canonicalize(b.nb, b.bits, b.m, 0, nullptr, &b.desc);
+      b.scost = b.sflops = 0.0;
+      for (const MOp& o : b.prog) { b.scost += o.cost; b.sflops += o.flops; }
+      // keep the structured form only when it is cheaper than the dense block and the dense form is not already diagonal
+      const double dense_cost = b.desc.diag ? 4.0 : (b.desc.k == 2 ? 16.0 : 8.0);
+      if (!use_prog || b.prog.empty() || b.scost >= dense_cost || (int)b.prog.size() > 12) b.sok = false;
+    }
     out.push_back(b);
   }
   blocks.swap(out);
@@ -901,7 +1208,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   }
   const size_t n = pass.size();
   std::vector<char> used(n, 0);
-  int ng = 0, nc = 0, nd = 0, nitems = 0;
+  int ng = 0, nc = 0, nd = 0, np = 0, nitems = 0;
   uint64_t ntiles = s->len >> T;
   size_t smem = sizeof(double2) << T;
   static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
@@ -918,6 +1225,11 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       P.nitems = nitems;
     P.stagger_ns = env_int("BT_TILE_STAGGER_NS", 0);
     P.n_sm = nsm;
+    if (env_int("BT_TILE_DEBUG", 0)) {
+      fprintf(stderr, "[tile] T=%d tma=%d items=%d gates=%d clusters=%d diags=%d progs=%d ops:", T, (int)use_tma, nitems, ng, nc, nd, np);
+      for (int q = 0; q < np; ++q) fprintf(stderr, " %u(%d,%d,%d,%d)", P.pr[q].nops, P.pr[q].lp[0], P.pr[q].lp[1], P.pr[q].lp[2], P.pr[q].lp[3]);
+      fprintf(stderr, "\n");
+    }
     bt_prof_begin(s, BT_CLS_TILE);
     if (use_tma) {
       k_tile_tma<<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
@@ -930,7 +1242,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     bt_prof_end(s);
     BT_CHECK_LAUNCH(s);
     g_fused_passes++;
-    ng = nc = nd = nitems = 0;
+    ng = nc = nd = np = nitems = 0;
     return BT_OK;
   };
 
@@ -987,9 +1299,94 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     }
   };
 
+  // a block can run inside a register program when it kept its structured form and all its bits are tile bits
+  const bool use_progs = env_int("BT_TILE_PROGS", 1) != 0 && T >= PROG_BITS;
+  auto prog_eligible = [&](const Block* b) -> bool {
+    if (!use_progs || !b->sok || b->opaque) return false;
+    for (int t = 0; t < b->nb; ++t) if (local_pos[b->bits[t]] < 0) return false;
+    return true;
+  };
+
   for (size_t i = 0; i < n; ++i) {
     if (used[i]) continue;
     const GateDesc& d0 = pass[i]->desc;
+    if (prog_eligible(pass[i]) && !d0.diag) {
+      // greedy register program seeded here: later blocks join while the union of bits stays within PROG_BITS and no skipped
+      // block shares a bit with them (order preserved)
+      int sbits[PROG_BITS], nsb = 0, nops = 0, ncoef = 0;
+      std::vector<size_t> members;
+      bool blocked[64] = {false};
+      for (size_t jj = i; jj < n && jj < i + 48; ++jj) {
+        if (used[jj]) continue;
+        const Block* hb = pass[jj];
+        bool dep = false;
+        for (int t : hb->touch) if (blocked[t]) dep = true;
+        bool fits = !dep && prog_eligible(hb);
+        if (fits) {
+          int extra = 0;
+          for (int t = 0; t < hb->nb; ++t) {
+            bool have = false;
+            for (int q = 0; q < nsb; ++q) if (sbits[q] == hb->bits[t]) have = true;
+            if (!have) extra++;
+          }
+          int hc = 0;
+          for (const MOp& o : hb->prog) hc += o.ncoef;
+          if (nsb + extra > PROG_BITS || nops + (int)hb->prog.size() > PROG_MAXOPS || ncoef + hc > PROG_MAXCOEF) fits = false;
+          if (fits) {
+            for (int t = 0; t < hb->nb; ++t) {
+              bool have = false;
+              for (int q = 0; q < nsb; ++q) if (sbits[q] == hb->bits[t]) have = true;
+              if (!have) sbits[nsb++] = hb->bits[t];
+            }
+            nops += (int)hb->prog.size(); ncoef += hc;
+            members.push_back(jj);
+          }
+        }
+        if (!fits) {
+          if (hb->touch.empty()) break;
+          for (int t : hb->touch) blocked[t] = true;
+        }
+      }
+      if (!members.empty()) {
+        if (np >= TILE_MAXP) BT_TRY(flush());
+        TileProg& G = P.pr[np];
+        // positions: program bits by ascending tile position, the rest from the top free tile bits
+        std::sort(sbits, sbits + nsb, [&](int a, int b) { return local_pos[a] < local_pos[b]; });
+        bool taken[32] = {false};
+        int pos_of[64];
+        for (int b = 0; b < 64; ++b) pos_of[b] = -1;
+        for (int q = 0; q < nsb; ++q) { G.lp[q] = local_pos[sbits[q]]; taken[G.lp[q]] = true; pos_of[sbits[q]] = q; }
+        int freeb = T - 1;
+        for (int q = nsb; q < PROG_BITS; ++q) {
+          while (freeb >= 0 && taken[freeb]) --freeb;
+          if (freeb < 0) BT_FAIL(BT_ERR_ARG, "internal: no free tile bit for a register program");
+          G.lp[q] = freeb; taken[freeb] = true;
+        }
+        uint32_t fixed = 0;
+        for (int q = 0; q < PROG_BITS; ++q) fixed |= 1u << G.lp[q];
+        if (build_group_walk(T, fixed, PROG_BITS, G.bit_sw, G.iter_sw, 8, &G.niter, P.swz_mode) != 0) BT_FAIL(BT_ERR_ARG, "internal: program loop too long");
+        int ko = 0, kc = 0;
+        double fl = 0.0;
+        for (size_t mj : members) {
+          for (const MOp& o : pass[mj]->prog) {
+            int site;
+            if (o.kind <= PK_PHASE) site = PROG_SITE_U1(o.kind, pos_of[o.b[0]]);
+            else if (o.kind == PK_CX) site = PROG_SITE_CX(pos_of[o.b[0]], pos_of[o.b[1]]);
+            else { int a = pos_of[o.b[0]], b = pos_of[o.b[1]]; site = PROG_SITE_CPHASE(std::min(a, b), std::max(a, b)); }
+            G.op[ko++] = (uint16_t)(site | (kc << 8));
+            for (int e = 0; e < o.ncoef; ++e) G.coef[kc++] = o.c[e];
+            fl += o.flops;
+          }
+          used[mj] = 1;
+        }
+        G.nops = (uint32_t)ko;
+        P.item[nitems++] = (uint8_t)(TILE_PBASE + np);
+        np++;
+        g_fused_blocks += members.size();
+        g_fused_flops.store(g_fused_flops.load() + fl * (double)s->len);
+        continue;
+      }
+    }
     bool made_cluster = false;
     if (use_clusters && cluster_eligible(d0)) {
       Try best; best.nm = 0;
@@ -1097,9 +1494,16 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
       }
       if (ok) {
         needed_bits(b.desc, need);
+        if (b.sok && !b.desc.diag) {
+          // structured blocks run in register programs only when ALL their bits are tile bits: ask for them when they fit
+          int extra_all = 0;
+          for (int t = 0; t < b.nb; ++t) if (!in_tile[b.bits[t]]) extra_all++;
+          if (tile_cnt + extra_all <= T) { need.clear(); for (int t = 0; t < b.nb; ++t) need.push_back(b.bits[t]); }
+        }
         int extra = 0;
         for (int t : need) if (!in_tile[t]) extra++;
         double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
+        if (b.sok && !b.desc.diag) c = std::max(0.2, b.scost / 16.0) + 0.1;
         if (tile_cnt + extra > T || (int)pass.size() >= 44 || (cost + c > (double)maxg && !pass.empty())) ok = false;
         if (ok) {
           for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
