@@ -36,6 +36,7 @@
 #define PROG_AMPS (1 << PROG_BITS)
 #define PROG_MAXOPS 40
 #define PROG_MAXCOEF 160 // doubles
+#define TILE_LOWB_MIN 3  // the tensor-copy kernel needs only bits 0..2 (one 128-byte row) in the tile: BT_TILE_LOWB=3..5
 #define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
 #define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
 #define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
@@ -543,7 +544,7 @@ __device__ __forceinline__ void run_item(int item, const TileParams& P, double2*
 
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __restrict__ a, const __grid_constant__ TileParams P) {
   extern __shared__ double2 sm[];
-  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
+  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB_MIN)];
   const int T = P.T, lowb = P.lowb;
   const uint32_t tid = threadIdx.x;
   const uint32_t nloc = 1u << T;
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __gr
 // FP64 phase.  With T = 11 this is 2 x 32 KB per CTA: still 3 CTAs per SM.
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __restrict__ a, uint64_t ntiles, int tiles_per_cta, const __grid_constant__ TileParams P) {
   extern __shared__ double2 smem[];
-  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB)];
+  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB_MIN)];
   const int T = P.T, lowb = P.lowb;
   const uint32_t tid = threadIdx.x;
   const uint32_t nloc = 1u << T;
@@ -909,6 +910,8 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+static int tile_lowb() { return std::max(TILE_LOWB_MIN, std::min(TILE_LOWB, env_int("BT_TILE_LOWB", TILE_LOWB))); }
+
 static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& blocks) {
   std::vector<int> last(64, -1);  // last block index touching a physical bit
   const bool use_prog = env_int("BT_TILE_PROGS", 1) != 0;
@@ -1127,7 +1130,7 @@ static PFN_encodeTiled get_encode_fn() {
 static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, TileParams& P) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc || T < 8) return false;
-  for (int b = 0; b < 5; ++b) if (!in[b]) return false;
+  for (int b = 0; b < 3; ++b) if (!in[b]) return false;
   int total_bits = 0;
   while ((1ull << total_bits) < s->len) ++total_bits;
   if ((1ull << total_bits) != s->len) return false;  // ragged batches stay on the cp.async path
@@ -1141,7 +1144,13 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
     run_start[nr] = b; run_len[nr] = e - b; nr++;
     b = e;
   }
-  if (nr == 0 || run_start[0] != 3) return false;
+  if (nr == 0) return false;
+  if (run_start[0] != 3) {
+    // bits 3 .. run_start[0]-1 are not tile bits: they take a dimension of their own with a box of 1
+    if (nr >= 4) return false;
+    for (int k = nr; k > 0; --k) { run_start[k] = run_start[k - 1]; run_len[k] = run_len[k - 1]; }
+    run_start[0] = 3; run_len[0] = 0; nr++;
+  }
   cuuint64_t gdim[5], gstride[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   gdim[0] = 16; box[0] = 16;  // 8 amplitudes = 16 doubles = 128 B
@@ -1170,7 +1179,7 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
 static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
   if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
   int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
-  int lowb = std::min(TILE_LOWB, T);
+  int lowb = std::min(tile_lowb(), T);
   const int tiles_per_cta = std::max(1, env_int("BT_TILE_PER_CTA", 8));
   const bool dbuf = env_int("BT_TILE_DB", 0) != 0 && (s->len >> T) >= 2 * (uint64_t)tiles_per_cta;
   const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= CL_BITS;
@@ -1458,7 +1467,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   std::vector<Block> blocks;
   fuse_blocks(gates, blocks);
   const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
-  const int lowb = std::min(TILE_LOWB, T);
+  const int lowb = std::min(tile_lowb(), T);
   const int maxg = std::max(1, std::min(40, env_int("BT_FUSE_MAX_GATES", 10)));
   const int window = env_int("BT_FUSE_WINDOW", 256);
   const size_t n = blocks.size();
