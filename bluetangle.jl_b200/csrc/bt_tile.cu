@@ -27,15 +27,15 @@
 #ifndef TILE_MAXC
 #define TILE_MAXC 4      // register-cluster slots per pass
 #endif
-#define TILE_MAXD 32     // diagonal-gate slots per pass (one run-time-indexed code copy: they carry <= 4 matrix entries)
+#define TILE_MAXD 16     // diagonal-gate slots per pass (one run-time-indexed code copy: they carry <= 4 matrix entries)
 #define TILE_DBASE 16    // item ids >= TILE_DBASE are diagonal slots
 #define TILE_PBASE 48    // item ids >= TILE_PBASE are register programs
 #define TILE_MAXP 8      // register programs per pass
 #define TILE_MAXITEMS (TILE_PBASE + TILE_MAXP)
 #define PROG_BITS 4      // a register program holds the 2^4 amplitudes spanned by 4 tile bits in each thread
 #define PROG_AMPS (1 << PROG_BITS)
-#define PROG_MAXOPS 40
-#define PROG_MAXCOEF 160 // doubles
+#define PROG_MAXOPS 64
+#define PROG_MAXCOEF 208 // doubles
 #define TILE_LOWB_MIN 3  // the tensor-copy kernel needs only bits 0..2 (one 128-byte row) in the tile: BT_TILE_LOWB=3..5
 #define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
 #define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
@@ -110,12 +110,20 @@ enum { PK_GEN = 0, PK_REAL = 1, PK_RXL = 2, PK_DIAG = 3, PK_PHASE = 4, PK_CX = 5
 #define PROG_SITE_U1(kind, p) ((kind) * 4 + (p))                 // 0..19
 #define PROG_SITE_CX(pc, pt) (20 + (pc) * 4 + (pt))              // 20..35 (pc != pt)
 #define PROG_SITE_CPHASE(pa, pb) (36 + (pa) * 4 + (pb))          // 36..51 (pa < pb)
+// Conditional ops: a control / phase bit that is NOT one of the program's four positions is a property of the thread's group
+// (tile-local bits, mask lm) or of the whole tile (bits outside the tile, mask em) -- "controls ride along for free".
+// coefficients: CSCALE, CPH1: re, im, em, lm (masks as raw 64-bit words); CCX1: em, lm
+#define PROG_SITE_CSCALE 52                                      // all 16 amplitudes *= d          when the masks match
+#define PROG_SITE_CPH1(p) (53 + (p))                             // amplitudes with bit p set *= d  when the masks match
+#define PROG_SITE_CCX1(p) (57 + (p))                             // X on position p                 when the masks match
 struct TileProg {
   int32_t lp[PROG_BITS];  // tile-local bit of cluster position p
   uint32_t bit_sw[8];
   uint32_t niter;
   uint32_t nops;
   uint32_t iter_sw[8];
+  uint32_t bit_lin[8];    // as bit_sw / iter_sw but unswizzled: the group's tile-local index, for the conditional ops
+  uint32_t iter_lin[8];
   uint16_t op[PROG_MAXOPS];
   double coef[PROG_MAXCOEF];
 };
@@ -460,6 +468,16 @@ __device__ __forceinline__ void prog_cx(double2 (&x)[PROG_AMPS]) {
     }
 }
 
+template <int PT>
+__device__ __forceinline__ void prog_x1(double2 (&x)[PROG_AMPS]) {
+#pragma unroll
+  for (int i = 0; i < PROG_AMPS; ++i)
+    if (!((i >> PT) & 1)) {
+      ip_swap(x[i].x, x[i | (1 << PT)].x);
+      ip_swap(x[i].y, x[i | (1 << PT)].y);
+    }
+}
+
 template <int PA, int PB>
 __device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const double* __restrict__ c) {
 #pragma unroll
@@ -474,9 +492,19 @@ __device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const doubl
   case PROG_SITE_U1(kind, 3): prog_u1<kind, 3>(x, c); break;
 #define PROG_CASE_CX(a, b) case PROG_SITE_CX(a, b): prog_cx<a, b>(x); break;
 #define PROG_CASE_CP(a, b) case PROG_SITE_CPHASE(a, b): prog_cphase<a, b>(x, c); break;
+#define PROG_CASE_CPH1(p)                                                                                           \
+  case PROG_SITE_CPH1(p): {                                                                                         \
+    const uint64_t em = (uint64_t)__double_as_longlong(c[2]), lm = (uint64_t)__double_as_longlong(c[3]);            \
+    if ((base & em) == em && (gl & lm) == lm) prog_u1<PK_PHASE, p>(x, c);                                           \
+  } break;
+#define PROG_CASE_CCX1(p)                                                                                           \
+  case PROG_SITE_CCX1(p): {                                                                                         \
+    const uint64_t em = (uint64_t)__double_as_longlong(c[0]), lm = (uint64_t)__double_as_longlong(c[1]);            \
+    if ((base & em) == em && (gl & lm) == lm) prog_x1<p>(x);                                                        \
+  } break;
 
 template <int NT>
-__device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* __restrict__ sm, uint32_t tid, uint32_t nloc) {
+__device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
   const TileProg& G = P.pr[pi];
   const int P_swz = P.swz_mode;
   const uint32_t ng = nloc >> PROG_BITS;
@@ -484,8 +512,10 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
   const uint32_t s0 = thread_slot(G.bit_sw, tid);
   const uint32_t o0 = swz(1u << G.lp[0], P_swz), o1 = swz(1u << G.lp[1], P_swz), o2 = swz(1u << G.lp[2], P_swz), o3 = swz(1u << G.lp[3], P_swz);
   const uint32_t nops = G.nops;
+  const uint32_t g0 = thread_slot(G.bit_lin, tid);
   for (uint32_t it = 0; it < G.niter; ++it) {
     const uint32_t b = s0 ^ G.iter_sw[it];
+    const uint64_t gl = g0 ^ G.iter_lin[it];
     double2 x[PROG_AMPS];
 #pragma unroll
     for (int j = 0; j < PROG_AMPS; ++j) x[j] = sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)];
@@ -504,6 +534,16 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
         PROG_CASE_CX(3, 0) PROG_CASE_CX(3, 1) PROG_CASE_CX(3, 2)
         PROG_CASE_CP(0, 1) PROG_CASE_CP(0, 2) PROG_CASE_CP(0, 3)
         PROG_CASE_CP(1, 2) PROG_CASE_CP(1, 3) PROG_CASE_CP(2, 3)
+        case PROG_SITE_CSCALE: {
+          const uint64_t em = (uint64_t)__double_as_longlong(c[2]), lm = (uint64_t)__double_as_longlong(c[3]);
+          if ((base & em) == em && (gl & lm) == lm) {
+            const double dr = c[0], di = c[1], ndi = -di;
+#pragma unroll
+            for (int i = 0; i < PROG_AMPS; ++i) ip_cmul(x[i].x, x[i].y, dr, di, ndi);
+          }
+        } break;
+        PROG_CASE_CPH1(0) PROG_CASE_CPH1(1) PROG_CASE_CPH1(2) PROG_CASE_CPH1(3)
+        PROG_CASE_CCX1(0) PROG_CASE_CCX1(1) PROG_CASE_CCX1(2) PROG_CASE_CCX1(3)
         default: break;
       }
     }
@@ -514,10 +554,11 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
 
 // one code copy per slot: the slot index is a compile-time constant inside, so every matrix element is a uniform-register /
 // constant-bank operand of its DFMA instead of a live register.  (A single run-time-indexed copy was measured 20 % slower.)
-template <int NT>
+template <int NT, bool FULL = true>
 __device__ __forceinline__ void run_item(int item, const TileParams& P, double2* __restrict__ sm, uint64_t base, uint32_t tid, uint32_t nloc) {
-  if (item >= TILE_PBASE) { run_prog<NT>(P, item - TILE_PBASE, sm, tid, nloc); return; }
+  if (item >= TILE_PBASE) { run_prog<NT>(P, item - TILE_PBASE, sm, base, tid, nloc); return; }
   if (item >= TILE_DBASE) { run_diag<NT>(P.d[item - TILE_DBASE], sm, base, tid, nloc, P.swz_mode); return; }
+  if (!FULL) return;  // the lite kernel (register programs + diagonal slots only) never sees dense slots
   switch (item) {
     case 0: run_gate<0, NT>(P, sm, base, tid, nloc); break;
     case 1: run_gate<1, NT>(P, sm, base, tid, nloc); break;
@@ -597,7 +638,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __res
 // run, box = the run.  This takes the global traffic off the LSU / L1TEX data pipe that the gates' shared-memory round trips need.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams P) {
+// FULL = false: passes made of register programs and diagonal slots only -- a third fewer registers (no dense 4x4 code), so
+// four to five CTAs fit an SM at T = 11 and more of them are in their compute phase at any time.
+#ifndef TILE_LITE_MINB
+#define TILE_LITE_MINB 3
+#endif
+template <bool FULL>
+__global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MINB) k_tile_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams P) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned tile (required by the 128-B swizzle), then the mbarrier
   const uint32_t raw = smem_u32(smem_raw);
@@ -623,7 +670,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
+  const int dbg = P.stagger_ns < 0 ? -P.stagger_ns : 0;  // measurement aid: 1 = no gates, 2 = no HBM traffic (results invalid)
+  if (tid == 0 && dbg != 2) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(sizeof(double2) << T)) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
@@ -631,7 +679,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __gr
         : "memory");
   }
   // wait for the tile (phase 0); bounded spin so that a descriptor mistake traps instead of hanging the GPU
-  {
+  if (dbg != 2) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
@@ -639,15 +687,15 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_tma(const __gr
     }
   }
 
-  for (int i = 0; i < P.nitems; ++i) {
-    run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
+  for (int i = 0; i < (dbg == 1 ? 0 : P.nitems); ++i) {
+    run_item<TILE_THREADS, FULL>(P.item[i], P, sm, base, tid, nloc);
     __syncthreads();
   }
 
   // generic-proxy writes -> visible to the async proxy, then one bulk tensor store
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && dbg != 2) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2),
                  "r"(c3), "r"(c4), "r"(dst)
                  : "memory");
@@ -836,8 +884,17 @@ static void mop_append(std::vector<MOp>& prog, const MOp& o) {
   prog.push_back(o);
 }
 
+// the bit an op acts on non-diagonally (it must be one of the program's positions), or -1
+static int mop_acting_bit(const MOp& o) {
+  if (o.kind == PK_GEN || o.kind == PK_REAL || o.kind == PK_RXL) return o.b[0];
+  if (o.kind == PK_CX) return o.b[1];
+  if (o.kind == PK_DIAG && o.c[0] == 0.0 && o.c[1] == 0.0) return o.b[0];  // d0 = 0 cannot be written as d0 * phase
+  return -1;
+}
+
 struct Block {
   std::vector<MOp> prog;  // structured form (valid when sok)
+  std::vector<int> abits; // bits the structured form acts on non-diagonally: they must be program positions (hence tile bits)
   bool sok = false;       // the structured form exists and is cheaper than the dense block
   double scost = 0.0, sflops = 0.0;
   int nb;            // number of bits (1 or 2 for fusable blocks; >2 => opaque)
@@ -1001,8 +1058,14 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
       b.scost = b.sflops = 0.0;
       for (const MOp& o : b.prog) { b.scost += o.cost; b.sflops += o.flops; }
       // keep the structured form only when it is cheaper than the dense block and the dense form is not already diagonal
-      const double dense_cost = b.desc.diag ? 4.0 : (b.desc.k == 2 ? 16.0 : 8.0);
-      if (!use_prog || b.prog.empty() || b.scost >= dense_cost || (int)b.prog.size() > 12) b.sok = false;
+      // (a diagonal block always does: its alternative is a shared-memory sweep + barrier of its own)
+      const double dense_cost = b.desc.k == 2 ? 16.0 : 8.0;
+      if (!use_prog || b.prog.empty() || (!b.desc.diag && b.scost >= dense_cost) || (int)b.prog.size() > 12) b.sok = false;
+      if (b.sok)
+        for (const MOp& o : b.prog) {
+          int a = mop_acting_bit(o);
+          if (a >= 0 && std::find(b.abits.begin(), b.abits.end(), a) == b.abits.end()) b.abits.push_back(a);
+        }
     }
     out.push_back(b);
   }
@@ -1022,7 +1085,8 @@ static void needed_bits(const GateDesc& d, std::vector<int>& out) {
 // Group enumeration for an item whose fixed tile positions are `fixed` (targets + local controls): group-index bit k walks
 // free tile position order[k].  The first three are chosen with distinct residues mod 3 so that 8 consecutive lanes hit 8
 // distinct bank groups under sw(); thread bits come first, loop-iteration bits after.
-static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bit_sw, uint32_t* iter_sw, int iter_cap, uint32_t* niter_out, int mode) {
+static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bit_sw, uint32_t* iter_sw, int iter_cap, uint32_t* niter_out, int mode,
+                            uint32_t* bit_lin = nullptr, uint32_t* iter_lin = nullptr) {
   int order[TILE_TMAX], n = 0;
   bool used[TILE_TMAX] = {false};
   bool res_taken[3] = {false, false, false};
@@ -1036,6 +1100,7 @@ static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bi
   int tbits = 0;
   while ((1 << tbits) < TILE_THREADS) ++tbits;
   for (int k = 0; k < 8; ++k) bit_sw[k] = (k < n && k < tbits) ? swz(1u << order[k], mode) : 0u;
+  if (bit_lin) for (int k = 0; k < 8; ++k) bit_lin[k] = (k < n && k < tbits) ? (1u << order[k]) : 0u;
   uint32_t ngroups = 1u << n;
   uint32_t niter = ngroups > (uint32_t)TILE_THREADS ? ngroups / TILE_THREADS : 1u;
   if ((int)niter > iter_cap) return -1;
@@ -1044,6 +1109,7 @@ static int build_group_walk(int T, uint32_t fixed_mask, int nfixed, uint32_t* bi
     for (int k = tbits; k < n; ++k)
       if ((it >> (k - tbits)) & 1u) c |= 1u << order[k];
     iter_sw[it] = swz(c, mode);
+    if (iter_lin) iter_lin[it] = c;
   }
   *niter_out = niter;
   return 0;
@@ -1223,7 +1289,8 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
   if (!attr_set[s->device & 63]) {
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
-    BT_CUDA(cudaFuncSetAttribute(k_tile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set[s->device & 63] = true;
   }
@@ -1241,7 +1308,8 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     }
     bt_prof_begin(s, BT_CLS_TILE);
     if (use_tma) {
-      k_tile_tma<<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
+      if (ng == 0 && nc == 0 && env_int("BT_TILE_LITE", 1)) k_tile_tma<false><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
+      else k_tile_tma<true><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
     } else if (dbuf) {
       uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
       k_tile_db<<<(unsigned)nct, TILE_THREADS, 2 * smem, s->stream>>>(s->amp, ntiles, tiles_per_cta, P);
@@ -1312,20 +1380,28 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   const bool use_progs = env_int("BT_TILE_PROGS", 1) != 0 && T >= PROG_BITS;
   auto prog_eligible = [&](const Block* b) -> bool {
     if (!use_progs || !b->sok || b->opaque) return false;
-    for (int t = 0; t < b->nb; ++t) if (local_pos[b->bits[t]] < 0) return false;
+    for (int t : b->abits) if (local_pos[t] < 0) return false;
     return true;
+  };
+  // ops / coefficients a block needs once its ops are resolved against a program (upper bounds: an out-of-program DIAG splits)
+  auto prog_demand = [&](const Block* b, int* nops, int* ncoef) {
+    *nops = 0; *ncoef = 0;
+    for (const MOp& o : b->prog) {
+      if (o.kind == PK_DIAG) { *nops += 2; *ncoef += 8; }
+      else { *nops += 1; *ncoef += std::max(o.ncoef, 4); }
+    }
   };
 
   for (size_t i = 0; i < n; ++i) {
     if (used[i]) continue;
     const GateDesc& d0 = pass[i]->desc;
-    if (prog_eligible(pass[i]) && !d0.diag) {
-      // greedy register program seeded here: later blocks join while the union of bits stays within PROG_BITS and no skipped
-      // block shares a bit with them (order preserved)
+    if (prog_eligible(pass[i])) {
+      // greedy register program seeded here: later blocks join while the union of ACTING bits stays within PROG_BITS and no
+      // skipped block shares a bit with them (order preserved); control / phase bits may lie anywhere
       int sbits[PROG_BITS], nsb = 0, nops = 0, ncoef = 0;
       std::vector<size_t> members;
       bool blocked[64] = {false};
-      for (size_t jj = i; jj < n && jj < i + 48; ++jj) {
+      for (size_t jj = i; jj < n && jj < i + 64; ++jj) {
         if (used[jj]) continue;
         const Block* hb = pass[jj];
         bool dep = false;
@@ -1333,21 +1409,21 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         bool fits = !dep && prog_eligible(hb);
         if (fits) {
           int extra = 0;
-          for (int t = 0; t < hb->nb; ++t) {
+          for (int t : hb->abits) {
             bool have = false;
-            for (int q = 0; q < nsb; ++q) if (sbits[q] == hb->bits[t]) have = true;
+            for (int q = 0; q < nsb; ++q) if (sbits[q] == t) have = true;
             if (!have) extra++;
           }
-          int hc = 0;
-          for (const MOp& o : hb->prog) hc += o.ncoef;
-          if (nsb + extra > PROG_BITS || nops + (int)hb->prog.size() > PROG_MAXOPS || ncoef + hc > PROG_MAXCOEF) fits = false;
+          int ho, hc;
+          prog_demand(hb, &ho, &hc);
+          if (nsb + extra > PROG_BITS || nops + ho > PROG_MAXOPS || ncoef + hc > PROG_MAXCOEF) fits = false;
           if (fits) {
-            for (int t = 0; t < hb->nb; ++t) {
+            for (int t : hb->abits) {
               bool have = false;
-              for (int q = 0; q < nsb; ++q) if (sbits[q] == hb->bits[t]) have = true;
-              if (!have) sbits[nsb++] = hb->bits[t];
+              for (int q = 0; q < nsb; ++q) if (sbits[q] == t) have = true;
+              if (!have) sbits[nsb++] = t;
             }
-            nops += (int)hb->prog.size(); ncoef += hc;
+            nops += ho; ncoef += hc;
             members.push_back(jj);
           }
         }
@@ -1359,7 +1435,28 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       if (!members.empty()) {
         if (np >= TILE_MAXP) BT_TRY(flush());
         TileProg& G = P.pr[np];
-        // positions: program bits by ascending tile position, the rest from the top free tile bits
+        // spare positions go to the tile bits the members' diagonal ops use most (their ops become unconditional), then to
+        // free tile bits from the top
+        {
+          int freq[64] = {0};
+          for (size_t mj : members)
+            for (const MOp& o : pass[mj]->prog)
+              for (int e = 0; e < 2; ++e) {
+                int t = o.b[e];
+                if (t >= 0 && local_pos[t] >= 0) freq[t]++;
+              }
+          while (nsb < PROG_BITS) {
+            int bestb = -1;
+            for (int t = 0; t < 64; ++t) {
+              if (freq[t] == 0) continue;
+              bool have = false;
+              for (int q = 0; q < nsb; ++q) if (sbits[q] == t) have = true;
+              if (!have && (bestb < 0 || freq[t] > freq[bestb])) bestb = t;
+            }
+            if (bestb < 0) break;
+            sbits[nsb++] = bestb;
+          }
+        }
         std::sort(sbits, sbits + nsb, [&](int a, int b) { return local_pos[a] < local_pos[b]; });
         bool taken[32] = {false};
         int pos_of[64];
@@ -1373,21 +1470,59 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         }
         uint32_t fixed = 0;
         for (int q = 0; q < PROG_BITS; ++q) fixed |= 1u << G.lp[q];
-        if (build_group_walk(T, fixed, PROG_BITS, G.bit_sw, G.iter_sw, 8, &G.niter, P.swz_mode) != 0) BT_FAIL(BT_ERR_ARG, "internal: program loop too long");
+        if (build_group_walk(T, fixed, PROG_BITS, G.bit_sw, G.iter_sw, 8, &G.niter, P.swz_mode, G.bit_lin, G.iter_lin) != 0)
+          BT_FAIL(BT_ERR_ARG, "internal: program loop too long");
         int ko = 0, kc = 0;
         double fl = 0.0;
+        auto emit = [&](int site, const double* c, int ncf) {
+          G.op[ko++] = (uint16_t)(site | (kc << 8));
+          for (int e = 0; e < ncf; ++e) G.coef[kc++] = c[e];
+        };
+        // condition masks of a bit that is not a program position: tile-local -> lm, outside the tile -> em
+        auto add_cond = [&](int bit, uint64_t* em, uint64_t* lm) {
+          if (local_pos[bit] >= 0) *lm |= 1ull << local_pos[bit]; else *em |= 1ull << bit;
+        };
+        auto as_double = [](uint64_t v) { double d; memcpy(&d, &v, sizeof(d)); return d; };
         for (size_t mj : members) {
           for (const MOp& o : pass[mj]->prog) {
-            int site;
-            if (o.kind <= PK_PHASE) site = PROG_SITE_U1(o.kind, pos_of[o.b[0]]);
-            else if (o.kind == PK_CX) site = PROG_SITE_CX(pos_of[o.b[0]], pos_of[o.b[1]]);
-            else { int a = pos_of[o.b[0]], b = pos_of[o.b[1]]; site = PROG_SITE_CPHASE(std::min(a, b), std::max(a, b)); }
-            G.op[ko++] = (uint16_t)(site | (kc << 8));
-            for (int e = 0; e < o.ncoef; ++e) G.coef[kc++] = o.c[e];
             fl += o.flops;
+            const int pa = pos_of[o.b[0]], pb = (o.kind == PK_CX || o.kind == PK_CPHASE) ? pos_of[o.b[1]] : -1;
+            uint64_t em = 0, lm = 0;
+            if (o.kind == PK_GEN || o.kind == PK_REAL || o.kind == PK_RXL) {
+              emit(PROG_SITE_U1(o.kind, pa), o.c, o.ncoef);
+            } else if (o.kind == PK_PHASE) {
+              if (pa >= 0) emit(PROG_SITE_U1(PK_PHASE, pa), o.c, 2);
+              else { add_cond(o.b[0], &em, &lm); double c[4] = {o.c[0], o.c[1], as_double(em), as_double(lm)}; emit(PROG_SITE_CSCALE, c, 4); }
+            } else if (o.kind == PK_DIAG) {
+              if (pa >= 0) emit(PROG_SITE_U1(PK_DIAG, pa), o.c, 4);
+              else {
+                // diag(d0, d1) on a bit outside the program = d0 * diag(1, d1 / d0)
+                const cplx d0(o.c[0], o.c[1]), r = cplx(o.c[2], o.c[3]) / d0;
+                double c0[4] = {o.c[0], o.c[1], as_double(0), as_double(0)};
+                emit(PROG_SITE_CSCALE, c0, 4);
+                add_cond(o.b[0], &em, &lm);
+                double c1[4] = {r.real(), r.imag(), as_double(em), as_double(lm)};
+                emit(PROG_SITE_CSCALE, c1, 4);
+              }
+            } else if (o.kind == PK_CX) {
+              if (pa >= 0) emit(PROG_SITE_CX(pa, pb), o.c, 0);
+              else { add_cond(o.b[0], &em, &lm); double c[2] = {as_double(em), as_double(lm)}; emit(PROG_SITE_CCX1(pb), c, 2); }
+            } else {  // PK_CPHASE
+              if (pa >= 0 && pb >= 0) emit(PROG_SITE_CPHASE(std::min(pa, pb), std::max(pa, pb)), o.c, 2);
+              else if (pa >= 0 || pb >= 0) {
+                add_cond(pa >= 0 ? o.b[1] : o.b[0], &em, &lm);
+                double c[4] = {o.c[0], o.c[1], as_double(em), as_double(lm)};
+                emit(PROG_SITE_CPH1(pa >= 0 ? pa : pb), c, 4);
+              } else {
+                add_cond(o.b[0], &em, &lm); add_cond(o.b[1], &em, &lm);
+                double c[4] = {o.c[0], o.c[1], as_double(em), as_double(lm)};
+                emit(PROG_SITE_CSCALE, c, 4);
+              }
+            }
           }
           used[mj] = 1;
         }
+        if (ko > PROG_MAXOPS || kc > PROG_MAXCOEF) BT_FAIL(BT_ERR_ARG, "internal: register program overflow");
         G.nops = (uint32_t)ko;
         P.item[nitems++] = (uint8_t)(TILE_PBASE + np);
         np++;
@@ -1503,16 +1638,11 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
       }
       if (ok) {
         needed_bits(b.desc, need);
-        if (b.sok && !b.desc.diag) {
-          // structured blocks run in register programs only when ALL their bits are tile bits: ask for them when they fit
-          int extra_all = 0;
-          for (int t = 0; t < b.nb; ++t) if (!in_tile[b.bits[t]]) extra_all++;
-          if (tile_cnt + extra_all <= T) { need.clear(); for (int t = 0; t < b.nb; ++t) need.push_back(b.bits[t]); }
-        }
+        if (b.sok) need = b.abits;  // structured blocks: the bits they act on non-diagonally must be program positions
         int extra = 0;
         for (int t : need) if (!in_tile[t]) extra++;
         double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
-        if (b.sok && !b.desc.diag) c = std::max(0.2, b.scost / 16.0) + 0.1;
+        if (b.sok) c = 0.15 * (double)b.prog.size() + 0.04 * b.scost;  // decode + arithmetic of the micro-ops
         if (tile_cnt + extra > T || (int)pass.size() >= 44 || (cost + c > (double)maxg && !pass.empty())) ok = false;
         if (ok) {
           for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }

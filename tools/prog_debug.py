@@ -7,7 +7,7 @@ bt = ge.load_package(); L = bt._lib
 from importlib import import_module
 wl = import_module("bluetangle_jl_b200.workloads")
 N = int(os.environ.get("DBG_N", "28")); depth = int(os.environ.get("DBG_DEPTH", "6"))
-specs = wl.layered(N, depth, 28)
+specs = wl.qft(N) if os.environ.get("DBG_CIRC", "layered") == "qft" else wl.layered(N, depth, 28)
 arr = bt.pack_gates(wl.to_ops(bt, specs))
 s = bt.zero_state(N)
 L.check(s.lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1)); s.sync()
