@@ -16,6 +16,14 @@ build/%.o: $(PKG)/csrc/%.cu $(PKG)/csrc/bt_internal.cuh include/bluetangle_cuda.
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
+# bt_tile.cu goes through nvcc's own steps with one extra pass over the PTX: the micro-op switch of the register programs
+# becomes an indirect branch (tools/ptx_brx.py; BT_NO_BRX=1 builds it with plain nvcc)
+ifndef BT_NO_BRX
+build/bt_tile.o: $(PKG)/csrc/bt_tile.cu $(PKG)/csrc/bt_internal.cuh include/bluetangle_cuda.h tools/nvcc_brx.py tools/ptx_brx.py
+	@mkdir -p build
+	python3 tools/nvcc_brx.py $(NVFLAGS) -c $< -o $@ 2> build/bt_tile.ptxas.log || (cat build/bt_tile.ptxas.log; exit 1)
+endif
+
 oracle: oracle/_build/libbt_oracle_c.so
 
 oracle/_build/libbt_oracle_c.so: oracle/strided_cpu.c

@@ -32,7 +32,9 @@
 #define TILE_PBASE 48    // item ids >= TILE_PBASE are register programs
 #define TILE_MAXP 8      // register programs per pass
 #define TILE_MAXITEMS (TILE_PBASE + TILE_MAXP)
-#define PROG_BITS 4      // a register program holds the 2^4 amplitudes spanned by 4 tile bits in each thread
+#ifndef PROG_BITS
+#define PROG_BITS 4      // a register program holds the 2^4 amplitudes spanned by 4 tile bits in each thread (5: 32 amplitudes)
+#endif
 #define PROG_AMPS (1 << PROG_BITS)
 #define PROG_MAXOPS 64
 #define PROG_MAXCOEF 208 // doubles
@@ -107,17 +109,17 @@ struct TileCluster {
 //   CPHASE  phase on |11> (CZ, CP)             1
 // op word: site | (first coefficient << 8); the site fixes kind and cluster positions so that register indices are static.
 enum { PK_GEN = 0, PK_REAL = 1, PK_RXL = 2, PK_DIAG = 3, PK_PHASE = 4, PK_CX = 5, PK_CPHASE = 6 };
-#define PROG_SITE_U1(kind, p) ((kind) * 4 + (p))                 // 0..19
-#define PROG_SITE_CX(pc, pt) (20 + (pc) * 4 + (pt))              // 20..35 (pc != pt)
-#define PROG_SITE_CPHASE(pa, pb) (36 + (pa) * 4 + (pb))          // 36..51 (pa < pb)
-// Conditional ops: a control / phase bit that is NOT one of the program's four positions is a property of the thread's group
+#define PROG_SITE_U1(kind, p) ((kind) * 8 + (p))                 // 0..39
+#define PROG_SITE_CX(pc, pt) (40 + (pc) * 8 + (pt))              // 40..103 (pc != pt)
+#define PROG_SITE_CPHASE(pa, pb) (104 + (pa) * 8 + (pb))         // 104..167 (pa < pb)
+// Conditional ops: a control / phase bit that is NOT one of the program's positions is a property of the thread's group
 // (tile-local bits, mask lm) or of the whole tile (bits outside the tile, mask em) -- "controls ride along for free".
 // coefficients: CSCALE, CPH1: re, im, em, lm (masks as raw 64-bit words); CCX1: em, lm
-#define PROG_SITE_CSCALE 52                                      // all 16 amplitudes *= d          when the masks match
-#define PROG_SITE_CPH1(p) (53 + (p))                             // amplitudes with bit p set *= d  when the masks match
-#define PROG_SITE_CCX1(p) (57 + (p))                             // X on position p                 when the masks match
+#define PROG_SITE_CSCALE 168                                     // all amplitudes *= d             when the masks match
+#define PROG_SITE_CPH1(p) (169 + (p))                            // amplitudes with bit p set *= d  when the masks match
+#define PROG_SITE_CCX1(p) (177 + (p))                            // X on position p                 when the masks match
 struct TileProg {
-  int32_t lp[PROG_BITS];  // tile-local bit of cluster position p
+  int32_t lp[8];          // tile-local bit of cluster position p < PROG_BITS
   uint32_t bit_sw[8];
   uint32_t niter;
   uint32_t nops;
@@ -485,20 +487,30 @@ __device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const doubl
     if (((i >> PA) & 1) && ((i >> PB) & 1)) ip_cmul(x[i].x, x[i].y, c[0], c[1], -c[1]);
 }
 
+// markers for tools/ptx_brx.py (PTX comments: no code)
+#define BT_CASE_MARK(site) asm volatile("// BT_CASE %0;" ::"n"(site))
+#if PROG_BITS >= 5
+#define PROG_CASE_U1_4(kind) case PROG_SITE_U1(kind, 4): BT_CASE_MARK(PROG_SITE_U1(kind, 4)); prog_u1<kind, 4>(x, c); break;
+#else
+#define PROG_CASE_U1_4(kind)
+#endif
 #define PROG_CASE_U1(kind)                                                   \
-  case PROG_SITE_U1(kind, 0): prog_u1<kind, 0>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 1): prog_u1<kind, 1>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 2): prog_u1<kind, 2>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 3): prog_u1<kind, 3>(x, c); break;
-#define PROG_CASE_CX(a, b) case PROG_SITE_CX(a, b): prog_cx<a, b>(x); break;
-#define PROG_CASE_CP(a, b) case PROG_SITE_CPHASE(a, b): prog_cphase<a, b>(x, c); break;
+  case PROG_SITE_U1(kind, 0): BT_CASE_MARK(PROG_SITE_U1(kind, 0)); prog_u1<kind, 0>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 1): BT_CASE_MARK(PROG_SITE_U1(kind, 1)); prog_u1<kind, 1>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 2): BT_CASE_MARK(PROG_SITE_U1(kind, 2)); prog_u1<kind, 2>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 3): BT_CASE_MARK(PROG_SITE_U1(kind, 3)); prog_u1<kind, 3>(x, c); break;                 \
+  PROG_CASE_U1_4(kind)
+#define PROG_CASE_CX(a, b) case PROG_SITE_CX(a, b): BT_CASE_MARK(PROG_SITE_CX(a, b)); prog_cx<a, b>(x); break;
+#define PROG_CASE_CP(a, b) case PROG_SITE_CPHASE(a, b): BT_CASE_MARK(PROG_SITE_CPHASE(a, b)); prog_cphase<a, b>(x, c); break;
 #define PROG_CASE_CPH1(p)                                                                                           \
   case PROG_SITE_CPH1(p): {                                                                                         \
+    BT_CASE_MARK(PROG_SITE_CPH1(p));                                                                               \
     const uint64_t em = (uint64_t)__double_as_longlong(c[2]), lm = (uint64_t)__double_as_longlong(c[3]);            \
     if ((base & em) == em && (gl & lm) == lm) prog_u1<PK_PHASE, p>(x, c);                                           \
   } break;
 #define PROG_CASE_CCX1(p)                                                                                           \
   case PROG_SITE_CCX1(p): {                                                                                         \
+    BT_CASE_MARK(PROG_SITE_CCX1(p));                                                                               \
     const uint64_t em = (uint64_t)__double_as_longlong(c[0]), lm = (uint64_t)__double_as_longlong(c[1]);            \
     if ((base & em) == em && (gl & lm) == lm) prog_x1<p>(x);                                                        \
   } break;
@@ -510,7 +522,9 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
   const uint32_t ng = nloc >> PROG_BITS;
   if (tid >= ng) return;
   const uint32_t s0 = thread_slot(G.bit_sw, tid);
-  const uint32_t o0 = swz(1u << G.lp[0], P_swz), o1 = swz(1u << G.lp[1], P_swz), o2 = swz(1u << G.lp[2], P_swz), o3 = swz(1u << G.lp[3], P_swz);
+  uint32_t o[PROG_BITS];
+#pragma unroll
+  for (int q = 0; q < PROG_BITS; ++q) o[q] = swz(1u << G.lp[q], P_swz);
   const uint32_t nops = G.nops;
   const uint32_t g0 = thread_slot(G.bit_lin, tid);
   for (uint32_t it = 0; it < G.niter; ++it) {
@@ -518,11 +532,18 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
     const uint64_t gl = g0 ^ G.iter_lin[it];
     double2 x[PROG_AMPS];
 #pragma unroll
-    for (int j = 0; j < PROG_AMPS; ++j) x[j] = sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)];
+    for (int j = 0; j < PROG_AMPS; ++j) {
+      uint32_t a = b;
+#pragma unroll
+      for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) a ^= o[q];
+      x[j] = sm[a];
+    }
     for (uint32_t k = 0; k < nops; ++k) {
       const uint32_t op = G.op[k];
       const double* __restrict__ c = G.coef + (op >> 8);
-      switch (op & 0xffu) {
+      const uint32_t site = op & 0xffu;
+      asm volatile("// BT_DISPATCH %0;" ::"r"(site));  // tools/ptx_brx.py turns the switch below into one brx.idx
+      switch (site) {
         PROG_CASE_U1(PK_GEN)
         PROG_CASE_U1(PK_REAL)
         PROG_CASE_U1(PK_RXL)
@@ -534,7 +555,14 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
         PROG_CASE_CX(3, 0) PROG_CASE_CX(3, 1) PROG_CASE_CX(3, 2)
         PROG_CASE_CP(0, 1) PROG_CASE_CP(0, 2) PROG_CASE_CP(0, 3)
         PROG_CASE_CP(1, 2) PROG_CASE_CP(1, 3) PROG_CASE_CP(2, 3)
+#if PROG_BITS >= 5
+        PROG_CASE_CX(0, 4) PROG_CASE_CX(1, 4) PROG_CASE_CX(2, 4) PROG_CASE_CX(3, 4)
+        PROG_CASE_CX(4, 0) PROG_CASE_CX(4, 1) PROG_CASE_CX(4, 2) PROG_CASE_CX(4, 3)
+        PROG_CASE_CP(0, 4) PROG_CASE_CP(1, 4) PROG_CASE_CP(2, 4) PROG_CASE_CP(3, 4)
+        PROG_CASE_CPH1(4) PROG_CASE_CCX1(4)
+#endif
         case PROG_SITE_CSCALE: {
+          BT_CASE_MARK(PROG_SITE_CSCALE);
           const uint64_t em = (uint64_t)__double_as_longlong(c[2]), lm = (uint64_t)__double_as_longlong(c[3]);
           if ((base & em) == em && (gl & lm) == lm) {
             const double dr = c[0], di = c[1], ndi = -di;
@@ -544,11 +572,16 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
         } break;
         PROG_CASE_CPH1(0) PROG_CASE_CPH1(1) PROG_CASE_CPH1(2) PROG_CASE_CPH1(3)
         PROG_CASE_CCX1(0) PROG_CASE_CCX1(1) PROG_CASE_CCX1(2) PROG_CASE_CCX1(3)
-        default: break;
+        default: BT_CASE_MARK(255); break;
       }
     }
 #pragma unroll
-    for (int j = 0; j < PROG_AMPS; ++j) sm[b ^ ((j & 1) ? o0 : 0u) ^ ((j & 2) ? o1 : 0u) ^ ((j & 4) ? o2 : 0u) ^ ((j & 8) ? o3 : 0u)] = x[j];
+    for (int j = 0; j < PROG_AMPS; ++j) {
+      uint32_t a = b;
+#pragma unroll
+      for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) a ^= o[q];
+      sm[a] = x[j];
+    }
   }
 }
 
@@ -641,7 +674,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // FULL = false: passes made of register programs and diagonal slots only -- a third fewer registers (no dense 4x4 code), so
 // four to five CTAs fit an SM at T = 11 and more of them are in their compute phase at any time.
 #ifndef TILE_LITE_MINB
-#define TILE_LITE_MINB 3
+#define TILE_LITE_MINB (PROG_BITS >= 5 ? 2 : 3)
 #endif
 template <bool FULL>
 __global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MINB) k_tile_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams P) {
