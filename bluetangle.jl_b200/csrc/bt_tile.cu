@@ -126,8 +126,8 @@ struct TileProg {
   uint32_t iter_sw[8];
   uint32_t bit_lin[8];    // as bit_sw / iter_sw but unswizzled: the group's tile-local index, for the conditional ops
   uint32_t iter_lin[8];
-  uint16_t op[PROG_MAXOPS];
-  double coef[PROG_MAXCOEF];
+  uint16_t op[PROG_MAXOPS + 2];   // + padding entry read by the op-word prefetch
+  double coef[PROG_MAXCOEF + 4];  // + slack: four coefficients are always fetched
 };
 
 struct TileParams {
@@ -417,10 +417,10 @@ __device__ __forceinline__ void ip_swap(double& a, double& b) {
 }
 
 template <int KIND, int PQ>
-__device__ __forceinline__ void prog_u1(double2 (&x)[PROG_AMPS], const double* __restrict__ cc) {
-  if (KIND == PK_GEN) {  // cc = re/im of m00, m01, m10, m11
-    const double c[8] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], cc[7]};
-    const double n[4] = {-cc[1], -cc[3], -cc[5], -cc[7]};
+__device__ __forceinline__ void prog_u1(double2 (&x)[PROG_AMPS], const double (&cc)[4], const double* __restrict__ cp) {
+  if (KIND == PK_GEN) {  // cc = re/im of m00, m01 (preloaded), cp[4..7] = re/im of m10, m11
+    const double c[8] = {cc[0], cc[1], cc[2], cc[3], cp[4], cp[5], cp[6], cp[7]};
+    const double n[4] = {-c[1], -c[3], -c[5], -c[7]};
 #pragma unroll
     for (int r = 0; r < PROG_AMPS / 2; ++r) {
       const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
@@ -481,7 +481,7 @@ __device__ __forceinline__ void prog_x1(double2 (&x)[PROG_AMPS]) {
 }
 
 template <int PA, int PB>
-__device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const double* __restrict__ c) {
+__device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const double (&c)[4]) {
 #pragma unroll
   for (int i = 0; i < PROG_AMPS; ++i)
     if (((i >> PA) & 1) && ((i >> PB) & 1)) ip_cmul(x[i].x, x[i].y, c[0], c[1], -c[1]);
@@ -490,15 +490,15 @@ __device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const doubl
 // markers for tools/ptx_brx.py (PTX comments: no code)
 #define BT_CASE_MARK(site) asm volatile("// BT_CASE %0;" ::"n"(site))
 #if PROG_BITS >= 5
-#define PROG_CASE_U1_4(kind) case PROG_SITE_U1(kind, 4): BT_CASE_MARK(PROG_SITE_U1(kind, 4)); prog_u1<kind, 4>(x, c); break;
+#define PROG_CASE_U1_4(kind) case PROG_SITE_U1(kind, 4): BT_CASE_MARK(PROG_SITE_U1(kind, 4)); prog_u1<kind, 4>(x, c, cp); break;
 #else
 #define PROG_CASE_U1_4(kind)
 #endif
 #define PROG_CASE_U1(kind)                                                   \
-  case PROG_SITE_U1(kind, 0): BT_CASE_MARK(PROG_SITE_U1(kind, 0)); prog_u1<kind, 0>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 1): BT_CASE_MARK(PROG_SITE_U1(kind, 1)); prog_u1<kind, 1>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 2): BT_CASE_MARK(PROG_SITE_U1(kind, 2)); prog_u1<kind, 2>(x, c); break;                 \
-  case PROG_SITE_U1(kind, 3): BT_CASE_MARK(PROG_SITE_U1(kind, 3)); prog_u1<kind, 3>(x, c); break;                 \
+  case PROG_SITE_U1(kind, 0): BT_CASE_MARK(PROG_SITE_U1(kind, 0)); prog_u1<kind, 0>(x, c, cp); break;                 \
+  case PROG_SITE_U1(kind, 1): BT_CASE_MARK(PROG_SITE_U1(kind, 1)); prog_u1<kind, 1>(x, c, cp); break;                 \
+  case PROG_SITE_U1(kind, 2): BT_CASE_MARK(PROG_SITE_U1(kind, 2)); prog_u1<kind, 2>(x, c, cp); break;                 \
+  case PROG_SITE_U1(kind, 3): BT_CASE_MARK(PROG_SITE_U1(kind, 3)); prog_u1<kind, 3>(x, c, cp); break;                 \
   PROG_CASE_U1_4(kind)
 #define PROG_CASE_CX(a, b) case PROG_SITE_CX(a, b): BT_CASE_MARK(PROG_SITE_CX(a, b)); prog_cx<a, b>(x); break;
 #define PROG_CASE_CP(a, b) case PROG_SITE_CPHASE(a, b): BT_CASE_MARK(PROG_SITE_CPHASE(a, b)); prog_cphase<a, b>(x, c); break;
@@ -506,7 +506,7 @@ __device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const doubl
   case PROG_SITE_CPH1(p): {                                                                                         \
     BT_CASE_MARK(PROG_SITE_CPH1(p));                                                                               \
     const uint64_t em = (uint64_t)__double_as_longlong(c[2]), lm = (uint64_t)__double_as_longlong(c[3]);            \
-    if ((base & em) == em && (gl & lm) == lm) prog_u1<PK_PHASE, p>(x, c);                                           \
+    if ((base & em) == em && (gl & lm) == lm) prog_u1<PK_PHASE, p>(x, c, cp);                                           \
   } break;
 #define PROG_CASE_CCX1(p)                                                                                           \
   case PROG_SITE_CCX1(p): {                                                                                         \
@@ -538,11 +538,19 @@ __device__ __forceinline__ void run_prog(const TileParams& P, int pi, double2* _
       for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) a ^= o[q];
       x[j] = sm[a];
     }
+    // Three dependent constant loads would sit on the critical path of every micro-op (op word -> jump-table entry ->
+    // coefficients) with only three warps per scheduler to hide them.  So: the op word of op k+1 is fetched during op k
+    // (op[nops] is a padding entry), and the first four coefficients are fetched BEFORE the indirect branch (the marker
+    // takes them as inputs), in the shadow of the jump-table load.
+    uint32_t opw = G.op[0];
     for (uint32_t k = 0; k < nops; ++k) {
-      const uint32_t op = G.op[k];
-      const double* __restrict__ c = G.coef + (op >> 8);
+      const uint32_t op = opw;
+      opw = G.op[k + 1];
+      const double* __restrict__ cp = G.coef + (op >> 8);
+      const double c[4] = {cp[0], cp[1], cp[2], cp[3]};
       const uint32_t site = op & 0xffu;
-      asm volatile("// BT_DISPATCH %0;" ::"r"(site));  // tools/ptx_brx.py turns the switch below into one brx.idx
+      // tools/ptx_brx.py turns the switch below into one brx.idx
+      asm volatile("// BT_DISPATCH %0;" ::"r"(site), "r"(opw), "d"(c[0]), "d"(c[1]), "d"(c[2]), "d"(c[3]));
       switch (site) {
         PROG_CASE_U1(PK_GEN)
         PROG_CASE_U1(PK_REAL)
@@ -1557,6 +1565,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         }
         if (ko > PROG_MAXOPS || kc > PROG_MAXCOEF) BT_FAIL(BT_ERR_ARG, "internal: register program overflow");
         G.nops = (uint32_t)ko;
+        G.op[ko] = (uint16_t)0xff;  // padding (fetched, never executed)
         P.item[nitems++] = (uint8_t)(TILE_PBASE + np);
         np++;
         g_fused_blocks += members.size();
