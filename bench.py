@@ -142,13 +142,16 @@ def bench_single(args):
     if counts[dom] > 0:
         avg_ms = cms[dom] / counts[dom]
         ach = bytes_per_launch / (avg_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_tile (fused multi-gate pass)" if dom == 0 else cls_names[dom], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k_tile_tma (fused multi-gate pass: TMA tile in/out + register programs)" if dom == 0 else cls_names[dom], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_step": cms[dom] / (ms.value), "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_spec": ach / 8000.0}
         if dom == 0 and cms[0] > 0:
             tf = (fl1.value - fl0.value) / (cms[0] / 1e3) / 1e12
             roof["fp64"] = {"achieved_tflops": tf, "peak_tflops_measured": 36.0, "frac": tf / 36.0,
-                            "note": "the fused pass is past the FP64 ridge by design (about 7 dense 4x4 blocks per HBM pass); peak = DFMA loop measured by tools/fp64_peak.cu"}
+                            "note": "useful FP64 flops of the structured micro-ops (real / RX-like / diagonal gates cost half of a dense 2x2, CX none); "
+                                    "a pass fuses ~30 gates, so it sits between the HBM and FP64 roofs and is bound by micro-op dispatch + FP64 issue "
+                                    "(profiles/r1_k_tile_tma_*): peak = DFMA loop measured by tools/fp64_peak.cu"}
+            roof["gates_per_launch"] = ngates * args.steps / max(1, int(counts[0]))
         tfile = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(tfile):
             try:

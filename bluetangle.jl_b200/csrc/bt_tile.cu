@@ -1645,7 +1645,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   fuse_blocks(gates, blocks);
   const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   const int lowb = std::min(tile_lowb(), T);
-  const int maxg = std::max(1, std::min(40, env_int("BT_FUSE_MAX_GATES", 10)));
+  const int maxg = std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", 28)));  // cost units per pass (measured sweep: profiles/r1_fusion_sweep.txt)
   const int window = env_int("BT_FUSE_WINDOW", 256);
   const size_t n = blocks.size();
   std::vector<char> done(n, 0);
@@ -1683,8 +1683,10 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
         if (b.sok) need = b.abits;  // structured blocks: the bits they act on non-diagonally must be program positions
         int extra = 0;
         for (int t : need) if (!in_tile[t]) extra++;
-        double c = b.desc.diag ? 0.25 : (b.desc.k == 2 ? 1.0 : 0.6);
-        if (b.sok) c = 0.15 * (double)b.prog.size() + 0.04 * b.scost;  // decode + arithmetic of the micro-ops
+        // cost units: a dense 4x4 block = 2.8 (the cap of 28 keeps ~10 of them per pass, the measured optimum for dense passes);
+        // a structured block pays per micro-op (dispatch) and per FP64 instruction
+        double c = b.desc.diag ? 0.7 : (b.desc.k == 2 ? 2.8 : 1.7);
+        if (b.sok) c = 0.15 * (double)b.prog.size() + 0.04 * b.scost;
         if (tile_cnt + extra > T || (int)pass.size() >= 44 || (cost + c > (double)maxg && !pass.empty())) ok = false;
         if (ok) {
           for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
