@@ -139,6 +139,8 @@ struct TileParams {
   int32_t swz_mode;     // 0: TMA-compatible 128-B swizzle, 1: all-digit swizzle
   int32_t tma_coord_shift[5];  // tensor-copy variant: coordinate k of a tile = (base >> shift[k]) & mask[k]
   uint32_t tma_coord_mask[5];
+  int32_t tma_ncopy;           // a tile whose bits form more than four runs moves as 2, 4 or 8 boxes: the top tile bits are enumerated
+  int32_t tma_c4add[8];        // copy e: added to coordinate 4; its shared-memory chunk is e * (tile bytes / ncopy)
   int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
   uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];
@@ -714,10 +716,12 @@ __global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MIN
   const int dbg = P.stagger_ns < 0 ? -P.stagger_ns : 0;  // measurement aid: 1 = no gates, 2 = no HBM traffic (results invalid)
   if (tid == 0 && dbg != 2) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(sizeof(double2) << T)) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
-        "l"(tm), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mb)
-        : "memory");
+    const uint32_t chunk = (uint32_t)(sizeof(double2) << T) / (uint32_t)P.tma_ncopy;
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst + e * chunk),
+          "l"(tm), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4 + P.tma_c4add[e]), "r"(mb)
+          : "memory");
   }
   // wait for the tile (phase 0); bounded spin so that a descriptor mistake traps instead of hanging the GPU
   if (dbg != 2) {
@@ -737,9 +741,11 @@ __global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MIN
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0 && dbg != 2) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2),
-                 "r"(c3), "r"(c4), "r"(dst)
-                 : "memory");
+    const uint32_t chunk = (uint32_t)(sizeof(double2) << T) / (uint32_t)P.tma_ncopy;
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2),
+                   "r"(c3), "r"(c4 + P.tma_c4add[e]), "r"(dst + e * chunk)
+                   : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay valid until it has been read
   }
@@ -1247,16 +1253,34 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
     if (!in[b]) { ++b; continue; }
     int e = b;
     while (e < s->n_local && in[e] && e - b < 8) ++e;
-    if (nr >= 4) return false;
+    if (nr >= 7) return false;
     run_start[nr] = b; run_len[nr] = e - b; nr++;
     b = e;
   }
   if (nr == 0) return false;
   if (run_start[0] != 3) {
     // bits 3 .. run_start[0]-1 are not tile bits: they take a dimension of their own with a box of 1
-    if (nr >= 4) return false;
     for (int k = nr; k > 0; --k) { run_start[k] = run_start[k - 1]; run_len[k] = run_len[k - 1]; }
     run_start[0] = 3; run_len[0] = 0; nr++;
+  }
+  // more than four runs: the tile bits of the runs above the fourth are enumerated -- one box per value (<= 8 boxes)
+  P.tma_ncopy = 1;
+  P.tma_c4add[0] = 0;
+  if (nr > 4) {
+    int ebits[8], ne = 0;
+    for (int k = 4; k < nr; ++k)
+      for (int j = 0; j < run_len[k]; ++j) {
+        if (ne >= 3) return false;
+        ebits[ne++] = run_start[k] + j;
+      }
+    P.tma_ncopy = 1 << ne;
+    for (int e = 0; e < (1 << ne); ++e) {
+      int64_t add = 0;
+      for (int j = 0; j < ne; ++j) if ((e >> j) & 1) add += (int64_t)1 << (ebits[j] - run_start[3]);
+      if (add > 0x7fffffff) return false;
+      P.tma_c4add[e] = (int32_t)add;
+    }
+    nr = 4;
   }
   cuuint64_t gdim[5], gstride[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
@@ -1343,6 +1367,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     P.stagger_ns = env_int("BT_TILE_STAGGER_NS", 0);
     P.n_sm = nsm;
     if (env_int("BT_TILE_DEBUG", 0)) {
+      if (!use_tma) { fprintf(stderr, "[tile] no tensor map for bits:"); for (int b = 0; b < 64; ++b) if (in[b]) fprintf(stderr, " %d", b); fprintf(stderr, "\n"); }
       fprintf(stderr, "[tile] T=%d tma=%d items=%d gates=%d clusters=%d diags=%d progs=%d ops:", T, (int)use_tma, nitems, ng, nc, nd, np);
       for (int q = 0; q < np; ++q) fprintf(stderr, " %u(%d,%d,%d,%d)", P.pr[q].nops, P.pr[q].lp[0], P.pr[q].lp[1], P.pr[q].lp[2], P.pr[q].lp[3]);
       fprintf(stderr, "\n");
