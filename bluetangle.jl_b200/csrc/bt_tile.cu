@@ -1389,6 +1389,14 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     return BT_OK;
   };
 
+  // a block can run inside a register program when it kept its structured form and the bits it acts on are tile bits
+  const bool use_progs = env_int("BT_TILE_PROGS", 1) != 0 && T >= PROG_BITS;
+  auto prog_eligible = [&](const Block* b) -> bool {
+    if (!use_progs || !b->sok || b->opaque) return false;
+    for (int t : b->abits) if (local_pos[t] < 0) return false;
+    return true;
+  };
+
   struct Try {
     int nm;
     uint32_t use;
@@ -1413,7 +1421,8 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       bool dep = false;
       for (int t : hb->touch) if (blocked[t]) dep = true;
       bool placed = false;
-      if (!dep && cluster_eligible(h)) {
+      // (a structured block only asked for the bits it acts on: its dense form may have a target outside the tile)
+      if (!dep && cluster_eligible(h) && !prog_eligible(hb) && local_pos[h.tb[0]] >= 0 && local_pos[h.tb[1]] >= 0) {
         int a = h.tb[0], b = h.tb[1];  // matrix bit 0 <-> a, bit 1 <-> b
         for (int sl = (jj == i ? seed_slot : 0); sl < CL_SLOTS && !placed; ++sl) {
           if (R.use & (1u << sl)) continue;
@@ -1442,13 +1451,6 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     }
   };
 
-  // a block can run inside a register program when it kept its structured form and all its bits are tile bits
-  const bool use_progs = env_int("BT_TILE_PROGS", 1) != 0 && T >= PROG_BITS;
-  auto prog_eligible = [&](const Block* b) -> bool {
-    if (!use_progs || !b->sok || b->opaque) return false;
-    for (int t : b->abits) if (local_pos[t] < 0) return false;
-    return true;
-  };
   // ops / coefficients a block needs once its ops are resolved against a program (upper bounds: an out-of-program DIAG splits)
   auto prog_demand = [&](const Block* b, int* nops, int* ncoef) {
     *nops = 0; *ncoef = 0;
@@ -1623,7 +1625,9 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         uint32_t fixed = 0;
         for (int p = 0; p < CL_BITS; ++p) fixed |= 1u << Cl.lp[p];
         Cl.use = best.use;
-        if (build_group_walk(T, fixed, CL_BITS, Cl.bit_sw, Cl.iter_sw, 8, &Cl.niter, P.swz_mode) != 0) BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long");
+        if (build_group_walk(T, fixed, CL_BITS, Cl.bit_sw, Cl.iter_sw, 8, &Cl.niter, P.swz_mode) != 0)
+          BT_FAIL(BT_ERR_ARG, "internal: cluster loop too long (T=%d fixed=0x%x lp=%d,%d,%d bits=%d,%d,%d,%d nm=%d)", T, fixed, Cl.lp[0], Cl.lp[1], Cl.lp[2],
+                  best.bit_at_pos[0], best.bit_at_pos[1], best.bit_at_pos[2], best.bit_at_pos[3], best.nm);
         for (int mI = 0; mI < best.nm; ++mI) {
           const GateDesc& h = pass[best.member[mI]]->desc;
           cplx mm[16];

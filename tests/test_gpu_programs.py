@@ -1,0 +1,151 @@
+"""GPU parity of the register programs of the fused tile kernel (bt_tile.cu: structured micro-ops kept from the named
+gates -- real / RX-like / diagonal / phase 1-qubit ops, CX, CPHASE -- plus the conditional forms for control and phase
+bits outside a program) against the kron-chain oracle, through bt_sv_apply_circuit.
+
+Every micro-op kind, every program position and the three homes of a control bit (program position, other tile bit,
+outside the tile) are reached by shrinking the tile (BT_TILE_BITS) and the always-in-tile low bits (BT_TILE_LOWB), which
+the library reads at every call.  Tolerance 1e-10 absolute on amplitudes (north star)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rand_state(N, seed):
+    g = np.random.default_rng(seed)
+    v = g.normal(size=1 << N) + 1j * g.normal(size=1 << N)
+    return v / np.linalg.norm(v)
+
+
+ONE = ["H", "X", "Y", "Z", "S", "SD", "T", "SX", "RX", "RY", "RZ", "P", "U3"]
+TWO = ["CX", "CNOT", "CZ", "CP", "RZZ"]
+
+
+def structured_circuit(bt, orc, N, n_ops, seed, far=True):
+    """named gates only (so that blocks keep a structured form), on random -- also distant -- qubits; controlled 1-qubit
+    gates with the control anywhere"""
+    g = np.random.default_rng(seed)
+    od, oo = [], []
+
+    def both(name, *a, **k):
+        od.append(bt.Op(name, *a, **k)); oo.append(orc.Op(name, *a, **k))
+
+    for _ in range(n_ops):
+        r = g.random()
+        th = round(float(g.uniform(-3, 3)), 3)
+        if r < 0.5 or N == 1:
+            n = ONE[int(g.integers(len(ONE)))]
+            q = int(g.integers(1, N + 1))
+            if n in ("RX", "RY", "RZ", "P"):
+                n = f"{n}({th})"
+            elif n == "U3":
+                n = f"U3({th},{round(th * 0.7, 3)},{round(-th * 1.3, 3)})"
+            both(n, q)
+        elif r < 0.85:
+            n = TWO[int(g.integers(len(TWO)))]
+            if far:
+                q, t = (int(x) + 1 for x in g.choice(N, 2, replace=False))
+            else:
+                q = int(g.integers(1, N)); t = q + 1
+                if g.random() < 0.5:
+                    q, t = t, q
+            if n in ("CP", "RZZ"):
+                n = f"{n}({th})"
+            both(n, q, t)
+        else:
+            q, c = (int(x) + 1 for x in g.choice(N, 2, replace=False))
+            n = ["X", "Z", "T", "S", f"RZ({th})", f"P({th})"][int(g.integers(6))]
+            both(n, q, control=c)
+    return od, oo
+
+
+class tile_env:
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def fused_vs_oracle(bt, orc, N, od, oo, seed):
+    v = rand_state(N, seed)
+    s = bt.CuState.from_numpy(v)
+    bt.apply(od, s)
+    ref = orc.apply_ops(v, oo)
+    return float(np.max(np.abs(s.to_numpy() - ref)))
+
+
+@pytest.mark.parametrize("N", [4, 5, 6, 8, 10, 12, 13, 14])
+def test_structured_circuits_default_tile(bt, orc, N):
+    od, oo = structured_circuit(bt, orc, N, 120, 1000 + N)
+    assert fused_vs_oracle(bt, orc, N, od, oo, N) < TOL
+
+
+@pytest.mark.parametrize("T,lowb", [(8, 3), (8, 5), (9, 4), (10, 3), (11, 5), (12, 3)])
+def test_structured_circuits_small_tiles(bt, orc, T, lowb):
+    """N = 14 with tiles of 8..12 bits: controls / phase bits fall outside the tile (tile-base predicate), inside the tile
+    but outside the program (thread predicate) and on program positions; tile bit sets with gaps exercise the tensor map
+    with a gap dimension and the multi-box copies."""
+    N = 14
+    with tile_env(BT_TILE_BITS=T, BT_TILE_LOWB=lowb):
+        for seed in range(3):
+            od, oo = structured_circuit(bt, orc, N, 150, 7 * T + lowb + 100 * seed)
+            assert fused_vs_oracle(bt, orc, N, od, oo, seed) < TOL
+
+
+def test_structured_brickwork_and_qft(bt, orc):
+    """the two shapes of the headline workload at a size the oracle finishes: QFT (chains of controlled phases around one
+    H per qubit) and H/RX/RY/RZ/T + CNOT/CZ/CP brickwork"""
+    N = 13
+    from importlib import import_module
+    wl = import_module(bt.__name__ + ".workloads")
+    for specs in (wl.qft(N), wl.layered(N, 12, 5), wl.c2_qft_layered(N, 6, 9)):
+        od = wl.to_ops(bt, specs)
+        oo = [orc.Op(n, q, t, control=c) for (n, q, t, c) in specs]
+        for env in ({}, {"BT_TILE_BITS": 9, "BT_TILE_LOWB": 3}, {"BT_FUSE_MAX_GATES": 3}):
+            with tile_env(**env):
+                assert fused_vs_oracle(bt, orc, N, od, oo, 1) < TOL
+
+
+def test_programs_equal_dense_path(bt):
+    """same circuit with the structured forms switched off (BT_TILE_PROGS=0: dense 4x4 blocks) and through the single-gate
+    kernels: three independent implementations, one answer"""
+    N = 16
+    from importlib import import_module
+    wl = import_module(bt.__name__ + ".workloads")
+    ops = wl.to_ops(bt, wl.c2_qft_layered(N, 10, 3))
+    arr = bt.pack_gates(ops)
+    L = bt._lib
+    outs = []
+    for env, fuse in (({}, 1), ({"BT_TILE_PROGS": 0}, 1), ({}, 0)):
+        with tile_env(**env):
+            s = bt.zero_state(N)
+            L.check(s.lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), fuse))
+            outs.append(s.to_numpy())
+    assert np.max(np.abs(outs[0] - outs[2])) < TOL
+    assert np.max(np.abs(outs[1] - outs[2])) < TOL
+
+
+def test_batched_states_through_programs(bt, orc):
+    """batch index bits are ordinary high index bits for the tile kernel: programs on a batch of 4 trajectories"""
+    N, B = 9, 4
+    od, oo = structured_circuit(bt, orc, N, 80, 77)
+    g = np.random.default_rng(5)
+    v = g.normal(size=(B, 1 << N)) + 1j * g.normal(size=(B, 1 << N))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    s = bt.CuState.from_numpy(v)
+    bt.apply(od, s)
+    got = s.to_numpy()
+    for t in range(B):
+        assert np.max(np.abs(got[t] - orc.apply_ops(v[t], oo))) < TOL
