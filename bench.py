@@ -236,7 +236,11 @@ def bench_sharded(args):
     D = import_module(ge.PKG_NAME + ".dist")
     rank, world, local = D.env_rank_world()
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 prints exactly ONE JSON line on stdout: NCCL writes its version banner to the process's stdout from C, so file
+    # descriptor 1 points at stderr while the job runs and the line goes out through a saved copy of the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = world.bit_length() - 1
@@ -309,12 +313,16 @@ def bench_sharded(args):
                "circuit_gates_per_s": ngates / (ms_per_step / 1e3), "clocks": clk, "gpu_launches": int(n1 - n0),
                "kernels_rank0": {n: {"launches": int(counts[i]), "ms": float(cms[i])} for i, n in enumerate(["tile", "dense", "diag", "other"])},
                "host_seconds_rank0": t_host,
+               "roofline": ({"bound": "hbm", "kernel": "k_tile_tma (fused multi-gate pass) on rank 0's shard", "achieved": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9,
+                             "peak": load_peaks()[0]["hbm_gbs"], "unit": "GB/s", "frac": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9 / load_peaks()[0]["hbm_gbs"],
+                             "traffic": None, "avg_launch_ms": cms[0] / counts[0], "bytes_per_launch": 32.0 * (1 << n_local)} if counts[0] else None),
                "remap": {"per_step": remaps, "nvlink_bytes_per_rank_per_step": rbytes, "ms_per_step": rms, "GBps_per_rank": (rbytes / (rms / 1e3) / 1e9) if rms > 0 else None,
                          "nvlink_peak_GBps": 900.0},
                "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes), "d2h_bytes_per_step": int(ez.nbytes + 8),
                        "note": "device-timed; the host API call (gate list in) is the timed call itself"},
                "checksum": {"norm2": float(nrm[0]), "sum_expect_Z": float(np.sum(ez))}}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
     del st
