@@ -751,6 +751,93 @@ __global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MIN
   }
 }
 
+// Pipelined tensor-copy variant (BT_TILE_PIPE = K > 1, tiles of <= 2^11 amplitudes): a CTA owns K consecutive tiles and two
+// tile buffers.  The load of tile i+1 (and i+2 once the store of tile i has left its buffer) is in flight while the items of
+// tile i run, and the store of tile i drains while tile i+1 computes: the only exposed copies are the first load and the
+// last store of the CTA.
+template <bool FULL>
+__global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MINB) k_tile_pipe(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileParams P,
+                                                                                               int K) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  const int T = P.T, lowb = P.lowb;
+  const uint32_t nloc = 1u << T;
+  const uint32_t tile_bytes = (uint32_t)(sizeof(double2) << T);
+  double2* buf0 = reinterpret_cast<double2*>(smem_raw + pad);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + pad + 2 * (size_t)tile_bytes);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t mb0 = smem_u32(mbar), dst0 = smem_u32(buf0);
+  const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+  const uint64_t t0 = (uint64_t)blockIdx.x * (uint64_t)K;
+  const uint32_t chunk = tile_bytes / (uint32_t)P.tma_ncopy;
+
+  auto tile_base = [&](uint64_t t) {
+    uint64_t base = t << lowb;
+    for (int j = lowb; j < T; ++j) {
+      int b = P.tbits[j];
+      base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
+    }
+    return base;
+  };
+  auto issue_load = [&](int i) {  // thread 0 only
+    const uint64_t base = tile_base(t0 + i);
+    const int32_t c1 = (int32_t)((base >> P.tma_coord_shift[1]) & P.tma_coord_mask[1]), c2 = (int32_t)((base >> P.tma_coord_shift[2]) & P.tma_coord_mask[2]);
+    const int32_t c3 = (int32_t)((base >> P.tma_coord_shift[3]) & P.tma_coord_mask[3]), c4 = (int32_t)((base >> P.tma_coord_shift[4]) & P.tma_coord_mask[4]);
+    const uint32_t mb = mb0 + 8u * (i & 1), dst = dst0 + (i & 1) * tile_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tile_bytes) : "memory");
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst + e * chunk),
+          "l"(tm), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4 + P.tma_c4add[e]), "r"(mb)
+          : "memory");
+  };
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb0 + 8u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    issue_load(0);
+    if (K > 1) issue_load(1);
+  }
+  for (int i = 0; i < K; ++i) {
+    const uint32_t mb = mb0 + 8u * (i & 1), dst = dst0 + (i & 1) * tile_bytes;
+    double2* sm = buf0 + (size_t)(i & 1) * nloc;
+    const uint64_t base = tile_base(t0 + i);
+    {
+      const uint32_t parity = (uint32_t)(i >> 1) & 1u;
+      uint32_t done = 0;
+      for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+        if (spin > (1u << 22)) __trap();
+      }
+    }
+    for (int it = 0; it < P.nitems; ++it) {
+      run_item<TILE_THREADS, FULL>(P.item[it], P, sm, base, tid, nloc);
+      __syncthreads();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const int32_t c1 = (int32_t)((base >> P.tma_coord_shift[1]) & P.tma_coord_mask[1]), c2 = (int32_t)((base >> P.tma_coord_shift[2]) & P.tma_coord_mask[2]);
+      const int32_t c3 = (int32_t)((base >> P.tma_coord_shift[3]) & P.tma_coord_mask[3]), c4 = (int32_t)((base >> P.tma_coord_shift[4]) & P.tma_coord_mask[4]);
+      for (int e = 0; e < P.tma_ncopy; ++e)
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(0), "r"(c1), "r"(c2),
+                     "r"(c3), "r"(c4 + P.tma_c4add[e]), "r"(dst + e * chunk)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (i + 2 < K) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the store has left this buffer: refill it
+        issue_load(i + 2);
+      }
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
 // 2^T buffer, tile i+1 streams into the other with cp.async, so each CTA keeps HBM requests in flight during its own
 // FP64 phase.  With T = 11 this is 2 x 32 KB per CTA: still 3 CTAs per SM.
@@ -1356,6 +1443,8 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
+    BT_CUDA(cudaFuncSetAttribute(k_tile_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set[s->device & 63] = true;
   }
@@ -1374,7 +1463,13 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     }
     bt_prof_begin(s, BT_CLS_TILE);
     if (use_tma) {
-      if (ng == 0 && nc == 0 && env_int("BT_TILE_LITE", 1)) k_tile_tma<false><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
+      const bool lite = ng == 0 && nc == 0 && env_int("BT_TILE_LITE", 1);
+      int K = env_int("BT_TILE_PIPE", 0);
+      while (K > 1 && (ntiles % (uint64_t)K != 0 || ntiles / (uint64_t)K < (uint64_t)(6 * nsm))) K >>= 1;
+      if (K > 1 && T <= 11 && (K & (K - 1)) == 0) {
+        if (lite) k_tile_pipe<false><<<(unsigned)(ntiles / K), TILE_THREADS, 2 * smem + 1024 + 64, s->stream>>>(tmap, P, K);
+        else k_tile_pipe<true><<<(unsigned)(ntiles / K), TILE_THREADS, 2 * smem + 1024 + 64, s->stream>>>(tmap, P, K);
+      } else if (lite) k_tile_tma<false><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
       else k_tile_tma<true><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
     } else if (dbuf) {
       uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
