@@ -1,0 +1,91 @@
+"""CPU checks of the build-time PTX rewrite (tools/ptx_brx.py) and of what the built library contains (SASS mnemonics)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ptx_brx  # noqa: E402
+
+PTX = """
+.visible .entry kern(
+	.param .u64 p
+)
+{
+	.reg .pred %p<9>;
+	.reg .b32 %r<9>;
+	and.b32  	%r7, %r8, 255;
+	// begin inline asm
+	// BT_DISPATCH %r7;
+	// end inline asm
+	setp.gt.s32 	%p1, %r7, 1;
+	@%p1 bra 	$L__BB0_3;
+	setp.eq.s32 	%p2, %r7, 0;
+	@%p2 bra 	$L__BB0_1;
+	bra.uni 	$L__BB0_2;
+$L__BB0_1:
+	// begin inline asm
+	// BT_CASE 0;
+	// end inline asm
+	add.s32 %r1, %r1, 1;
+	bra.uni 	$L__BB0_9;
+$L__BB0_2:
+	// begin inline asm
+	// BT_CASE 1;
+	// end inline asm
+	add.s32 %r1, %r1, 2;
+	bra.uni 	$L__BB0_9;
+$L__BB0_3:
+	setp.eq.s32 	%p3, %r7, 3;
+	@%p3 bra 	$L__BB0_4;
+	bra.uni 	$L__BB0_9;
+$L__BB0_4:
+	// begin inline asm
+	// BT_CASE 3;
+	// end inline asm
+	add.s32 %r1, %r1, 3;
+$L__BB0_9:
+	// begin inline asm
+	// BT_CASE 255;
+	// end inline asm
+	ret;
+}
+"""
+
+
+def test_switch_becomes_one_indirect_branch():
+    out = ptx_brx.patch(PTX)
+    assert "brx.idx %bt_idx, $BT_TBL_0;" in out
+    line = [l for l in out.splitlines() if ".branchtargets" in l][0]
+    # sites 0, 1, hole (2 -> default), 3, and the clamp entry for indices past the table
+    assert line.split(".branchtargets")[1].strip() == "$L__BB0_1, $L__BB0_2, $L__BB0_9, $L__BB0_4, $L__BB0_9;"
+    assert "min.u32 %bt_idx, %r7, 4;" in out
+    # the compare tree is left in place (unreachable after the indirect branch; ptxas drops it)
+    assert out.count("setp") == PTX.count("setp")
+
+
+def test_rewrite_refuses_unsafe_trees():
+    # an instruction with side effects inside the compare tree: the function must be left untouched
+    bad = PTX.replace("	setp.eq.s32 	%p3, %r7, 3;", "	st.global.u32 [%r2], %r3;\n	setp.eq.s32 	%p3, %r7, 3;")
+    assert ptx_brx.patch(bad) == bad
+    # duplicated dispatch marker (the compiler cloned the loop): untouched
+    dup = PTX.replace("	ret;", "	// BT_DISPATCH %r7;\n	ret;")
+    assert ptx_brx.patch(dup) == dup
+    # no default marker: untouched
+    nodef = PTX.replace("// BT_CASE 255;", "// nothing")
+    assert ptx_brx.patch(nodef) == nodef
+
+
+def test_library_holds_tensor_copies_and_indirect_branch():
+    """the fused tile kernel must contain the TMA tensor load/store (UTMALDG / UTMASTG), the mbarrier wait and the BRX dispatch"""
+    lib = os.path.join(ROOT, "bluetangle.jl_b200", "lib", "libbluetangle_cuda.so")
+    if not os.path.exists(lib) or shutil.which("cuobjdump") is None:
+        pytest.skip("library or cuobjdump not present")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z10k_tile_tmaILb0EEv14CUtensorMap_st10TileParams", lib], capture_output=True, text=True).stdout
+    assert "UTMALDG.5D" in sass and "UTMASTG.5D" in sass and "SYNCS.PHASECHK" in sass
+    if os.environ.get("BT_NO_BRX"):
+        return
+    assert "BRX" in sass, "micro-op dispatch was not rewritten to brx.idx (tools/ptx_brx.py)"
