@@ -1076,6 +1076,37 @@ def hamiltonian_expect(x: State, terms) -> float:
     return tot
 
 
+def shadow(circuit, number_of_experiment: int, rng=None) -> np.ndarray:
+    """``shadow(circuit, number_of_experiment)`` -- src/ops.jl:145-185: classical-shadow estimate of the circuit's density
+    matrix.  Per experiment, in the reference's draw order: run the circuit (noise / mid-circuit draws), then for qubit 1..N
+    draw a basis ``rand(1:3)`` and rotate with H / HSP / I (``m_list``, :148), then one ``sample(state, 1)`` shot; the
+    snapshot is kron_i (3 U_i' |b_i><b_i| U_i - I) and rho is their mean.  The circuit, the N rotations (one fused call)
+    and the shot run on the device; the 2^N x 2^N estimate is assembled on the host (dense; the reference returns a sparse
+    matrix) -- as in the reference this is a small-N tool.  Throws like the reference when tr(rho) is not 1."""
+    r = _rng(rng)
+    circ = circuit if isinstance(circuit, Circuit) else compile(list(circuit))
+    N = circ.N
+    m_list = [gate["H"], gate["HSP"], gate["I"]]
+    names = ["Xbasis", "Ybasis", "Zbasis"]
+    eye = np.eye(2, dtype=np.complex128)
+    rho = np.zeros((1 << N, 1 << N), dtype=np.complex128)
+    for _ in range(number_of_experiment):
+        state = to_state(circ, rng=r)
+        basis = [r.randint(3) for _ in range(N)]
+        apply([Op(names[m], m_list[m], q + 1) for q, m in enumerate(basis) if m != 2], state)
+        bits = int2bin(int(sample(state, 1, rng=r)[0]), N)
+        snap = np.ones((1, 1), dtype=np.complex128)
+        for b, m in zip(bits, basis):
+            bv = np.zeros((2, 1), dtype=np.complex128)
+            bv[b, 0] = 1.0
+            um = m_list[m]
+            snap = np.kron(snap, 3.0 * (um.conj().T @ bv @ bv.conj().T @ um) - eye)
+        rho += snap / number_of_experiment
+    if not np.isclose(np.trace(rho), 1.0):
+        raise ValueError("la.tr(rho)!≈1")
+    return rho
+
+
 def entanglement_entropy(state: CuState) -> float:
     """src/func.jl:299-312: Schmidt spectrum across the cut between the first N - N/2 and the last N/2 qubits (Julia reshapes
     column-major, so its rows are the LOW N/2 index bits).  The SVD runs on the host on a downloaded copy: a convenience for

@@ -1072,6 +1072,34 @@ def run(ops, N: int, shots: int, noise=False, draws: Optional[Draws] = None) -> 
     return out
 
 
+def shadow(ops, N: int, number_of_experiment: int, noise=False, draws: Optional[Draws] = None) -> np.ndarray:
+    """src/ops.jl:145-185: classical shadow.  Draw order per experiment as in the reference: circuit draws (to_state, :152),
+    then ``rand(1:3)`` per qubit (:157), then the single shot (:162).  Dense instead of sparse."""
+    draws = draws or Draws(0)
+    m_list = [GATE["H"], GATE["HSP"], GATE["I"]]
+    eye = np.eye(2, dtype=C)
+    rho = np.zeros((1 << N, 1 << N), dtype=C)
+    for _ in range(number_of_experiment):
+        state = to_state(ops, N, noise=noise, draws=draws)
+        basis = []
+        for q in range(1, N + 1):
+            m = draws.randint(3)
+            state = apply(state, Op(["Xbasis", "Ybasis", "Zbasis"][m], q, mat=m_list[m]))  # a rotation, not a measurement (:158)
+            basis.append(m)
+        k = int(sample(state, [draws.uniform()])[0])
+        bits = int2bin(k, N)
+        snap = np.ones((1, 1), dtype=C)
+        for b, m in zip(bits, basis):
+            bv = np.zeros((2, 1), dtype=C)
+            bv[b, 0] = 1.0
+            um = m_list[m]
+            snap = np.kron(snap, 3.0 * (um.conj().T @ bv @ bv.conj().T @ um) - eye)  # :173
+        rho += snap / number_of_experiment
+    if not np.isclose(np.trace(rho), 1.0):
+        raise ValueError("la.tr(rho)!≈1")
+    return rho
+
+
 def final_measurement(state: np.ndarray, basis: str = "Z", draws: Optional[Draws] = None) -> np.ndarray:
     """src/ops.jl:856-914 without readout noise (broken in the reference, SURVEY App. A.5 #6)."""
     N = get_N(state)

@@ -28,3 +28,21 @@ def test_monitored_fixture_from_logged_draws():
         s, mids = O.apply_ops(O.zero_state(6), ops, noise=nm, draws=O.ListDraws(G[f"mon{seed}_draws"]), track_measurements=True)
         assert list(mids) == list(G[f"mon{seed}_mids"])
         assert np.max(np.abs(s - G[f"mon{seed}_state"])) < 1e-14
+
+
+def test_oracle_shadow_converges_and_follows_the_draw_order():
+    """src/ops.jl:145-185 restated: tr(rho) = 1 exactly; the estimate converges to |psi><psi|; the bases are exactly the
+    integers drawn between the circuit and the shot (ListDraws replays them)."""
+    import numpy as np
+    from oracle import bt_oracle as O
+    ops = [O.Op("H", 1), O.Op("CNOT", 1, 2), O.Op("RY(0.7)", 3)]
+    psi = O.apply_ops(O.zero_state(3), ops)
+    rho = O.shadow(ops, 3, 3000, draws=O.Draws(5))
+    assert abs(np.trace(rho) - 1) < 1e-9
+    assert abs(np.real(psi.conj() @ rho @ psi) - 1) < 0.1
+    # one experiment, all qubits in the Z basis (index 2), shot u = 0.0 -> first basis state with support (|000>)
+    one = O.shadow(ops, 3, 1, draws=O.ListDraws([0.0], ints=[2, 2, 2]))
+    snap = np.ones((1, 1))
+    for _ in range(3):
+        snap = np.kron(snap, 3 * np.diag([1.0, 0.0]) - np.eye(2))
+    assert np.max(np.abs(one - snap)) < 1e-12

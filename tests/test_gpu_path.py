@@ -448,3 +448,21 @@ def test_qasm_circuit_end_to_end(bt, orc):
         else:
             ref = oo.expand(5) @ ref
     assert np.max(np.abs(st.to_numpy() - ref)) < TOL
+
+
+# ---- classical shadow (src/ops.jl:145-185) ---------------------------------------------------------
+def test_shadow_matches_oracle_draw_for_draw(bt, orc):
+    """same PCG64 stream on both sides: identical basis choices and shots, so the shadow estimates agree to rounding;
+    noiseless circuit and a noisy one with a mid-circuit measurement (trajectory draws precede the basis draws)."""
+    def ops(m):
+        return [m.Op("H", 1), m.Op("CX", 1, 2), m.Op("RY(0.37)", 3), m.Op("CP(0.8)", 2, 3), m.Op("MZ", 2), m.Op("RX(1.1)", 1)]
+    N, n_exp = 3, 60
+    rd = bt.shadow(ops(bt), n_exp, rng=bt.Draws(42))
+    ro = orc.shadow(ops(orc), N, n_exp, draws=orc.Draws(42))
+    assert abs(np.trace(rd) - 1) < 1e-12
+    assert np.max(np.abs(rd - ro)) < TOL
+    nm_d, nm_o = bt.NoiseModel("amplitude_damping", 0.1), orc.NoiseModel.model("amplitude_damping", 0.1)
+    circ = bt.compile(ops(bt), bt.Options(noise=nm_d))
+    rd = bt.shadow(circ, n_exp, rng=bt.Draws(7))
+    ro = orc.shadow(ops(orc), N, n_exp, noise=nm_o, draws=orc.Draws(7))
+    assert np.max(np.abs(rd - ro)) < TOL
