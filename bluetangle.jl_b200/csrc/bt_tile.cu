@@ -134,7 +134,7 @@ struct TileParams {
   int32_t T;            // tile bits
   int32_t lowb;         // min(TILE_LOWB, T)
   int32_t nitems;
-  int32_t stagger_ns;   // first-wave CTAs of SM slot r (= blockIdx / #SMs) start r * stagger_ns late: breaks the load/compute lockstep
+  int32_t stagger_ns;   // < 0: measurement modes (-1 = no gates, -2 = no HBM traffic; results invalid); BT_TILE_STAGGER_NS
   int32_t n_sm;
   int32_t swz_mode;     // 0: TMA-compatible 128-B swizzle, 1: all-digit swizzle
   int32_t tma_coord_shift[5];  // tensor-copy variant: coordinate k of a tile = (base >> shift[k]) & mask[k]
@@ -632,12 +632,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile(double2* __res
   const int T = P.T, lowb = P.lowb;
   const uint32_t tid = threadIdx.x;
   const uint32_t nloc = 1u << T;
-  if (P.stagger_ns > 0 && blockIdx.x < 3u * (uint32_t)P.n_sm) {
-    // all CTAs are identical, so the resident CTAs of an SM would load, compute and store in lockstep (HBM idle while
-    // FP64 runs and vice versa); a one-off offset per SM slot keeps their phases apart for the rest of the kernel
-    uint32_t r = blockIdx.x / (uint32_t)P.n_sm;
-    for (uint32_t w = 0; w < r; ++w) __nanosleep((unsigned)P.stagger_ns);
-  }
   // base index of this tile: blockIdx with zeros inserted at every tile bit position
   uint64_t base = (uint64_t)blockIdx.x << lowb;
   for (int j = lowb; j < T; ++j) {
@@ -836,70 +830,6 @@ __global__ void __launch_bounds__(TILE_THREADS, FULL ? TILE_MINB : TILE_LITE_MIN
     }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// Double-buffered variant: a CTA walks `tiles_per_cta` consecutive tiles; while the items of tile i run out of one
-// 2^T buffer, tile i+1 streams into the other with cp.async, so each CTA keeps HBM requests in flight during its own
-// FP64 phase.  With T = 11 this is 2 x 32 KB per CTA: still 3 CTAs per SM.
-__global__ void __launch_bounds__(TILE_THREADS, TILE_MINB) k_tile_db(double2* __restrict__ a, uint64_t ntiles, int tiles_per_cta, const __grid_constant__ TileParams P) {
-  extern __shared__ double2 smem[];
-  __shared__ uint64_t hi_off[1 << (TILE_TMAX - TILE_LOWB_MIN)];
-  const int T = P.T, lowb = P.lowb;
-  const uint32_t tid = threadIdx.x;
-  const uint32_t nloc = 1u << T;
-  const uint32_t nhi = 1u << (T - lowb);
-  const int dbg = P.stagger_ns < 0 ? -P.stagger_ns : 0;  // measurement aid: 1 = no gates, 2 = no HBM traffic (results invalid)
-  for (uint32_t h = tid; h < nhi; h += TILE_THREADS) {
-    uint64_t o = 0;
-    for (int j = lowb; j < T; ++j)
-      if ((h >> (j - lowb)) & 1u) o |= 1ull << P.tbits[j];
-    hi_off[h] = o;
-  }
-  __syncthreads();
-  const uint32_t lmask = (1u << lowb) - 1u;
-  auto tile_base = [&](uint64_t t) {
-    uint64_t base = t << lowb;
-    for (int j = lowb; j < T; ++j) {
-      int b = P.tbits[j];
-      base = ((base >> b) << (b + 1)) | (base & ((1ull << b) - 1ull));
-    }
-    return base;
-  };
-  auto issue_load = [&](uint64_t base, double2* buf) {
-    if (dbg != 2)
-      for (uint32_t c = tid; c < nloc; c += TILE_THREADS) __pipeline_memcpy_async(&buf[sw(c)], a + (base + hi_off[c >> lowb] + (c & lmask)), sizeof(double2));
-    __pipeline_commit();
-  };
-  uint64_t tile = (uint64_t)blockIdx.x * (uint64_t)tiles_per_cta;
-  if (tile >= ntiles) return;
-  const uint64_t tend = (tile + (uint64_t)tiles_per_cta < ntiles) ? tile + (uint64_t)tiles_per_cta : ntiles;
-  int cur = 0;
-  uint64_t base = tile_base(tile);
-  issue_load(base, smem);
-  while (true) {
-    const uint64_t next = tile + 1;
-    const bool have_next = next < tend;
-    uint64_t nbase = 0;
-    if (have_next) {
-      nbase = tile_base(next);
-      issue_load(nbase, smem + ((size_t)(cur ^ 1) << T));
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
-    double2* sm = smem + ((size_t)cur << T);
-    if (dbg != 1)
-      for (int i = 0; i < P.nitems; ++i) {
-        run_item<TILE_THREADS>(P.item[i], P, sm, base, tid, nloc);
-        __syncthreads();
-      }
-    if (dbg != 2)
-      for (uint32_t c = tid; c < nloc; c += TILE_THREADS) a[base + hi_off[c >> lowb] + (c & lmask)] = sm[sw(c)];
-    if (!have_next) break;
-    __syncthreads();  // everyone is done reading this buffer before the next prefetch overwrites it
-    tile = next; base = nbase; cur ^= 1;
-  }
 }
 
 // ---- host: fusion ------------------------------------------------------------------------------------------------------
@@ -1398,8 +1328,6 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
   int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   int lowb = std::min(tile_lowb(), T);
-  const int tiles_per_cta = std::max(1, env_int("BT_TILE_PER_CTA", 8));
-  const bool dbuf = env_int("BT_TILE_DB", 0) != 0 && (s->len >> T) >= 2 * (uint64_t)tiles_per_cta;
   const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= CL_BITS;
   // tile bits: low bits + requested + padding with the lowest free bits
   bool in[64] = {false};
@@ -1414,7 +1342,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   memset(&P, 0, sizeof(P));
   P.T = T; P.lowb = lowb;
   alignas(64) CUtensorMap tmap;
-  const bool use_tma = env_int("BT_TILE_TMA", 1) != 0 && !dbuf && build_tensor_map(s, in, T, &tmap, P);
+  const bool use_tma = env_int("BT_TILE_TMA", 1) != 0 && build_tensor_map(s, in, T, &tmap, P);
   P.swz_mode = use_tma ? 0 : 1;
   int local_pos[64];
   for (int b = 0; b < 64; ++b) local_pos[b] = -1;
@@ -1445,7 +1373,6 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     BT_CUDA(cudaFuncSetAttribute(k_tile_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
-    BT_CUDA(cudaFuncSetAttribute(k_tile_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(double2) << TILE_TMAX)));
     attr_set[s->device & 63] = true;
   }
   int nsm = 148;
@@ -1471,9 +1398,6 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
         else k_tile_pipe<true><<<(unsigned)(ntiles / K), TILE_THREADS, 2 * smem + 1024 + 64, s->stream>>>(tmap, P, K);
       } else if (lite) k_tile_tma<false><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
       else k_tile_tma<true><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap, P);
-    } else if (dbuf) {
-      uint64_t nct = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
-      k_tile_db<<<(unsigned)nct, TILE_THREADS, 2 * smem, s->stream>>>(s->amp, ntiles, tiles_per_cta, P);
     } else {
       k_tile<<<(unsigned)ntiles, TILE_THREADS, smem, s->stream>>>(s->amp, P);
     }

@@ -11,7 +11,7 @@ arr = bt.pack_gates(wl.to_ops(bt, specs))
 s = bt.zero_state(N); lib = s.lib
 cfgs = [tuple(int(x) for x in c.split(",")) for c in os.environ.get("PROBE_CFGS", "12,0,8;12,0,10").split(";")]
 for (tb, db, mg) in cfgs:
-    os.environ["BT_TILE_BITS"] = str(tb); os.environ["BT_TILE_DB"] = str(db); os.environ["BT_FUSE_MAX_GATES"] = str(mg)
+    os.environ["BT_TILE_BITS"] = str(tb); os.environ["BT_FUSE_MAX_GATES"] = str(mg)
     L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1)); s.sync()
     ms = C.c_float(); n0 = s.launch_count()
     L.check(lib.bt_sv_timer_start(s.h))
