@@ -1,19 +1,23 @@
-// bt_tile.cu -- host-side gate fusion + the multi-gate shared-memory tile kernel.
+// bt_tile.cu -- host-side gate fusion + the multi-gate shared-memory tile kernels.
 //
 // No reference analogue: the reference applies one 2^N x 2^N sparse matrix per op (src/hilbert.jl:505); the
 // nearest ideas are the full-circuit product sa.sparse(circ) (src/struct.jl:877-888) and the duplicate-cancelling
 // optimize_simple (src/ops.jl:335-367).  Here:
-//   1. fusion: runs of 1- and 2-qubit gates are multiplied into dense 4x4 blocks on their qubit pair (a 1-qubit gate
-//      is absorbed by the block that last touched / first touches its qubit), then re-canonicalised (a lone CX comes
-//      back out as control + X, a CZ/CP chain as a diagonal);
-//   2. scheduling: blocks are packed greedily (dependency order preserved) into passes whose non-diagonal target
-//      bits fit a tile of T index bits (the low bits, for coalescing, plus chosen high bits); controls and
-//      diagonal factors on bits outside the tile ride along for free because they only depend on the tile's base index;
-//   3. each pass is ONE kernel: a CTA stages a 2^T-amplitude tile in shared memory with cp.async (XOR-swizzled
-//      16-byte slots), applies the pass's gates in place between __syncthreads, and writes the tile back: one HBM
-//      read + write for up to TILE_MAXG blocks.
-// HBM roofline per pass: 32 B per amplitude; FP64/shared-memory work per dense block ~ a quarter of that time on B200,
-// hence the default cap of blocks per pass (BT_FUSE_MAX_GATES) that keeps the kernel near the HBM bound.
+//   1. fusion (fuse_blocks): gates are grouped into blocks on one or two qubits.  A block keeps its dense product
+//      (re-canonicalised: a lone CX comes back out as control + X, a CZ/CP chain as a diagonal) AND the list of its gates
+//      as structured micro-ops (real / RX-like / diagonal / phase 1-qubit ops, CX, CPHASE), which costs about half the
+//      FP64 work of the dense 4x4 for the named gates;
+//   2. scheduling (bt_fuse_and_run): blocks are packed greedily (dependency order preserved) into passes whose
+//      non-diagonally-acted bits fit a tile of T index bits (low bits, for coalescing, plus chosen high bits); controls
+//      and diagonal factors on other bits ride along: they only depend on the thread's group or on the tile's base index;
+//   3. each pass is ONE kernel (launch_pass): a CTA brings a 2^T-amplitude tile into shared memory -- one TMA tensor
+//      copy (k_tile_tma; 128-byte hardware swizzle) or cp.async (k_tile, when the tile's bits do not form a tensor box)
+//      -- runs the pass's items in place between __syncthreads, and writes the tile back.  Items: register programs (a
+//      thread holds the 16 amplitudes of 4 tile bits and interprets a micro-op list: run_prog), dense register clusters
+//      and single dense gates with per-slot code (run_cluster, run_gate), diagonal sweeps (run_diag).
+// HBM roofline per pass: 32 B per amplitude.  A pass carries ~30 gates, so the kernel sits between the HBM and FP64 roofs
+// and is tuned as a compute kernel (measurements in profiles/r1_fusion_sweep.txt).
+// Build: tools/nvcc_brx.py rewrites the micro-op switch of run_prog into one indirect branch between cicc and ptxas.
 #include "bt_internal.cuh"
 #include <cuda_pipeline_primitives.h>
 #include <cuda.h>   // CUtensorMap (driver types only; the encode function is fetched through cudaGetDriverEntryPoint)
