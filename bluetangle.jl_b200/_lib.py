@@ -52,6 +52,8 @@ PROTOTYPES = {
     "bt_set_strict": [_i],
     "bt_fusion_stats": [C.POINTER(_u64), C.POINTER(_u64)],
     "bt_fusion_flops": [_pd],
+    "bt_jit_stats": [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _pd],
+    "bt_jit_selftest": [C.c_char_p, _u64],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],
     "bt_pool_release": [],

@@ -25,135 +25,7 @@
 #include <atomic>
 #include <algorithm>
 
-#ifndef TILE_MAXG
-#define TILE_MAXG 8      // single-gate slots per pass
-#endif
-#ifndef TILE_MAXC
-#define TILE_MAXC 4      // register-cluster slots per pass
-#endif
-#define TILE_MAXD 16     // diagonal-gate slots per pass (one run-time-indexed code copy: they carry <= 4 matrix entries)
-#define TILE_DBASE 16    // item ids >= TILE_DBASE are diagonal slots
-#define TILE_PBASE 48    // item ids >= TILE_PBASE are register programs
-#define TILE_MAXP 8      // register programs per pass
-#define TILE_MAXITEMS (TILE_PBASE + TILE_MAXP)
-#ifndef PROG_BITS
-#define PROG_BITS 4      // a register program holds the 2^4 amplitudes spanned by 4 tile bits in each thread (5: 32 amplitudes)
-#endif
-#define PROG_AMPS (1 << PROG_BITS)
-#define PROG_MAXOPS 64
-#define PROG_MAXCOEF 208 // doubles
-#define TILE_LOWB_MIN 3  // the tensor-copy kernel needs only bits 0..2 (one 128-byte row) in the tile: BT_TILE_LOWB=3..5
-#define TILE_LOWB 5      // the 5 lowest index bits are always in the tile: a warp's 32 lanes cover one 512 B run
-#define TILE_TMAX 12     // largest tile: 2^12 amplitudes = 64 KB of shared memory
-#define TILE_TDEF 12     // default tile (measured best on B200: T=12 single-buffered; T=11 double-buffered is ~12 % slower)
-#ifndef TILE_THREADS
-#define TILE_THREADS 128 // 3 CTAs x 128 threads: up to 170 registers per thread for the 16-amplitude clusters
-#endif
-#ifndef TILE_MINB
-#define TILE_MINB 3
-#endif
-#ifndef CL_BITS
-#define CL_BITS 3        // cluster width: 3 tile bits = 8 amplitudes per thread, slots (0,1),(1,2),(0,1); 4 = 16 amplitudes,
-                         // slots (0,1),(2,3),(1,2), 168 registers: measured 4 % slower on C2
-#endif
-#define CL_AMPS (1 << CL_BITS)
-#ifndef CL_PIPE
-#define CL_PIPE 0         // 1 = software-pipeline two cluster groups per thread (measured: no gain, 166 registers)
-#endif
-#ifndef CL_SLOTS
-#define CL_SLOTS 3       // cluster pattern on positions (0,1),(2,3),(1,2) [5 = + (0,1),(2,3): measured 4 % slower, code size]
-#endif
-
-struct TileGate {
-  int32_t kind;       // 0 dense, 1 diagonal
-  int32_t k;          // matrix index bits (<= 2)
-  int32_t tloc[2];    // tile-local position of matrix bit t, or -1 when the bit lies outside the tile (diagonal only)
-  int32_t text[2];    // physical position when outside the tile
-  int32_t ni;         // tile-local inserted positions (local targets + local controls), ascending
-  uint32_t bit_sw[8];  // swizzled slot contribution of thread-index bit k (host picks which free tile bit each thread bit walks)
-  uint32_t lcmask;    // local controls, forced to 1
-  uint32_t niter;     // group-loop trip count = max(1, (2^T >> ni) / TILE_THREADS)
-  uint64_t ext_cmask; // controls outside the tile: all must be 1 in the tile's base index
-  uint32_t iter_sw[32]; // swizzled slot offset contributed by loop iteration i: sw(expand(i * TILE_THREADS))
-  double2 m[16];      // dense: row-major (1<<k)^2 ; diagonal: first 1<<k entries
-};
-
-// Diagonal gate (k <= 2 targets, any of them possibly outside the tile, plus controls): cheap, so it gets many slots.
-struct TileDiag {
-  int32_t k;
-  int32_t ni;
-  int32_t tloc[2];
-  int32_t text[2];
-  uint32_t lcmask;
-  uint32_t niter;
-  uint64_t ext_cmask;
-  uint32_t bit_sw[8];
-  uint32_t iter_sw[16];
-  double2 m[4];
-};
-
-// A register-resident cluster: each thread holds the 16 amplitudes spanned by 4 tile bits (positions 0..3) and applies up
-// to five dense 4x4 blocks on position pairs (0,1),(2,3),(1,2),(0,1),(2,3) before writing back -- one shared-memory round
-// trip for e.g. the brickwork triple (a,b),(c,d),(b,c) instead of three.
-struct TileCluster {
-  int32_t lp[4];        // tile-local bit of cluster position p
-  uint32_t bit_sw[8];   // as in TileGate
-  uint32_t use;         // bit s set: pattern slot s carries a block
-  uint32_t niter;       // max(1, (2^T >> 4) / TILE_THREADS)
-  uint32_t iter_sw[8];
-  double2 m[CL_SLOTS][16];  // row-major 4x4, matrix bit 0 <-> lower position of the slot's pair
-};
-
-// A register program: each thread loads the 16 amplitudes spanned by 4 tile bits (positions 0..3) and runs a list of
-// STRUCTURED micro-ops on them before writing back -- one shared-memory round trip for e.g. two brickwork layers on 4 qubits.
-// The micro-ops keep the gates' structure instead of multiplying it away into dense 4x4 blocks (16 FP64 ops / amplitude):
-//   U1_GEN  general 2x2                        8 ops / amplitude      U1_DIAG  diag(d0, d1)        4
-//   U1_REAL real 2x2 (H, RY, X, Z ...)         4                      U1_PHASE diag(1, d)          2
-//   U1_RXL  real diagonal, imaginary off-diag  4 (RX, Y ...)          CX       register moves      0
-//   CPHASE  phase on |11> (CZ, CP)             1
-// op word: site | (first coefficient << 8); the site fixes kind and cluster positions so that register indices are static.
-enum { PK_GEN = 0, PK_REAL = 1, PK_RXL = 2, PK_DIAG = 3, PK_PHASE = 4, PK_CX = 5, PK_CPHASE = 6 };
-#define PROG_SITE_U1(kind, p) ((kind) * 8 + (p))                 // 0..39
-#define PROG_SITE_CX(pc, pt) (40 + (pc) * 8 + (pt))              // 40..103 (pc != pt)
-#define PROG_SITE_CPHASE(pa, pb) (104 + (pa) * 8 + (pb))         // 104..167 (pa < pb)
-// Conditional ops: a control / phase bit that is NOT one of the program's positions is a property of the thread's group
-// (tile-local bits, mask lm) or of the whole tile (bits outside the tile, mask em) -- "controls ride along for free".
-// coefficients: CSCALE, CPH1: re, im, em, lm (masks as raw 64-bit words); CCX1: em, lm
-#define PROG_SITE_CSCALE 168                                     // all amplitudes *= d             when the masks match
-#define PROG_SITE_CPH1(p) (169 + (p))                            // amplitudes with bit p set *= d  when the masks match
-#define PROG_SITE_CCX1(p) (177 + (p))                            // X on position p                 when the masks match
-struct TileProg {
-  int32_t lp[8];          // tile-local bit of cluster position p < PROG_BITS
-  uint32_t bit_sw[8];
-  uint32_t niter;
-  uint32_t nops;
-  uint32_t iter_sw[8];
-  uint32_t bit_lin[8];    // as bit_sw / iter_sw but unswizzled: the group's tile-local index, for the conditional ops
-  uint32_t iter_lin[8];
-  uint16_t op[PROG_MAXOPS + 2];   // + padding entry read by the op-word prefetch
-  double coef[PROG_MAXCOEF + 4];  // + slack: four coefficients are always fetched
-};
-
-struct TileParams {
-  int32_t T;            // tile bits
-  int32_t lowb;         // min(TILE_LOWB, T)
-  int32_t nitems;
-  int32_t stagger_ns;   // < 0: measurement modes (-1 = no gates, -2 = no HBM traffic; results invalid); BT_TILE_STAGGER_NS
-  int32_t n_sm;
-  int32_t swz_mode;     // 0: TMA-compatible 128-B swizzle, 1: all-digit swizzle
-  int32_t tma_coord_shift[5];  // tensor-copy variant: coordinate k of a tile = (base >> shift[k]) & mask[k]
-  uint32_t tma_coord_mask[5];
-  int32_t tma_ncopy;           // a tile whose bits form more than four runs moves as 2, 4 or 8 boxes: the top tile bits are enumerated
-  int32_t tma_c4add[8];        // copy e: added to coordinate 4; its shared-memory chunk is e * (tile bytes / ncopy)
-  int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
-  uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
-  TileGate g[TILE_MAXG];
-  TileCluster cl[TILE_MAXC];
-  TileDiag d[TILE_MAXD];
-  TileProg pr[TILE_MAXP];
-};
-
-static_assert(sizeof(TileParams) + 128 <= 32764, "kernel parameters (tensor map + TileParams) must fit the 32 KB parameter space");
+#include "bt_tile_types.cuh"
 
 // XOR swizzle of 16-byte slots: linear over GF(2), so sw(a | b) = sw(a) ^ sw(b) for disjoint a, b
 // (slot index bits 0..2 select the 16-byte bank group; they become the XOR of ALL 3-bit digits of the tile index, so a run
@@ -390,108 +262,7 @@ __device__ __forceinline__ void run_cluster(const TileParams& P, double2* __rest
 }
 
 // ---- register programs ------------------------------------------------------------------------------------------------
-// In-place primitives written as PTX with tied operands: every micro-op leaves amplitude j in the registers it found it in,
-// so the run-time op loop carries x[] without the ~64 register moves per op that the compiler's phi resolution otherwise adds.
-// (a, b) <- (c0 a + c1 b, c2 a + c3 b)
-__device__ __forceinline__ void ip_real(double& a, double& b, double c0, double c1, double c2, double c3) {
-  asm("{\n\t.reg .f64 t;\n\tmul.f64 t, %0, %4;\n\tmul.f64 %0, %0, %2;\n\tfma.rn.f64 %0, %1, %3, %0;\n\tfma.rn.f64 %1, %1, %5, t;\n\t}"
-      : "+d"(a), "+d"(b)
-      : "d"(c0), "d"(c1), "d"(c2), "d"(c3));
-}
-// (x + i y) <- (dr + i di)(x + i y); ndi = -di
-__device__ __forceinline__ void ip_cmul(double& x, double& y, double dr, double di, double ndi) {
-  asm("{\n\t.reg .f64 t;\n\tmul.f64 t, %0, %3;\n\tmul.f64 %0, %0, %2;\n\tfma.rn.f64 %0, %1, %4, %0;\n\tfma.rn.f64 %1, %1, %2, t;\n\t}"
-      : "+d"(x), "+d"(y)
-      : "d"(dr), "d"(di), "d"(ndi));
-}
-// general complex 2x2 on the pair (a, b); c = re/im of m00, m01, m10, m11; n = -im of the same
-__device__ __forceinline__ void ip_gen(double2& a, double2& b, const double (&c)[8], const double (&n)[4]) {
-  asm("{\n\t.reg .f64 t1, t2, u;\n\t"
-      "mul.f64 t1, %0, %8;\n\tfma.rn.f64 t1, %1, %14, t1;\n\tfma.rn.f64 t1, %2, %10, t1;\n\tfma.rn.f64 t1, %3, %15, t1;\n\t"
-      "mul.f64 t2, %1, %8;\n\tfma.rn.f64 t2, %0, %9, t2;\n\tfma.rn.f64 t2, %3, %10, t2;\n\tfma.rn.f64 t2, %2, %11, t2;\n\t"
-      "mul.f64 u, %0, %4;\n\tfma.rn.f64 u, %1, %12, u;\n\tfma.rn.f64 u, %2, %6, u;\n\tfma.rn.f64 u, %3, %13, u;\n\t"
-      "mul.f64 %1, %1, %4;\n\tfma.rn.f64 %1, %0, %5, %1;\n\tfma.rn.f64 %1, %3, %6, %1;\n\tfma.rn.f64 %1, %2, %7, %1;\n\t"
-      "mov.f64 %0, u;\n\tmov.f64 %2, t1;\n\tmov.f64 %3, t2;\n\t}"
-      : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y)
-      : "d"(c[0]), "d"(c[1]), "d"(c[2]), "d"(c[3]), "d"(c[4]), "d"(c[5]), "d"(c[6]), "d"(c[7]), "d"(n[0]), "d"(n[1]), "d"(n[2]), "d"(n[3]));
-}
-
-// in-place exchange (XOR swap: a register-renaming swap would make the op loop shuffle all 64 data registers every iteration)
-__device__ __forceinline__ void ip_swap(double& a, double& b) {
-  asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, %0;\n\tmov.b64 q, %1;\n\txor.b64 p, p, q;\n\txor.b64 q, q, p;\n\txor.b64 p, p, q;\n\tmov.b64 %0, p;\n\tmov.b64 %1, q;\n\t}"
-      : "+d"(a), "+d"(b));
-}
-
-template <int KIND, int PQ>
-__device__ __forceinline__ void prog_u1(double2 (&x)[PROG_AMPS], const double (&cc)[4], const double* __restrict__ cp) {
-  if (KIND == PK_GEN) {  // cc = re/im of m00, m01 (preloaded), cp[4..7] = re/im of m10, m11
-    const double c[8] = {cc[0], cc[1], cc[2], cc[3], cp[4], cp[5], cp[6], cp[7]};
-    const double n[4] = {-c[1], -c[3], -c[5], -c[7]};
-#pragma unroll
-    for (int r = 0; r < PROG_AMPS / 2; ++r) {
-      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
-      ip_gen(x[i0], x[i1], c, n);
-    }
-  } else if (KIND == PK_REAL) {  // cc = m00, m01, m10, m11 (real)
-    const double c0 = cc[0], c1 = cc[1], c2 = cc[2], c3 = cc[3];
-#pragma unroll
-    for (int r = 0; r < PROG_AMPS / 2; ++r) {
-      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
-      ip_real(x[i0].x, x[i1].x, c0, c1, c2, c3);
-      ip_real(x[i0].y, x[i1].y, c0, c1, c2, c3);
-    }
-  } else if (KIND == PK_RXL) {  // cc = m00, Im m01, Im m10, m11: a' = m00 a + i s01 b, b' = i s10 a + m11 b
-    const double c0 = cc[0], s01 = cc[1], s10 = cc[2], c3 = cc[3], ns01 = -s01, ns10 = -s10;
-#pragma unroll
-    for (int r = 0; r < PROG_AMPS / 2; ++r) {
-      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
-      ip_real(x[i0].x, x[i1].y, c0, ns01, s10, c3);
-      ip_real(x[i0].y, x[i1].x, c0, s01, ns10, c3);
-    }
-  } else if (KIND == PK_DIAG) {  // cc = re/im of d0, d1
-    const double d0r = cc[0], d0i = cc[1], d1r = cc[2], d1i = cc[3], nd0i = -d0i, nd1i = -d1i;
-#pragma unroll
-    for (int r = 0; r < PROG_AMPS / 2; ++r) {
-      const int i0 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)), i1 = i0 | (1 << PQ);
-      ip_cmul(x[i0].x, x[i0].y, d0r, d0i, nd0i);
-      ip_cmul(x[i1].x, x[i1].y, d1r, d1i, nd1i);
-    }
-  } else {  // PK_PHASE: cc = re/im of d
-    const double dr = cc[0], di = cc[1], ndi = -di;
-#pragma unroll
-    for (int r = 0; r < PROG_AMPS / 2; ++r) {
-      const int i1 = ((r >> PQ) << (PQ + 1)) | (r & ((1 << PQ) - 1)) | (1 << PQ);
-      ip_cmul(x[i1].x, x[i1].y, dr, di, ndi);
-    }
-  }
-}
-
-template <int PC, int PT>
-__device__ __forceinline__ void prog_cx(double2 (&x)[PROG_AMPS]) {
-#pragma unroll
-  for (int i = 0; i < PROG_AMPS; ++i)
-    if (((i >> PC) & 1) && !((i >> PT) & 1)) {
-      ip_swap(x[i].x, x[i | (1 << PT)].x);
-      ip_swap(x[i].y, x[i | (1 << PT)].y);
-    }
-}
-
-template <int PT>
-__device__ __forceinline__ void prog_x1(double2 (&x)[PROG_AMPS]) {
-#pragma unroll
-  for (int i = 0; i < PROG_AMPS; ++i)
-    if (!((i >> PT) & 1)) {
-      ip_swap(x[i].x, x[i | (1 << PT)].x);
-      ip_swap(x[i].y, x[i | (1 << PT)].y);
-    }
-}
-
-template <int PA, int PB>
-__device__ __forceinline__ void prog_cphase(double2 (&x)[PROG_AMPS], const double (&c)[4]) {
-#pragma unroll
-  for (int i = 0; i < PROG_AMPS; ++i)
-    if (((i >> PA) & 1) && ((i >> PB) & 1)) ip_cmul(x[i].x, x[i].y, c[0], c[1], -c[1]);
-}
+#include "bt_prog_ops.cuh"
 
 // markers for tools/ptx_brx.py (PTX comments: no code)
 #define BT_CASE_MARK(site) asm volatile("// BT_CASE %0;" ::"n"(site))
@@ -1328,6 +1099,8 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
   return r == CUDA_SUCCESS;
 }
 
+int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, uint64_t ntiles, size_t tile_bytes, int np);  // bt_jit.cu
+
 static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
   if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
   int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
@@ -1393,7 +1166,9 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       fprintf(stderr, "\n");
     }
     bt_prof_begin(s, BT_CLS_TILE);
-    if (use_tma) {
+    if (use_tma && ng == 0 && nc == 0 && nd == 0 && np > 0 && bt_jit_try_launch(s, P, tmap, ntiles, smem, np) == 1) {
+      // launched as a specialised straight-line kernel (bt_jit.cu)
+    } else if (use_tma) {
       const bool lite = ng == 0 && nc == 0 && env_int("BT_TILE_LITE", 1);
       int K = env_int("BT_TILE_PIPE", 0);
       while (K > 1 && (ntiles % (uint64_t)K != 0 || ntiles / (uint64_t)K < (uint64_t)(6 * nsm))) K >>= 1;

@@ -79,9 +79,14 @@ int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse);
  * the outcomes are the handle's device-side record of the last bt_sv_measure_z call) */
 int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int want);
 int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
-int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); 
+int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); /* cumulative: fused tile-kernel launches and blocks they carried */
 int bt_fusion_flops(double* flops); /* cumulative FP64 flops issued by the fused passes (FMA = 2 flops) */
- /* cumulative: fused tile-kernel launches and blocks they carried */
+/* Pass specialiser (csrc/bt_jit.cu): fused passes that recur are compiled once (NVRTC) into straight-line kernels.
+ * bt_jit_stats: modules compiled, specialised launches, structures that fell back to the interpreter, seconds spent compiling.
+ * bt_jit_selftest: host-only check (no device): generate and compile a synthetic pass using every micro-op; 0 = ok;
+ * `source` (optional, `cap` bytes) receives the generated CUDA text.  No reference analogue. */
+int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* failed, double* compile_seconds);
+int bt_jit_selftest(char* source, uint64_t cap);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */

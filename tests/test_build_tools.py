@@ -89,3 +89,21 @@ def test_library_holds_tensor_copies_and_indirect_branch():
     if os.environ.get("BT_NO_BRX"):
         return
     assert "BRX" in sass, "micro-op dispatch was not rewritten to brx.idx (tools/ptx_brx.py)"
+
+
+def test_pass_specialiser_generates_and_compiles_on_the_host():
+    """bt_jit_selftest: a synthetic pass with every micro-op site kind is turned into CUDA text and compiled by NVRTC for
+    sm_100a -- no device needed.  Skipped when libnvrtc is not installed (the library then simply keeps interpreting)."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    bt = ge.load_package()
+    lib = bt._lib.load()
+    buf = C.create_string_buffer(1 << 20)
+    rc = lib.bt_jit_selftest(buf, 1 << 20)
+    if rc == -2:
+        pytest.skip("libnvrtc not available")
+    assert rc == 0, lib.bt_last_error().decode()
+    src = buf.value.decode()
+    for needle in ("bt_jit_pass", "cp.async.bulk.tensor.5d", "prog_u1<1, 1>", "prog_cx<0, 2>", "prog_cphase<1, 3>", "prog_x1<1>", "ip_cmul"):
+        assert needle in src

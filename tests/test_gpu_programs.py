@@ -149,3 +149,38 @@ def test_batched_states_through_programs(bt, orc):
     got = s.to_numpy()
     for t in range(B):
         assert np.max(np.abs(got[t] - orc.apply_ops(v[t], oo))) < TOL
+
+
+def test_specialised_passes_equal_the_interpreter(bt, orc):
+    """csrc/bt_jit.cu: the straight-line kernel compiled for a pass runs the same micro-op code in the same order as the
+    interpreter, so the amplitudes must be IDENTICAL (not merely within tolerance), and equal to the oracle within 1e-10.
+    BT_TILE_JIT=2 compiles every pass at first sight; the statistics must show specialised launches."""
+    import ctypes as C
+    L = bt._lib
+    lib = L.load()
+    N = 13
+    od, oo = structured_circuit(bt, orc, N, 60, 4242)
+    v = rand_state(N, 5)
+    outs = {}
+    c0, l0, f0 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.bt_jit_stats(C.byref(c0), C.byref(l0), C.byref(f0), None)
+    for mode in (0, 2):
+        with tile_env(BT_TILE_JIT=mode, BT_TILE_BITS=10, BT_TILE_LOWB=3):
+            s = bt.CuState.from_numpy(v)
+            bt.apply(od, s)
+            outs[mode] = s.to_numpy()
+    c1, l1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.bt_jit_stats(C.byref(c1), C.byref(l1), C.byref(f1), None)
+    if c1.value == c0.value and f1.value > f0.value:
+        pytest.skip("NVRTC not available on this box: passes stay on the interpreter")
+    assert l1.value > l0.value and c1.value > c0.value
+    assert np.array_equal(outs[0], outs[2])
+    assert np.max(np.abs(outs[2] - orc.apply_ops(v, oo))) < TOL
+    # second run of the same structure with other angles: cached modules, new coefficients
+    with tile_env(BT_TILE_JIT=2, BT_TILE_BITS=10, BT_TILE_LOWB=3):
+        s = bt.CuState.from_numpy(v)
+        bt.apply(od, s)
+        c2 = C.c_uint64()
+        lib.bt_jit_stats(C.byref(c2), None, None, None)
+        assert c2.value == c1.value          # nothing recompiled
+        assert np.array_equal(s.to_numpy(), outs[2])
