@@ -4,7 +4,7 @@ PKG       := bluetangle.jl_b200
 CSRC      := $(wildcard $(PKG)/csrc/*.cu)
 OBJ       := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(CSRC))
 LIB       := $(PKG)/lib/libbluetangle_cuda.so
-NVFLAGS   := -O3 -std=c++17 -Ibuild -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
 
 all: $(LIB) oracle
 
@@ -15,13 +15,6 @@ $(LIB): $(OBJ)
 build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) include/bluetangle_cuda.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
-
-# the micro-op header as text for NVRTC (bt_jit.cu)
-build/bt_prog_ops_src.h: $(PKG)/csrc/bt_prog_ops.cuh tools/embed_src.py
-	@mkdir -p build
-	python3 tools/embed_src.py $< $@ k_prog_ops_src
-
-build/bt_jit.o: build/bt_prog_ops_src.h
 
 # bt_tile.cu goes through nvcc's own steps with one extra pass over the PTX: the micro-op switch of the register programs
 # becomes an indirect branch (tools/ptx_brx.py; BT_NO_BRX=1 builds it with plain nvcc)

@@ -106,9 +106,14 @@ def bench_single(args):
         L.check(lib.bt_sv_set_basis(s.h, 0))
         L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), ngates, 1))
 
+    # the library specialises a fused pass the second time it sees it (csrc/bt_jit.cu); here every pass is compiled at first
+    # sight so that the compilation always falls into the untimed warm-up, whatever W is
+    os.environ.setdefault("BT_TILE_JIT_AFTER", "1")
+    t_w0 = time.perf_counter()
     for _ in range(args.warmup):
         step()
     s.sync()
+    warmup_seconds = time.perf_counter() - t_w0
     clocks = ClockSampler(0)
     clocks.start()
     L.check(lib.bt_sv_profile_enable(s.h, 1))
@@ -194,8 +199,19 @@ def bench_single(args):
            "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers (H/RX/RY/RZ/T + CNOT/CZ/CP brickwork), {ngates} gates, seed 28",
                       "fusion": "host fusion pass + shared-memory tile kernel", "l2": f"inputs larger than L2 ({(16 << N) / 2**30:.1f} GiB state)", "parallelism": "1 GPU"},
            "clocks": clk, "e2e": e2e, "gpu_launches": int(n1 - n0), "roofline": roof, "kernels": per_cls, "unfused_gate_kernels": micro,
-           "cpu_baseline": cpu, "state_norm2": norm}
+           "cpu_baseline": cpu, "state_norm2": norm, "jit": jit_stats(lib, warmup_seconds)}
     print(json.dumps(out))
+
+
+def jit_stats(lib, warmup_seconds=None):
+    """pass specialiser statistics: modules compiled (all during warm-up), specialised launches, compile time"""
+    jc, jl, jf, jt = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
+    lib.bt_jit_stats(C.byref(jc), C.byref(jl), C.byref(jf), C.byref(jt))
+    out = {"modules_compiled": int(jc.value), "specialised_launches": int(jl.value), "fell_back": int(jf.value), "compile_seconds": float(jt.value),
+           "note": "recurring fused passes are compiled once by NVRTC into straight-line kernels; compilation happens in the untimed warm-up"}
+    if warmup_seconds is not None:
+        out["warmup_seconds"] = warmup_seconds
+    return out
 
 
 def cpu_baseline_port(N, specs, budget_s=15.0):
@@ -260,6 +276,7 @@ def bench_sharded(args):
         L.check(lib.bt_sv_set_basis(st.h, 0))
         L.check(lib.bt_sv_apply_circuit(st.h, L.ptr(arr), ngates, 1))
 
+    os.environ.setdefault("BT_TILE_JIT_AFTER", "1")  # specialise every fused pass at first sight: compilation stays in the warm-up
     for _ in range(args.warmup):
         step()
     st.sync()
@@ -312,7 +329,7 @@ def bench_sharded(args):
                           "l2": "inputs larger than L2"},
                "circuit_gates_per_s": ngates / (ms_per_step / 1e3), "clocks": clk, "gpu_launches": int(n1 - n0),
                "kernels_rank0": {n: {"launches": int(counts[i]), "ms": float(cms[i])} for i, n in enumerate(["tile", "dense", "diag", "other"])},
-               "host_seconds_rank0": t_host,
+               "host_seconds_rank0": t_host, "jit_rank0": jit_stats(lib),
                "roofline": ({"bound": "hbm", "kernel": "k_tile_tma (fused multi-gate pass) on rank 0's shard", "achieved": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9,
                              "peak": load_peaks()[0]["hbm_gbs"], "unit": "GB/s", "frac": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9 / load_peaks()[0]["hbm_gbs"],
                              "traffic": None, "avg_launch_ms": cms[0] / counts[0], "bytes_per_launch": 32.0 * (1 << n_local)} if counts[0] else None),

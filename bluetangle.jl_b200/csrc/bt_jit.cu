@@ -24,12 +24,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <complex>
+#include <math.h>
 #include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
-#include "bt_prog_ops_src.h"  // k_prog_ops_src: text of bt_prog_ops.cuh (generated by tools/embed_src.py)
 
 namespace {
 
@@ -52,9 +53,11 @@ Nvrtc& nvrtc() {
   if (tried) return n;
   tried = true;
   void* h = nullptr;
+  const char* user = getenv("BT_NVRTC_LIB");  // explicit path to libnvrtc.so.12 (its builtins library must sit next to it)
+  if (user && *user) h = dlopen(user, RTLD_NOW | RTLD_LOCAL);
   for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
-    h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     if (h) break;
+    h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
   }
   if (!h) return n;
 #define BT_NVRTC_SYM(f) *(void**)(&n.f) = dlsym(h, "nvrtc" #f); if (!n.f) return n;
@@ -104,59 +107,288 @@ void appf(std::string& s, const char* fmt, ...) {
 
 uint64_t as_u64(double d) { uint64_t v; memcpy(&v, &d, 8); return v; }
 
-// Emits the kernel for pass P; `coef` receives the numeric coefficients in the order the kernel indexes them.  Returns false
-// when the pass holds something the specialiser does not cover.
-bool generate(const TileParams& P, int np, std::string& src, std::vector<double>& coef, bool want_source) {
+// ---- planning: ops of a pass in specialised form ----------------------------------------------------------------------
+// Straight-line code needs none of the interpreter's in-place discipline, so the specialiser also reshapes the arithmetic:
+//   * a real / RX-like 2x2 is divided by a pivot entry s (|s| within 10x of the largest entry, chosen to leave the most
+//     entries equal to +-1 or 0): a rotation [[c,-s],[s,c]] becomes c [[1,-t],[t,1]] -- one FMA per scalar instead of two
+//     instructions, H becomes two additions; diag(d0,d1) becomes d0 diag(1, d1/d0).  The factors s multiply up into ONE
+//     complex scalar per pass, applied to every amplitude at the end of the last program (a pass has ~30 ops, so the
+//     intermediate scale stays far from the floating-point range limits);
+//   * CX is a renaming of the amplitude variables (no instruction); CZ a sign change.
+// Which entries are +-1 / 0 and which pivot was taken is part of the structure key (the code differs), their values are not.
+enum { JK_LIN2 = 0, JK_GEN, JK_PHASE, JK_CX, JK_CPHASE, JK_CZ, JK_CSCALE, JK_CPH1, JK_CCX1 };
+
+struct JOp {
+  int kind = 0;
+  int p = 0, q = 0;        // positions (LIN2 / GEN / PHASE / CPH1 / CCX1: p; CX: control p, target q; CPHASE / CZ: p, q)
+  int rxl = 0;             // LIN2: 0 = pairs (ax,bx),(ay,by); 1 = pairs (ax,by),(ay,bx) with the RX-like signs
+  signed char pat[4] = {2, 2, 2, 2};  // LIN2 entries after the pivot division: 0 zero, +1 / -1 unit, 2 general (takes a coefficient)
+  int c0 = 0;              // first coefficient of this op in the coefficient block
+  uint64_t em = 0, lm = 0; // condition masks
+};
+
+struct Plan {
+  std::vector<std::vector<JOp>> prog;  // per item
+  std::vector<double> coef;
+  int scale_at = -1;                   // coefficient index of the pass scalar (re, im)
+  bool complex_scale = false;
+};
+
+typedef std::complex<double> cd;
+
+// divide the real 2x2 (m0 m1; m2 m3) by a pivot; returns the pivot.  pat/out describe the quotient.
+double pivot_real(const double m[4], signed char pat[4], double out[4]) {
+  double big = 0;
+  for (int i = 0; i < 4; ++i) big = std::max(big, fabs(m[i]));
+  int best = -1, best_cost = 99;
+  for (int c = 0; c < 4; ++c) {
+    if (fabs(m[c]) < 0.1 * big || m[c] == 0.0) continue;
+    int cost = 0;
+    for (int i = 0; i < 4; ++i) {
+      const double r = m[i] / m[c];
+      if (!(r == 0.0 || r == 1.0 || r == -1.0)) cost++;
+    }
+    if (cost < best_cost || (cost == best_cost && fabs(m[c]) > fabs(m[best]))) { best = c; best_cost = cost; }
+  }
+  if (best < 0) { for (int i = 0; i < 4; ++i) { out[i] = m[i]; pat[i] = m[i] == 0.0 ? 0 : (m[i] == 1.0 ? 1 : (m[i] == -1.0 ? -1 : 2)); } return 1.0; }
+  for (int i = 0; i < 4; ++i) {
+    const double r = m[i] / m[best];
+    out[i] = r;
+    pat[i] = r == 0.0 ? 0 : (r == 1.0 ? 1 : (r == -1.0 ? -1 : 2));
+  }
+  return m[best];
+}
+
+bool make_plan(const TileParams& P, int np, Plan& pl) {
   if (P.swz_mode != 0 || np <= 0 || P.nitems != np) return false;
-  const int T = P.T;
-  const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
-  std::string body;
-  coef.clear();
+  pl.prog.assign((size_t)P.nitems, {});
+  pl.coef.clear();
+  cd gs(1.0, 0.0);
   for (int it = 0; it < P.nitems; ++it) {
     const int pi = (int)P.item[it] - TILE_PBASE;
     if (pi < 0 || pi >= TILE_MAXP) return false;
     const TileProg& G = P.pr[pi];
-    if (G.niter > 8) return false;
-    bool need_gl = false;
-    std::string ops;
+    if (G.niter > 8 || G.iter_sw[0] != 0) return false;
     for (uint32_t k = 0; k < G.nops; ++k) {
-      const uint32_t site = G.op[k] & 0xffu, co = G.op[k] >> 8;
-      const double* c = G.coef + co;
-      const int kc = (int)coef.size();
+      const uint32_t site = G.op[k] & 0xffu;
+      const double* c = G.coef + (G.op[k] >> 8);
+      JOp o;
+      o.c0 = (int)pl.coef.size();
       if (site < 40) {
-        const int kind = site / 8, p = site % 8;
-        const int nc = kind == PK_GEN ? 8 : (kind == PK_PHASE ? 2 : 4);
-        for (int e = 0; e < nc; ++e) coef.push_back(c[e]);
-        appf(ops, "      { const double cc[4] = {C.c[%d], C.c[%d], C.c[%d], C.c[%d]}; prog_u1<%d, %d>(x, cc, C.c + %d); }\n", kc, kc + 1, kc + 2, kc + 3, kind, p, kc);
-      } else if (site < 104) {
-        appf(ops, "      prog_cx<%d, %d>(x);\n", (site - 40) / 8, (site - 40) % 8);
-      } else if (site < 168) {
-        coef.push_back(c[0]); coef.push_back(c[1]);
-        appf(ops, "      { const double cc[4] = {C.c[%d], C.c[%d], 0.0, 0.0}; prog_cphase<%d, %d>(x, cc); }\n", kc, kc + 1, (site - 104) / 8, (site - 104) % 8);
-      } else if (site == PROG_SITE_CSCALE || (site >= 169 && site < 177)) {
-        const uint64_t em = as_u64(c[2]), lm = as_u64(c[3]);
-        coef.push_back(c[0]); coef.push_back(c[1]);
-        if (lm) need_gl = true;
-        appf(ops, "      if ((base & 0x%llxull) == 0x%llxull && (gl & 0x%llxull) == 0x%llxull) {\n", (unsigned long long)em, (unsigned long long)em, (unsigned long long)lm,
-             (unsigned long long)lm);
-        if (site == PROG_SITE_CSCALE) {
-          appf(ops, "        const double dr = C.c[%d], di = C.c[%d], ndi = -di;\n", kc, kc + 1);
-          ops += "#pragma unroll\n        for (int i = 0; i < PROG_AMPS; ++i) ip_cmul(x[i].x, x[i].y, dr, di, ndi);\n";
-        } else {
-          appf(ops, "        const double cc[4] = {C.c[%d], C.c[%d], 0.0, 0.0}; prog_u1<PK_PHASE, %d>(x, cc, C.c + %d);\n", kc, kc + 1, (int)site - 169, kc);
+        const int kind = site / 8;
+        o.p = site % 8;
+        if (kind == PK_REAL || kind == PK_RXL) {
+          o.kind = JK_LIN2; o.rxl = kind == PK_RXL;
+          double q[4];
+          gs *= pivot_real(c, o.pat, q);
+          for (int i = 0; i < 4; ++i) if (o.pat[i] == 2) pl.coef.push_back(q[i]);
+        } else if (kind == PK_DIAG) {
+          // diag(d0, d1) = d0 diag(1, d1/d0)  (or d1 diag(d0/d1, 1) when d0 is the small one: phase on the bit = 0 half)
+          const cd d0(c[0], c[1]), d1(c[2], c[3]);
+          if (std::abs(d0) >= 0.1 * std::abs(d1) && d0 != cd(0, 0)) { gs *= d0; const cd r = d1 / d0; o.kind = JK_PHASE; o.q = 1; pl.coef.push_back(r.real()); pl.coef.push_back(r.imag()); }
+          else if (d1 != cd(0, 0)) { gs *= d1; const cd r = d0 / d1; o.kind = JK_PHASE; o.q = 0; pl.coef.push_back(r.real()); pl.coef.push_back(r.imag()); }
+          else return false;
+        } else if (kind == PK_PHASE) {
+          o.kind = JK_PHASE; o.q = 1; pl.coef.push_back(c[0]); pl.coef.push_back(c[1]);
+        } else {  // PK_GEN: divide by the largest entry; the quotient keeps 8 coefficients (the unit entry is simply 1 + 0i)
+          int best = 0;
+          for (int i = 1; i < 4; ++i) if (std::abs(cd(c[2 * i], c[2 * i + 1])) > std::abs(cd(c[2 * best], c[2 * best + 1]))) best = i;
+          const cd pv(c[2 * best], c[2 * best + 1]);
+          if (pv == cd(0, 0)) return false;
+          gs *= pv;
+          o.kind = JK_GEN; o.q = best;
+          for (int i = 0; i < 4; ++i) { const cd r = cd(c[2 * i], c[2 * i + 1]) / pv; pl.coef.push_back(r.real()); pl.coef.push_back(r.imag()); }
         }
-        ops += "      }\n";
+      } else if (site < 104) {
+        o.kind = JK_CX; o.p = (site - 40) / 8; o.q = (site - 40) % 8;
+      } else if (site < 168) {
+        o.p = (site - 104) / 8; o.q = (site - 104) % 8;
+        if (c[0] == -1.0 && c[1] == 0.0) o.kind = JK_CZ;
+        else { o.kind = JK_CPHASE; pl.coef.push_back(c[0]); pl.coef.push_back(c[1]); }
+      } else if (site == PROG_SITE_CSCALE || (site >= 169 && site < 177)) {
+        o.kind = site == PROG_SITE_CSCALE ? JK_CSCALE : JK_CPH1;
+        o.p = site == PROG_SITE_CSCALE ? 0 : (int)site - 169;
+        o.em = as_u64(c[2]); o.lm = as_u64(c[3]);
+        if (o.kind == JK_CSCALE && o.em == 0 && o.lm == 0) { gs *= cd(c[0], c[1]); continue; }  // unconditional scalar: joins the pass scalar
+        pl.coef.push_back(c[0]); pl.coef.push_back(c[1]);
       } else if (site >= 177 && site < 185) {
-        const uint64_t em = as_u64(c[0]), lm = as_u64(c[1]);
-        if (lm) need_gl = true;
-        appf(ops, "      if ((base & 0x%llxull) == 0x%llxull && (gl & 0x%llxull) == 0x%llxull) prog_x1<%d>(x);\n", (unsigned long long)em, (unsigned long long)em,
-             (unsigned long long)lm, (unsigned long long)lm, (int)site - 177);
+        o.kind = JK_CCX1; o.p = (int)site - 177; o.em = as_u64(c[0]); o.lm = as_u64(c[1]);
       } else {
         return false;
       }
+      pl.prog[(size_t)it].push_back(o);
+    }
+  }
+  pl.scale_at = (int)pl.coef.size();
+  pl.complex_scale = gs.imag() != 0.0;
+  pl.coef.push_back(gs.real());
+  pl.coef.push_back(gs.imag());
+  return true;
+}
+
+// structure key: everything the generator turns into literals or code shape (numeric coefficients excluded)
+void make_key(const TileParams& P, const Plan& pl, int device, std::string& key) {
+  key.clear();
+  auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
+  put(&device, 4); put(&P.T, 4); put(&P.lowb, 4); put(&P.nitems, 4); put(&P.swz_mode, 4);
+  put(P.tma_coord_shift, sizeof(P.tma_coord_shift)); put(P.tma_coord_mask, sizeof(P.tma_coord_mask));
+  put(&P.tma_ncopy, 4); put(P.tma_c4add, sizeof(int32_t) * (size_t)std::max(1, P.tma_ncopy));
+  put(P.tbits, sizeof(int32_t) * (size_t)P.T);
+  put(P.item, (size_t)P.nitems);
+  const char cs = pl.complex_scale ? 1 : 0;
+  put(&cs, 1);
+  for (int it = 0; it < P.nitems; ++it) {
+    const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
+    put(G.lp, sizeof(int32_t) * PROG_BITS); put(G.bit_sw, sizeof(G.bit_sw)); put(&G.niter, 4);
+    put(G.iter_sw, sizeof(G.iter_sw)); put(G.bit_lin, sizeof(G.bit_lin)); put(G.iter_lin, sizeof(G.iter_lin));
+    const uint32_t n = (uint32_t)pl.prog[(size_t)it].size();
+    put(&n, 4);
+    for (const JOp& o : pl.prog[(size_t)it]) {
+      const int32_t h[4] = {o.kind, o.p, o.q, o.rxl};
+      put(h, sizeof(h)); put(o.pat, 4); put(&o.em, 8); put(&o.lm, 8);
+    }
+  }
+}
+
+// "t = alpha * a + beta * b" with alpha, beta given as pattern + coefficient reference; sa / sb flip the sign of a term
+std::string lin(const char* out, signed char pa, int ka, bool na, const std::string& a, signed char pb, int kb, bool nb, const std::string& b) {
+  auto term_coef = [](signed char pat, int k, bool neg) {  // textual coefficient of a general term
+    char buf[48];
+    snprintf(buf, sizeof(buf), neg ? "(-C.c[%d])" : "C.c[%d]", k);
+    return std::string(buf);
+  };
+  auto unit_sign = [](signed char pat, bool neg) { return (pat > 0) != neg; };  // true: +, false: -
+  std::string e;
+  const bool za = pa == 0, zb = pb == 0, ua = pa == 1 || pa == -1, ub = pb == 1 || pb == -1;
+  if (za && zb) e = "0.0";
+  else if (za) e = ub ? (unit_sign(pb, nb) ? b : "-" + b) : term_coef(pb, kb, nb) + " * " + b;
+  else if (zb) e = ua ? (unit_sign(pa, na) ? a : "-" + a) : term_coef(pa, ka, na) + " * " + a;
+  else if (ua && ub) e = std::string(unit_sign(pa, na) ? "" : "-") + a + (unit_sign(pb, nb) ? " + " : " - ") + b;
+  else if (ua) e = "fma(" + term_coef(pb, kb, nb) + ", " + b + ", " + (unit_sign(pa, na) ? "" : "-") + a + ")";
+  else if (ub) e = "fma(" + term_coef(pa, ka, na) + ", " + a + ", " + (unit_sign(pb, nb) ? "" : "-") + b + ")";
+  else e = "fma(" + term_coef(pb, kb, nb) + ", " + b + ", " + term_coef(pa, ka, na) + " * " + a + ")";
+  return std::string("const double ") + out + " = " + e + ";";
+}
+
+std::string cond_open(const JOp& o) {
+  char buf[160];
+  snprintf(buf, sizeof(buf), "      if ((base & 0x%llxull) == 0x%llxull && (gl & 0x%llxull) == 0x%llxull) {\n", (unsigned long long)o.em, (unsigned long long)o.em,
+           (unsigned long long)o.lm, (unsigned long long)o.lm);
+  return buf;
+}
+
+// Emits the kernel for the planned pass.
+bool generate(const TileParams& P, const Plan& pl, std::string& s) {
+  const int T = P.T;
+  const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
+  std::string body;
+  for (int it = 0; it < P.nitems; ++it) {
+    const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
+    const bool last = it == P.nitems - 1;
+    bool need_gl = false;
+    for (const JOp& o : pl.prog[(size_t)it]) if (o.lm) need_gl = true;
+    int perm[PROG_AMPS];  // logical amplitude (index bits = program positions) -> variable
+    for (int j = 0; j < PROG_AMPS; ++j) perm[j] = j;
+    std::string ops;
+    auto X = [&](int logical, char part) { char b[24]; snprintf(b, sizeof(b), "x%c[%d]", part, perm[logical]); return std::string(b); };
+    for (const JOp& o : pl.prog[(size_t)it]) {
+      int k = o.c0;
+      if (o.kind == JK_LIN2) {
+        int kk[4];
+        for (int i = 0; i < 4; ++i) kk[i] = o.pat[i] == 2 ? k++ : -1;
+        for (int r = 0; r < PROG_AMPS / 2; ++r) {
+          const int i0 = ((r >> o.p) << (o.p + 1)) | (r & ((1 << o.p) - 1)), i1 = i0 | (1 << o.p);
+          ops += "      { ";
+          if (!o.rxl) {
+            for (char part : {'r', 'i'}) {
+              const std::string a = X(i0, part), b = X(i1, part);
+              ops += lin(part == 'r' ? "ta" : "tc", o.pat[0], kk[0], false, a, o.pat[1], kk[1], false, b) + " ";
+              ops += lin(part == 'r' ? "tb" : "td", o.pat[2], kk[2], false, a, o.pat[3], kk[3], false, b) + " ";
+            }
+            ops += X(i0, 'r') + " = ta; " + X(i1, 'r') + " = tb; " + X(i0, 'i') + " = tc; " + X(i1, 'i') + " = td; }\n";
+          } else {
+            // a' = m0 a + i m1 b, b' = i m2 a + m3 b:  (ar, bi) <- [[m0, -m1], [m2, m3]],  (ai, br) <- [[m0, m1], [-m2, m3]]
+            const std::string ar = X(i0, 'r'), ai = X(i0, 'i'), br = X(i1, 'r'), bi = X(i1, 'i');
+            ops += lin("ta", o.pat[0], kk[0], false, ar, o.pat[1], kk[1], true, bi) + " ";
+            ops += lin("tb", o.pat[2], kk[2], false, ar, o.pat[3], kk[3], false, bi) + " ";
+            ops += lin("tc", o.pat[0], kk[0], false, ai, o.pat[1], kk[1], false, br) + " ";
+            ops += lin("td", o.pat[2], kk[2], true, ai, o.pat[3], kk[3], false, br) + " ";
+            ops += ar + " = ta; " + bi + " = tb; " + ai + " = tc; " + br + " = td; }\n";
+          }
+        }
+      } else if (o.kind == JK_GEN) {
+        for (int r = 0; r < PROG_AMPS / 2; ++r) {
+          const int i0 = ((r >> o.p) << (o.p + 1)) | (r & ((1 << o.p) - 1)), i1 = i0 | (1 << o.p);
+          const std::string ar = X(i0, 'r'), ai = X(i0, 'i'), br = X(i1, 'r'), bi = X(i1, 'i');
+          char buf[640];
+          // entry o.q was the pivot: it equals 1 + 0i exactly, the compiler folds the multiplications by the literal away
+          snprintf(buf, sizeof(buf),
+                   "      { const double ta = C.c[%d] * %s - C.c[%d] * %s + C.c[%d] * %s - C.c[%d] * %s, tc = C.c[%d] * %s + C.c[%d] * %s + C.c[%d] * %s + C.c[%d] * %s,\n"
+                   "          tb = C.c[%d] * %s - C.c[%d] * %s + C.c[%d] * %s - C.c[%d] * %s, td = C.c[%d] * %s + C.c[%d] * %s + C.c[%d] * %s + C.c[%d] * %s;\n",
+                   k, ar.c_str(), k + 1, ai.c_str(), k + 2, br.c_str(), k + 3, bi.c_str(), k, ai.c_str(), k + 1, ar.c_str(), k + 2, bi.c_str(), k + 3, br.c_str(),  //
+                   k + 4, ar.c_str(), k + 5, ai.c_str(), k + 6, br.c_str(), k + 7, bi.c_str(), k + 4, ai.c_str(), k + 5, ar.c_str(), k + 6, bi.c_str(), k + 7, br.c_str());
+          ops += buf;
+          ops += "        " + ar + " = ta; " + ai + " = tc; " + br + " = tb; " + bi + " = td; }\n";
+        }
+      } else if (o.kind == JK_PHASE || o.kind == JK_CPH1) {
+        if (o.kind == JK_CPH1) ops += cond_open(o);
+        const int half = o.kind == JK_CPH1 ? 1 : o.q;
+        for (int j = 0; j < PROG_AMPS; ++j)
+          if (((j >> o.p) & 1) == half) {
+            const std::string r = X(j, 'r'), i = X(j, 'i');
+            char buf[256];
+            snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * %s - C.c[%d] * %s, ti = C.c[%d] * %s + C.c[%d] * %s; %s = tr; %s = ti; }\n", k, r.c_str(), k + 1, i.c_str(), k,
+                     i.c_str(), k + 1, r.c_str(), r.c_str(), i.c_str());
+            ops += buf;
+          }
+        if (o.kind == JK_CPH1) ops += "      }\n";
+      } else if (o.kind == JK_CX) {
+        for (int j = 0; j < PROG_AMPS; ++j)
+          if (((j >> o.p) & 1) && !((j >> o.q) & 1)) std::swap(perm[j], perm[j | (1 << o.q)]);
+      } else if (o.kind == JK_CPHASE || o.kind == JK_CZ) {
+        for (int j = 0; j < PROG_AMPS; ++j)
+          if (((j >> o.p) & 1) && ((j >> o.q) & 1)) {
+            const std::string r = X(j, 'r'), i = X(j, 'i');
+            char buf[256];
+            if (o.kind == JK_CZ) snprintf(buf, sizeof(buf), "      %s = -%s; %s = -%s;\n", r.c_str(), r.c_str(), i.c_str(), i.c_str());
+            else
+              snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * %s - C.c[%d] * %s, ti = C.c[%d] * %s + C.c[%d] * %s; %s = tr; %s = ti; }\n", k, r.c_str(), k + 1, i.c_str(), k,
+                       i.c_str(), k + 1, r.c_str(), r.c_str(), i.c_str());
+            ops += buf;
+          }
+      } else if (o.kind == JK_CSCALE) {
+        ops += cond_open(o);
+        for (int j = 0; j < PROG_AMPS; ++j) {
+          char buf[256];
+          snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * xr[%d] - C.c[%d] * xi[%d], ti = C.c[%d] * xi[%d] + C.c[%d] * xr[%d]; xr[%d] = tr; xi[%d] = ti; }\n", k, j, k + 1, j, k, j,
+                   k + 1, j, j, j);
+          ops += buf;
+        }
+        ops += "      }\n";
+      } else if (o.kind == JK_CCX1) {
+        ops += cond_open(o);
+        for (int j = 0; j < PROG_AMPS; ++j)
+          if (!((j >> o.p) & 1)) {
+            const std::string ar = X(j, 'r'), ai = X(j, 'i'), br = X(j | (1 << o.p), 'r'), bi = X(j | (1 << o.p), 'i');
+            ops += "      { const double tr = " + ar + ", ti = " + ai + "; " + ar + " = " + br + "; " + ai + " = " + bi + "; " + br + " = tr; " + bi + " = ti; }\n";
+          }
+        ops += "      }\n";
+      }
+    }
+    if (last) {  // the pass scalar: product of all pivots and unconditional scalars
+      const int k = pl.scale_at;
+      for (int j = 0; j < PROG_AMPS; ++j) {
+        char buf[256];
+        if (pl.complex_scale)
+          snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * xr[%d] - C.c[%d] * xi[%d], ti = C.c[%d] * xi[%d] + C.c[%d] * xr[%d]; xr[%d] = tr; xi[%d] = ti; }\n", k, j, k + 1, j, k, j,
+                   k + 1, j, j, j);
+        else
+          snprintf(buf, sizeof(buf), "      xr[%d] *= C.c[%d]; xi[%d] *= C.c[%d];\n", j, k, j, k);
+        ops += buf;
+      }
     }
     // program frame
-    appf(body, "  if (tid < %uu) {  // program %d: tile bits %d %d %d %d, %u ops\n", ng, it, G.lp[0], G.lp[1], G.lp[2], G.lp[3], G.nops);
+    appf(body, "  if (tid < %uu) {  // program %d: tile bits %d %d %d %d\n", ng, it, G.lp[0], G.lp[1], G.lp[2], G.lp[3]);
     body += "    uint32_t s0 = 0u;\n";
     for (int k = 0; k < 8; ++k)
       if (G.bit_sw[k]) appf(body, "    if (tid & %uu) s0 ^= %uu;\n", 1u << k, G.bit_sw[k]);
@@ -170,37 +402,33 @@ bool generate(const TileParams& P, int np, std::string& src, std::vector<double>
     appf(body, "#pragma unroll 1\n    for (uint32_t it = 0; it < %uu; ++it) {\n", G.niter);
     body += "      uint32_t b = s0;\n";
     for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) b = s0 ^ %uu;\n", i, G.iter_sw[i]);
-    if (G.iter_sw[0]) return false;  // iteration 0 is the identity offset by construction
     if (need_gl) {
       body += "      uint64_t gl = g0;\n";
       for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) gl = g0 ^ %uu;\n", i, G.iter_lin[i]);
     } else {
       body += "      const uint64_t gl = 0ull;\n";
     }
-    body += "      double2 x[PROG_AMPS];\n";
+    body += "      double xr[PROG_AMPS], xi[PROG_AMPS];\n";
     for (int j = 0; j < PROG_AMPS; ++j) {
       uint32_t off = 0;
       for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) off ^= o[q];
-      appf(body, "      x[%d] = sm[b ^ %uu];\n", j, off);
+      appf(body, "      { const double2 v = sm[b ^ %uu]; xr[%d] = v.x; xi[%d] = v.y; }\n", off, j, j);
     }
     body += ops;
-    for (int j = 0; j < PROG_AMPS; ++j) {
+    for (int j = 0; j < PROG_AMPS; ++j) {  // logical amplitude j lives in variable perm[j] (CX renamings)
       uint32_t off = 0;
       for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) off ^= o[q];
-      appf(body, "      sm[b ^ %uu] = x[%d];\n", off, j);
+      appf(body, "      sm[b ^ %uu] = make_double2(xr[%d], xi[%d]);\n", off, perm[j], perm[j]);
     }
     body += "      (void)gl;\n    }\n  }\n  __syncthreads();\n";
   }
-  if (coef.empty()) coef.push_back(0.0);
-  const int ncoef = (int)coef.size() + 8;  // slack: prog_u1 reads four coefficients whatever the kind
+  const int ncoef = (int)pl.coef.size();
 
   // ---- prelude + kernel frame
-  std::string s;
-  s.reserve(sizeof(k_prog_ops_src) + body.size() + 8192);
+  s.clear();
+  s.reserve(body.size() + 8192);
   s += "typedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\ntypedef int int32_t;\n";
-  appf(s, "#define PROG_BITS %d\n#define PROG_AMPS %d\n", PROG_BITS, PROG_AMPS);
-  s += "enum { PK_GEN = 0, PK_REAL = 1, PK_RXL = 2, PK_DIAG = 3, PK_PHASE = 4, PK_CX = 5, PK_CPHASE = 6 };\n";
-  s += k_prog_ops_src;
+  appf(s, "#define PROG_AMPS %d\n", PROG_AMPS);
   s += "struct __align__(64) BtTensorMap { unsigned long long opaque[16]; };\n";
   appf(s, "struct BtCoefs { double c[%d]; };\n", ncoef);
   s += "__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }\n";
@@ -236,33 +464,7 @@ bool generate(const TileParams& P, int np, std::string& src, std::vector<double>
          "\"r\"(c3), \"r\"(c4 + %d), \"r\"(dst + %uu) : \"memory\");\n",
          P.tma_c4add[e], e * chunk);
   s += "    asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n    asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n  }\n}\n";
-  if (want_source) src.swap(s); else src.clear();
   return true;
-}
-
-// structure key: everything generate() turns into literals (the numeric coefficients are excluded)
-void make_key(const TileParams& P, int device, std::string& key) {
-  key.clear();
-  auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
-  put(&device, 4); put(&P.T, 4); put(&P.lowb, 4); put(&P.nitems, 4); put(&P.swz_mode, 4);
-  put(P.tma_coord_shift, sizeof(P.tma_coord_shift)); put(P.tma_coord_mask, sizeof(P.tma_coord_mask));
-  put(&P.tma_ncopy, 4); put(P.tma_c4add, sizeof(int32_t) * (size_t)std::max(1, P.tma_ncopy));
-  put(P.tbits, sizeof(int32_t) * (size_t)P.T);
-  put(P.item, (size_t)P.nitems);
-  for (int it = 0; it < P.nitems; ++it) {
-    const int pi = (int)P.item[it] - TILE_PBASE;
-    if (pi < 0 || pi >= TILE_MAXP) continue;
-    const TileProg& G = P.pr[pi];
-    put(G.lp, sizeof(int32_t) * PROG_BITS); put(G.bit_sw, sizeof(G.bit_sw)); put(&G.niter, 4); put(&G.nops, 4);
-    put(G.iter_sw, sizeof(G.iter_sw)); put(G.bit_lin, sizeof(G.bit_lin)); put(G.iter_lin, sizeof(G.iter_lin));
-    for (uint32_t k = 0; k < G.nops; ++k) {
-      const uint16_t site = G.op[k] & 0xffu;
-      put(&site, 2);
-      const double* c = G.coef + (G.op[k] >> 8);
-      if (site == PROG_SITE_CSCALE || (site >= 169 && site < 177)) put(c + 2, 16);
-      else if (site >= 177 && site < 185) put(c, 16);
-    }
-  }
 }
 
 struct Entry {
@@ -313,18 +515,20 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   const int mode = env_i("BT_TILE_JIT", 1);
   if (mode == 0 || np <= 0 || P.nitems != np || P.swz_mode != 0) return 0;
   if (mode != 2 && s->len < (1ull << env_i("BT_TILE_JIT_MINBITS", 22))) return 0;
+  Plan pl;
+  if (!make_plan(P, np, pl)) return 0;
   std::string key;
-  make_key(P, s->device, key);
+  make_key(P, pl, s->device, key);
   std::lock_guard<std::mutex> lk(g_mu);
+  if (g_cache.size() > 8192 && g_cache.find(key) == g_cache.end()) return 0;  // bounded: a long-running host with ever-new passes keeps interpreting
   Entry& e = g_cache[key];
   e.seen++;
   if (e.state < 0) return 0;
-  std::vector<double> coef;
-  std::string src;
   if (e.state == 0) {
     if (mode != 2 && e.seen < env_i("BT_TILE_JIT_AFTER", 2)) return 0;
     const auto t0 = std::chrono::steady_clock::now();
-    const bool ok = generate(P, np, src, coef, true) && compile(src, e, (int)(tile_bytes + 1024 + 64));
+    std::string src;
+    const bool ok = generate(P, pl, src) && compile(src, e, (int)(tile_bytes + 1024 + 64));
     g_compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!ok) {
       e.state = -1;
@@ -333,12 +537,12 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
       return 0;
     }
     e.state = 1;
-    e.ncoef = (int)coef.size();
+    e.ncoef = (int)pl.coef.size();
     g_compiled++;
-  } else {
-    if (!generate(P, np, src, coef, false) || (int)coef.size() != e.ncoef) return 0;
+  } else if ((int)pl.coef.size() != e.ncoef) {
+    return 0;
   }
-  coef.resize((size_t)e.ncoef + 8, 0.0);
+  std::vector<double>& coef = pl.coef;
   void* args[2] = {(void*)&tmap, (void*)coef.data()};
   if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, TILE_THREADS, 1, 1, (unsigned)(tile_bytes + 1024 + 64), (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
     e.state = -1;
@@ -372,7 +576,7 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
   for (int k = 0; k < 7; ++k) { G.bit_sw[k] = 1u << (2 * k); G.bit_lin[k] = 1u << (2 * k); }
   G.niter = 2; G.iter_sw[1] = 1u << 10; G.iter_lin[1] = 1u << 10;
   int ko = 0, kc = 0;
-  auto emit = [&](int site, int ncf) { G.op[ko++] = (uint16_t)(site | (kc << 8)); for (int e = 0; e < ncf; ++e) G.coef[kc++] = 0.25 * (e + 1); };
+  auto emit = [&](int site, int ncf) { G.op[ko++] = (uint16_t)(site | (kc << 8)); for (int e = 0; e < ncf; ++e) G.coef[kc++] = (e == 3 ? 0.25 : 0.25 * (e + 1)); };
   for (int kind = 0; kind < 5; ++kind) emit(PROG_SITE_U1(kind, kind % PROG_BITS), kind == 0 ? 8 : 4);
   emit(PROG_SITE_CX(0, 2), 0); emit(PROG_SITE_CPHASE(1, 3), 2);
   { double m; uint64_t em = 1ull << 20, lm = 1ull << 6; emit(PROG_SITE_CSCALE, 2); memcpy(&m, &em, 8); G.coef[kc++] = m; memcpy(&m, &lm, 8); G.coef[kc++] = m; }
@@ -380,9 +584,9 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
   { double m; uint64_t em = 1ull << 22, lm = 0; emit(PROG_SITE_CCX1(1), 0); memcpy(&m, &em, 8); G.coef[kc++] = m; memcpy(&m, &lm, 8); G.coef[kc++] = m; }
   G.nops = (uint32_t)ko;
   std::string src;
-  std::vector<double> coef;
+  Plan pl;
   int rc = 0;
-  if (!generate(P, 1, src, coef, true)) rc = -1;
+  if (!make_plan(P, 1, pl) || !generate(P, pl, src)) rc = -1;
   if (rc == 0 && source && cap) { strncpy(source, src.c_str(), cap - 1); source[cap - 1] = 0; }
   if (rc == 0) {
     Nvrtc& n = nvrtc();

@@ -105,5 +105,8 @@ def test_pass_specialiser_generates_and_compiles_on_the_host():
         pytest.skip("libnvrtc not available")
     assert rc == 0, lib.bt_last_error().decode()
     src = buf.value.decode()
-    for needle in ("bt_jit_pass", "cp.async.bulk.tensor.5d", "prog_u1<1, 1>", "prog_cx<0, 2>", "prog_cphase<1, 3>", "prog_x1<1>", "ip_cmul"):
+    for needle in ("bt_jit_pass", "cp.async.bulk.tensor.5d", "mbarrier.try_wait", "fma(C.c[", "if ((base & 0x100000ull) == 0x100000ull", "make_double2("):
         assert needle in src
+    # the CX of the synthetic pass is a renaming: amplitudes are stored from permuted variables, no swap code is emitted
+    stores = [l for l in src.splitlines() if "make_double2(" in l]
+    assert len(stores) == 16 and any("xr[5]" in l for l in stores) and "xr[1] = xr[5]" not in src

@@ -152,9 +152,10 @@ def test_batched_states_through_programs(bt, orc):
 
 
 def test_specialised_passes_equal_the_interpreter(bt, orc):
-    """csrc/bt_jit.cu: the straight-line kernel compiled for a pass runs the same micro-op code in the same order as the
-    interpreter, so the amplitudes must be IDENTICAL (not merely within tolerance), and equal to the oracle within 1e-10.
-    BT_TILE_JIT=2 compiles every pass at first sight; the statistics must show specialised launches."""
+    """csrc/bt_jit.cu: the straight-line kernel compiled for a pass applies the same ops in the same order as the interpreter
+    (with the 2x2 blocks rescaled by a pivot and the pass scalar applied once), so the amplitudes agree to rounding (1e-13)
+    and with the oracle within 1e-10.  BT_TILE_JIT=2 compiles every pass at first sight; the statistics must show
+    specialised launches, and a second run of the same structure must reuse the modules."""
     import ctypes as C
     L = bt._lib
     lib = L.load()
@@ -174,7 +175,7 @@ def test_specialised_passes_equal_the_interpreter(bt, orc):
     if c1.value == c0.value and f1.value > f0.value:
         pytest.skip("NVRTC not available on this box: passes stay on the interpreter")
     assert l1.value > l0.value and c1.value > c0.value
-    assert np.array_equal(outs[0], outs[2])
+    assert np.max(np.abs(outs[0] - outs[2])) < 1e-13
     assert np.max(np.abs(outs[2] - orc.apply_ops(v, oo))) < TOL
     # second run of the same structure with other angles: cached modules, new coefficients
     with tile_env(BT_TILE_JIT=2, BT_TILE_BITS=10, BT_TILE_LOWB=3):
