@@ -28,7 +28,7 @@ oracle: oracle/_build/libbt_oracle_c.so
 
 oracle/_build/libbt_oracle_c.so: oracle/strided_cpu.c
 	@mkdir -p oracle/_build
-	gcc -O3 -march=native -fopenmp -fPIC -shared -o $@ $< -lm
+	gcc -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -o $@ $< -lm
 
 clean:
 	rm -rf build $(LIB) oracle/_build

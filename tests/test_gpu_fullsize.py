@@ -121,3 +121,55 @@ def test_c4_20q_monitored_trajectories_batched(bt, orc):
         sv, mo = S.SV(N).apply_ops(oops, draws=orc.ListDraws(U[t]), track_measurements=True)
         assert list(out[t]) == mo                       # identical outcomes under shared uniform draws
         assert np.max(np.abs(ez[t] - sv.expect_z_all())) < 1e-10
+
+
+def test_specialised_passes_default_tiles_24q_vs_strided_oracle(bt, orc):
+    """the headline configuration of the fused path as bench.py runs it -- default 2^12-amplitude tiles, every pass compiled by
+    the pass specialiser (csrc/bt_jit.cu) -- at 24 qubits (QFT + 5 random layers, ~500 gates), amplitude by amplitude against
+    the strided CPU oracle (1e-10 absolute, north star); then the SAME pass structures with other angles (cached modules, new
+    coefficient blocks) against the interpreter."""
+    from oracle import strided as S
+
+    wl = mods()
+    L = bt._lib
+    lib = L.load()
+    N = 24
+    specs = wl.c2_qft_layered(N, 5, 24)
+    arr = bt.pack_gates(wl.to_ops(bt, specs))
+    ref = S.SV(N)
+    ref.apply_ops(wl.to_ops(orc, specs))
+    old = {k: os.environ.get(k) for k in ("BT_TILE_JIT",)}
+    try:
+        os.environ["BT_TILE_JIT"] = "2"
+        c0, l0, f0 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.bt_jit_stats(C.byref(c0), C.byref(l0), C.byref(f0), None)
+        s = bt.zero_state(N)
+        L.check(s.lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1))
+        got = s.to_numpy()
+        c1, l1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.bt_jit_stats(C.byref(c1), C.byref(l1), C.byref(f1), None)
+        assert np.max(np.abs(got - ref.v)) < 1e-10
+        del got, s
+        if c1.value > c0.value:  # NVRTC present: the passes above were specialised launches
+            assert l1.value > l0.value
+        # same structure, other angles: angles only enter the coefficient block, the modules are reused
+        specs2 = [(n, q, t, c) for (n, q, t, c) in wl.c2_qft_layered(N, 5, 24)]
+        g = np.random.default_rng(99)
+        import re
+        specs2 = [(re.sub(r"^(RX|RY|RZ)\(.*\)$", lambda m: f"{m.group(1)}({float(g.uniform(0.1, 3.0))!r})", n), q, t, c) for (n, q, t, c) in specs2]
+        arr2 = bt.pack_gates(wl.to_ops(bt, specs2))
+        a = bt.zero_state(N)
+        L.check(a.lib.bt_sv_apply_circuit(a.h, L.ptr(arr2), len(arr2), 1))
+        c2 = C.c_uint64()
+        lib.bt_jit_stats(C.byref(c2), None, None, None)
+        os.environ["BT_TILE_JIT"] = "0"
+        b = bt.zero_state(N)
+        L.check(b.lib.bt_sv_apply_circuit(b.h, L.ptr(arr2), len(arr2), 1))
+        assert abs(bt.inner(a, b) - bt.norm2(b)) < 1e-12 and abs(bt.norm2(a) - bt.norm2(b)) < 1e-12  # same state (T is rounded to 10 digits in the reference: norm != 1)
+        assert np.max(np.abs(bt.expect(a, "Z") - bt.expect(b, "Z"))) < 1e-12
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
