@@ -91,6 +91,7 @@ PROTOTYPES = {
     "bt_sv_expect_1q_all": [_vp, _vp, _pd],
     "bt_sv_expect_product": [_vp, _i, C.POINTER(_i), _vp, _pd],
     "bt_sv_expect_matrix2q": [_vp, _i, _i, _vp, _pd],
+    "bt_sv_expect_pauli_sum": [_vp, _i, C.c_char_p, _pd, _pd],
     "bt_sv_sample": [_vp, _pd, _u64, _pi64],
     "bt_sv_sample_batched": [_vp, _pd, _u64, _pi64],
     "bt_dm_create": [_i, C.POINTER(_vp)],

@@ -644,6 +644,188 @@ extern "C" int bt_sv_expect_pauli(const bt_sv* cs, const char* paulis, double* o
   return BT_OK;
 }
 
+// ---- Pauli-sum expectation values (Hamiltonians): sum_k c_k <P_k> ---------------------------------------------------
+// The reference builds H = sum_k c_k expand_multi_op(P_k) as one 2^N x 2^N sparse matrix (hamiltonian, src/vqa.jl:36-67)
+// and takes real(state' * H * state) (src/func.jl:91; the VQE loss, src/vqa.jl:282-283).  Here the terms are never
+// expanded.  Terms that are diagonal in a common product basis form a group (greedy qubit-wise grouping: a TFIM chain is
+// 2 groups, a Heisenberg chain 3); a group costs ONE read of the state: rotate a scratch copy into the group's basis
+// (H for X, H*S' for Y: one fused pass per <= 12 qubits, nothing for an all-Z group), then k_zsum accumulates
+//   sum_i |a_i|^2 f(i),  f(i) = sum_k c_k (-1)^popc(i & z_k)
+// for all terms of the group at once.  f is evaluated with a Walsh-Hadamard step: a thread holds the 16 probabilities
+// of index bits 8..11, transforms them in registers (4 additions per amplitude), and a term then costs one sign and one
+// addition per 16 amplitudes (terms pre-sorted by their pattern on bits 8..11), so a chain Hamiltonian of ~2N terms stays
+// HBM-bound (16 B per amplitude per group) instead of one pass per term.
+#define ZS_MAXT 160
+struct ZsumParams {
+  int32_t start[17];      // terms sorted by m = (z >> 8) & 15; start[m]..start[m+1]
+  int32_t n;
+  uint64_t z[ZS_MAXT];    // physical-bit parity mask
+  double c[ZS_MAXT];
+};
+
+__global__ void __launch_bounds__(RB) k_zsum(const double2* __restrict__ a, int n_local, const __grid_constant__ ZsumParams P, double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const double2* base = a + ((uint64_t)traj << n_local);
+  const uint64_t nsg = 1ull << (n_local - 12);  // supergroups of 2^12 amplitudes: bits 0..7 thread, 8..11 registers
+  double acc[1] = {0.0};
+  for (uint64_t sg = blockIdx.x; sg < nsg; sg += (uint64_t)nblk) {
+    const uint64_t i0 = (sg << 12) | threadIdx.x;
+    double w[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const double2 x = base[i0 | ((uint64_t)it << 8)];
+      w[it] = x.x * x.x + x.y * x.y;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (!((j >> b) & 1)) {
+          const double u = w[j], v = w[j | (1 << b)];
+          w[j] = u + v;
+          w[j | (1 << b)] = u - v;
+        }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      double g = 0.0;
+      for (int k = P.start[m]; k < P.start[m + 1]; ++k) g += (__popcll(i0 & P.z[k]) & 1) ? -P.c[k] : P.c[k];
+      acc[0] = fma(w[m], g, acc[0]);
+    }
+  }
+  block_reduce_store<1>(acc, part + ((size_t)traj * nblk + blockIdx.x));
+}
+
+// states of fewer than 2^12 amplitudes: plain loop over the terms
+__global__ void __launch_bounds__(RB) k_zsum_small(const double2* __restrict__ a, int n_local, const __grid_constant__ ZsumParams P, double* __restrict__ part, int nblk) {
+  const int64_t traj = blockIdx.y;
+  const double2* base = a + ((uint64_t)traj << n_local);
+  const uint64_t n = 1ull << n_local;
+  double acc[1] = {0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (uint64_t)nblk * RB) {
+    const double2 x = base[i];
+    double f = 0.0;
+    for (int k = 0; k < P.n; ++k) f += (__popcll(i & P.z[k]) & 1) ? -P.c[k] : P.c[k];
+    acc[0] = fma(x.x * x.x + x.y * x.y, f, acc[0]);
+  }
+  block_reduce_store<1>(acc, part + ((size_t)traj * nblk + blockIdx.x));
+}
+
+// sum over the terms (z, c) of c * sum_i |amp_i|^2 (-1)^popc(i & z) on the handle's CURRENT amp buffer, added to acc[n_batch]
+static int zsum_accumulate(bt_sv* s, const std::vector<uint64_t>& z, const std::vector<double>& c, double* acc) {
+  for (size_t k0 = 0; k0 < z.size(); k0 += ZS_MAXT) {
+    const size_t k1 = std::min(z.size(), k0 + (size_t)ZS_MAXT);
+    ZsumParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = (int)(k1 - k0);
+    int fill = 0;
+    for (int m = 0; m < 16; ++m) {  // bucket by the pattern on index bits 8..11 (small states: one bucket, see k_zsum_small)
+      P.start[m] = fill;
+      for (size_t k = k0; k < k1; ++k) {
+        const int mk = s->n_local >= 12 ? (int)((z[k] >> 8) & 15) : 0;
+        if (mk != m) continue;
+        P.z[fill] = z[k];
+        P.c[fill] = c[k];
+        fill++;
+      }
+    }
+    P.start[16] = fill;
+    if (fill != P.n) BT_FAIL(BT_ERR_ARG, "internal: term bucketing lost a term");
+    int nblk;
+    if (s->n_local >= 12) {
+      nblk = pick_nblk(s, (uint64_t)RB << (s->n_local - 12));
+      BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk));
+      dim3 grid(nblk, (unsigned)s->n_batch);
+      k_zsum<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+    } else {
+      nblk = pick_nblk(s, 1ull << s->n_local);
+      BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk));
+      dim3 grid(nblk, (unsigned)s->n_batch);
+      k_zsum_small<<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+    }
+    BT_CHECK_LAUNCH(s);
+    BT_TRY(finish(s, nblk, 1, 0));
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch));
+    for (int64_t t = 0; t < s->n_batch; ++t) acc[t] += s->h_res[t];
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_expect_pauli_sum(const bt_sv* cs, int n_terms, const char* paulis, const double* coefs, double* out) {
+  BT_TRY(bt_check_sv(cs));
+  if (n_terms < 0 || (n_terms > 0 && (!paulis || !coefs)) || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  const int N = s->n_qubits;
+  for (int k = 0; k < n_terms; ++k)
+    for (int q = 0; q < N; ++q) {
+      const char ch = paulis[(size_t)k * N + q];
+      if (!(ch == 'I' || ch == 'X' || ch == 'Y' || ch == 'Z')) BT_FAIL(BT_ERR_ARG, "Pauli strings may only contain I, X, Y, Z (term %d)", k);
+    }
+  for (int64_t t = 0; t < s->n_batch; ++t) out[t] = 0.0;
+  if (s->world > 1) {
+    // sharded state: term by term (the scratch-copy rotation below would have to remap both buffers)
+    std::vector<double> one((size_t)s->n_batch);
+    std::string str((size_t)N, 'I');
+    for (int k = 0; k < n_terms; ++k) {
+      str.assign(paulis + (size_t)k * N, (size_t)N);
+      BT_TRY(bt_sv_expect_pauli(s, str.c_str(), one.data()));
+      for (int64_t t = 0; t < s->n_batch; ++t) out[t] += coefs[k] * one[t];
+    }
+    return BT_OK;
+  }
+  // greedy qubit-wise grouping: a term joins the first group whose basis assignment it does not contradict
+  struct Group { std::string basis; std::vector<int> terms; };
+  std::vector<Group> groups;
+  for (int k = 0; k < n_terms; ++k) {
+    const char* tk = paulis + (size_t)k * N;
+    Group* home = nullptr;
+    for (Group& g : groups) {
+      bool ok = true;
+      for (int q = 0; q < N && ok; ++q)
+        if (tk[q] != 'I' && g.basis[q] != 'I' && g.basis[q] != tk[q]) ok = false;
+      if (ok) { home = &g; break; }
+    }
+    if (!home) { groups.push_back(Group{std::string((size_t)N, 'I'), {}}); home = &groups.back(); }
+    for (int q = 0; q < N; ++q) if (tk[q] != 'I') home->basis[q] = tk[q];
+    home->terms.push_back(k);
+  }
+  const double r = 0.70710678118654752440;
+  for (const Group& g : groups) {
+    std::vector<uint64_t> z;
+    std::vector<double> c;
+    for (int k : g.terms) {
+      uint64_t m = 0;
+      for (int q = 0; q < N; ++q)
+        if (paulis[(size_t)k * N + q] != 'I') m |= 1ull << s->phys_of_bit[N - 1 - q];
+      z.push_back(m);
+      c.push_back(coefs[k]);
+    }
+    std::vector<bt_gate> rot;
+    for (int q = 0; q < N; ++q) {
+      if (g.basis[q] != 'X' && g.basis[q] != 'Y') continue;
+      bt_gate u;
+      memset(&u, 0, sizeof(u));
+      u.nq = 1; u.qubit = q + 1; u.target = -1; u.control = -2;
+      // column-major 2x2: X -> H;  Y -> H * S' = [[1, -i], [1, i]] / sqrt(2)   (U' Z U = P, so <psi|P|psi> = <U psi|Z|U psi>)
+      if (g.basis[q] == 'X') { u.m[0].re = r; u.m[1].re = r; u.m[2].re = r; u.m[3].re = -r; }
+      else { u.m[0].re = r; u.m[1].re = r; u.m[2].im = -r; u.m[3].im = r; }
+      rot.push_back(u);
+    }
+    if (rot.empty()) {
+      BT_TRY(zsum_accumulate(s, z, c, out));
+      continue;
+    }
+    BT_TRY(bt_ensure_alt(s));
+    BT_CUDA(cudaMemcpyAsync(s->alt, s->amp, s->len * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+    std::swap(s->amp, s->alt);  // the rotations and the reduction act on the copy
+    int rc = bt_sv_apply_circuit(s, rot.data(), rot.size(), 1);
+    if (rc == BT_OK) rc = zsum_accumulate(s, z, c, out);
+    std::swap(s->amp, s->alt);
+    if (rc != BT_OK) return rc;
+  }
+  return BT_OK;
+}
+
 int bt_build_gate(const bt_sv* s, int nq, int qubit, int target, int control, const bt_c64* m, GateDesc* out);
 
 extern "C" int bt_sv_expect_product(const bt_sv* cs, int n_ops, const int* qubits, const bt_c64* mats, double* out) {

@@ -119,6 +119,11 @@ int bt_sv_expect_pauli(const bt_sv* s, const char* paulis /* n chars from IXYZ, 
 int bt_sv_expect_1q_all(const bt_sv* s, const bt_c64 m[4], double* out /* n_batch x n : Re<psi|m_q|psi> */);
 int bt_sv_expect_product(const bt_sv* s, int n_ops, const int* qubits, const bt_c64* mats /* n_ops x 4 */, double* out /* n_batch */);
 int bt_sv_expect_matrix2q(const bt_sv* s, int qubit, int target, const bt_c64 m[16], double* out);
+/* Pauli-sum (Hamiltonian) expectation value sum_k coefs[k] * <P_k>: the scalar real(state' * hamiltonian(...) * state) of
+ * src/vqa.jl:36-67 + src/func.jl:91 (the VQE loss, src/vqa.jl:282-283) without building the 2^N x 2^N operator.  paulis =
+ * n_terms strings of n characters (I/X/Y/Z, qubit 1 first, no separators).  Terms diagonal in a common product basis are
+ * evaluated together in one read of the state (a scratch copy is rotated into that basis first); out[n_batch]. */
+int bt_sv_expect_pauli_sum(const bt_sv* s, int n_terms, const char* paulis, const double* coefs, double* out /* n_batch */);
 
 /* ---- sampling: sample src/ops.jl:46-62 as inverse CDF on caller-supplied uniforms:
  * t = u*sum(p); index = first i with cumsum_i >= t.  n_batch must be 1 unless per_traj != 0, in which case
