@@ -252,4 +252,30 @@ function inner(a::CuState, b::CuState)
 end
 fidelity(a::CuState, b::CuState) = abs2.(inner(a, b))
 
+# Pauli-sum Hamiltonians (hamiltonian src/vqa.jl:36-67 + expect src/func.jl:91, the VQE loss src/vqa.jl:282-283): the term list
+# stays a list; one device call evaluates sum_k c_k <P_k> with one read of the state per commuting group of terms.
+struct PauliSum
+    N::Int
+    coefs::Vector{Float64}
+    strings::String          # N characters (I/X/Y/Z, qubit 1 first) per term, concatenated
+end
+function pauli_sum(N::Int, string_of_ops::Vector, boundary::String="open")           # same arguments as hamiltonian(N, ...)
+    coefs = Float64[]; io = IOBuffer()
+    for id in 2:2:length(string_of_ops)
+        names = String.(split(string_of_ops[id], ",")); k = length(names)
+        sites = boundary == "open" ? (1:N-(k-1)) : (1:N)
+        for site in sites
+            s = fill('I', N)
+            for (j, n) in enumerate(names); s[mod1(site + j - 1, N)] = uppercase(n)[1]; end
+            write(io, String(s)); push!(coefs, Float64(string_of_ops[id-1]))
+        end
+    end
+    PauliSum(N, coefs, String(take!(io)))
+end
+function expect(s::CuState, H::PauliSum)
+    out = Vector{Float64}(undef, s.n_batch)
+    check(ccall((:bt_sv_expect_pauli_sum, LIB), Cint, (Ptr{Cvoid}, Cint, Cstring, Ptr{Float64}, Ptr{Float64}), s.h, length(H.coefs), H.strings, H.coefs, out))
+    return s.n_batch == 1 ? out[1] : out
+end
+
 end # module

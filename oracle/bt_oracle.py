@@ -1134,3 +1134,92 @@ def entanglement_entropy(psi: np.ndarray) -> float:
     spec = np.linalg.svd(mat, compute_uv=False) ** 2
     spec = spec[spec > 0]
     return float(np.sum(-spec * np.log(spec)))
+
+
+# ---- variational front end (callers of apply + expect): src/vqa.jl ---------------------------------------------
+GATES_WITH_PHASE = ["P", "RX", "RY", "RZ", "U1", "U2", "U3", "CP", "GIVENS", "FSIM", "SWAPA", "RXX", "RYY", "RZZ", "RXY"]  # src/gates.jl:361
+TWO_QUBIT_GATES = ["CX", "CNOT", "CY", "CZ", "CP", "RXX", "RYY", "RZZ", "RXY", "GIVENS", "FSIM", "SWAP", "ISWAP", "FSWAP", "SYC", "ECR"]  # src/gates.jl:65
+_N_ARGS = {"U2": 2, "U3": 3, "FSIM": 2}  # _find_argument_number of the gate functions (src/gates.jl:369-420); every other phase gate takes 1
+
+
+def hamiltonian(N: int, string_of_ops: Sequence, boundary: str = "open"):
+    """src/vqa.jl:36-67: H as a 2^N x 2^N sparse matrix, summed term by term with expand_multi_op."""
+    couplings = [o for i, o in enumerate(string_of_ops) if i % 2 == 0]
+    names = [o for i, o in enumerate(string_of_ops) if i % 2 == 1]
+    Hm = sp.csc_matrix((1 << N, 1 << N), dtype=C)
+    for idx, op in enumerate(names):
+        len_op = len(op.split(","))
+        if boundary == "open":
+            for site in range(1, N - (len_op - 1) + 1):
+                Hm = Hm + couplings[idx] * expand_multi_op(op, list(range(site, site + len_op)), N)
+        elif boundary == "periodic":
+            for site in range(1, N + 1):
+                Hm = Hm + couplings[idx] * expand_multi_op(op, [(i - 1) % N + 1 for i in range(site, site + len_op)], N)
+    return Hm
+
+
+def variational_circuit_from_string(N: int, ops: Sequence[str], deep_circuit: bool = False):
+    """src/vqa.jl:340-404 -> ([(name, qubit, target), ...], args per op, dim)."""
+    out, args, dim, brick_c = [], [], 0, 0
+    for gate_name in ops:
+        gate_name = _clean_name(gate_name)
+        two = gate_name in TWO_QUBIT_GATES
+        c = 1
+        mb = 0 if deep_circuit else brick_c % 2
+        while c <= N:
+            if two:
+                if mb + c >= N:
+                    break
+                r = (gate_name, mb + c, mb + c + 1)
+                c = c + 1 if deep_circuit else c + 2
+            else:
+                r = (gate_name, c, -1)
+                c = c + 1
+            a = _N_ARGS.get(gate_name, 1) if gate_name in GATES_WITH_PHASE else 0
+            dim += a
+            args.append(a)
+            out.append(r)
+        if two:
+            brick_c += 1
+    return out, args, dim
+
+
+def efficient_su2(N: int, reps: int = 1, gate_names: Sequence[str] = ("RY", "RZ"), deep_circuit: bool = True):
+    """src/vqa.jl:302-314."""
+    gl: List[str] = []
+    for i in range(1, reps + 2):
+        gl += list(gate_names)
+        if i <= reps:
+            gl.append("CX")
+    return variational_circuit_from_string(N, gl, deep_circuit)
+
+
+def variational_apply(pars: Sequence[float], N: int, vops, args, init: Optional[np.ndarray] = None, noise=False, draws: Optional[Draws] = None) -> np.ndarray:
+    """src/vqa.jl:420-456: op by op, the next ``fn`` parameters go into the op's matrix function; noise after every op."""
+    state = zero_state(N) if init is None else np.array(init, dtype=C)
+    c = 0
+    for (name, q, t), fn in zip(vops, args):
+        full = name if fn == 0 else f"{name}({','.join(repr(float(p)) for p in pars[c:c + fn])})"
+        op = Op(full, q, t) if t != -1 else Op(full, q)
+        state = apply(state, op)
+        c += fn
+        if isinstance(noise, NoiseModel):
+            state = apply_noise(state, op, noise, draws)
+    return state
+
+
+def loss_and_grad_paramshift(p: Sequence[float], loss, N: int, vops, args, init: Optional[np.ndarray] = None):
+    """src/vqa.jl:588-611: shift pi/2, g_i = (f(p + s e_i) - f(p - s e_i)) / 2."""
+    p = np.asarray(p, dtype=float)
+    f = lambda v: float(loss(variational_apply(v, N, vops, args, init)))
+    l0 = f(p)
+    g = np.zeros(len(p))
+    base = p.copy()
+    for i in range(len(p)):
+        base[i] = p[i] + math.pi / 2
+        fp = f(base)
+        base[i] = p[i] - math.pi / 2
+        fm = f(base)
+        g[i] = 0.5 * (fp - fm)
+        base[i] = p[i]
+    return l0, g

@@ -55,3 +55,12 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not pat.search(src), f
+
+
+def test_julia_shim_binds_only_declared_entry_points():
+    """julia/BlueTangleCUDA.jl cannot be executed here (no Julia); at least every symbol it ccalls must be one the header
+    declares and the library exports."""
+    src = open(os.path.join(ROOT, "julia", "BlueTangleCUDA.jl")).read()
+    called = set(re.findall(r"ccall\(\(:(bt_[a-z0-9_]+)", src))
+    assert len(called) >= 25
+    assert called <= set(declared_symbols()), sorted(called - set(declared_symbols()))

@@ -1,0 +1,153 @@
+"""GPU parity of the variational callers of the hot path: Pauli-sum expectation values
+(bt_sv_expect_pauli_sum: hamiltonian src/vqa.jl:36-67 + expect src/func.jl:91 without the 2^N x 2^N operator),
+variational_apply (src/vqa.jl:420-456), the parameter-shift gradient (:590-611) and the gradient loop (:563-582)
+against the oracle's restatement.  Tolerance 1e-10 absolute (north star)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rand_state(N, seed):
+    g = np.random.default_rng(seed)
+    v = g.normal(size=1 << N) + 1j * g.normal(size=1 << N)
+    return v / np.linalg.norm(v)
+
+
+def ref_energy(orc, v, ps):
+    """sum_k c_k <v| expand_multi_op(P_k) |v> with the oracle's operators"""
+    N = ps.N
+    tot = 0.0
+    for c, names, qs in ps.terms:
+        tot += c * float(np.real(np.vdot(v, orc.expand_multi_op(names, qs, N) @ v)))
+    return tot
+
+
+@pytest.mark.parametrize("N", [3, 5, 11, 12, 13, 16])
+def test_chain_hamiltonians_one_read_per_basis_group(bt, orc, N):
+    """TFIM (2 groups: all Z,Z terms; all X terms after H on every qubit), Heisenberg (3 groups incl. the H*S' rotation
+    for Y), a 3-body mixed term; open and periodic boundaries; small states (plain kernel) and >= 2^12 amplitudes (register
+    Walsh-Hadamard kernel).  The state itself must come back untouched (the rotations act on a scratch copy)."""
+    v = rand_state(N, 100 + N)
+    s = bt.CuState.from_numpy(v)
+    for spec, boundary in (([-1.0, "Z,Z", -0.7, "X"], "open"), ([0.5, "X,X", 0.25, "Y,Y", -1.5, "Z,Z"], "periodic"),
+                           ([0.3, "X,Y,Z", 1.1, "Y", -0.2, "Z,X"], "open")):
+        ps = bt.hamiltonian(N, spec, boundary)
+        got = ps.expect(s)
+        if N <= 13:
+            want = float(np.real(np.vdot(v, orc.hamiltonian(N, spec, boundary) @ v)))  # the reference's own route: one sparse H
+        else:
+            want = ref_energy(orc, v, ps)
+        assert abs(got - want) < TOL, (spec, boundary, got, want)
+        assert abs(got - bt.hamiltonian_expect(s, ps.terms)) < TOL  # term-by-term path (one pass per term)
+    assert np.array_equal(s.to_numpy(), v)
+
+
+def test_random_pauli_sums_many_terms_and_batches(bt, orc):
+    """random strings over all of I/X/Y/Z (greedy grouping produces many groups), more terms than one launch carries
+    (ZS_MAXT = 160 per launch), the identity string, and a batch of trajectories evaluated in one call"""
+    g = np.random.default_rng(7)
+    for N, K in ((6, 50), (13, 40)):
+        terms = []
+        for k in range(K):
+            w = int(g.integers(0, min(N, 5) + 1))
+            qs = sorted(int(q) + 1 for q in g.choice(N, w, replace=False))
+            names = [["X", "Y", "Z"][int(g.integers(3))] for _ in qs]
+            if w == 0:
+                qs, names = [1], ["I"]
+            terms.append((float(g.normal()), ",".join(names), qs))
+        ps = bt.PauliSum(N, terms)
+        B = 3
+        vs = [rand_state(N, 50 + t) for t in range(B)]
+        s = bt.CuState.from_numpy(np.stack(vs))
+        got = ps.expect(s)
+        for t in range(B):
+            assert abs(got[t] - ref_energy(orc, vs[t], ps)) < TOL
+    # 400 all-Z terms on 13 qubits: three launches of the diagonal kernel, no rotation
+    N = 13
+    terms = []
+    for k in range(400):
+        w = int(g.integers(1, 7))
+        terms.append((float(g.normal()), ",".join(["Z"] * w), sorted(int(q) + 1 for q in g.choice(N, w, replace=False))))
+    ps = bt.PauliSum(N, terms)
+    v = rand_state(N, 9)
+    p = np.abs(v) ** 2
+    idx = np.arange(1 << N)
+    want = 0.0
+    for c, names, qs in terms:
+        par = np.zeros(1 << N, dtype=np.int64)
+        for q in qs:
+            par ^= (idx >> (N - q)) & 1
+        want += c * float(np.sum(p * (1 - 2 * par)))
+    s = bt.CuState.from_numpy(v)
+    n0 = s.launch_count()
+    assert abs(ps.expect(s) - want) < TOL
+    assert s.launch_count() - n0 <= 8  # 3 x (k_zsum + final sum), not 400 passes
+
+
+def test_pauli_sum_rejects_bad_strings(bt):
+    s = bt.zero_state(4)
+    out = np.empty(1)
+    c = np.ones(1)
+    rc = s.lib.bt_sv_expect_pauli_sum(s.h, 1, b"ZZQI", bt._lib.pdouble(c), bt._lib.pdouble(out))
+    assert rc == -1 and b"I, X, Y, Z" in s.lib.bt_last_error()
+
+
+def test_variational_apply_loss_and_parameter_shift_gradient(bt, orc):
+    """EfficientSU2-style ansatz (RY, RZ layers + CX ladder) on a TFIM chain: state, energy and every gradient component
+    against the oracle's op-by-op restatement"""
+    N = 6
+    names = ["RY", "RZ", "CX", "RY", "RZ", "CX", "RX", "RZZ"]
+    ham = [-1.0, "Z,Z", -0.7, "X"]
+    opt = bt.AnsatzOptions(N=N, ops=names, loss=bt.hamiltonian(N, ham), rng=bt.Draws(11))
+    vops, args, dim = orc.variational_circuit_from_string(N, names, False)
+    assert opt.dim == dim == len(opt.pars_initial)
+    p = opt.pars_initial
+    st = bt.variational_apply(p, opt)
+    ref = orc.variational_apply(p, N, vops, args)
+    assert np.max(np.abs(st.to_numpy() - ref)) < TOL
+    Hm = orc.hamiltonian(N, ham)
+    loss = lambda x: float(np.real(np.vdot(x, Hm @ x)))
+    l0, g = bt.loss_and_grad_paramshift(p, opt)
+    r0, rg = orc.loss_and_grad_paramshift(p, loss, N, vops, args)
+    assert abs(l0 - r0) < TOL and np.max(np.abs(g - rg)) < TOL
+    # a non-zero initial state is copied, not consumed
+    init = bt.CuState.from_numpy(rand_state(N, 4))
+    opt2 = bt.AnsatzOptions(N=N, ops=names, loss=bt.hamiltonian(N, ham), init=init, pars_initial=p)
+    a = bt.variational_apply(p, opt2).to_numpy()
+    assert np.max(np.abs(a - orc.variational_apply(p, N, vops, args, init=init.to_numpy()))) < TOL
+    assert abs(bt.norm2(init) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("model", ["descent", "adam"])
+def test_vqa_gradient_loop_matches_the_oracle_loop(bt, orc, model):
+    """src/vqa.jl:563-582: same parameters and energy history as the loop run on the oracle (parameter-shift gradient,
+    Optimisers.Descent / Adam update rules); the energy goes down."""
+    N = 4
+    names = ["RY", "CX", "RY"]
+    ham = [-1.0, "Z,Z", -1.0, "X"]
+    p0 = np.random.default_rng(5).uniform(0, math.pi, 8)
+    opt = bt.AnsatzOptions(N=N, ops=names, loss=bt.hamiltonian(N, ham), model=model, number_of_iterations=6, learning_rate=0.1, pars_initial=p0)
+    hist, p, phist = bt.VQA(opt)
+    vops, args, dim = orc.variational_circuit_from_string(N, names, False)
+    Hm = orc.hamiltonian(N, ham)
+    loss = lambda x: float(np.real(np.vdot(x, Hm @ x)))
+    q = p0.copy()
+    m, v = np.zeros(dim), np.zeros(dim)
+    want = []
+    for it in range(1, 7):
+        _, g = orc.loss_and_grad_paramshift(q, loss, N, vops, args)
+        if model == "adam":
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            q = q - 0.1 * (m / (1 - 0.9 ** it)) / (np.sqrt(v / (1 - 0.999 ** it)) + 1e-8)
+        else:
+            q = q - 0.1 * g
+        want.append(loss(orc.variational_apply(q, N, vops, args)))
+    assert np.max(np.abs(np.array(hist) - np.array(want))) < 1e-9
+    assert np.max(np.abs(p - q)) < 1e-9 and len(phist) == 6
+    assert hist[-1] < hist[0]
