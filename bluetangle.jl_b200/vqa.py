@@ -188,11 +188,19 @@ class AnsatzOptions:
         return out
 
 
-def variational_apply(pars: Sequence[float], opt: AnsatzOptions, noise_override=False, rng=None) -> "H.CuState":
+def variational_apply(pars: Sequence[float], opt: AnsatzOptions, noise_override=False, rng=None, out: Optional["H.CuState"] = None) -> "H.CuState":
     """src/vqa.jl:420-456: the ansatz with the given parameters on a copy of the initial state.  Without noise the whole
     op list goes to the device in one fused call; with a NoiseModel the per-op loop of the reference is kept (apply, then
-    apply_noise, drawing from ``rng``)."""
-    state = H.zero_state(opt.N) if opt.init is None else opt.init.copy()
+    apply_noise, drawing from ``rng``).  ``out``: an existing device state to overwrite instead of allocating a new one
+    (the optimisation loops evaluate the ansatz thousands of times; a 28-qubit state is 4 GiB)."""
+    if out is None:
+        state = H.zero_state(opt.N) if opt.init is None else opt.init.copy()
+    else:
+        state = out
+        if opt.init is None:
+            L.check(state.lib.bt_sv_set_basis(state.h, 0))
+        else:
+            L.check(state.lib.bt_sv_copy(state.h, opt.init.h))
     noise = noise_override if isinstance(noise_override, H.NoiseModel) else opt.noise
     ops = opt.bound_ops(pars)
     if isinstance(noise, H.NoiseModel):
@@ -203,7 +211,11 @@ def variational_apply(pars: Sequence[float], opt: AnsatzOptions, noise_override=
 
 
 def _loss(p, opt: AnsatzOptions) -> float:
-    return float(opt.loss(variational_apply(p, opt)))
+    """loss at p on the options' work state (allocated once, overwritten by every evaluation)"""
+    work = getattr(opt, "_work", None)
+    if work is None:
+        work = opt._work = H.zero_state(opt.N) if opt.init is None else opt.init.copy()
+    return float(opt.loss(variational_apply(p, opt, out=work)))
 
 
 def loss_and_grad_paramshift(p: Sequence[float], opt: AnsatzOptions) -> Tuple[float, np.ndarray]:
