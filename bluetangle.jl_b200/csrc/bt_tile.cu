@@ -898,7 +898,12 @@ static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& 
       for (const MOp& o : b.prog) { b.scost += o.cost; b.sflops += o.flops; }
       // keep the structured form only when it is cheaper than the dense block and the dense form is not already diagonal
       // (a diagonal block always does: its alternative is a shared-memory sweep + barrier of its own)
-      const double dense_cost = b.desc.k == 2 ? 16.0 : 8.0;
+      // With the pass specialiser on (bt_jit.cu) a pass made of structured blocks only becomes a straight-line kernel (1.6 instead
+      // of 2.6 ms at 28 qubits) in which real / RX-like ops cost about half of the interpreter's table: the structured form is
+      // kept up to BT_FUSE_STRUCT_SLACK_PCT (150) per cent of the dense cost, so the 4-op blocks at the head of a circuit
+      // (1-qubit gates on both sides of the first CX) and lone general 1-qubit blocks no longer force an interpreted pass.
+      const double slack = env_int("BT_TILE_JIT", 1) != 0 ? 0.01 * (double)std::max(100, env_int("BT_FUSE_STRUCT_SLACK_PCT", 150)) : 1.0;
+      const double dense_cost = (b.desc.k == 2 ? 16.0 : 8.0) * slack;
       if (!use_prog || b.prog.empty() || (!b.desc.diag && b.scost >= dense_cost) || (int)b.prog.size() > 12) b.sok = false;
       if (b.sok)
         for (const MOp& o : b.prog) {
@@ -1055,14 +1060,14 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
     for (int k = nr; k > 0; --k) { run_start[k] = run_start[k - 1]; run_len[k] = run_len[k - 1]; }
     run_start[0] = 3; run_len[0] = 0; nr++;
   }
-  // more than four runs: the tile bits of the runs above the fourth are enumerated -- one box per value (<= 8 boxes)
+  // more than four runs: the tile bits of the runs above the fourth are enumerated -- one box per value (<= 16 boxes of >= 4 KB)
   P.tma_ncopy = 1;
   P.tma_c4add[0] = 0;
   if (nr > 4) {
-    int ebits[8], ne = 0;
+    int ebits[8], ne = 0;  // at most 4 used
     for (int k = 4; k < nr; ++k)
       for (int j = 0; j < run_len[k]; ++j) {
-        if (ne >= 3) return false;
+        if (ne >= 4 || T - ne < 6) return false;  // every box stays a multiple of the 1 KB swizzle pattern
         ebits[ne++] = run_start[k] + j;
       }
     P.tma_ncopy = 1 << ne;

@@ -121,8 +121,8 @@ struct TileParams {
   int32_t swz_mode;     // 0: TMA-compatible 128-B swizzle, 1: all-digit swizzle
   int32_t tma_coord_shift[5];  // tensor-copy variant: coordinate k of a tile = (base >> shift[k]) & mask[k]
   uint32_t tma_coord_mask[5];
-  int32_t tma_ncopy;           // a tile whose bits form more than four runs moves as 2, 4 or 8 boxes: the top tile bits are enumerated
-  int32_t tma_c4add[8];        // copy e: added to coordinate 4; its shared-memory chunk is e * (tile bytes / ncopy)
+  int32_t tma_ncopy;           // a tile whose bits form more than four runs moves as 2, 4, 8 or 16 boxes: the top tile bits are enumerated
+  int32_t tma_c4add[16];        // copy e: added to coordinate 4; its shared-memory chunk is e * (tile bytes / ncopy)
   int32_t tbits[TILE_TMAX];  // physical positions of the tile bits, ascending; tbits[j] = j for j < lowb
   uint8_t item[TILE_MAXITEMS];  // item i: < TILE_MAXG -> gate slot, else cluster slot (item - TILE_MAXG)
   TileGate g[TILE_MAXG];

@@ -185,3 +185,39 @@ def test_specialised_passes_equal_the_interpreter(bt, orc):
         lib.bt_jit_stats(C.byref(c2), None, None, None)
         assert c2.value == c1.value          # nothing recompiled
         assert np.array_equal(s.to_numpy(), outs[2])
+
+
+@pytest.mark.parametrize("free_bits", [(6, 9, 11, 13, 16, 17, 19), (7, 14, 16, 18, 21, 22, 23), (5, 8, 10, 12, 14, 16, 18)])
+def test_tiles_with_many_runs_move_as_up_to_16_tensor_boxes(bt, orc, free_bits):
+    """bt_tile.cu build_tensor_map: a tile whose bits form more than four runs enumerates the tile bits of the runs above
+    the fourth -- up to 4 bits = 16 boxes of 4 KB (the shapes the scheduler produces on the 28-qubit headline circuit, e.g.
+    bits {0-4, 6, 9, 13, 20, 23, 24, 26}).  One pass acting on 7 scattered qubits at 24 qubits, interpreter and specialised
+    kernel, against the strided CPU oracle; the pass must be a tensor-copy pass (it is specialised when NVRTC is present)."""
+    import ctypes as C
+    from oracle import strided as S
+
+    N = 24
+    lib = bt._lib.load()
+    names = ["H", "RY(0.3)", "RX(1.1)", "H", "RY(2.2)", "RX(0.7)", "H"]
+    qubits = [N - b for b in free_bits]
+    specs = [(n, q, -1, -2) for n, q in zip(names, qubits)]
+    specs += [("CX", qubits[0], qubits[3], -2), ("CZ", qubits[1], qubits[5], -2), ("RZ(0.4)", qubits[6], -1, -2), ("CX", qubits[2], qubits[4], -2),
+              ("CP(0.9)", qubits[6], N - 20, -2), ("RY(0.5)", qubits[3], -1, -2)]
+    od = [bt.Op(n, q, t, control=c) for n, q, t, c in specs]
+    oo = [orc.Op(n, q, t, control=c) for n, q, t, c in specs]
+    v = rand_state(N, 77)
+    ref = S.SV(N, v)
+    ref.apply_ops(oo)
+    for mode in (0, 2):
+        c0, l0 = C.c_uint64(), C.c_uint64()
+        lib.bt_jit_stats(C.byref(c0), C.byref(l0), None, None)
+        with tile_env(BT_TILE_JIT=mode):
+            s = bt.CuState.from_numpy(v)
+            n0 = s.launch_count()
+            bt.apply(od, s)
+            assert s.launch_count() - n0 <= 2          # one fused pass (two if the scheduler splits)
+            assert np.max(np.abs(s.to_numpy() - ref.v)) < TOL
+        c1, l1, f1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.bt_jit_stats(C.byref(c1), C.byref(l1), C.byref(f1), None)
+        if mode == 2 and c1.value > c0.value:
+            assert l1.value >= l0.value + 1            # the specialiser only takes tensor-copy passes
