@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -38,7 +39,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The process is started BEFORE the warm-up
+    (nvidia-smi's own start-up initialises NVML over every GPU of the box and can hold up CUDA calls of the ranks for
+    hundreds of milliseconds -- that belongs into the warm-up, not into a timed step); only the samples that arrive
+    between begin() and stop() are reported."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -46,10 +50,13 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.p = None
+        self.t_begin = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            if os.environ.get("BENCH_NO_CLOCKS", "") not in ("", "0"):
+                raise RuntimeError("clock sampling switched off")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_CLOCKS_MS", "100")],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -58,20 +65,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        """the timed region starts now"""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
         except Exception:
             pass
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for (t, r) in self.rows if t0 <= t <= t_end + 0.12]
+        if not rows:  # region shorter than one sampling period: take the nearest samples
+            rows = [r for (_, r) in self.rows[-2:]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -109,13 +125,17 @@ def bench_single(args):
     # the library specialises a fused pass the second time it sees it (csrc/bt_jit.cu); here every pass is compiled at first
     # sight so that the compilation always falls into the untimed warm-up, whatever W is
     os.environ.setdefault("BT_TILE_JIT_AFTER", "1")
+    clocks = ClockSampler(0)
+    clocks.start()
     t_w0 = time.perf_counter()
     for _ in range(args.warmup):
         step()
     s.sync()
     warmup_seconds = time.perf_counter() - t_w0
-    clocks = ClockSampler(0)
-    clocks.start()
+    time.sleep(max(0.0, 1.5 - warmup_seconds))  # nvidia-smi has finished starting up before the timed region
+    gc.collect()
+    gc.disable()  # no cyclic-GC pause inside the timed region (a full collection with torch imported takes ~0.5 s)
+    clocks.begin()
     L.check(lib.bt_sv_profile_enable(s.h, 1))
     fl0 = C.c_double()
     L.check(lib.bt_fusion_flops(C.byref(fl0)))
@@ -135,6 +155,7 @@ def bench_single(args):
     L.check(lib.bt_sv_profile_read(s.h, counts, cms))
     L.check(lib.bt_sv_profile_enable(s.h, 0))
     clk = clocks.stop()
+    gc.enable()
     ms_per_step = ms.value / args.steps
     value = ngates / (ms_per_step / 1e3)
     norm = bt.norm2(s)
@@ -266,6 +287,10 @@ def bench_sharded(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    debug = os.environ.get("BENCH_DEBUG", "") not in ("", "0")
+    if debug:  # per-rank stderr file: every rank's own timings (and the library's BT_TILE_DEBUG lines, if switched on)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.dup2(os.open(os.path.join(ROOT, "gpurun_out", f"bench_rank{rank}.err"), os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644), 2)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g = world.bit_length() - 1
@@ -280,29 +305,38 @@ def bench_sharded(args):
     ngates = len(arr)
     st = D.ShardedState(N)
     lib = st.lib
+    t_start = time.perf_counter()
 
     def step():
         L.check(lib.bt_sv_set_basis(st.h, 0))
         L.check(lib.bt_sv_apply_circuit(st.h, L.ptr(arr), ngates, 1))
 
     os.environ.setdefault("BT_TILE_JIT_AFTER", "1")  # specialise every fused pass at first sight: compilation stays in the warm-up
-    for _ in range(args.warmup):
-        step()
-    st.sync()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    st.sync()
+    if rank == 0:
+        time.sleep(max(0.0, 1.5 - (time.perf_counter() - t_start)))  # nvidia-smi has finished starting up before the timed region
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()  # no cyclic-GC pause inside the timed region (a full collection with torch imported takes ~0.5 s)
+    clocks.begin()
     r0 = st.remap_stats()
     n0 = st.launch_count()
     ms = C.c_float()
     L.check(lib.bt_sv_profile_enable(st.h, 1))
     t_host0 = time.perf_counter()
     L.check(lib.bt_sv_timer_start(st.h))
+    step_host = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         step()
+        step_host.append(time.perf_counter() - t_s)
     L.check(lib.bt_sv_timer_stop(st.h, C.byref(ms)))
     t_host = time.perf_counter() - t_host0
     counts = (C.c_uint64 * 4)()
@@ -314,11 +348,16 @@ def bench_sharded(args):
     torch.cuda.synchronize()
     n1 = st.launch_count()
     r1 = st.remap_stats()
+    if debug:
+        sys.stderr.write(f"[bench rank {rank}] timed region {ms.value:.1f} ms (device events), host {t_host * 1e3:.1f} ms, host time to enqueue each step {[round(x * 1e3, 1) for x in step_host]} ms, "
+                         f"launches {n1 - n0}, classes {[(int(counts[i]), round(float(cms[i]), 1)) for i in range(4)]}, remaps {r1[0] - r0[0]} in {r1[2] - r0[2]:.1f} ms, jit {jit_stats(lib)}\n")
+        sys.stderr.flush()
     t = torch.tensor([ms.value], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+    gc.enable()
     # end to end through the host API: gate list in host memory -> <Z_q> for every qubit and the norm back in host memory,
     # host wall clock between barriers, max over ranks, median of up to 3 steps
     ez = np.empty(N)

@@ -4,7 +4,7 @@
 set +e
 mkdir -p gpurun_out
 T0=$(date +%s)
-stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round3.log; }
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/session_2gpu.log; }
 stamp "bench n2"
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_c5_n2.json 2> gpurun_out/bench_c5_n2.err; stamp "bench n2 rc=$?"
 cat gpurun_out/bench_c5_n2.json | cut -c1-1500; tail -5 gpurun_out/bench_c5_n2.err
@@ -17,4 +17,4 @@ tail -5 gpurun_out/pytest_multi.log
 stamp "vqa bench"
 timeout 200 python tools/vqa_bench.py 28 > gpurun_out/vqa_bench.txt 2> gpurun_out/vqa_bench.err; stamp "vqa bench rc=$?"
 cat gpurun_out/vqa_bench.txt
-cat gpurun_out/round3.log
+cat gpurun_out/session_2gpu.log

@@ -3,7 +3,7 @@
 set +e
 mkdir -p gpurun_out
 T0=$(date +%s)
-stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round5.log; }
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/session_ab.log; }
 stamp "full gpu suite"
 timeout 500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu5.log 2>&1; stamp "pytest rc=$?"
 tail -4 gpurun_out/pytest_gpu5.log
@@ -23,4 +23,4 @@ j=d.get("jit") or d.get("jit_rank0")
 print("$f", round(d["value"]), round(d["ms_per_step"],1), k["tile"], j["modules_compiled"], j["specialised_launches"], d["clocks"])
 PY
 done
-cat gpurun_out/round5.log
+cat gpurun_out/session_ab.log

@@ -4,7 +4,7 @@
 set +e
 mkdir -p gpurun_out
 T0=$(date +%s)
-stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round.log; }
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/session_bench.log; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 stamp "pytest -m gpu"
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; stamp "pytest rc=$?"
@@ -23,4 +23,4 @@ BT_TILE_LOWB=3 timeout 200 python bench.py --no-cpu --steps 3 --warmup 1 > gpuru
 BT_TILE_LOWB=3 BT_FUSE_MAX_GATES=44 timeout 200 python bench.py --no-cpu --steps 3 --warmup 1 > gpurun_out/bench_lowb3_cap44.json 2>/dev/null; stamp "lowb3cap44 rc=$?"
 if [ "$1" = "configs" ]; then timeout 300 python tools/config_runs.py > gpurun_out/configs.txt 2>&1; stamp "configs rc=$?"; fi
 tail -3 gpurun_out/pytest_gpu.log
-cat gpurun_out/round.log
+cat gpurun_out/session_bench.log

@@ -4,7 +4,7 @@
 set +e
 mkdir -p gpurun_out
 T0=$(date +%s)
-stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round2.log; }
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/session_vqa.log; }
 stamp "pytest vqa"
 timeout 300 python -m pytest tests/test_gpu_vqa.py -q > gpurun_out/pytest_vqa.log 2>&1; stamp "pytest vqa rc=$?"
 tail -25 gpurun_out/pytest_vqa.log
@@ -20,4 +20,4 @@ BT_TILE_BITS=11 BT_TILE_LOWB=4 timeout 200 python bench.py --no-cpu --steps 3 --
 stamp "full gpu suite"
 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu2.log 2>&1; stamp "pytest rc=$?"
 tail -3 gpurun_out/pytest_gpu2.log
-cat gpurun_out/round2.log
+cat gpurun_out/session_vqa.log
