@@ -3,7 +3,7 @@
 set +e
 mkdir -p gpurun_out
 T0=$(date +%s)
-stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/round10.log; }
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a gpurun_out/session_final.log; }
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; stamp "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 timeout 400 python bench.py > gpurun_out/bench_n1_final.json 2> gpurun_out/bench_n1_final.err; stamp "bench rc=$?"
 timeout 100 python bench.py --impl reference --steps 3 --warmup 1 --cpu-budget 12 > gpurun_out/bench_reference_final.json 2>/dev/null; stamp "ref rc=$?"
