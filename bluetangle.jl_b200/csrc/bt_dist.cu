@@ -54,6 +54,66 @@ __global__ void __launch_bounds__(256) k_remap_pull(double2* __restrict__ dst, u
   }
 }
 
+// T[t][v] = OR over the set bits j of v of (1 << sigma[t * REMAP_TBITS + j]): where the t-th digit of a destination index goes
+struct RemapSigma { int s[64]; };
+__global__ void k_remap_tables(uint64_t* __restrict__ tab, const __grid_constant__ RemapSigma SG) {
+  const int t = blockIdx.x;
+  const uint32_t v = threadIdx.x;
+  uint64_t o = 0;
+#pragma unroll
+  for (int j = 0; j < REMAP_TBITS; ++j) {
+    const int src = SG.s[t * REMAP_TBITS + j];
+    if (src >= 0 && ((v >> j) & 1u)) o |= 1ull << src;
+  }
+  tab[((size_t)t << REMAP_TBITS) + v] = o;
+}
+
+// ---- device-side synchronisation of a remap (multi-process shards, one GPU per process) --------------------------------
+// A remap needs two agreements between the ranks: "everyone's previous kernels have finished writing the buffer I am about to
+// read" and "everyone has finished reading the buffer I am about to overwrite".  Made on the host (stream synchronise + barrier,
+// twice per remap) they stop the host from running ahead of the GPU, and every delay of a host thread at one of those points idles
+// all GPUs.  Here both are epoch flags in peer memory: after its segment's kernels a rank stores the remap's epoch into its slot of
+// every peer's flag page (k_flag_signal, st.release.sys over NVLink); the pull is preceded by k_flag_wait, which polls the own page
+// (ld.acquire.sys) until every slot has reached the epoch.  Everything is stream-ordered; the host never blocks in a remap.
+struct FlagPeers { uint32_t* page[16]; };
+
+__device__ __forceinline__ unsigned long long bt_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// which = 0: "ready" slots [0..15], which = 1: "done" slots [16..31]
+__global__ void k_flag_signal(const __grid_constant__ FlagPeers P, int world, int rank, int which, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    uint32_t* p = P.page[r] + which * 16 + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(epoch) : "memory");
+  }
+}
+
+__global__ void k_flag_wait(const uint32_t* __restrict__ page, int world, int which, uint32_t epoch, int32_t* __restrict__ err, unsigned long long timeout_ns) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const uint32_t* p = page + which * 16 + r;
+    const unsigned long long t0 = bt_globaltimer();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      __nanosleep(256);
+      if (bt_globaltimer() - t0 > timeout_ns) {  // a peer died or never reached this remap: fail loudly instead of hanging the box
+        *err = 7;
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+
 extern "C" int bt_sv_create_shard(int n_qubits_total, int rank, int world, bt_sv** out) {
   if (world < 1 || world > 16 || (world & (world - 1))) BT_FAIL(BT_ERR_ARG, "world must be a power of two <= 16");
   if (rank < 0 || rank >= world) BT_FAIL(BT_ERR_ARG, "rank out of range");
@@ -66,6 +126,8 @@ extern "C" int bt_sv_create_shard(int n_qubits_total, int rank, int world, bt_sv
   for (int r = 0; r < 16; ++r) { s->peer_amp[r] = nullptr; s->peer_alt[r] = nullptr; }
   s->peer_amp[rank] = s->amp;
   s->peer_alt[rank] = s->alt;
+  for (int r = 0; r < 16; ++r) s->peer_flags[r] = nullptr;
+  s->peer_flags[rank] = s->flags;
   if (world == 1) s->peers_attached = true;
   // |0..0> lives on rank 0 only
   return bt_sv_set_basis(s, 0);
@@ -76,6 +138,7 @@ extern "C" int bt_sv_ipc_export(bt_sv* s, void* handles) {
   if (!handles) BT_FAIL(BT_ERR_ARG, "null output");
   if (!s->alt) BT_FAIL(BT_ERR_ARG, "not a shard handle");
   static_assert(sizeof(cudaIpcMemHandle_t) <= BT_IPC_HANDLE_BYTES, "IPC handle size");
+  if (s->amp != s->buf0) BT_FAIL(BT_ERR_ARG, "export the IPC handles before the first remap");
   cudaIpcMemHandle_t h0, h1;
   BT_CUDA(cudaIpcGetMemHandle(&h0, s->amp));
   BT_CUDA(cudaIpcGetMemHandle(&h1, s->alt));
@@ -98,6 +161,8 @@ extern "C" int bt_sv_ipc_attach(bt_sv* s, const void* all_handles) {
     BT_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
     s->peer_amp[r] = (double2*)p0;
     s->peer_alt[r] = (double2*)p1;
+    // the peer's flag page sits behind the amplitudes of its first buffer (same shard size on every rank)
+    s->peer_flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p0) + s->len * sizeof(double2));
   }
   s->ipc_opened = true;
   s->peers_attached = true;
@@ -146,8 +211,28 @@ extern "C" int bt_sv_layout(const bt_sv* s, int* phys) {
   return BT_OK;
 }
 
+// durations of the remaps enqueued without a host synchronisation: read back once their stop event has completed
+static void drain_remap_events(bt_sv* s, bool wait) {
+  if (!s->remap_ev) return;
+  std::vector<cudaEvent_t>& v = *s->remap_ev;
+  size_t keep = 0;
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    const bool done = wait ? (cudaEventSynchronize(v[i + 1]) == cudaSuccess) : (cudaEventQuery(v[i + 1]) == cudaSuccess);
+    if (done) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) s->remap_ms += ms;
+      cudaEventDestroy(v[i]); cudaEventDestroy(v[i + 1]);
+    } else {
+      v[keep++] = v[i]; v[keep++] = v[i + 1];
+    }
+  }
+  v.resize(keep);
+  cudaGetLastError();
+}
+
 extern "C" int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* bytes_remote, float* ms_total) {
   if (!s) BT_FAIL(BT_ERR_ARG, "null handle");
+  drain_remap_events(const_cast<bt_sv*>(s), true);
   if (n_remaps) *n_remaps = s->n_remaps;
   if (bytes_remote) *bytes_remote = s->remap_bytes;
   if (ms_total) *ms_total = s->remap_ms;
@@ -175,53 +260,68 @@ extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
   if (identity) return BT_OK;
   for (int d = 0; d < REMAP_KEEP; ++d)
     if (sigma[d] != d) BT_FAIL(BT_ERR_ARG, "the %d lowest physical bits must stay in place (coalescing)", REMAP_KEEP);
-  // digit tables
-  std::vector<uint64_t> tab((size_t)REMAP_NT << REMAP_TBITS, 0);
-  for (int t = 0; t < REMAP_NT; ++t)
-    for (uint64_t v = 0; v < (1ull << REMAP_TBITS); ++v) {
-      uint64_t o = 0;
-      for (int j = 0; j < REMAP_TBITS; ++j) {
-        int d = t * REMAP_TBITS + j;
-        if (d < n && ((v >> j) & 1)) o |= 1ull << sigma[d];
-      }
-      tab[((size_t)t << REMAP_TBITS) + v] = o;
-    }
-  uint64_t* d_tab = nullptr;
-  BT_CUDA(cudaMallocAsync(&d_tab, tab.size() * sizeof(uint64_t), s->stream));
-  BT_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  // digit tables, built on the device from the bit permutation (no host buffer has to outlive the call, no copy to wait for);
+  // one table per handle: the next remap's build is stream-ordered behind this remap's pull
+  RemapSigma SG;
+  for (int d = 0; d < 64; ++d) SG.s[d] = d < n ? sigma[d] : -1;
+  if (!s->d_remap_tab) BT_CUDA(cudaMalloc(&s->d_remap_tab, ((size_t)REMAP_NT << REMAP_TBITS) * sizeof(uint64_t)));
+  uint64_t* d_tab = s->d_remap_tab;
+  k_remap_tables<<<REMAP_NT, 1 << REMAP_TBITS, 0, s->stream>>>(d_tab, SG);
+  BT_CUDA(cudaGetLastError());
   // fraction of the new shard that comes from other ranks (for the NVLink traffic figure)
   int moved_global = 0;
   for (int d = s->n_local; d < n; ++d) if (sigma[d] < s->n_local) moved_global++;
-  // everyone's previous kernels must have finished writing `amp`
-  BT_CUDA(cudaStreamSynchronize(s->stream));
-  if (s->barrier) s->barrier(s->barrier_ctx);
   RemapParams P;
   for (int r = 0; r < 16; ++r) P.src[r] = (r < s->world) ? s->peer_amp[r] : nullptr;
   P.n_local = s->n_local;
   P.rank = s->rank;
-  cudaEvent_t e0 = s->ev0, e1 = s->ev1;
+  uint64_t nloc = 1ull << s->n_local;
+  unsigned grid = (unsigned)std::min<uint64_t>((s->len / 4 + 255) / 256 + 1, 148ull * 8);
   cudaEvent_t t0, t1;
   BT_CUDA(cudaEventCreate(&t0));
   BT_CUDA(cudaEventCreate(&t1));
-  (void)e0; (void)e1;
-  BT_CUDA(cudaEventRecord(t0, s->stream));
-  uint64_t nloc = 1ull << s->n_local;
-  unsigned grid = (unsigned)std::min<uint64_t>((s->len / 4 + 255) / 256 + 1, 148ull * 8);
-  k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
-  BT_CHECK_LAUNCH(s);
-  BT_CUDA(cudaEventRecord(t1, s->stream));
-  BT_CUDA(cudaFreeAsync(d_tab, s->stream));
-  BT_CUDA(cudaStreamSynchronize(s->stream));
-  float ms = 0;
-  BT_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-  cudaEventDestroy(t0); cudaEventDestroy(t1);
-  // nobody may overwrite the buffer others are still reading
-  if (s->barrier) s->barrier(s->barrier_ctx);
+  bool dev_sync = s->world > 1 && s->ipc_opened && s->flags != nullptr;
+  if (dev_sync) { const char* v = getenv("BT_REMAP_DEVICE_SYNC"); if (v && *v && atoi(v) == 0) dev_sync = false; }
+  if (dev_sync) {
+    // flags in peer memory: nothing here blocks the host (see k_flag_signal / k_flag_wait)
+    FlagPeers F;
+    for (int r = 0; r < 16; ++r) F.page[r] = (r < s->world) ? s->peer_flags[r] : nullptr;
+    const uint32_t epoch = ++s->remap_epoch;
+    unsigned long long timeout_s = 120;  // a peer that has not reached the remap by then has died: trap instead of hanging (BT_REMAP_TIMEOUT_S)
+    { const char* v = getenv("BT_REMAP_TIMEOUT_S"); if (v && *v && atoi(v) > 0) timeout_s = (unsigned long long)atoi(v); }
+    const unsigned long long timeout_ns = timeout_s * 1000000000ull;
+    k_flag_signal<<<1, 32, 0, s->stream>>>(F, s->world, s->rank, 0, epoch);   // my previous kernels are done: my amp may be read
+    k_flag_wait<<<1, 32, 0, s->stream>>>(s->flags, s->world, 0, epoch, s->d_err, timeout_ns);
+    BT_CUDA(cudaEventRecord(t0, s->stream));
+    k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
+    BT_CHECK_LAUNCH(s);
+    BT_CUDA(cudaEventRecord(t1, s->stream));
+    k_flag_signal<<<1, 32, 0, s->stream>>>(F, s->world, s->rank, 1, epoch);   // I have read everything I need from the peers
+    k_flag_wait<<<1, 32, 0, s->stream>>>(s->flags, s->world, 1, epoch, s->d_err, timeout_ns);  // nobody reads my old buffer any more
+    BT_CUDA(cudaGetLastError());
+    if (!s->remap_ev) s->remap_ev = new std::vector<cudaEvent_t>();
+    s->remap_ev->push_back(t0); s->remap_ev->push_back(t1);
+    if (s->remap_ev->size() >= 64) drain_remap_events(s, false);
+  } else {
+    // everyone's previous kernels must have finished writing `amp`
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->barrier) s->barrier(s->barrier_ctx);
+    BT_CUDA(cudaEventRecord(t0, s->stream));
+    k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
+    BT_CHECK_LAUNCH(s);
+    BT_CUDA(cudaEventRecord(t1, s->stream));
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    BT_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    s->remap_ms += ms;
+    // nobody may overwrite the buffer others are still reading
+    if (s->barrier) s->barrier(s->barrier_ctx);
+  }
   std::swap(s->amp, s->alt);
   for (int r = 0; r < s->world; ++r) std::swap(s->peer_amp[r], s->peer_alt[r]);
   for (int lb = 0; lb < n; ++lb) s->phys_of_bit[lb] = new_phys[lb];
   s->n_remaps++;
-  s->remap_ms += ms;
   // bytes pulled from other ranks: a fraction (1 - 2^-moved_global) of the shard
   double frac = 1.0 - ldexp(1.0, -moved_global);
   s->remap_bytes += (uint64_t)(frac * (double)s->len * 16.0);

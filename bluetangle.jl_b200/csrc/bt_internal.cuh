@@ -41,6 +41,8 @@ void bt_set_error(const char* fmt, ...);
   } while (0)
 
 // ---- handle -------------------------------------------------------------------------------------------
+#define BT_FLAG_PAGE_BYTES 4096
+
 struct bt_sv {
   int n_qubits;      // qubits per trajectory, whole (possibly sharded) register
   int n_local;       // index bits held locally per trajectory
@@ -84,6 +86,14 @@ struct bt_sv {
   bt_barrier_fn barrier; void* barrier_ctx;
   bt_allreduce_fn allreduce; void* allreduce_ctx;
   uint64_t n_remaps, remap_bytes; float remap_ms;
+  // device-side remap synchronisation (multi-process shards): a 4 KB flag page behind the first buffer of every shard, mapped
+  // by the peers together with the buffer; peer r writes its epoch into slot r (ready: [0..15], done: [16..31])
+  double2* buf0;             // the allocation that carries the flag page (amp and alt swap roles, buf0 does not)
+  uint32_t* flags;           // own flag page, or nullptr
+  uint32_t* peer_flags[16];  // every rank's flag page as seen from this device
+  uint32_t remap_epoch;
+  uint64_t* d_remap_tab;     // digit tables of the remap in flight (built on the device)
+  std::vector<cudaEvent_t>* remap_ev;  // (start, stop) pairs of remaps whose duration has not been read back yet
   // density-matrix view
   bool is_dm; int dm_n;
 };

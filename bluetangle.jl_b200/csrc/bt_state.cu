@@ -122,13 +122,19 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
   s->len = (uint64_t)n_batch << n_local;
   s->rank = 0; s->world = 1; s->g = 0;
   for (int b = 0; b < 64; ++b) s->phys_of_bit[b] = b;
-  cudaError_t ea = cudaMalloc(&s->amp, s->len * sizeof(double2));
+  // shards: the first buffer carries a 4 KB flag page behind the amplitudes (bt_dist.cu: device-side remap synchronisation)
+  cudaError_t ea = cudaMalloc(&s->amp, s->len * sizeof(double2) + (want_alt ? BT_FLAG_PAGE_BYTES : 0));
   if (ea != cudaSuccess) { delete s; cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "cudaMalloc of %llu bytes failed: %s", (unsigned long long)(s->len * sizeof(double2)), cudaGetErrorString(ea)); }
   if (want_alt) {
     ea = cudaMalloc(&s->alt, s->len * sizeof(double2));
     if (ea != cudaSuccess) { cudaFree(s->amp); delete s; cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "cudaMalloc (second buffer) failed: %s", cudaGetErrorString(ea)); }
   }
   BT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  s->buf0 = s->amp;
+  if (want_alt) {
+    s->flags = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->amp) + s->len * sizeof(double2));
+    BT_CUDA(cudaMemset(s->flags, 0, BT_FLAG_PAGE_BYTES));
+  }
   BT_CUDA(cudaEventCreate(&s->ev0));
   BT_CUDA(cudaEventCreate(&s->ev1));
   s->res_cap = std::max<size_t>(4096, (size_t)n_batch * 128);
@@ -171,6 +177,8 @@ static void really_destroy(bt_sv* s) {
       if (s->peer_alt[r]) cudaIpcCloseMemHandle(s->peer_alt[r]);
     }
   }
+  if (s->remap_ev) { for (cudaEvent_t e : *s->remap_ev) cudaEventDestroy(e); delete s->remap_ev; }
+  if (s->d_remap_tab) cudaFree(s->d_remap_tab);
   cudaFree(s->amp);
   if (s->alt) cudaFree(s->alt);
   if (s->d_part) cudaFree(s->d_part);
