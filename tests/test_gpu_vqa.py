@@ -151,3 +151,25 @@ def test_vqa_gradient_loop_matches_the_oracle_loop(bt, orc, model):
     assert np.max(np.abs(np.array(hist) - np.array(want))) < 1e-9
     assert np.max(np.abs(p - q)) < 1e-9 and len(phist) == 6
     assert hist[-1] < hist[0]
+
+
+def test_vqa_golden_fixture_on_the_device(bt):
+    """committed fixture tests/golden/golden_vqa_r1.npz (oracle-generated): ansatz state, the three Pauli-sum energies at
+    6 and 12 qubits and the parameter-shift gradient through the C ABI, 1e-10 absolute"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_vqa as M
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_vqa_r1.npz"))
+    N = 6
+    opt = bt.AnsatzOptions(N=N, ops=M.NAMES, loss=bt.hamiltonian(N, *M.HAMS["tfim_open"]), pars_initial=G["n6_pars"])
+    st = bt.variational_apply(G["n6_pars"], opt)
+    assert np.max(np.abs(st.to_numpy() - G["n6_state"])) < TOL
+    big = bt.CuState.from_numpy(G["n12_state"])
+    for key, (spec, bc) in M.HAMS.items():
+        assert abs(bt.hamiltonian(N, spec, bc).expect(st) - float(G[f"n6_energy_{key}"])) < TOL
+        assert abs(bt.hamiltonian(12, spec, bc).expect(big) - float(G[f"n12_energy_{key}"])) < TOL
+    l0, g = bt.loss_and_grad_paramshift(G["n6_pars"], opt)
+    assert abs(l0 - float(G["n6_energy_tfim_open"])) < TOL
+    assert np.max(np.abs(g - G["n6_grad_tfim_open"])) < TOL

@@ -69,3 +69,22 @@ def test_parameter_shift_equals_the_derivative(orc):
         fd[i] = (loss(orc.variational_apply(p + e, N, vops, args)) - loss(orc.variational_apply(p - e, N, vops, args))) / (2 * h)
     assert np.max(np.abs(g - fd)) < 1e-7
     assert abs(l0 - loss(orc.variational_apply(p, N, vops, args))) < 1e-14
+
+
+def test_vqa_golden_fixture_is_reproduced_by_the_oracle(orc):
+    """tests/golden/golden_vqa_r1.npz (made by tests/golden/make_golden_vqa.py): regression pin of the restated ansatz,
+    hamiltonian and parameter-shift gradient."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_vqa as M
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_vqa_r1.npz"))
+    N = 6
+    vops, args, dim = orc.variational_circuit_from_string(N, M.NAMES, False)
+    st = orc.variational_apply(G["n6_pars"], N, vops, args)
+    assert np.max(np.abs(st - G["n6_state"])) < 1e-14
+    for key, (spec, bc) in M.HAMS.items():
+        for n, v in ((6, st), (12, G["n12_state"])):
+            e = float(np.real(np.vdot(v, orc.hamiltonian(n, spec, bc) @ v)))
+            assert abs(e - float(G[f"n{n}_energy_{key}"])) < 1e-12
