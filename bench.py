@@ -330,6 +330,7 @@ def bench_sharded(args):
     n0 = st.launch_count()
     ms = C.c_float()
     L.check(lib.bt_sv_profile_enable(st.h, 1))
+    jit0 = jit_stats(lib)["specialised_launches"]
     t_host0 = time.perf_counter()
     L.check(lib.bt_sv_timer_start(st.h))
     step_host = []
@@ -339,6 +340,7 @@ def bench_sharded(args):
         step_host.append(time.perf_counter() - t_s)
     L.check(lib.bt_sv_timer_stop(st.h, C.byref(ms)))
     t_host = time.perf_counter() - t_host0
+    jit_timed = jit_stats(lib)["specialised_launches"] - jit0
     counts = (C.c_uint64 * 4)()
     cms = (C.c_double * 4)()
     L.check(lib.bt_sv_profile_read(st.h, counts, cms))
@@ -393,7 +395,7 @@ def bench_sharded(args):
                "circuit_gates_per_s": ngates / (ms_per_step / 1e3), "clocks": clk, "gpu_launches": int(n1 - n0),
                "kernels_rank0": {n: {"launches": int(counts[i]), "ms": float(cms[i])} for i, n in enumerate(["tile", "dense", "diag", "other"])},
                "host_seconds_rank0": t_host, "jit_rank0": jit_stats(lib),
-               "roofline": ({"bound": "hbm", "kernel": "k_tile_tma (fused multi-gate pass) on rank 0's shard", "achieved": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9,
+               "roofline": ({"bound": "hbm", "kernel": ("bt_jit_pass (fused multi-gate pass specialised by NVRTC)" if 2 * jit_timed >= int(counts[0]) else "k_tile_tma (fused multi-gate pass)") + " on rank 0's shard", "achieved": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9,
                              "peak": load_peaks()[0]["hbm_gbs"], "unit": "GB/s", "frac": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9 / load_peaks()[0]["hbm_gbs"],
                              "traffic": None, "avg_launch_ms": cms[0] / counts[0], "bytes_per_launch": 32.0 * (1 << n_local)} if counts[0] else None),
                "remap": {"per_step": remaps, "nvlink_bytes_per_rank_per_step": rbytes, "ms_per_step": rms, "GBps_per_rank": (rbytes / (rms / 1e3) / 1e9) if rms > 0 else None,
