@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <algorithm>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 #include <chrono>
 #include <complex>
@@ -480,14 +481,74 @@ uint64_t g_compiled = 0, g_launches = 0, g_failed = 0;
 double g_compile_seconds = 0.0;
 std::string g_last_log;
 
-bool compile(const std::string& src, Entry& e, int smem_bytes) {
-  Nvrtc& n = nvrtc();
+// ---- optional on-disk cubin cache (BT_JIT_CACHE_DIR; off when unset) -----------------------------------------------------
+// A pass structure costs ~0.2 s of NVRTC time; a process that runs the same circuits as an earlier one (the next job of a
+// parameter sweep, the next rank of a node) can take the cubin from disk instead.  File name = two independent 64-bit FNV-1a
+// hashes of the generated source + the compile options; written to a temporary name and renamed, so a reader never sees a
+// partial file; any I/O or load failure simply falls through to a fresh compilation.
+uint64_t fnv1a(const std::string& s, uint64_t h) {
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+
+const char* const kJitOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+
+std::string cache_path(const std::string& src) {
+  const char* dir = getenv("BT_JIT_CACHE_DIR");
+  if (!dir || !*dir) return std::string();
+  std::string salted = src;
+  for (const char* o : kJitOptions) { salted += '\n'; salted += o; }
+  char name[80];
+  snprintf(name, sizeof(name), "/btjit_%016llx%016llx.cubin", (unsigned long long)fnv1a(salted, 14695981039346656037ull),
+           (unsigned long long)fnv1a(salted, 0x9e3779b97f4a7c15ull));
+  return std::string(dir) + name;
+}
+
+bool cache_read(const std::string& path, std::vector<char>& cubin) {
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  bool ok = false;
+  if (fseek(f, 0, SEEK_END) == 0) {
+    const long n = ftell(f);
+    if (n > 0 && n < (64l << 20) && fseek(f, 0, SEEK_SET) == 0) {
+      cubin.resize((size_t)n);
+      ok = fread(cubin.data(), 1, (size_t)n, f) == (size_t)n;
+    }
+  }
+  fclose(f);
+  return ok && cubin.size() > 4 && memcmp(cubin.data(), "\x7f" "ELF", 4) == 0;
+}
+
+void cache_write(const std::string& path, const std::vector<char>& cubin) {
+  if (path.empty() || cubin.empty()) return;
+  char tmp[32];
+  snprintf(tmp, sizeof(tmp), ".tmp%ld", (long)getpid());
+  const std::string t = path + tmp;
+  FILE* f = fopen(t.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  if (fclose(f) != 0 || !ok || rename(t.c_str(), path.c_str()) != 0) remove(t.c_str());
+}
+
+uint64_t g_cache_hits = 0;
+
+bool load_cubin(const std::vector<char>& cubin, Entry& e, int smem_bytes) {
   Driver& d = driver();
-  if (!n.ok || !d.ok) { g_last_log = "libnvrtc or the driver entry points are not available"; return false; }
+  CUmodule mod = nullptr;
+  if (d.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) { g_last_log = "cuModuleLoadData failed"; return false; }
+  if (d.ModuleGetFunction(&e.fn, mod, "bt_jit_pass") != CUDA_SUCCESS) { g_last_log = "cuModuleGetFunction failed"; return false; }
+  if (d.FuncSetAttribute(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_bytes) != CUDA_SUCCESS) { g_last_log = "cuFuncSetAttribute failed"; return false; }
+  return true;
+}
+
+// source text -> cubin through NVRTC (no device needed)
+bool nvrtc_to_cubin(const std::string& src, std::vector<char>& cubin) {
+  Nvrtc& n = nvrtc();
+  if (!n.ok) { g_last_log = "libnvrtc is not available"; return false; }
   nvrtcProgram prog = nullptr;
   if (n.CreateProgram(&prog, src.c_str(), "bt_jit_pass.cu", 0, nullptr, nullptr) != 0) return false;
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-  const int rc = n.CompileProgram(prog, 3, opts);
+  const int rc = n.CompileProgram(prog, 3, kJitOptions);
   if (rc != 0) {
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
@@ -498,13 +559,22 @@ bool compile(const std::string& src, Entry& e, int smem_bytes) {
   }
   size_t cs = 0;
   n.GetCUBINSize(prog, &cs);
-  std::vector<char> cubin(cs);
+  cubin.resize(cs);
   n.GetCUBIN(prog, cubin.data());
   n.DestroyProgram(&prog);
-  CUmodule mod = nullptr;
-  if (d.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) { g_last_log = "cuModuleLoadData failed"; return false; }
-  if (d.ModuleGetFunction(&e.fn, mod, "bt_jit_pass") != CUDA_SUCCESS) { g_last_log = "cuModuleGetFunction failed"; return false; }
-  if (d.FuncSetAttribute(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_bytes) != CUDA_SUCCESS) { g_last_log = "cuFuncSetAttribute failed"; return false; }
+  return cs > 0;
+}
+
+bool compile(const std::string& src, Entry& e, int smem_bytes) {
+  Driver& d = driver();
+  if (!d.ok) { g_last_log = "the driver entry points are not available"; return false; }
+  const std::string path = cache_path(src);
+  std::vector<char> cubin;
+  if (cache_read(path, cubin) && load_cubin(cubin, e, smem_bytes)) { g_cache_hits++; return true; }
+  cubin.clear();
+  if (!nvrtc_to_cubin(src, cubin)) return false;
+  if (!load_cubin(cubin, e, smem_bytes)) return false;
+  cache_write(path, cubin);
   return true;
 }
 
@@ -589,22 +659,20 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
   if (!make_plan(P, 1, pl) || !generate(P, pl, src)) rc = -1;
   if (rc == 0 && source && cap) { strncpy(source, src.c_str(), cap - 1); source[cap - 1] = 0; }
   if (rc == 0) {
-    Nvrtc& n = nvrtc();
-    if (!n.ok) rc = -2;
+    if (!nvrtc().ok) rc = -2;
     else {
-      nvrtcProgram prog = nullptr;
-      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17"};
-      if (n.CreateProgram(&prog, src.c_str(), "bt_jit_pass.cu", 0, nullptr, nullptr) != 0) rc = -3;
-      else {
-        if (n.CompileProgram(prog, 2, opts) != 0) {
-          rc = -4;
-          size_t ls = 0;
-          n.GetProgramLogSize(prog, &ls);
-          std::string log(ls, '\0');
-          if (ls) n.GetProgramLog(prog, &log[0]);
-          bt_set_error("%s", log.substr(0, 900).c_str());
+      std::vector<char> cubin;
+      if (!nvrtc_to_cubin(src, cubin)) {
+        rc = -4;
+        bt_set_error("%s", g_last_log.substr(0, 900).c_str());
+      } else {
+        // the on-disk cache, when BT_JIT_CACHE_DIR is set: what was written must come back byte for byte
+        const std::string path = cache_path(src);
+        if (!path.empty()) {
+          std::vector<char> back;
+          cache_write(path, cubin);
+          if (!cache_read(path, back) || back != cubin) rc = -5;
         }
-        n.DestroyProgram(&prog);
       }
     }
   }

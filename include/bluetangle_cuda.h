@@ -84,7 +84,8 @@ int bt_fusion_flops(double* flops); /* cumulative FP64 flops issued by the fused
 /* Pass specialiser (csrc/bt_jit.cu): fused passes that recur are compiled once (NVRTC) into straight-line kernels.
  * bt_jit_stats: modules compiled, specialised launches, structures that fell back to the interpreter, seconds spent compiling.
  * bt_jit_selftest: host-only check (no device): generate and compile a synthetic pass using every micro-op; 0 = ok;
- * `source` (optional, `cap` bytes) receives the generated CUDA text.  No reference analogue. */
+ * `source` (optional, `cap` bytes) receives the generated CUDA text; with BT_JIT_CACHE_DIR set (opt-in on-disk cubin cache of the
+ * specialiser) it also writes the cubin there and reads it back (-5 = it did not come back).  No reference analogue. */
 int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* failed, double* compile_seconds);
 int bt_jit_selftest(char* source, uint64_t cap);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */

@@ -110,3 +110,31 @@ def test_pass_specialiser_generates_and_compiles_on_the_host():
     # the CX of the synthetic pass is a renaming: amplitudes are stored from permuted variables, no swap code is emitted
     stores = [l for l in src.splitlines() if "make_double2(" in l]
     assert len(stores) == 16 and any("xr[5]" in l for l in stores) and "xr[1] = xr[5]" not in src
+
+
+def test_pass_specialiser_disk_cache_round_trip(tmp_path, monkeypatch):
+    """BT_JIT_CACHE_DIR (opt-in): the cubin of a compiled pass is written under a content-hashed name (temporary file +
+    rename) and read back byte for byte; with the variable unset nothing is written."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    bt = ge.load_package()
+    lib = bt._lib.load()
+    monkeypatch.delenv("BT_JIT_CACHE_DIR", raising=False)
+    rc = lib.bt_jit_selftest(None, 0)
+    if rc == -2:
+        pytest.skip("libnvrtc not available")
+    assert rc == 0
+    assert list(tmp_path.iterdir()) == []
+    monkeypatch.setenv("BT_JIT_CACHE_DIR", str(tmp_path))
+    assert lib.bt_jit_selftest(None, 0) == 0
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.startswith("btjit_") and files[0].suffix == ".cubin"
+    assert files[0].read_bytes()[:4] == b"\x7fELF" and files[0].stat().st_size > 10000
+    # a truncated / foreign file is not accepted (the library then recompiles and rewrites it)
+    files[0].write_bytes(b"garbage")
+    assert lib.bt_jit_selftest(None, 0) == 0
+    assert files[0].read_bytes()[:4] == b"\x7fELF"
+    # an unwritable directory: the self test reports that nothing came back (-5); the product path just compiles as usual
+    monkeypatch.setenv("BT_JIT_CACHE_DIR", "/proc/nonexistent-dir")
+    assert lib.bt_jit_selftest(None, 0) == -5
