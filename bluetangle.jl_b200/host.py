@@ -427,6 +427,31 @@ class ifOp(QuantumOps):
 # ----------------------------------------------------------------------------------------------------------
 # low-level calls
 # ----------------------------------------------------------------------------------------------------------
+class OpF(QuantumOps):
+    """``OpF(name, f)`` / ``OpF(name, ops)`` -- src/struct.jl:703-744: an op that is a function of the state.  ``f`` receives the
+    device-resident state and may update it in place (returning None or the state) or return another device state; an op list
+    is applied in order (the reference's ``o * state`` loop, :725-741) as one fused device call.  The third form of the
+    reference, a full 2^N x 2^N matrix (:716-721), has no device counterpart -- the backend never builds operators of the
+    whole register -- and raises."""
+
+    def __init__(self, name: str, data):
+        self.q = 1
+        self.name = name
+        self.type = ""
+        self.noisy = False
+        self.data = data
+        if callable(data):
+            self.apply = lambda state, **kw: data(state, **kw)
+        elif isinstance(data, (list, tuple)) and all(isinstance(o, QuantumOps) for o in data):
+            ops = list(data)
+            self.apply = lambda state, **kw: apply(ops, state)
+        else:
+            raise NotImplementedError("OpF with a full-register matrix (src/struct.jl:716-721) is not available on the device backend: pass the op list or a function of the state")
+
+    def __repr__(self):
+        return f"OpF({self.name!r})"
+
+
 def _apply_matrix(x: State, q: int, mat: np.ndarray, qubit: int, target: int, control: int, want: Optional[int] = None) -> None:
     lib = x.lib
     if isinstance(x, CuRho):
@@ -595,15 +620,19 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
                 o.run(x)
                 continue
             if track_measurements and isinstance(x, CuState):
-                _, m = apply(x, o, noise=noise, rng=rng, track_measurements=True)
+                x, m = apply(x, o, noise=noise, rng=rng, track_measurements=True)
                 mids.extend(m)
             else:
-                apply(x, o, noise=noise, rng=rng)
+                x = apply(x, o, noise=noise, rng=rng)
         return (x, mids) if track_measurements else x
     if isinstance(op, tuple):
         op = Op(*op)
     mid: List = []
-    if isinstance(op, OpQC):
+    if isinstance(op, OpF):  # src/hilbert.jl:486-487: state = op.apply(state)
+        r = op.apply(x)
+        if isinstance(r, (CuState, CuRho)):
+            x = r
+    elif isinstance(op, OpQC):
         if op.name.upper() in ("RES", "RESET") and isinstance(x, CuState):
             _reset_Z(x, op.qubit, rng)
         else:

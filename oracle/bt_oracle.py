@@ -702,6 +702,26 @@ class ifOp:
 # --------------------------------------------------------------------------------------------------
 
 
+class OpF:
+    """src/struct.jl:703-744: f(state) -> state; a full-register matrix (mat * state); or an op list applied in order."""
+
+    def __init__(self, name: str, data):
+        self.q = 1
+        self.name = name
+        self.type = ""
+        self.data = data
+        if callable(data):
+            self.apply = lambda state, **kw: data(state, **kw)
+        elif isinstance(data, (list, tuple)):
+            def _run(state, **kw):
+                for o in data:  # src/struct.jl:733-735: state = o * state (all.jl:41-49: apply without noise)
+                    state = apply(state, o)
+                return state
+            self.apply = _run
+        else:
+            self.apply = lambda state, **kw: data @ state
+
+
 def _normalize(v: np.ndarray) -> np.ndarray:
     return v / np.linalg.norm(v)
 
@@ -854,7 +874,9 @@ def apply(state: np.ndarray, op, noise=False, draws: Optional[Draws] = None, tra
         return _apply_rho(state, op, noise)
     N = get_N(state)
     mid: List[int] = []
-    if isinstance(op, OpQC):
+    if isinstance(op, OpF):  # src/hilbert.jl:486-487
+        state = op.apply(state)
+    elif isinstance(op, OpQC):
         if op.name.upper() in ("RES", "RESET"):
             state, _ = reset_Z(state, op.qubit, draws)
         else:

@@ -466,3 +466,31 @@ def test_shadow_matches_oracle_draw_for_draw(bt, orc):
     rd = bt.shadow(circ, n_exp, rng=bt.Draws(7))
     ro = orc.shadow(ops(orc), N, n_exp, noise=nm_o, draws=orc.Draws(7))
     assert np.max(np.abs(rd - ro)) < TOL
+
+
+def test_opf_function_and_op_list_forms(bt, orc):
+    """OpF (src/struct.jl:703-744, dispatched at src/hilbert.jl:486-487): an op list as one op, and a function of the
+    device-resident state, alone and inside an op list with a tracked mid-circuit measurement."""
+    N = 6
+    v = rand_state(N, 21)
+    block_d = random_ops(bt, N, 3, 77)
+    block_o = random_ops(orc, N, 3, 77)
+    s = bt.CuState.from_numpy(v)
+    out = bt.apply(s, bt.OpF("block", block_d))
+    assert out is s
+    ref = orc.apply(v, orc.OpF("block", block_o))
+    assert np.max(np.abs(s.to_numpy() - ref)) < TOL
+
+    def flip_d(st):
+        bt.apply(st, bt.Op("X", 2))            # in place, returns nothing
+
+    def flip_o(st):
+        return orc.apply(st, orc.Op("X", 2))
+
+    ops_d = [bt.Op("H", 1), bt.OpF("flip", flip_d), bt.Op("CX", 1, 2), bt.Op("MZ", 2), bt.Op("RY(0.4)", 3)]
+    ops_o = [orc.Op("H", 1), orc.OpF("flip", flip_o), orc.Op("CX", 1, 2), orc.Op("MZ", 2), orc.Op("RY(0.4)", 3)]
+    s2 = bt.CuState.from_numpy(v)
+    s2, mids_d = bt.apply(ops_d, s2, rng=bt.Draws(3), track_measurements=True)
+    ref2, mids_o = orc.apply_ops(v, ops_o, draws=orc.Draws(3), track_measurements=True)
+    assert mids_d == mids_o
+    assert np.max(np.abs(s2.to_numpy() - ref2)) < TOL

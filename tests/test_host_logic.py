@@ -129,3 +129,29 @@ def test_qasm_front_door(bt):
     assert np.allclose(ops[2].mat, bt.gates("RZ(0.25*pi)"))
     with pytest.raises(ValueError):
         bt.from_qasm("foo q[0];")
+
+
+def test_opf_dispatch_and_forms(bt, orc):
+    """OpF (src/struct.jl:703-744): apply() hands the state to the op's function (src/hilbert.jl:486-487); op lists and
+    functions are accepted, a full-register matrix is refused by the device mirror and applied by the oracle."""
+    import numpy as np
+
+    seen = []
+    fake = object.__new__(bt.CuState)          # no device needed: the function form never touches the library here
+    op = bt.OpF("probe", lambda st: seen.append(st))
+    assert bt.apply(fake, op) is fake and seen == [fake]
+    assert bt.apply(op, fake) is fake          # (op, state) argument order, src/hilbert.jl:555-557
+    other = object.__new__(bt.CuState)
+    assert bt.apply(fake, bt.OpF("swap-in", lambda st: other)) is other   # a function may return another device state
+    bt.OpF("block", [bt.Op("H", 1), bt.Op("CX", 1, 2)])
+    with pytest.raises(NotImplementedError):
+        bt.OpF("dense", np.eye(4))
+    # oracle: the three forms agree with each other
+    v = np.random.default_rng(0).normal(size=8) + 1j * np.random.default_rng(1).normal(size=8)
+    v /= np.linalg.norm(v)
+    ops = [orc.Op("H", 1), orc.Op("CX", 1, 3), orc.Op("RZ(0.3)", 2)]
+    seq = orc.apply_ops(v, ops)
+    M = ops[2].expand(3) @ ops[1].expand(3) @ ops[0].expand(3)
+    assert np.max(np.abs(orc.apply(v, orc.OpF("block", ops)) - seq)) < 1e-14
+    assert np.max(np.abs(orc.apply(v, orc.OpF("dense", M)) - seq)) < 1e-14
+    assert np.max(np.abs(orc.apply(v, orc.OpF("fn", lambda st: M @ st)) - seq)) < 1e-14
