@@ -71,18 +71,19 @@ end
 cmat(m) = Matrix{ComplexF64}(m)   # Julia matrices are column-major: exactly what the ABI expects
 
 # ---- gates: op.expand(N)*state (src/hilbert.jl:505) ------------------------------------------------------------------
-function _apply_matrix!(s::CuState, op)
+# `mat`: the op's matrix, or for variational ops (op.type == "f", src/hilbert.jl:500-501) the matrix function applied to `pars`
+function _apply_matrix!(s::CuState, op, mat=op.mat)
     if op.q == 1
-        check(ccall((:bt_sv_apply_1q, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Cint), s.h, op.qubit, cmat(op.mat), op.control))
+        check(ccall((:bt_sv_apply_1q, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Cint), s.h, op.qubit, cmat(mat), op.control))
     else
-        check(ccall((:bt_sv_apply_2q, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint), s.h, op.qubit, op.target_qubit, cmat(op.mat), op.control))
+        check(ccall((:bt_sv_apply_2q, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint), s.h, op.qubit, op.target_qubit, cmat(mat), op.control))
     end
 end
-function _apply_matrix!(r::CuRho, op)
+function _apply_matrix!(r::CuRho, op, mat=op.mat)
     if op.q == 1
-        check(ccall((:bt_dm_apply_1q, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Cint), r.h, op.qubit, cmat(op.mat), op.control))
+        check(ccall((:bt_dm_apply_1q, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Cint), r.h, op.qubit, cmat(mat), op.control))
     else
-        check(ccall((:bt_dm_apply_2q, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint), r.h, op.qubit, op.target_qubit, cmat(op.mat), op.control))
+        check(ccall((:bt_dm_apply_2q, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint), r.h, op.qubit, op.target_qubit, cmat(mat), op.control))
     end
 end
 
@@ -138,7 +139,15 @@ end
 function apply(x::Union{CuState,CuRho}, op::QuantumOps; noise::Union{NoiseModel,Bool}=false, track_measurements::Bool=false, kwargs...)
     mid = Int[]
     if isa(op, OpF)
-        throw(ArgumentError("OpF closures cannot run on a device-resident state"))
+        # src/struct.jl:703-744: op.apply is a closure typed for the CPU states; op.data holds what it was built from
+        if op.data isa Function
+            r = op.data(x)
+            r isa Union{CuState,CuRho} && (x = r)
+        elseif op.data isa AbstractVector
+            for o in op.data; apply(x, o); end
+        else
+            throw(ArgumentError("OpF with a full-register matrix cannot run on a device-resident state"))
+        end
     elseif isa(op, OpQC)
         if x isa CuState && uppercase(op.name) in ("RES", "RESET")
             _reset_Z(x, op.qubit)
@@ -156,6 +165,8 @@ function apply(x::Union{CuState,CuRho}, op::QuantumOps; noise::Union{NoiseModel,
             _, ind = _born_measure(x, op)
         end
         track_measurements && push!(mid, ind)
+    elseif op.type == "f"                                      # variational gates: matrix from the parameters (src/hilbert.jl:500-501)
+        _apply_matrix!(x, op, op.mat(kwargs[:pars]...))
     else
         _apply_matrix!(x, op)
     end
