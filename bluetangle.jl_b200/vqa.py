@@ -12,14 +12,13 @@ Everything numeric runs through the C ABI: the circuit is one ``bt_sv_apply_circ
 structure from step to step, only the angles change, so the pass specialiser compiles them once and every later step of the
 optimisation reuses the modules), the loss is one ``bt_sv_expect_pauli_sum`` call (one read of the state per commuting
 group of terms instead of one 2^N x 2^N sparse operator).  The derivative-free optimisers the reference reaches through
-PRIMA.jl (cobyla, ...) and its ForwardDiff path are host libraries outside this repo's scope: VQE() here offers the
+PRIMA.jl (cobyla, ...) and its ForwardDiff path are host libraries outside this repo's scope: VQA() here offers the
 gradient models only and raises for the others.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
-from typing import Callable, List, Optional, Sequence, Tuple, Union
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
