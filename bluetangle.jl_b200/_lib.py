@@ -54,6 +54,8 @@ PROTOTYPES = {
     "bt_fusion_flops": [_pd],
     "bt_jit_stats": [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _pd],
     "bt_jit_selftest": [C.c_char_p, _u64],
+    "bt_jit_wait": [C.POINTER(_u64)],
+    "bt_jit_cache_info": [C.POINTER(_u64), C.c_char_p, _u64],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],
     "bt_pool_release": [],
@@ -126,6 +128,8 @@ PROTOTYPES = {
     "bt_plan_circuit_host": [_i, _i, _vp, _u64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i],
     "bt_sv_layout": [_vp, C.POINTER(_i)],
     "bt_sv_remap_stats": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(C.c_float)],
+    "bt_remap_walk_host": [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), _u64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
+    "bt_sv_remap_log": [_vp, _i, C.POINTER(C.c_float), C.POINTER(_i)],
     "bt_sv_set_allreduce": [_vp, ALLREDUCE_FN, _vp],
 }
 

@@ -16,9 +16,32 @@ struct RemapParams {
   const double2* src[16];
   int n_local;
   int rank;
+  // Iteration order.  The kernel walks a LOOP index; sel_n of its bits, starting at bit sel_lo, are the destination bits
+  // that decide which rank an amplitude comes from (sel_pos[], ascending), the other loop bits fill the remaining destination
+  // bits in order.  Consecutive 2^sel_lo-amplitude chunks of the walk therefore come from different ranks: every rank reads
+  // from all of its peers all the time, and (rot = own rank bits) no two ranks start on the same peer.  A linear walk of the
+  // destination (sel_n = 0) makes all ranks read one peer's HBM at a time -- an incast on that peer's NVLink egress.
+  int sel_n, sel_lo;
+  int sel_pos[4];
+  uint32_t rot;
 };
 
-// dst[i] = src_rank(P)[local(P)] with P = T0[d0] | T1[d1] | T2[d2] | T3[d3], d* = digits of ((rank << n_local) | i)
+// loop index (local bits, rotation already applied) -> destination index
+__host__ __device__ static inline uint64_t remap_dest(uint64_t l, int sel_n, int sel_lo, const int* sel_pos) {
+  if (sel_n == 0) return l;
+  const uint64_t low = l & ((1ull << sel_lo) - 1);
+  const uint64_t selv = (l >> sel_lo) & ((1ull << sel_n) - 1);
+  uint64_t x = low | ((l >> (sel_lo + sel_n)) << sel_lo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < sel_n) {
+      const int p = sel_pos[j];
+      x = ((x >> p) << (p + 1)) | (x & ((1ull << p) - 1)) | (((selv >> j) & 1ull) << p);
+    }
+  return x;
+}
+
+// dst[D(l)] = src_rank(S)[local(S)] with S = T0[d0] | T1[d1] | T2[d2] | T3[d3], d* = digits of ((rank << n_local) | l), l = loop index
 __global__ void __launch_bounds__(256) k_remap_pull(double2* __restrict__ dst, uint64_t n, int64_t n_batch,
                                                      const __grid_constant__ RemapParams P, const uint64_t* __restrict__ tables) {
   __shared__ uint64_t T[REMAP_NT << REMAP_TBITS];
@@ -26,6 +49,7 @@ __global__ void __launch_bounds__(256) k_remap_pull(double2* __restrict__ dst, u
   __syncthreads();
   const uint64_t lmask = (1ull << P.n_local) - 1;
   const uint64_t rank_hi = (uint64_t)P.rank << P.n_local;
+  const uint64_t rotm = (uint64_t)P.rot << P.sel_lo;
   const uint64_t total = n * (uint64_t)n_batch;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t dm = (1ull << REMAP_TBITS) - 1;
@@ -33,28 +57,32 @@ __global__ void __launch_bounds__(256) k_remap_pull(double2* __restrict__ dst, u
   // 4 independent 16-byte loads in flight per thread: NVLink round trips are ~2-4 us
   for (; i + 3 * stride < total; i += 4 * stride) {
     double2 v[4];
+    uint64_t o[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       uint64_t idx = i + u * stride;
       uint64_t t = idx >> P.n_local;  // trajectory
-      uint64_t d = rank_hi | (idx & lmask);
+      uint64_t l = (idx & lmask) ^ rotm;
+      uint64_t d = rank_hi | l;
       uint64_t s = T[d & dm] | T[(1 << REMAP_TBITS) + ((d >> REMAP_TBITS) & dm)] | T[(2 << REMAP_TBITS) + ((d >> (2 * REMAP_TBITS)) & dm)] |
                    T[(3 << REMAP_TBITS) + ((d >> (3 * REMAP_TBITS)) & dm)];
+      o[u] = (t << P.n_local) | remap_dest(l, P.sel_n, P.sel_lo, P.sel_pos);
       v[u] = P.src[s >> P.n_local][(t << P.n_local) | (s & lmask)];
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
+    for (int u = 0; u < 4; ++u) dst[o[u]] = v[u];
   }
   for (; i < total; i += stride) {
     uint64_t t = i >> P.n_local;
-    uint64_t d = rank_hi | (i & lmask);
+    uint64_t l = (i & lmask) ^ rotm;
+    uint64_t d = rank_hi | l;
     uint64_t s = T[d & dm] | T[(1 << REMAP_TBITS) + ((d >> REMAP_TBITS) & dm)] | T[(2 << REMAP_TBITS) + ((d >> (2 * REMAP_TBITS)) & dm)] |
                  T[(3 << REMAP_TBITS) + ((d >> (3 * REMAP_TBITS)) & dm)];
-    dst[i] = P.src[s >> P.n_local][(t << P.n_local) | (s & lmask)];
+    dst[(t << P.n_local) | remap_dest(l, P.sel_n, P.sel_lo, P.sel_pos)] = P.src[s >> P.n_local][(t << P.n_local) | (s & lmask)];
   }
 }
 
-// T[t][v] = OR over the set bits j of v of (1 << sigma[t * REMAP_TBITS + j]): where the t-th digit of a destination index goes
+// T[t][v] = OR over the set bits j of v of (1 << src_of_loop_bit[t * REMAP_TBITS + j]): where the t-th digit of a loop index comes from
 struct RemapSigma { int s[64]; };
 __global__ void k_remap_tables(uint64_t* __restrict__ tab, const __grid_constant__ RemapSigma SG) {
   const int t = blockIdx.x;
@@ -187,6 +215,7 @@ extern "C" int bt_sv_attach_local_peers(bt_sv** shards, int world) {
       }
       s->peer_amp[q] = shards[q]->amp;
       s->peer_alt[q] = shards[q]->alt;
+      s->local_peers[q] = shards[q];
     }
     s->peers_attached = true;
   }
@@ -211,19 +240,29 @@ extern "C" int bt_sv_layout(const bt_sv* s, int* phys) {
   return BT_OK;
 }
 
-// durations of the remaps enqueued without a host synchronisation: read back once their stop event has completed
+// durations of the remaps enqueued without a host synchronisation: read back once their last event has completed
+static void remap_log_push(bt_sv* s, float wait_ms, float pull_ms, float done_ms) {
+  if (!s->remap_log) s->remap_log = new std::vector<float>();
+  if (s->remap_log->size() >= 3 * 4096) s->remap_log->erase(s->remap_log->begin(), s->remap_log->begin() + 3 * 2048);
+  s->remap_log->push_back(wait_ms); s->remap_log->push_back(pull_ms); s->remap_log->push_back(done_ms);
+  s->remap_ms += pull_ms;
+}
+
 static void drain_remap_events(bt_sv* s, bool wait) {
   if (!s->remap_ev) return;
   std::vector<cudaEvent_t>& v = *s->remap_ev;
   size_t keep = 0;
-  for (size_t i = 0; i + 1 < v.size(); i += 2) {
-    const bool done = wait ? (cudaEventSynchronize(v[i + 1]) == cudaSuccess) : (cudaEventQuery(v[i + 1]) == cudaSuccess);
+  for (size_t i = 0; i + 3 < v.size(); i += 4) {
+    const bool done = wait ? (cudaEventSynchronize(v[i + 3]) == cudaSuccess) : (cudaEventQuery(v[i + 3]) == cudaSuccess);
     if (done) {
-      float ms = 0;
-      if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) s->remap_ms += ms;
-      cudaEventDestroy(v[i]); cudaEventDestroy(v[i + 1]);
+      float w = 0, p = 0, d = 0;
+      cudaEventElapsedTime(&w, v[i], v[i + 1]);
+      cudaEventElapsedTime(&p, v[i + 1], v[i + 2]);
+      cudaEventElapsedTime(&d, v[i + 2], v[i + 3]);
+      remap_log_push(s, w, p, d);
+      for (int k = 0; k < 4; ++k) cudaEventDestroy(v[i + k]);
     } else {
-      v[keep++] = v[i]; v[keep++] = v[i + 1];
+      for (int k = 0; k < 4; ++k) v[keep++] = v[i + k];
     }
   }
   v.resize(keep);
@@ -239,6 +278,89 @@ extern "C" int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* b
   return BT_OK;
 }
 
+// per-remap record since the last call: (ms waiting for the peers' "ready", ms in the pull, ms until all peers are "done"); cleared on return
+extern "C" int bt_sv_remap_log(bt_sv* s, int cap, float* out, int* n) {
+  if (!s || !n) BT_FAIL(BT_ERR_ARG, "null argument");
+  drain_remap_events(s, true);
+  int have = s->remap_log ? (int)(s->remap_log->size() / 3) : 0;
+  int take = std::min(have, std::max(cap, 0));
+  if (out) for (int i = 0; i < 3 * take; ++i) out[i] = (*s->remap_log)[3 * (have - take) + i];
+  *n = take;
+  if (s->remap_log) s->remap_log->clear();
+  return BT_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Host half of a remap: validates the new layout and derives what the pull kernel needs -- sigma[dst phys bit] = src phys bit,
+// the iteration order (RemapParams) and, per LOOP bit, the source bit it feeds (RemapSigma, turned into digit tables on the device).
+static int remap_build(int n, int n_local, int rank, int world, const int* cur_phys, const int* new_phys, RemapParams* P, RemapSigma* SG,
+                       int* sigma, bool* identity) {
+  bool seen[64] = {false};
+  *identity = true;
+  for (int lb = 0; lb < n; ++lb) {
+    int d = new_phys[lb];
+    if (d < 0 || d >= n || seen[d]) BT_FAIL(BT_ERR_ARG, "layout is not a permutation");
+    seen[d] = true;
+    sigma[d] = cur_phys[lb];
+    if (sigma[d] != d) *identity = false;
+  }
+  if (*identity) return BT_OK;
+  for (int d = 0; d < REMAP_KEEP; ++d)
+    if (sigma[d] != d) BT_FAIL(BT_ERR_ARG, "the %d lowest physical bits must stay in place (coalescing)", REMAP_KEEP);
+  P->n_local = n_local;
+  P->rank = rank;
+  // iteration order of the pull (see RemapParams): the destination bits that select the source rank cycle fastest above sel_lo
+  P->sel_n = 0; P->sel_lo = REMAP_KEEP; P->rot = 0;
+  for (int j = 0; j < 4; ++j) P->sel_pos[j] = 0;
+  if (world > 1 && env_int("BT_REMAP_ORDER", 1) != 0) {
+    for (int d = REMAP_KEEP; d < n_local && P->sel_n < 4; ++d)
+      if (sigma[d] >= n_local) P->sel_pos[P->sel_n++] = d;
+    int lo = env_int("BT_REMAP_SEL_LO", 8);
+    lo = std::max(lo, REMAP_KEEP);
+    lo = std::min(lo, n_local - P->sel_n);
+    P->sel_lo = lo;
+    if (env_int("BT_REMAP_ROT", 1) != 0)
+      for (int j = 0; j < P->sel_n; ++j) P->rot |= (uint32_t)((rank >> (sigma[P->sel_pos[j]] - n_local)) & 1) << j;
+  }
+  for (int lb = 0; lb < 64; ++lb) {
+    if (lb >= n) { SG->s[lb] = -1; continue; }
+    int dbit = lb;
+    if (lb < n_local) {
+      uint64_t img = remap_dest(1ull << lb, P->sel_n, P->sel_lo, P->sel_pos);
+      dbit = 0;
+      while (!((img >> dbit) & 1ull)) ++dbit;
+    }
+    SG->s[lb] = sigma[dbit];
+  }
+  return BT_OK;
+}
+
+// Pure host (no device): where the pull kernel of rank `rank` would write (dest: local index) and read (src: physical index =
+// (source rank << n_local) | local) for the given loop indices.  tests/test_host_logic.py checks that the walk is a bijection
+// of the shard and that src = sigma(dest) for every iteration order.
+extern "C" int bt_remap_walk_host(int n_qubits, int n_local, int rank, const int* cur_phys, const int* new_phys, uint64_t n_idx, const uint64_t* loop_idx,
+                                  uint64_t* dest, uint64_t* src) {
+  if (!cur_phys || !new_phys || (n_idx && (!loop_idx || !dest || !src))) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (n_qubits < 1 || n_qubits > 62 || n_local < REMAP_KEEP || n_local > n_qubits || n_qubits - n_local > 4) BT_FAIL(BT_ERR_ARG, "invalid shard shape");
+  RemapParams P; RemapSigma SG; int sigma[64]; bool identity;
+  BT_TRY(remap_build(n_qubits, n_local, rank, 1 << (n_qubits - n_local), cur_phys, new_phys, &P, &SG, sigma, &identity));
+  const uint64_t lmask = (1ull << n_local) - 1;
+  for (uint64_t k = 0; k < n_idx; ++k) {
+    if (identity) { dest[k] = loop_idx[k] & lmask; src[k] = ((uint64_t)rank << n_local) | dest[k]; continue; }
+    const uint64_t l = (loop_idx[k] & lmask) ^ ((uint64_t)P.rot << P.sel_lo);
+    const uint64_t d = ((uint64_t)rank << n_local) | l;
+    uint64_t sidx = 0;
+    for (int lb = 0; lb < n_qubits; ++lb) if ((d >> lb) & 1ull) sidx |= 1ull << SG.s[lb];
+    dest[k] = remap_dest(l, P.sel_n, P.sel_lo, P.sel_pos);
+    src[k] = sidx;
+  }
+  return BT_OK;
+}
+
 // new_phys[lb] = physical bit position of logical bit lb after the remap (a permutation of 0..n-1)
 extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
   BT_TRY(bt_check_sv(s));
@@ -246,24 +368,12 @@ extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
   int n = s->n_qubits;
   if (s->world == 1 && !s->alt) BT_TRY(bt_ensure_alt(s));
   if (!s->peers_attached) BT_FAIL(BT_ERR_ARG, "shard peers are not attached (bt_sv_ipc_attach / bt_sv_attach_local_peers)");
-  // validate permutation; sigma[dst phys bit] = src phys bit
-  int sigma[64];
-  bool seen[64] = {false};
-  bool identity = true;
-  for (int lb = 0; lb < n; ++lb) {
-    int d = new_phys[lb];
-    if (d < 0 || d >= n || seen[d]) BT_FAIL(BT_ERR_ARG, "layout is not a permutation");
-    seen[d] = true;
-    sigma[d] = s->phys_of_bit[lb];
-    if (sigma[d] != d) identity = false;
-  }
+  RemapParams P; RemapSigma SG; int sigma[64]; bool identity;
+  BT_TRY(remap_build(n, s->n_local, s->rank, s->world, s->phys_of_bit, new_phys, &P, &SG, sigma, &identity));
   if (identity) return BT_OK;
-  for (int d = 0; d < REMAP_KEEP; ++d)
-    if (sigma[d] != d) BT_FAIL(BT_ERR_ARG, "the %d lowest physical bits must stay in place (coalescing)", REMAP_KEEP);
+  for (int r = 0; r < 16; ++r) P.src[r] = (r < s->world) ? s->peer_amp[r] : nullptr;
   // digit tables, built on the device from the bit permutation (no host buffer has to outlive the call, no copy to wait for);
   // one table per handle: the next remap's build is stream-ordered behind this remap's pull
-  RemapSigma SG;
-  for (int d = 0; d < 64; ++d) SG.s[d] = d < n ? sigma[d] : -1;
   if (!s->d_remap_tab) BT_CUDA(cudaMalloc(&s->d_remap_tab, ((size_t)REMAP_NT << REMAP_TBITS) * sizeof(uint64_t)));
   uint64_t* d_tab = s->d_remap_tab;
   k_remap_tables<<<REMAP_NT, 1 << REMAP_TBITS, 0, s->stream>>>(d_tab, SG);
@@ -271,40 +381,42 @@ extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
   // fraction of the new shard that comes from other ranks (for the NVLink traffic figure)
   int moved_global = 0;
   for (int d = s->n_local; d < n; ++d) if (sigma[d] < s->n_local) moved_global++;
-  RemapParams P;
-  for (int r = 0; r < 16; ++r) P.src[r] = (r < s->world) ? s->peer_amp[r] : nullptr;
-  P.n_local = s->n_local;
-  P.rank = s->rank;
   uint64_t nloc = 1ull << s->n_local;
-  unsigned grid = (unsigned)std::min<uint64_t>((s->len / 4 + 255) / 256 + 1, 148ull * 8);
-  cudaEvent_t t0, t1;
-  BT_CUDA(cudaEventCreate(&t0));
-  BT_CUDA(cudaEventCreate(&t1));
+  unsigned grid = (unsigned)std::min<uint64_t>((s->len / 4 + 255) / 256 + 1, 148ull * (unsigned)std::max(1, env_int("BT_REMAP_CTAS_PER_SM", 8)));
   bool dev_sync = s->world > 1 && s->ipc_opened && s->flags != nullptr;
-  if (dev_sync) { const char* v = getenv("BT_REMAP_DEVICE_SYNC"); if (v && *v && atoi(v) == 0) dev_sync = false; }
+  if (dev_sync && env_int("BT_REMAP_DEVICE_SYNC", 1) == 0) dev_sync = false;
   if (dev_sync) {
     // flags in peer memory: nothing here blocks the host (see k_flag_signal / k_flag_wait)
+    cudaEvent_t ev[4];
+    for (int k = 0; k < 4; ++k) BT_CUDA(cudaEventCreate(&ev[k]));
     FlagPeers F;
     for (int r = 0; r < 16; ++r) F.page[r] = (r < s->world) ? s->peer_flags[r] : nullptr;
     const uint32_t epoch = ++s->remap_epoch;
-    unsigned long long timeout_s = 120;  // a peer that has not reached the remap by then has died: trap instead of hanging (BT_REMAP_TIMEOUT_S)
-    { const char* v = getenv("BT_REMAP_TIMEOUT_S"); if (v && *v && atoi(v) > 0) timeout_s = (unsigned long long)atoi(v); }
-    const unsigned long long timeout_ns = timeout_s * 1000000000ull;
+    // a peer that has not reached the remap by then has died: trap instead of hanging (BT_REMAP_TIMEOUT_S)
+    const unsigned long long timeout_ns = (unsigned long long)std::max(1, env_int("BT_REMAP_TIMEOUT_S", 120)) * 1000000000ull;
+    BT_CUDA(cudaEventRecord(ev[0], s->stream));
     k_flag_signal<<<1, 32, 0, s->stream>>>(F, s->world, s->rank, 0, epoch);   // my previous kernels are done: my amp may be read
     k_flag_wait<<<1, 32, 0, s->stream>>>(s->flags, s->world, 0, epoch, s->d_err, timeout_ns);
-    BT_CUDA(cudaEventRecord(t0, s->stream));
+    BT_CUDA(cudaEventRecord(ev[1], s->stream));
     k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
     BT_CHECK_LAUNCH(s);
-    BT_CUDA(cudaEventRecord(t1, s->stream));
+    BT_CUDA(cudaEventRecord(ev[2], s->stream));
     k_flag_signal<<<1, 32, 0, s->stream>>>(F, s->world, s->rank, 1, epoch);   // I have read everything I need from the peers
     k_flag_wait<<<1, 32, 0, s->stream>>>(s->flags, s->world, 1, epoch, s->d_err, timeout_ns);  // nobody reads my old buffer any more
+    BT_CUDA(cudaEventRecord(ev[3], s->stream));
     BT_CUDA(cudaGetLastError());
     if (!s->remap_ev) s->remap_ev = new std::vector<cudaEvent_t>();
-    s->remap_ev->push_back(t0); s->remap_ev->push_back(t1);
-    if (s->remap_ev->size() >= 64) drain_remap_events(s, false);
+    for (int k = 0; k < 4; ++k) s->remap_ev->push_back(ev[k]);
+    if (s->remap_ev->size() >= 128) drain_remap_events(s, false);
   } else {
-    // everyone's previous kernels must have finished writing `amp`
+    // everyone's previous kernels must have finished writing `amp`: shards of this process by their streams (they may have been
+    // driven shard by shard, e.g. LocalShards.apply), shards of other processes through the host barrier
+    cudaEvent_t t0, t1;
+    BT_CUDA(cudaEventCreate(&t0));
+    BT_CUDA(cudaEventCreate(&t1));
     BT_CUDA(cudaStreamSynchronize(s->stream));
+    for (int r = 0; r < s->world; ++r)
+      if (s->local_peers[r] && s->local_peers[r] != s) BT_CUDA(cudaStreamSynchronize(s->local_peers[r]->stream));
     if (s->barrier) s->barrier(s->barrier_ctx);
     BT_CUDA(cudaEventRecord(t0, s->stream));
     k_remap_pull<<<grid, 256, 0, s->stream>>>(s->alt, nloc, s->n_batch, P, d_tab);
@@ -314,7 +426,7 @@ extern "C" int bt_sv_remap(bt_sv* s, const int* new_phys) {
     float ms = 0;
     BT_CUDA(cudaEventElapsedTime(&ms, t0, t1));
     cudaEventDestroy(t0); cudaEventDestroy(t1);
-    s->remap_ms += ms;
+    remap_log_push(s, 0.f, ms, 0.f);
     // nobody may overwrite the buffer others are still reading
     if (s->barrier) s->barrier(s->barrier_ctx);
   }

@@ -93,7 +93,9 @@ struct bt_sv {
   uint32_t* peer_flags[16];  // every rank's flag page as seen from this device
   uint32_t remap_epoch;
   uint64_t* d_remap_tab;     // digit tables of the remap in flight (built on the device)
-  std::vector<cudaEvent_t>* remap_ev;  // (start, stop) pairs of remaps whose duration has not been read back yet
+  std::vector<cudaEvent_t>* remap_ev;  // 4 events per remap (before the ready flags, before the pull, after it, after the done flags) not read back yet
+  std::vector<float>* remap_log;       // per remap: ms waiting for the peers, ms pulling, ms until everybody has finished reading
+  bt_sv* local_peers[16];              // single-process shards (bt_sv_attach_local_peers): the other handles, for stream ordering
   // density-matrix view
   bool is_dm; int dm_n;
 };

@@ -8,10 +8,15 @@
 // condition masks -- is a literal, and the coefficients are a by-value parameter block read through constant-bank
 // operands.  Keyed by structure only, so a re-run with other angles reuses the module.
 //
-// Policy: a structure is compiled the BT_TILE_JIT_AFTER-th time it is seen (default 2) on states of at least
-// 2^BT_TILE_JIT_MINBITS amplitudes (default 22); BT_TILE_JIT=0 switches the specialiser off, BT_TILE_JIT=2 compiles at first
-// sight regardless of size (tests).  Any failure (no libnvrtc, compile error, driver entry point missing) marks the
-// structure as interpreter-only; the result is never different, only slower.
+// Policy: a structure is handed to the compile workers the BT_TILE_JIT_AFTER-th time it is seen (default 1) on states of at
+// least 2^BT_TILE_JIT_MINBITS amplitudes (default 22).  Compilation never stalls the caller: NVRTC runs on a small pool of
+// worker threads (BT_JIT_THREADS, default min(8, cores)) while the pass keeps running on the interpreter; the cubin is loaded
+// by the calling thread the next time the structure comes by.  Cubins are also kept on disk (BT_JIT_CACHE_DIR, default
+// $XDG_CACHE_HOME/bluetangle_cuda or ~/.cache/bluetangle_cuda; empty string = off), so a later process pays a file read
+// instead of 0.2 s of NVRTC per structure.  BT_TILE_JIT=0 switches the specialiser off, BT_TILE_JIT=2 compiles synchronously
+// at first sight regardless of size (tests), BT_TILE_JIT_ASYNC=0 compiles synchronously under the normal policy.  bt_jit_wait()
+// blocks until the workers are idle (benchmarks call it at the end of their warm-up).  Any failure (no libnvrtc, compile
+// error, driver entry point missing) marks the structure as interpreter-only; the result is never different, only slower.
 //
 // No reference analogue (the reference builds one sparse matrix per op, src/hilbert.jl:505).
 #include "bt_internal.cuh"
@@ -27,8 +32,12 @@
 #include <chrono>
 #include <complex>
 #include <math.h>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <sys/stat.h>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -470,13 +479,16 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
 
 struct Entry {
   int seen = 0;
-  int state = 0;  // 0 = not compiled, 1 = ready, -1 = interpreter only
+  int state = 0;  // 0 = not compiled, 1 = ready, -1 = interpreter only, 2 = with the compile workers, 3 = cubin ready, module not loaded yet
   CUfunction fn = nullptr;
   int ncoef = 0;
+  int smem_bytes = 0;
+  std::vector<char> cubin;  // state 3 only
 };
 
 std::mutex g_mu;
-std::unordered_map<std::string, Entry> g_cache;
+std::condition_variable g_cv_jobs, g_cv_idle;
+std::unordered_map<std::string, Entry> g_cache;  // node-based: Entry addresses are stable, the workers keep pointers
 uint64_t g_compiled = 0, g_launches = 0, g_failed = 0;
 double g_compile_seconds = 0.0;
 std::string g_last_log;
@@ -493,15 +505,35 @@ uint64_t fnv1a(const std::string& s, uint64_t h) {
 
 const char* const kJitOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
 
-std::string cache_path(const std::string& src) {
+void mkdir_p(const std::string& d) {
+  for (size_t i = 1; i <= d.size(); ++i)
+    if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0755);
+}
+
+// BT_JIT_CACHE_DIR set: that directory ("" = no cache); unset: $XDG_CACHE_HOME/bluetangle_cuda, else ~/.cache/bluetangle_cuda
+std::string cache_dir() {
   const char* dir = getenv("BT_JIT_CACHE_DIR");
-  if (!dir || !*dir) return std::string();
+  std::string d;
+  if (dir) d = dir;
+  else if (const char* x = getenv("XDG_CACHE_HOME"); x && *x) d = std::string(x) + "/bluetangle_cuda";
+  else if (const char* h = getenv("HOME"); h && *h) d = std::string(h) + "/.cache/bluetangle_cuda";
+  if (d.empty()) return d;
+  static std::mutex mu;
+  static std::string made;
+  std::lock_guard<std::mutex> lk(mu);
+  if (made != d) { mkdir_p(d); made = d; }
+  return d;
+}
+
+std::string cache_path(const std::string& src) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return std::string();
   std::string salted = src;
   for (const char* o : kJitOptions) { salted += '\n'; salted += o; }
   char name[80];
   snprintf(name, sizeof(name), "/btjit_%016llx%016llx.cubin", (unsigned long long)fnv1a(salted, 14695981039346656037ull),
            (unsigned long long)fnv1a(salted, 0x9e3779b97f4a7c15ull));
-  return std::string(dir) + name;
+  return dir + name;
 }
 
 bool cache_read(const std::string& path, std::vector<char>& cubin) {
@@ -522,8 +554,8 @@ bool cache_read(const std::string& path, std::vector<char>& cubin) {
 
 void cache_write(const std::string& path, const std::vector<char>& cubin) {
   if (path.empty() || cubin.empty()) return;
-  char tmp[32];
-  snprintf(tmp, sizeof(tmp), ".tmp%ld", (long)getpid());
+  char tmp[64];
+  snprintf(tmp, sizeof(tmp), ".tmp%ld_%llx", (long)getpid(), (unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id()));
   const std::string t = path + tmp;
   FILE* f = fopen(t.c_str(), "wb");
   if (!f) return;
@@ -542,18 +574,18 @@ bool load_cubin(const std::vector<char>& cubin, Entry& e, int smem_bytes) {
   return true;
 }
 
-// source text -> cubin through NVRTC (no device needed)
-bool nvrtc_to_cubin(const std::string& src, std::vector<char>& cubin) {
+// source text -> cubin through NVRTC (no device needed; safe to call from several threads, one program each)
+bool nvrtc_to_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
   Nvrtc& n = nvrtc();
-  if (!n.ok) { g_last_log = "libnvrtc is not available"; return false; }
+  if (!n.ok) { log = "libnvrtc is not available"; return false; }
   nvrtcProgram prog = nullptr;
   if (n.CreateProgram(&prog, src.c_str(), "bt_jit_pass.cu", 0, nullptr, nullptr) != 0) return false;
   const int rc = n.CompileProgram(prog, 3, kJitOptions);
   if (rc != 0) {
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
-    g_last_log.assign(ls, '\0');
-    if (ls) n.GetProgramLog(prog, &g_last_log[0]);
+    log.assign(ls, '\0');
+    if (ls) n.GetProgramLog(prog, &log[0]);
     n.DestroyProgram(&prog);
     return false;
   }
@@ -565,17 +597,56 @@ bool nvrtc_to_cubin(const std::string& src, std::vector<char>& cubin) {
   return cs > 0;
 }
 
-bool compile(const std::string& src, Entry& e, int smem_bytes) {
-  Driver& d = driver();
-  if (!d.ok) { g_last_log = "the driver entry points are not available"; return false; }
+// cubin for a source text: from the disk cache or through NVRTC (and then into the cache).  No CUDA context needed.
+bool obtain_cubin(const std::string& src, std::vector<char>& cubin, std::string& log, bool* from_cache) {
   const std::string path = cache_path(src);
-  std::vector<char> cubin;
-  if (cache_read(path, cubin) && load_cubin(cubin, e, smem_bytes)) { g_cache_hits++; return true; }
+  *from_cache = false;
+  if (cache_read(path, cubin)) { *from_cache = true; return true; }
   cubin.clear();
-  if (!nvrtc_to_cubin(src, cubin)) return false;
-  if (!load_cubin(cubin, e, smem_bytes)) return false;
+  if (!nvrtc_to_cubin(src, cubin, log)) return false;
   cache_write(path, cubin);
   return true;
+}
+
+// ---- compile workers -----------------------------------------------------------------------------------------------------
+struct Job { std::string src; Entry* e; };
+std::deque<Job>* g_jobs = nullptr;   // heap objects that are never destroyed: the detached workers may outlive static destructors
+int g_workers = 0, g_pending = 0;
+
+void worker_main() {
+  for (;;) {
+    Job j;
+    {
+      std::unique_lock<std::mutex> lk(g_mu);
+      g_cv_jobs.wait(lk, [] { return !g_jobs->empty(); });
+      j = std::move(g_jobs->front());
+      g_jobs->pop_front();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    bool hit = false;
+    const bool ok = obtain_cubin(j.src, cubin, log, &hit);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_compile_seconds += dt;
+      if (ok) { j.e->cubin = std::move(cubin); j.e->state = 3; if (hit) g_cache_hits++; }
+      else { j.e->state = -1; g_failed++; g_last_log = log; }
+      if (--g_pending == 0) g_cv_idle.notify_all();
+    }
+  }
+}
+
+// g_mu held
+void enqueue_compile(std::string&& src, Entry* e) {
+  if (!g_jobs) g_jobs = new std::deque<Job>();
+  const int want = std::max(1, std::min(env_i("BT_JIT_THREADS", 8), (int)std::max(1u, std::thread::hardware_concurrency())));
+  while (g_workers < want) { std::thread(worker_main).detach(); ++g_workers; }
+  e->state = 2;
+  g_pending++;
+  g_jobs->push_back(Job{std::move(src), e});
+  g_cv_jobs.notify_one();
 }
 
 }  // namespace
@@ -593,12 +664,21 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   if (g_cache.size() > 8192 && g_cache.find(key) == g_cache.end()) return 0;  // bounded: a long-running host with ever-new passes keeps interpreting
   Entry& e = g_cache[key];
   e.seen++;
-  if (e.state < 0) return 0;
+  if (e.state < 0 || e.state == 2) return 0;
   if (e.state == 0) {
-    if (mode != 2 && e.seen < env_i("BT_TILE_JIT_AFTER", 2)) return 0;
-    const auto t0 = std::chrono::steady_clock::now();
+    if (mode != 2 && e.seen < env_i("BT_TILE_JIT_AFTER", 1)) return 0;
+    if (!driver().ok || !nvrtc().ok) { e.state = -1; g_failed++; g_last_log = "NVRTC or the driver entry points are not available"; return 0; }
     std::string src;
-    const bool ok = generate(P, pl, src) && compile(src, e, (int)(tile_bytes + 1024 + 64));
+    if (!generate(P, pl, src)) { e.state = -1; g_failed++; return 0; }
+    e.ncoef = (int)pl.coef.size();
+    e.smem_bytes = (int)(tile_bytes + 1024 + 64);
+    if (mode != 2 && env_i("BT_TILE_JIT_ASYNC", 1) != 0) {
+      enqueue_compile(std::move(src), &e);  // the interpreter runs this pass; the cubin is picked up at a later launch
+      return 0;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    bool hit = false;
+    const bool ok = obtain_cubin(src, e.cubin, g_last_log, &hit);
     g_compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!ok) {
       e.state = -1;
@@ -606,20 +686,42 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
       if (env_i("BT_TILE_DEBUG", 0)) fprintf(stderr, "[jit] pass not specialised: %s\n", g_last_log.c_str());
       return 0;
     }
-    e.state = 1;
-    e.ncoef = (int)pl.coef.size();
-    g_compiled++;
-  } else if ((int)pl.coef.size() != e.ncoef) {
-    return 0;
+    if (hit) g_cache_hits++;
+    e.state = 3;
   }
+  if (e.state == 3) {  // module load needs the caller's CUDA context: done here, not on the workers
+    const bool ok = load_cubin(e.cubin, e, e.smem_bytes);
+    std::vector<char>().swap(e.cubin);
+    if (!ok) { e.state = -1; g_failed++; return 0; }
+    e.state = 1;
+    g_compiled++;
+  }
+  if ((int)pl.coef.size() != e.ncoef) return 0;
   std::vector<double>& coef = pl.coef;
   void* args[2] = {(void*)&tmap, (void*)coef.data()};
-  if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, TILE_THREADS, 1, 1, (unsigned)(tile_bytes + 1024 + 64), (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
+  if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, TILE_THREADS, 1, 1, (unsigned)e.smem_bytes, (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
     e.state = -1;
     return 0;
   }
   g_launches++;
   return 1;
+}
+
+// blocks until the compile workers are idle; *pending_before = structures that were still being compiled at the call
+extern "C" int bt_jit_wait(uint64_t* pending_before) {
+  std::unique_lock<std::mutex> lk(g_mu);
+  if (pending_before) *pending_before = (uint64_t)g_pending;
+  g_cv_idle.wait(lk, [] { return g_pending == 0; });
+  return BT_OK;
+}
+
+// modules taken from the on-disk cache instead of NVRTC, and the cache directory in use ("" = off)
+extern "C" int bt_jit_cache_info(uint64_t* disk_hits, char* dir, uint64_t cap) {
+  const std::string d = cache_dir();
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (disk_hits) *disk_hits = g_cache_hits;
+  if (dir && cap) { strncpy(dir, d.c_str(), cap - 1); dir[cap - 1] = 0; }
+  return BT_OK;
 }
 
 extern "C" int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* failed, double* compile_seconds) {
@@ -662,9 +764,10 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
     if (!nvrtc().ok) rc = -2;
     else {
       std::vector<char> cubin;
-      if (!nvrtc_to_cubin(src, cubin)) {
+      std::string log;
+      if (!nvrtc_to_cubin(src, cubin, log)) {
         rc = -4;
-        bt_set_error("%s", g_last_log.substr(0, 900).c_str());
+        bt_set_error("%s", log.substr(0, 900).c_str());
       } else {
         // the on-disk cache, when BT_JIT_CACHE_DIR is set: what was written must come back byte for byte
         const std::string path = cache_path(src);

@@ -178,6 +178,7 @@ static void really_destroy(bt_sv* s) {
     }
   }
   if (s->remap_ev) { for (cudaEvent_t e : *s->remap_ev) cudaEventDestroy(e); delete s->remap_ev; }
+  delete s->remap_log;
   if (s->d_remap_tab) cudaFree(s->d_remap_tab);
   cudaFree(s->amp);
   if (s->alt) cudaFree(s->alt);

@@ -84,10 +84,15 @@ int bt_fusion_flops(double* flops); /* cumulative FP64 flops issued by the fused
 /* Pass specialiser (csrc/bt_jit.cu): fused passes that recur are compiled once (NVRTC) into straight-line kernels.
  * bt_jit_stats: modules compiled, specialised launches, structures that fell back to the interpreter, seconds spent compiling.
  * bt_jit_selftest: host-only check (no device): generate and compile a synthetic pass using every micro-op; 0 = ok;
- * `source` (optional, `cap` bytes) receives the generated CUDA text; with BT_JIT_CACHE_DIR set (opt-in on-disk cubin cache of the
- * specialiser) it also writes the cubin there and reads it back (-5 = it did not come back).  No reference analogue. */
+ * `source` (optional, `cap` bytes) receives the generated CUDA text; unless the on-disk cubin cache is off (BT_JIT_CACHE_DIR="")
+ * it also writes the cubin there and reads it back (-5 = it did not come back).  No reference analogue. */
 int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* failed, double* compile_seconds);
 int bt_jit_selftest(char* source, uint64_t cap);
+/* Compilation runs on worker threads while the interpreter keeps executing the pass; bt_jit_wait blocks until they are idle
+ * (*pending_before, optional: structures still compiling at the call).  bt_jit_cache_info: modules that came from the on-disk
+ * cubin cache instead of NVRTC, and the cache directory in use (BT_JIT_CACHE_DIR; default ~/.cache/bluetangle_cuda; "" = off). */
+int bt_jit_wait(uint64_t* pending_before);
+int bt_jit_cache_info(uint64_t* disk_hits, char* dir, uint64_t cap);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */
@@ -184,7 +189,14 @@ int bt_group_apply_circuit(bt_sv** shards, int world, const bt_gate* g, uint64_t
 int bt_plan_circuit_host(int n_qubits, int world, const bt_gate* g, uint64_t n, int* n_segments, int* seg_gates, int* seg_remap,
                          int* layouts /* cap x n_qubits */, int* order /* n gate indices in execution order */, int cap);
 int bt_sv_layout(const bt_sv* s, int* phys_of_logical_bit /* n_qubits_total */);
+/* pure host (no device needed): for the given loop indices of rank `rank`'s pull kernel, the local destination index it writes and
+ * the physical source index ((source rank << n_local) | local) it reads -- the remap's index arithmetic, testable on a CPU */
+int bt_remap_walk_host(int n_qubits, int n_local, int rank, const int* cur_phys, const int* new_phys, uint64_t n_idx, const uint64_t* loop_idx,
+                       uint64_t* dest, uint64_t* src);
 int bt_sv_remap_stats(const bt_sv* s, uint64_t* n_remaps, uint64_t* bytes_pulled_remote, float* ms_total);
+/* per-remap timing record since the last call (at most `cap` most recent remaps; cleared on return): out[3*i + 0] = ms this rank
+ * waited for its peers to reach the remap, [1] = ms in the pull kernel, [2] = ms until every peer had finished reading */
+int bt_sv_remap_log(bt_sv* s, int cap, float* out /* cap x 3 */, int* n);
 /* scalars returned by reductions on a shard are LOCAL partial sums unless an all-reduce callback is set */
 typedef void (*bt_allreduce_fn)(void* ctx, double* buf, int n);
 int bt_sv_set_allreduce(bt_sv* s, bt_allreduce_fn fn, void* ctx);

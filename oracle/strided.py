@@ -39,12 +39,24 @@ def lib():
         l.bto_axpy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         l.bto_axpy.restype = None
         l.bto_num_threads.restype = C.c_int
+        l.bto_set_threads.argtypes = [C.c_int]
+        l.bto_set_threads.restype = None
         _lib = l
     return _lib
 
 
 def num_threads() -> int:
     return int(lib().bto_num_threads())
+
+
+def use_all_cores() -> int:
+    """OpenMP threads := the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().bto_set_threads(max(1, n))
+    return num_threads()
 
 
 def _ints(v: Sequence[int]):

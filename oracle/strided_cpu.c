@@ -39,6 +39,15 @@ int bto_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the benchmark states its thread count explicitly */
+void bto_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* y = M x on the k target bits tb[] (matrix index bit t <-> tb[t]), only where all control bits cb[] are 1.
  * m: row-major (1<<k)x(1<<k), interleaved re/im.  n_bits: total index bits.  k <= 4. */
 int bto_apply(double* amp_, int n_bits, int k, const int* tb, const double* m_, int nc, const int* cb) {

@@ -71,6 +71,33 @@ def main():
                   f"outcome={out[0]}=={o2[0]} p0={p0[0]:.6f} post={e5:.1e} remaps={nrem[0]} {'OK' if good else 'FAIL'}", flush=True)
         del st
         dist.barrier()
+    # back-to-back steps without any host synchronisation in between (what bench.py's timed loop does): the remaps of
+    # consecutive steps are ordered by the device-side flags alone.  Every step starts from a different basis state, so a
+    # stale or torn pull cannot cancel out; amplitudes after the last step are compared with the single-GPU state.
+    Nb = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    for order in ("1", "0"):
+        os.environ["BT_REMAP_ORDER"] = order
+        arr = bt.pack_gates(wl.to_ops(bt, wl.c5_random(Nb, 6, 31)))
+        st = D.ShardedState(Nb)
+        basis = 0
+        for k in range(steps):
+            basis = (k * 977 + 5) % (1 << Nb)
+            L.check(st.lib.bt_sv_set_basis(st.h, basis))
+            L.check(st.lib.bt_sv_apply_circuit(st.h, L.ptr(arr), len(arr), 1))
+        full = st.gather_logical()
+        nrem = st.remap_stats()
+        if rank == 0:
+            ref = bt.basis_state(Nb, basis)
+            L.check(ref.lib.bt_sv_apply_circuit(ref.h, L.ptr(arr), len(arr), 0))
+            e1 = float(np.max(np.abs(full - ref.to_numpy())))
+            good = e1 < 1e-12 and nrem[0] >= steps
+            ok = ok and good
+            print(f"[mp_shard_check] back-to-back N={Nb} world={world} steps={steps} order={order}: amp={e1:.1e} remaps={nrem[0]} {'OK' if good else 'FAIL'}", flush=True)
+            del ref
+        del st
+        dist.barrier()
+    os.environ.pop("BT_REMAP_ORDER", None)
     if rank == 0:
         print("MP_SHARD_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()

@@ -113,19 +113,30 @@ def test_pass_specialiser_generates_and_compiles_on_the_host():
 
 
 def test_pass_specialiser_disk_cache_round_trip(tmp_path, monkeypatch):
-    """BT_JIT_CACHE_DIR (opt-in): the cubin of a compiled pass is written under a content-hashed name (temporary file +
-    rename) and read back byte for byte; with the variable unset nothing is written."""
+    """On-disk cubin cache (BT_JIT_CACHE_DIR; default under ~/.cache, "" = off): the cubin of a compiled pass is written under a
+    content-hashed name (temporary file + rename) and read back byte for byte; with the cache off nothing is written; with the
+    variable unset the default directory under $XDG_CACHE_HOME is used."""
     import ctypes as C
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
     bt = ge.load_package()
     lib = bt._lib.load()
-    monkeypatch.delenv("BT_JIT_CACHE_DIR", raising=False)
+    monkeypatch.setenv("BT_JIT_CACHE_DIR", "")
+    monkeypatch.setenv("XDG_CACHE_HOME", str(tmp_path / "xdg"))
     rc = lib.bt_jit_selftest(None, 0)
     if rc == -2:
         pytest.skip("libnvrtc not available")
     assert rc == 0
     assert list(tmp_path.iterdir()) == []
+    monkeypatch.delenv("BT_JIT_CACHE_DIR", raising=False)
+    assert lib.bt_jit_selftest(None, 0) == 0
+    d = C.create_string_buffer(512)
+    hits = C.c_uint64()
+    assert lib.bt_jit_cache_info(C.byref(hits), d, 512) == 0
+    assert d.value.decode() == str(tmp_path / "xdg" / "bluetangle_cuda")
+    assert len(list((tmp_path / "xdg" / "bluetangle_cuda").iterdir())) == 1
+    import shutil
+    shutil.rmtree(tmp_path / "xdg")
     monkeypatch.setenv("BT_JIT_CACHE_DIR", str(tmp_path))
     assert lib.bt_jit_selftest(None, 0) == 0
     files = list(tmp_path.iterdir())

@@ -155,3 +155,56 @@ def test_opf_dispatch_and_forms(bt, orc):
     assert np.max(np.abs(orc.apply(v, orc.OpF("block", ops)) - seq)) < 1e-14
     assert np.max(np.abs(orc.apply(v, orc.OpF("dense", M)) - seq)) < 1e-14
     assert np.max(np.abs(orc.apply(v, orc.OpF("fn", lambda st: M @ st)) - seq)) < 1e-14
+
+
+def test_remap_walk_is_a_bijection_and_reads_sigma_of_dest(bt, monkeypatch):
+    """bt_remap_walk_host = the index arithmetic of k_remap_pull on the host: for every iteration order the walk must
+    write every local destination index exactly once and read physical source index sigma(rank|dest)."""
+    import ctypes as C
+
+    L = bt._lib
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    N = 14
+    for g in (1, 2, 3):
+        nl = N - g
+        world = 1 << g
+        for trial in range(6):
+            cur = list(range(N))
+            if trial % 2:  # start from a permuted layout (low 5 bits fixed)
+                hi = list(rng.permutation(np.arange(5, N)))
+                cur = list(range(5)) + [int(x) for x in hi]
+            new = cur[:]
+            movable = [lb for lb in range(N) if cur[lb] >= 5]
+            perm = rng.permutation(len(movable))
+            for a, b in zip(movable, perm):
+                new[a] = cur[movable[int(b)]]
+            sigma = [0] * N  # sigma[dst phys] = src phys
+            for lb in range(N):
+                sigma[new[lb]] = cur[lb]
+            for order, sel_lo, rot in ((0, 8, 1), (1, 5, 1), (1, 8, 1), (1, 8, 0), (1, 11, 1)):
+                monkeypatch.setenv("BT_REMAP_ORDER", str(order))
+                monkeypatch.setenv("BT_REMAP_SEL_LO", str(sel_lo))
+                monkeypatch.setenv("BT_REMAP_ROT", str(rot))
+                for rank in range(world):
+                    loop = np.arange(1 << nl, dtype=np.uint64)
+                    dest = np.empty_like(loop)
+                    src = np.empty_like(loop)
+                    ci = (C.c_int * N)(*cur)
+                    ni = (C.c_int * N)(*new)
+                    pu = C.POINTER(C.c_uint64)
+                    L.check(lib.bt_remap_walk_host(N, nl, rank, ci, ni, loop.size, loop.ctypes.data_as(pu), dest.ctypes.data_as(pu), src.ctypes.data_as(pu)))
+                    assert np.array_equal(np.sort(dest), loop)  # every destination exactly once
+                    full = (np.uint64(rank) << np.uint64(nl)) | dest
+                    want = np.zeros_like(full)
+                    for d in range(N):
+                        want |= ((full >> np.uint64(d)) & np.uint64(1)) << np.uint64(sigma[d])
+                    assert np.array_equal(src, want)
+                    assert np.array_equal(dest & np.uint64(31), loop & np.uint64(31))  # lanes keep their 512-byte run
+                    if order == 1 and g > 1 and sel_lo == 8:
+                        # consecutive 2^sel_lo chunks of the walk come from different ranks (if the remap moves rank bits at all)
+                        srcrank = (src >> np.uint64(nl)).reshape(-1, 1 << sel_lo)
+                        assert np.all(srcrank == srcrank[:, :1])
+                        nsel = sum(1 for d in range(5, nl) if sigma[d] >= nl)
+                        if nsel:
+                            assert len(set(srcrank[: 1 << nsel, 0].tolist())) == 1 << nsel
