@@ -8,7 +8,8 @@ N = 1: workload C2 of BASELINE.json configs[1] -- 28-qubit state vector, QFT(28)
        ComplexF64.  One step = reset to |0..0> + the whole circuit.
 N > 1: workload C5 -- (31 + log2 N)-qubit random circuit sharded over N ranks (torchrun, one rank per GPU); value is
        reported in 28-qubit-equivalent gates/s (gates x local amplitudes / 2^28, summed over ranks) so that the
-       numbers at different N measure the same per-GPU work ("weak" scaling).
+       numbers at different N measure the same per-GPU work ("weak" scaling).  `unit` is "gates/s" at every N
+       (the normalisation is spelled out in `unit_note`).
 metric: gates/s.  `value` is device-resident throughput (CUDA events on the launching stream); `e2e` goes through
 the public host API with host buffers (gate list in, expectation values and samples out).
 """
@@ -102,6 +103,128 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def _timed_sv(L, lib, h, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    t = C.c_float()
+    L.check(lib.bt_sv_timer_start(h))
+    for _ in range(reps):
+        fn()
+    L.check(lib.bt_sv_timer_stop(h, C.byref(t)))
+    return t.value / reps
+
+
+def kraus_block(bt, L, s, N, peak):
+    """SV Kraus trajectory steps (__QuantumChannel_new_apply, src/struct.jl:31-41) at N qubits: one step = RDM read
+    (16 B/amp) + decision + scaled-Kraus apply (32 B/amp) = 48 B x 2^N algorithmic bytes."""
+    lib = s.lib
+    K1 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01)])
+    K2 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01, True)])
+    A1 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("amplitude_damping", 0.02)])
+    ua = np.array([0.5])
+    out = {}
+    byts = 48.0 * (1 << N)
+    L.check(lib.bt_sv_set_plus(s.h))
+    cases = [("sv_1q_depolarizing_q%d" % (N // 2), lambda: L.check(lib.bt_sv_kraus(s.h, 1, N // 2, -1, L.ptr(K1), 4, L.pdouble(ua), None))),
+             ("sv_1q_depolarizing_q%d" % N, lambda: L.check(lib.bt_sv_kraus(s.h, 1, N, -1, L.ptr(K1), 4, L.pdouble(ua), None))),
+             ("sv_1q_amplitude_damping_q3", lambda: L.check(lib.bt_sv_kraus(s.h, 1, 3, -1, L.ptr(A1), 2, L.pdouble(ua), None))),
+             ("sv_2q_depolarizing_q3_q17", lambda: L.check(lib.bt_sv_kraus(s.h, 2, 3, min(17, N), L.ptr(K2), 16, L.pdouble(ua), None))),
+             ("sv_2q_depolarizing_q%d_q%d" % (N - 1, N), lambda: L.check(lib.bt_sv_kraus(s.h, 2, N - 1, N, L.ptr(K2), 16, L.pdouble(ua), None)))]
+    for name, fn in cases:
+        ms = _timed_sv(L, lib, s.h, fn, 5)
+        g = byts / (ms / 1e3) / 1e9
+        out[name] = {"ms": ms, "GBps": g, "frac_of_measured": g / peak, "frac_of_8TBs_spec": g / 8000.0}
+    out["algorithmic_bytes"] = "48 B x 2^N per step: RDM read 16 B/amp + scaled-Kraus apply 32 B/amp"
+    return out
+
+
+def dm14_block(bt, L, wl, peak, n=14, depth=20):
+    """Config C3 (BASELINE.json configs[2]): n-qubit density matrix, depolarizing + amplitude damping after every gate
+    (to_rho's loop, src/ops.jl:813-841 with apply(rho,op) src/hilbert.jl:655-656 and the channels of src/struct.jl:58-76),
+    fused superoperators vs op by op, plus the single-kernel rooflines (32 B x 4^n per pass)."""
+    ops3 = []
+    for e in wl.c3_noisy_dm(n, depth, 14):
+        if e[0] == "gate":
+            name, q, t, c = e[1]
+            ops3.append(bt.Op(name, q, t, control=c))
+        else:
+            _, model, p, q, t = e
+            ops3.append(bt.OpQC(model, p, q, t))
+    ngate = sum(1 for o in ops3 if isinstance(o, bt.Op))
+    out = {"workload": f"C3: {n}-qubit density matrix, C1-style brickwork depth {depth}, depolarizing(0.01) + amplitude_damping(0.02) after every gate: {ngate} gates + {len(ops3) - ngate} Kraus channels"}
+    pass_bytes = 32.0 * 4 ** n
+    for fused in (True, False):
+        best = None
+        for _ in range(2):
+            rho = bt.CuRho(n)
+            rho.sync()
+            ms = C.c_float()
+            n0 = rho.launch_count()
+            L.check(rho.lib.bt_dm_timer_start(rho.h))
+            if fused:
+                bt.apply(ops3, rho)
+            else:
+                for o in ops3:
+                    bt.apply(rho, o)
+            L.check(rho.lib.bt_dm_timer_stop(rho.h, C.byref(ms)))
+            nl = rho.launch_count() - n0
+            tr = L.bt_c64()
+            L.check(rho.lib.bt_dm_trace(rho.h, C.byref(tr)))
+            if best is None or ms.value < best["ms"]:
+                g = pass_bytes * nl / (ms.value / 1e3) / 1e9
+                best = {"ms": ms.value, "passes": int(nl), "ops_per_s": len(ops3) / (ms.value / 1e3), "gates_per_s": ngate / (ms.value / 1e3),
+                        "GBps": g, "frac_of_measured": g / peak, "frac_of_8TBs_spec": g / 8000.0, "trace": tr.re}
+            del rho
+        out["fused_superoperators" if fused else "op_by_op"] = best
+    # single kernels on rho
+    d = bt.CuRho(n)
+    dl = d.lib
+
+    def timed_dm(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ms = C.c_float()
+        L.check(dl.bt_dm_timer_start(d.h))
+        for _ in range(reps):
+            fn()
+        L.check(dl.bt_dm_timer_stop(d.h, C.byref(ms)))
+        return ms.value / reps
+
+    H = L.cmat(bt.gate["H"], 2)
+    U4 = L.cmat(bt.gates("FSIM(0.3,0.2)"), 4)
+    K1 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01)])
+    A1 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("amplitude_damping", 0.02)])
+    K2 = np.stack([np.asfortranarray(k).reshape(-1, order="F") for k in bt.noise_model("depolarizing", 0.01, True)])
+    kern = {}
+    for name, fn in (("dm_1q_unitary_q%d" % (n // 2), lambda: L.check(dl.bt_dm_apply_1q(d.h, n // 2, L.ptr(H), -2))),
+                     ("dm_2q_unitary_q2_q9", lambda: L.check(dl.bt_dm_apply_2q(d.h, 2, min(9, n), L.ptr(U4), -2))),
+                     ("dm_1q_depolarizing_q%d" % n, lambda: L.check(dl.bt_dm_kraus(d.h, 1, n, -1, L.ptr(K1), 4))),
+                     ("dm_1q_amplitude_damping_q1", lambda: L.check(dl.bt_dm_kraus(d.h, 1, 1, -1, L.ptr(A1), 2))),
+                     ("dm_2q_depolarizing_16_kraus_q%d_q%d" % (n - 1, n), lambda: L.check(dl.bt_dm_kraus(d.h, 2, n - 1, n, L.ptr(K2), 16)))):
+        ms = timed_dm(fn)
+        g = pass_bytes / (ms / 1e3) / 1e9
+        kern[name] = {"ms": ms, "GBps": g, "frac_of_measured": g / peak, "frac_of_8TBs_spec": g / 8000.0}
+    out["kernels"] = kern
+    out["algorithmic_bytes"] = f"32 B x 4^{n} = {pass_bytes / 1e9:.2f} GB per unitary or channel (one pass whatever the number of Kraus operators)"
+    del d
+    return out
+
+
+def fp64_peak(lib, L, clocks_index=0):
+    """FP64 FMA peak measured in this run (bt_fp64_peak: DFMA loop on every SM, best of 5), with the SM clock nvidia-smi reports
+    right after it -- a measured, clock-stamped denominator instead of a constant in the source."""
+    tf, ms = C.c_double(), C.c_double()
+    L.check(lib.bt_fp64_peak(C.byref(tf), C.byref(ms), 5))
+    sm = None
+    try:
+        r = subprocess.run(["nvidia-smi", "-i", str(clocks_index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+        f = [x.strip() for x in r.stdout.strip().split(",")]
+        sm = {"sm_mhz_after": float(f[0]), "sm_max_mhz": float(f[1])}
+    except Exception:
+        pass
+    return {"tflops": tf.value, "ms_per_launch": ms.value, "clock": sm, "how": "bt_fp64_peak: 8 independent DFMA chains per thread, 8 x 256 threads per SM, register operands, CUDA events, best of 5 (measured in this run)"}
+
+
 def bench_single(args):
     import __graft_entry__ as ge
 
@@ -122,12 +245,18 @@ def bench_single(args):
         L.check(lib.bt_sv_set_basis(s.h, 0))
         L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), ngates, 1))
 
-    # the library specialises a fused pass the second time it sees it (csrc/bt_jit.cu); here every pass is compiled at first
-    # sight so that the compilation always falls into the untimed warm-up, whatever W is
-    os.environ.setdefault("BT_TILE_JIT_AFTER", "1")
     clocks = ClockSampler(0)
     clocks.start()
+    # ---- cold start: the very first execution of the circuit in this process.  The library hands every fused pass to its
+    # compile workers (NVRTC, or the on-disk cubin cache of an earlier process) and runs the pass on the interpreter meanwhile.
+    s.sync()
     t_w0 = time.perf_counter()
+    step()
+    s.sync()
+    cold_first_step_s = time.perf_counter() - t_w0
+    pend = C.c_uint64()
+    L.check(lib.bt_jit_wait(C.byref(pend)))
+    jit_ready_s = time.perf_counter() - t_w0
     for _ in range(args.warmup):
         step()
     s.sync()
@@ -166,6 +295,7 @@ def bench_single(args):
     per_cls = {cls_names[i]: {"launches": int(counts[i]), "ms": float(cms[i])} for i in range(4)}
     dom = max(range(4), key=lambda i: cms[i])
     bytes_per_launch = 32.0 * (1 << N)
+    fp64 = fp64_peak(lib, L)
     roof = None
     if counts[dom] > 0:
         avg_ms = cms[dom] / counts[dom]
@@ -181,31 +311,44 @@ def bench_single(args):
                 "share_of_step": cms[dom] / (ms.value), "bytes_per_launch": bytes_per_launch, "frac_of_8TBs_spec": ach / 8000.0}
         if dom == 0 and cms[0] > 0:
             tf = (fl1.value - fl0.value) / (cms[0] / 1e3) / 1e12
-            roof["fp64"] = {"achieved_tflops": tf, "peak_tflops_measured": 36.0, "frac": tf / 36.0,
+            roof["fp64"] = {"achieved_tflops": tf, "peak_tflops_measured": fp64["tflops"], "frac": tf / fp64["tflops"], "peak": fp64,
                             "note": "useful FP64 flops of the structured micro-ops (real / RX-like / diagonal gates cost half of a dense 2x2, CX none); "
-                                    "a pass fuses ~30 gates, so it sits between the HBM and FP64 roofs (profiles/r1_bt_jit_pass_ncu_full.txt, r1_k_tile_tma_*): "
-                                    "peak = DFMA loop measured by tools/fp64_peak.cu"}
+                                    "a pass fuses ~30 gates, so it sits between the HBM and FP64 roofs"}
             roof["gates_per_launch"] = ngates * args.steps / max(1, int(counts[0]))
-        tfile = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.exists(tfile):
-            try:
-                tj = json.load(open(tfile))
-                roof["traffic"] = tj.get("bt_jit_pass_dram_bytes_per_launch" if 2 * jit_timed >= counts[0] else "k_tile_dram_bytes_per_launch", tj.get("k_tile_dram_bytes_per_launch"))
-            except Exception:
-                pass
+        for tname in ("traffic_r2.json", "traffic_r1.json"):
+            tfile = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tfile):
+                try:
+                    tj = json.load(open(tfile))
+                    roof["traffic"] = tj.get("bt_jit_pass_dram_bytes_per_launch" if 2 * jit_timed >= counts[0] else "k_tile_dram_bytes_per_launch", tj.get("k_tile_dram_bytes_per_launch"))
+                    roof["traffic_source"] = "profiles/" + tname
+                    break
+                except Exception:
+                    pass
+
+    # the same circuit on the interpreter alone (what a circuit that is executed once costs): specialiser off
+    os.environ["BT_TILE_JIT"] = "0"
+    step()
+    mi = C.c_float()
+    L.check(lib.bt_sv_timer_start(s.h))
+    for _ in range(2):
+        step()
+    L.check(lib.bt_sv_timer_stop(s.h, C.byref(mi)))
+    del os.environ["BT_TILE_JIT"]
+    interp = {"ms_per_step": mi.value / 2, "gates_per_s": ngates / (mi.value / 2 / 1e3),
+              "hbm_equivalent_GBps": None, "note": "BT_TILE_JIT=0: every fused pass on the pre-compiled interpreter kernel (k_tile_tma)"}
+    if counts[0] > 0:
+        passes_per_step = counts[0] / args.steps
+        interp["hbm_equivalent_GBps"] = bytes_per_launch * passes_per_step / (mi.value / 2 / 1e3) / 1e9
+        interp["frac_of_measured"] = interp["hbm_equivalent_GBps"] / peaks["hbm_gbs"]
 
     # unfused single-gate kernels on the same state: the per-gate HBM roofline the north star quotes
     micro = {}
     for name, fn in (("1q_dense_H_q14", lambda: L.check(lib.bt_sv_apply_1q(s.h, N // 2, L.ptr(L.cmat(bt.gate["H"], 2)), -2))),
                      ("2q_dense_q3_q17", lambda: L.check(lib.bt_sv_apply_2q(s.h, 3, min(17, N), L.ptr(L.cmat(bt.gates("FSIM(0.3,0.2)"), 4)), -2)))):
-        for _ in range(3):
-            fn()
-        t = C.c_float()
-        L.check(lib.bt_sv_timer_start(s.h))
-        for _ in range(10):
-            fn()
-        L.check(lib.bt_sv_timer_stop(s.h, C.byref(t)))
-        micro[name] = {"ms": t.value / 10, "GBps": bytes_per_launch / (t.value / 10 / 1e3) / 1e9}
+        t = _timed_sv(L, lib, s.h, fn, 10, warm=3)
+        g = bytes_per_launch / (t / 1e3) / 1e9
+        micro[name] = {"ms": t, "GBps": g, "frac_of_measured": g / peaks["hbm_gbs"], "frac_of_8TBs_spec": g / 8000.0}
 
     # end to end through the host API: gate list in (host), <Z_q> for every qubit and 4096 samples out (host)
     us = np.random.Generator(np.random.PCG64(7)).random(4096)
@@ -223,13 +366,34 @@ def bench_single(args):
     e2e = {"value": ngates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes + us.nbytes), "d2h_bytes_per_step": int(ez.nbytes + smp.nbytes + 8),
            "seconds_per_step": e2e_s, "api": "bt_sv_set_basis + bt_sv_apply_circuit(host gate list) + bt_sv_expect_1q_all + bt_sv_sample"}
 
+    # the other half of BASELINE's metric, driver-run: Kraus trajectory steps at N qubits, the 14-qubit density matrix (C3)
+    extra_err = {}
+    try:
+        kraus = kraus_block(bt, L, s, N, peaks["hbm_gbs"]) if not args.no_blocks else None
+    except Exception as e:  # the headline must not be lost to a side block
+        kraus, extra_err["kraus"] = None, repr(e)
+    jitst = jit_stats(lib, warmup_seconds)
+    hits, cdir = C.c_uint64(), C.create_string_buffer(512)
+    L.check(lib.bt_jit_cache_info(C.byref(hits), cdir, 512))
+    jitst.update({"cold_first_step_s": cold_first_step_s, "all_modules_ready_s": jit_ready_s, "structures_compiling_after_first_step": int(pend.value),
+                  "disk_cache_hits": int(hits.value), "disk_cache_dir": cdir.value.decode(),
+                  "note": "first execution runs on the interpreter while worker threads compile (or read the on-disk cubin cache); steady-state steps use the specialised kernels"})
+    del s
+    try:
+        dm14 = dm14_block(bt, L, wl, peaks["hbm_gbs"]) if not args.no_blocks else None
+    except Exception as e:
+        dm14, extra_err["dm14"] = None, repr(e)
+
     cpu = cpu_baseline_port(N, specs, budget_s=args.cpu_budget) if not args.no_cpu else None
     out = {"metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
            "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers (H/RX/RY/RZ/T + CNOT/CZ/CP brickwork), {ngates} gates, seed 28",
                       "fusion": "host fusion pass + shared-memory tile kernel", "l2": f"inputs larger than L2 ({(16 << N) / 2**30:.1f} GiB state)", "parallelism": "1 GPU"},
            "clocks": clk, "e2e": e2e, "gpu_launches": int(n1 - n0), "roofline": roof, "kernels": per_cls, "unfused_gate_kernels": micro,
-           "cpu_baseline": cpu, "state_norm2": norm, "jit": jit_stats(lib, warmup_seconds)}
+           "interpreter": interp, "cold_first_step_s": cold_first_step_s, "kraus": kraus, "dm14": dm14,
+           "cpu_baseline": cpu, "state_norm2": norm, "jit": jitst}
+    if extra_err:
+        out["block_errors"] = extra_err
     print(json.dumps(out))
 
 
@@ -238,7 +402,7 @@ def jit_stats(lib, warmup_seconds=None):
     jc, jl, jf, jt = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
     lib.bt_jit_stats(C.byref(jc), C.byref(jl), C.byref(jf), C.byref(jt))
     out = {"modules_compiled": int(jc.value), "specialised_launches": int(jl.value), "fell_back": int(jf.value), "compile_seconds": float(jt.value),
-           "note": "recurring fused passes are compiled once by NVRTC into straight-line kernels; compilation happens in the untimed warm-up"}
+           "note": "recurring fused passes are compiled once by NVRTC (worker threads, on-disk cubin cache) into straight-line kernels; bench.py waits for the workers in the untimed warm-up"}
     if warmup_seconds is not None:
         out["warmup_seconds"] = warmup_seconds
     return out
@@ -251,6 +415,7 @@ def cpu_baseline_port(N, specs, budget_s=15.0):
     from oracle import strided as S
 
     try:
+        S.use_all_cores()  # the launcher's OMP_NUM_THREADS (torchrun: 1) does not decide the baseline's core count
         layered = specs[N * (N + 1) // 2:]  # skip the QFT prefix
         sv = S.SV(N)
         t0 = time.perf_counter()
@@ -268,6 +433,14 @@ def cpu_baseline_port(N, specs, budget_s=15.0):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def remap_log(L, st):
+    """per-remap (ms waiting for the peers, ms in the pull kernel, ms until every peer has finished reading) since the last call"""
+    buf = (C.c_float * (3 * 512))()
+    n = C.c_int()
+    L.check(st.lib.bt_sv_remap_log(st.h, 512, buf, C.byref(n)))
+    return [(round(buf[3 * i], 3), round(buf[3 * i + 1], 3), round(buf[3 * i + 2], 3)) for i in range(n.value)]
+
+
 def bench_sharded(args):
     import torch
     import torch.distributed as dist
@@ -311,10 +484,17 @@ def bench_sharded(args):
         L.check(lib.bt_sv_set_basis(st.h, 0))
         L.check(lib.bt_sv_apply_circuit(st.h, L.ptr(arr), ngates, 1))
 
-    os.environ.setdefault("BT_TILE_JIT_AFTER", "1")  # specialise every fused pass at first sight: compilation stays in the warm-up
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    # first execution: interpreter, the library's compile workers specialise the fused passes meanwhile; then wait for them
+    st.sync()
+    t_c0 = time.perf_counter()
+    step()
+    st.sync()
+    cold_first_step_s = time.perf_counter() - t_c0
+    L.check(lib.bt_jit_wait(None))
+    jit_ready_s = time.perf_counter() - t_c0
     for _ in range(args.warmup):
         step()
     st.sync()
@@ -327,6 +507,7 @@ def bench_sharded(args):
     gc.disable()  # no cyclic-GC pause inside the timed region (a full collection with torch imported takes ~0.5 s)
     clocks.begin()
     r0 = st.remap_stats()
+    remap_log(L, st)  # drop the warm-up's records
     n0 = st.launch_count()
     ms = C.c_float()
     L.check(lib.bt_sv_profile_enable(st.h, 1))
@@ -350,7 +531,9 @@ def bench_sharded(args):
     torch.cuda.synchronize()
     n1 = st.launch_count()
     r1 = st.remap_stats()
+    rlog = remap_log(L, st)
     if debug:
+        sys.stderr.write(f"[bench rank {rank}] per remap (ms waiting for peers, ms pulling, ms until all peers done): {rlog}\n")
         sys.stderr.write(f"[bench rank {rank}] timed region {ms.value:.1f} ms (device events), host {t_host * 1e3:.1f} ms, host time to enqueue each step {[round(x * 1e3, 1) for x in step_host]} ms, "
                          f"launches {n1 - n0}, classes {[(int(counts[i]), round(float(cms[i]), 1)) for i in range(4)]}, remaps {r1[0] - r0[0]} in {r1[2] - r0[2]:.1f} ms, jit {jit_stats(lib)}\n")
         sys.stderr.flush()
@@ -386,7 +569,8 @@ def bench_sharded(args):
         remaps = (r1[0] - r0[0]) / args.steps
         rbytes = (r1[1] - r0[1]) / args.steps
         rms = (r1[2] - r0[2]) / args.steps
-        out = {"metric": "gates/s", "value": value, "unit": "gates/s (28-qubit-equivalent: gates x shard amplitudes / 2^28, summed over ranks)", "n_gpus": world,
+        pulls = [p for (_, p, _) in rlog]
+        out = {"metric": "gates/s", "value": value, "unit": "gates/s", "unit_note": "28-qubit-equivalent gates/s: circuit gates x shard amplitudes / 2^28, summed over ranks (equal per-GPU work at every N)", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total_qubits > 0 else "weak", "vs_baseline": None,
                "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
                "config": {"workload": f"C5: {N}-qubit state vector random circuit (depth {args.c5_depth}: random 1q gate per qubit + CNOT/CZ brickwork, seed 31), {ngates} gates, "
@@ -399,7 +583,10 @@ def bench_sharded(args):
                              "peak": load_peaks()[0]["hbm_gbs"], "unit": "GB/s", "frac": 32.0 * (1 << n_local) / (cms[0] / counts[0] / 1e3) / 1e9 / load_peaks()[0]["hbm_gbs"],
                              "traffic": None, "avg_launch_ms": cms[0] / counts[0], "bytes_per_launch": 32.0 * (1 << n_local)} if counts[0] else None),
                "remap": {"per_step": remaps, "nvlink_bytes_per_rank_per_step": rbytes, "ms_per_step": rms, "GBps_per_rank": (rbytes / (rms / 1e3) / 1e9) if rms > 0 else None,
-                         "nvlink_peak_GBps": 900.0},
+                         "nvlink_peak_GBps": 900.0, "pull_ms_rank0": {"min": min(pulls), "median": float(np.median(pulls)), "max": max(pulls)} if pulls else None,
+                         "wait_for_peers_ms_rank0_median": float(np.median([w for (w, _, _) in rlog])) if rlog else None,
+                         "sync": "device-side epoch flags in peer memory" if os.environ.get("BT_REMAP_DEVICE_SYNC", "1") != "0" else "host barriers"},
+               "cold_first_step_s": cold_first_step_s, "all_modules_ready_s": jit_ready_s,
                "e2e": {"value": equiv / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": int(arr.nbytes), "d2h_bytes_per_step": int(ez.nbytes + 8), "seconds_per_step": e2e_s,
                        "api": "host wall clock, max over ranks: bt_sv_set_basis + bt_sv_apply_circuit(host gate list) + bt_sv_expect_1q_all + bt_sv_norm2 (results in host memory)"},
                "checksum": {"norm2": float(nrm[0]), "sum_expect_Z": float(np.sum(ez))}}
@@ -415,7 +602,9 @@ def bench_sharded(args):
 # ------------------------------------------------------------------------------------------------------------------
 def bench_reference(args):
     """Reference arm: the reference path's CPU port on the host cores (Julia itself is not installable here).  Value =
-    the oracle's strided C port (all host threads) on a bounded sample of the same 28-qubit circuit; the kron-chain
+    the oracle's strided C port, all the cores this process may use (set explicitly -- torchrun exports OMP_NUM_THREADS=1),
+    on a bounded sample of the repo arm's workload at the same --gpus: C2 (28 qubits) for N = 1, C5 for N > 1 (consecutive
+    gates of the same circuit on a state of the per-GPU shard size, in the same 28-qubit-equivalent gates/s).  The kron-chain
     restatement of the reference ALGORITHM (2^N x 2^N sparse operator per gate) is timed beside it on what it can reach."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -428,14 +617,36 @@ def bench_reference(args):
     from oracle import bt_oracle as O
     from oracle import strided as S
 
-    N, depth = args.qubits, args.depth
-    specs = wl.c2_qft_layered(N, depth, 28)
-    layered = specs[N * (N + 1) // 2:]
+    cores = S.use_all_cores()
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)
+    sharded = world > 1 or args.workload == "c5"
+    if sharded:
+        g = world.bit_length() - 1
+        n_total = args.total_qubits if args.total_qubits > 0 else args.shard_qubits + g
+        n_cpu = min(n_total, args.shard_qubits if args.total_qubits <= 0 else args.total_qubits)
+        try:  # a 31-qubit state is 32 GiB of host memory: fall back to what fits
+            import psutil
+            while n_cpu > 24 and (24 << n_cpu) > psutil.virtual_memory().available:
+                n_cpu -= 1
+        except Exception:
+            pass
+        specs_full = wl.c5_random(n_total, args.c5_depth, 31)
+        # the same layers restricted to the qubits the CPU state holds (labels above n_cpu dropped): same gate mix per qubit
+        layered = [(nm, q, t, c) for (nm, q, t, c) in wl.c5_random(n_cpu, args.c5_depth, 31)]
+        scale = 2.0 ** (n_cpu - 28)
+        N = n_cpu
+        workload = (f"C5: {n_total}-qubit state vector random circuit (depth {args.c5_depth}, {len(specs_full)} gates) -- bounded sample: consecutive gates of the same "
+                    f"generator at {n_cpu} qubits (the per-GPU shard size), reported in 28-qubit-equivalent gates/s")
+    else:
+        N, depth = args.qubits, args.depth
+        specs = wl.c2_qft_layered(N, depth, 28)
+        layered = specs[N * (N + 1) // 2:]
+        scale = 1.0
+        workload = f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers, bounded sample of the layered section"
     budget = max(4.0, args.cpu_budget)
     sv = S.SV(N)
-    for name, q, t, c in layered[:2]:  # warm-up (page in 4 GiB)
+    for name, q, t, c in layered[:2]:  # warm-up (pages the state in)
         sv.apply(O.Op(name, q, t, control=c))
-    vals = []
     tot_g, tot_t = 0, 0.0
     pos = 2
     for _ in range(max(1, args.steps)):
@@ -448,11 +659,9 @@ def bench_reference(args):
             n += 1
             if time.perf_counter() - t0 > budget / max(1, args.steps) and n >= 2:
                 break
-        dt = time.perf_counter() - t0
-        vals.append(n / dt)
         tot_g += n
-        tot_t += dt
-    value = tot_g / tot_t
+        tot_t += time.perf_counter() - t0
+    value = tot_g / tot_t * scale
     # the reference ALGORITHM (kron chain + sparse mat-vec), on a size it can hold
     nk = 16
     ks = wl.layered(nk, 1, 28)[:12]
@@ -464,12 +673,15 @@ def bench_reference(args):
     kron = {"qubits": nk, "gates_per_s": len(ks) / kdt, "gates_per_s_28q_equivalent": len(ks) / kdt * 2.0 ** (nk - 28),
             "note": "restatement of hilbert()+SpMV (src/hilbert.jl:18-159,505) in scipy, single thread like the reference; cannot reach 28 qubits"}
     out = {"impl": "reference", "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
-           "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers, bounded sample of the layered section", "parallelism": "host CPU"},
-           "cpu_baseline": {"value": value, "unit": "gates/s", "cores": S.num_threads(), "kind": "port",
-                            "sample": f"{tot_g} consecutive gates of the layered section at {N} qubits, in-place strided C + OpenMP ({tot_t:.1f} s)"},
+           "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if args.total_qubits > 0 else "weak", "vs_baseline": None,
+           "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
+           "config": {"workload": workload, "parallelism": "host CPU"},
+           "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port",
+                            "sample": f"{tot_g} consecutive gates at {N} qubits, in-place strided C + OpenMP on {cores} threads ({tot_t:.1f} s)"},
            "reference_algorithm": kron,
            "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if sharded:
+        out["unit_note"] = "28-qubit-equivalent gates/s: gates x state amplitudes / 2^28 (the repo arm's unit at N > 1)"
     print(json.dumps(out))
 
 
@@ -486,6 +698,7 @@ def main():
     ap.add_argument("--c5-depth", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the kraus / dm14 side blocks of the N = 1 line")
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5"], help="auto: C2 (28q) on 1 GPU, C5 (31q per GPU, sharded) on N > 1")
     args = ap.parse_args()
     if args.impl == "reference":

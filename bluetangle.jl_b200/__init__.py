@@ -9,5 +9,5 @@ from .host import *  # noqa: F401,F403
 from .host import _born_measure, _reset_Z, _final_measurement, _sample_to_expectation  # noqa: F401
 from .gates import gate, gates, noise_model, is_valid_quantum_channel  # noqa: F401
 from .qasm import from_qasm  # noqa: F401,E402
-from .vqa import (PauliSum, hamiltonian, VOp, AnsatzOptions, variational_apply, loss_and_grad_paramshift, VQA, VQE,  # noqa: F401,E402
+from .vqa import (PauliSum, hamiltonian, VOp, AnsatzOptions, variational_apply, loss_and_grad_paramshift, loss_and_grad, shift_rule, VQA, VQE,  # noqa: F401,E402
                   EfficientSU2, generate_ansatz_circuit, _variational_circuit_from_string)

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "bt_device_count": [C.POINTER(_i)],
     "bt_set_device": [_i],
     "bt_set_strict": [_i],
+    "bt_fp64_peak": [_pd, _pd, _i],
     "bt_fusion_stats": [C.POINTER(_u64), C.POINTER(_u64)],
     "bt_fusion_flops": [_pd],
     "bt_jit_stats": [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _pd],

@@ -360,3 +360,46 @@ extern "C" int bt_sv_profile_read(bt_sv* s, uint64_t* counts, double* ms) {
   }
   return BT_OK;
 }
+
+// ---- FP64 FMA peak of the current device, measured (bench.py's FP64 roofline denominator) ------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 0.5;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// Dependent-chain-free DFMA loop on every SM (8 independent chains per thread, 8 CTAs of 256 threads per SM), best of `reps`
+// launches of ~`ms_target` ms each, timed with CUDA events: the FP64 vector peak bench.py divides by (no tensor-core FP64 path is used).
+extern "C" int bt_fp64_peak(double* tflops, double* ms_per_launch, int reps) {
+  if (!tflops) BT_FAIL(BT_ERR_ARG, "null output");
+  int dev = 0, sms = 0;
+  BT_CUDA(cudaGetDevice(&dev));
+  BT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 40000;
+  double* d = nullptr;
+  BT_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  BT_CUDA(cudaEventCreate(&e0));
+  BT_CUDA(cudaEventCreate(&e1));
+  k_fp64_peak<<<blocks, threads>>>(d, 1000);
+  float best = 1e30f;
+  for (int r = 0; r < std::max(1, reps); ++r) {
+    cudaEventRecord(e0);
+    k_fp64_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  BT_CUDA(cudaGetLastError());
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  if (ms_per_launch) *ms_per_launch = best;
+  return BT_OK;
+}

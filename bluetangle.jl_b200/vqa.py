@@ -29,6 +29,33 @@ from .gates import clean_name, gates_with_phase, two_qubit_gates
 _ARGS = {"P": 1, "RX": 1, "RY": 1, "RZ": 1, "U1": 1, "U2": 2, "U3": 3, "CP": 1, "GIVENS": 1, "FSIM": 2, "SWAPA": 1, "RXX": 1, "RYY": 1, "RZZ": 1, "RXY": 1}
 
 
+# Parameter-shift rules per gate argument: the derivative of loss(theta) with respect to ONE gate parameter is exact as a
+# short linear combination of shifted evaluations once the frequencies of the gate in that parameter are known (differences of
+# the eigenvalues of its generator).  ("two", w): frequency w alone -> w/2 * (f(x + pi/2w) - f(x - pi/2w)); "four": frequencies
+# {1, 2} -> sum_mu (-1)^(mu-1) / (8 sin^2(x_mu/2)) f(x + x_mu), x_mu = (2 mu - 1) pi/4, mu = 1..4.  The reference differentiates
+# with ForwardDiff (src/vqa.jl:564) and is exact for every gate; its own loss_and_grad_paramshift (:590-611) uses w = 1 throughout.
+#   RX RY RZ P U1 U2 U3 CP RZZ: generator gap 1.   RXX, RYY: exp(-i phi XX) (cos phi, not the half angle: src/gates.jl:401-403) -> w = 2.
+#   SWAPA(a): eigenphases 1 and exp(i pi a) -> w = pi.   GIVENS(theta), FSIM(theta, .), RXY(phi): rotation of the {01, 10} block,
+#   generator eigenvalues {0, 0, +1, -1} -> frequencies {1, 2}.
+_RULES = {"P": [("two", 1.0)], "U1": [("two", 1.0)], "RX": [("two", 1.0)], "RY": [("two", 1.0)], "RZ": [("two", 1.0)],
+          "U2": [("two", 1.0)] * 2, "U3": [("two", 1.0)] * 3, "CP": [("two", 1.0)], "RZZ": [("two", 1.0)],
+          "RXX": [("two", 2.0)], "RYY": [("two", 2.0)], "SWAPA": [("two", math.pi)],
+          "GIVENS": [("four", 0.0)], "FSIM": [("four", 0.0), ("two", 1.0)], "RXY": [("four", 0.0)]}
+
+
+def shift_rule(gate_name: str, arg: int) -> List[Tuple[float, float]]:
+    """[(shift, coefficient)]: d loss / d parameter = sum coefficient * loss(parameter + shift), exact for this gate argument."""
+    kind, w = _RULES[clean_name(gate_name)][arg]
+    if kind == "two":
+        s = math.pi / (2.0 * w)
+        return [(s, 0.5 * w), (-s, -0.5 * w)]
+    out = []
+    for mu in range(1, 5):
+        x = (2 * mu - 1) * math.pi / 4.0
+        out.append((x, (-1.0) ** (mu - 1) / (8.0 * math.sin(x / 2.0) ** 2)))
+    return out
+
+
 class PauliSum:
     """H = sum_k coef_k * (operator string on qubits): what ``hamiltonian`` (src/vqa.jl:36-67) sums up, kept as terms."""
 
@@ -218,7 +245,8 @@ def _loss(p, opt: AnsatzOptions) -> float:
 
 
 def loss_and_grad_paramshift(p: Sequence[float], opt: AnsatzOptions) -> Tuple[float, np.ndarray]:
-    """src/vqa.jl:590-611: g_i = (loss(p + pi/2 e_i) - loss(p - pi/2 e_i)) / 2 for every parameter, in order."""
+    """src/vqa.jl:590-611 as written there: g_i = (loss(p + pi/2 e_i) - loss(p - pi/2 e_i)) / 2 for every parameter, in order
+    (exact for the frequency-1 gates only -- "for Pauli/Pauli-string rotations", :595; ``loss_and_grad`` is exact for all)."""
     p = np.asarray(p, dtype=np.float64)
     l0 = _loss(p, opt)
     shift = math.pi / 2
@@ -234,10 +262,39 @@ def loss_and_grad_paramshift(p: Sequence[float], opt: AnsatzOptions) -> Tuple[fl
     return l0, g
 
 
+def loss_and_grad(p: Sequence[float], opt: AnsatzOptions) -> Tuple[float, np.ndarray]:
+    """Exact gradient of the loss for every parametrised gate of the table (the stand-in for ForwardDiff.gradient, src/vqa.jl:564):
+    per parameter the shift rule of its gate (``shift_rule``).  For the frequency-1 gates this is loss_and_grad_paramshift."""
+    p = np.asarray(p, dtype=np.float64)
+    l0 = _loss(p, opt)
+    g = np.zeros(len(p))
+    base = p.copy()
+    i = 0
+    for op, fn in zip(opt.ops, opt.args):
+        for k in range(fn):
+            rule = shift_rule(op.name, k)
+            if len(rule) == 2:  # same arithmetic as the reference's fixed rule: w/2 * (f+ - f-)
+                base[i] = p[i] + rule[0][0]
+                fp = _loss(base, opt)
+                base[i] = p[i] + rule[1][0]
+                fm = _loss(base, opt)
+                g[i] = rule[0][1] * (fp - fm)
+            else:
+                acc = 0.0
+                for sh, c in rule:
+                    base[i] = p[i] + sh
+                    acc += c * _loss(base, opt)
+                g[i] = acc
+            base[i] = p[i]
+            i += 1
+    return l0, g
+
+
 def VQA(opt: AnsatzOptions):
     """src/vqa.jl:488-583, the gradient branch (:563-582): per iteration the gradient, one optimiser update, and -- when
     ``history`` -- the loss at the NEW parameters.  The reference differentiates with ForwardDiff; across the C ABI the
-    parameter-shift rule (exact for the Pauli rotations of the ansatz generators) takes its place.  Models: "descent" /
+    per-gate parameter-shift rules (``loss_and_grad``: exact for every parametrised gate the ansatz generators accept,
+    including RXX/RYY, SWAPA and the two-frequency gates GIVENS/FSIM/RXY) take its place.  Models: "descent" /
     "gradient" (Optimisers.Descent: p -= lr * g) and "adam" (Optimisers.Adam defaults beta = (0.9, 0.999), eps = 1e-8).
     Returns (energy_history, pars, pars_history) or, with history = False, (loss, pars) like the reference."""
     model = opt.model.lower()
@@ -248,7 +305,7 @@ def VQA(opt: AnsatzOptions):
     b1, b2, eps = 0.9, 0.999, 1e-8
     energy_history, pars_history = [], []
     for it in range(1, opt.number_of_iterations + 1):
-        _, g = loss_and_grad_paramshift(p, opt)
+        _, g = loss_and_grad(p, opt)
         if model == "adam":
             m = b1 * m + (1 - b1) * g
             v = b2 * v + (1 - b2) * g * g

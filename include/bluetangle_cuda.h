@@ -49,6 +49,9 @@ const char* bt_last_error(void);
 int bt_version(void);
 int bt_device_count(int* n);
 int bt_set_device(int device);
+/* measured FP64 FMA peak of the current device (register-operand DFMA loop on every SM, best of `reps` launches, CUDA events):
+ * the FP64 roofline denominator bench.py reports against.  No reference analogue. */
+int bt_fp64_peak(double* tflops, double* ms_per_launch, int reps);
 
 /* ---- state vector life cycle: zero_state/one_state/plus_state/product_state src/hilbert.jl:835-882 -- */
 int bt_sv_create(int n_qubits, int64_t n_batch, bt_sv** out);     /* on the current device, |0..0> in every trajectory */

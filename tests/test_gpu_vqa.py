@@ -173,3 +173,33 @@ def test_vqa_golden_fixture_on_the_device(bt):
     l0, g = bt.loss_and_grad_paramshift(G["n6_pars"], opt)
     assert abs(l0 - float(G["n6_energy_tfim_open"])) < TOL
     assert np.max(np.abs(g - G["n6_grad_tfim_open"])) < TOL
+
+
+def test_exact_gradient_for_multi_frequency_gates(bt, orc):
+    """loss_and_grad (the stand-in for ForwardDiff.gradient, src/vqa.jl:564) on an ansatz with RXX / RYY (frequency 2),
+    SWAPA (frequency pi) and the two-frequency gates GIVENS / FSIM / RXY: every component equals the central finite
+    difference of the oracle's loss; the reference's fixed pi/2 rule gives 0 for the RXX / RYY parameters."""
+    N = 5
+    names = ["RY", "RXX", "RYY", "RX", "GIVENS", "FSIM", "SWAPA", "RXY", "RZ"]
+    ham = [-1.0, "Z,Z", -0.6, "X", 0.3, "Y"]
+    opt = bt.AnsatzOptions(N=N, ops=names, loss=bt.hamiltonian(N, ham), rng=bt.Draws(3))
+    vops, args, dim = orc.variational_circuit_from_string(N, names, False)
+    assert opt.dim == dim
+    p = np.asarray(opt.pars_initial)
+    Hm = orc.hamiltonian(N, ham)
+    loss = lambda q: float(np.real(np.vdot(orc.variational_apply(q, N, vops, args), Hm @ orc.variational_apply(q, N, vops, args))))
+    l0, g = bt.loss_and_grad(p, opt)
+    assert abs(l0 - loss(p)) < TOL
+    h = 1e-5
+    fd = np.zeros(dim)
+    for i in range(dim):
+        e = np.zeros(dim)
+        e[i] = h
+        fd[i] = (loss(p + e) - loss(p - e)) / (2 * h)
+    assert np.max(np.abs(g - fd)) < 1e-7, (g, fd)
+    _, gfixed = bt.loss_and_grad_paramshift(p, opt)
+    i = 0
+    for op, fn in zip(opt.ops, opt.args):
+        if op.name in ("RXX", "RYY"):
+            assert abs(gfixed[i]) < 1e-10 and abs(fd[i]) > 1e-4
+        i += fn

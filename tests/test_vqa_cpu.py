@@ -88,3 +88,36 @@ def test_vqa_golden_fixture_is_reproduced_by_the_oracle(orc):
         for n, v in ((6, st), (12, G["n12_state"])):
             e = float(np.real(np.vdot(v, orc.hamiltonian(n, spec, bc) @ v)))
             assert abs(e - float(G[f"n{n}_energy_{key}"])) < 1e-12
+
+
+def test_shift_rules_are_exact_for_every_parametrised_gate(bt):
+    """shift_rule(gate, arg): sum c * f(theta + s) equals d/dtheta Re<psi|U(theta)' O U(theta)|psi> for every parametrised gate
+    of the table (pure numpy: the gate matrices of gates.py, a random state and observable); the reference's fixed pi/2 rule
+    (src/vqa.jl:590-611) is exact only for the frequency-1 gates -- for RXX/RYY it is identically zero."""
+    rng = np.random.default_rng(11)
+    nargs = {"P": 1, "RX": 1, "RY": 1, "RZ": 1, "U1": 1, "U2": 2, "U3": 3, "CP": 1, "GIVENS": 1, "FSIM": 2, "SWAPA": 1, "RXX": 1, "RYY": 1, "RZZ": 1, "RXY": 1}
+    for name, na in nargs.items():
+        dim = bt.gates(f"{name}({','.join(['0.3'] * na)})").shape[0]
+        psi = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+        psi /= np.linalg.norm(psi)
+        A = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        O = A + A.conj().T
+        th0 = rng.uniform(0, 2 * np.pi, size=na)
+
+        def f(th):
+            U = bt.gates(f"{name}({','.join(repr(float(t)) for t in th)})")
+            v = U @ psi
+            return float(np.real(np.vdot(v, O @ v)))
+
+        for k in range(na):
+            def fk(x):
+                th = th0.copy()
+                th[k] = x
+                return f(th)
+            h = 1e-5
+            num = (fk(th0[k] + h) - fk(th0[k] - h)) / (2 * h)
+            got = sum(c * fk(th0[k] + s) for s, c in bt.shift_rule(name, k))
+            assert abs(got - num) < 1e-7, (name, k, got, num)
+            if name in ("RXX", "RYY"):
+                fixed = 0.5 * (fk(th0[k] + np.pi / 2) - fk(th0[k] - np.pi / 2))
+                assert abs(fixed) < 1e-12 and abs(num) > 1e-3

@@ -111,10 +111,15 @@ def main():
 
     set_knobs({})
     t0 = time.perf_counter()
+    step()
+    st.sync()
+    t1 = time.perf_counter()
+    L.check(lib.bt_jit_wait(None))  # the first step ran on the interpreter while the workers compiled
+    t2 = time.perf_counter()
     for _ in range(2):
         step()
     st.sync()
-    say(f"[step] warm-up (2 steps incl. specialiser) {time.perf_counter() - t0:.1f} s")
+    say(f"[step] warm-up: first step (interpreter, compile in the background) {t1 - t0:.2f} s, waiting for the compile workers {t2 - t1:.2f} s, 2 more steps {time.perf_counter() - t2:.2f} s")
     step_variants = [
         ("linear walk, device flags, profile on", {"BT_REMAP_ORDER": 0}, True, False),
         ("linear walk, device flags, profile off", {"BT_REMAP_ORDER": 0}, False, False),
