@@ -88,6 +88,7 @@ PROTOTYPES = {
     "bt_sv_probs": [_vp, _pd],
     "bt_sv_measure_z": [_vp, _i, _pd, _pi32, _pd, _i],
     "bt_sv_outcomes": [_vp, _pi32],
+    "bt_sv_set_mask": [_vp, _pi32],
     "bt_sv_kraus": [_vp, _i, _i, _i, _vp, _i, _pd, _pi32],
     "bt_sv_kraus_probs": [_vp, _i, _i, _i, _vp, _i, _pd],
     "bt_sv_expect_pauli": [_vp, C.c_char_p, _pd],

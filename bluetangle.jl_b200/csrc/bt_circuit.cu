@@ -170,6 +170,7 @@ static int run_segment_gates(bt_sv* s, const std::vector<GateDesc>& L, const Seg
 extern "C" int bt_sv_apply_circuit(bt_sv* s, const bt_gate* g, uint64_t n, int fuse) {
   BT_TRY(bt_check_sv(s));
   if (n && !g) BT_FAIL(BT_ERR_ARG, "null gate list");
+  if (s->mask_on) fuse = 0;  // the fused tile kernel has no per-trajectory predicate: masked circuits run gate by gate
   std::vector<GateDesc> L;
   BT_TRY(build_logical(s->n_qubits, g, n, L));
   std::vector<Segment> plan;

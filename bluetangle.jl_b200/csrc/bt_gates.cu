@@ -218,7 +218,9 @@ static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const
   uint64_t per_block = 256ull * U;
   unsigned grid = (unsigned)((ngroups + per_block - 1) / per_block);
   bt_prof_begin(s, BT_CLS_DENSE);
-  if (dmats) {
+  if (dmats && cond) {
+    k_dense<K, U, true, true><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, cond, want);
+  } else if (dmats) {
     k_dense<K, U, true, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, nullptr, 0);
   } else if (cond) {
     k_dense<K, U, false, true><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, cond, want);
@@ -284,6 +286,11 @@ int bt_localize(const bt_sv* s, GateDesc* g) {
 
 int bt_launch_gate(bt_sv* s, const GateDesc& g_in, const int32_t* cond, int want) {
   GateDesc g = g_in;
+  if (s->mask_on) {  // trajectory mask (bt_sv_set_mask): the same per-trajectory predicate the ifOp branches use
+    if (cond) BT_FAIL(BT_ERR_UNSUPPORTED, "outcome-conditional gates cannot be combined with a trajectory mask: fold the outcome into the mask");
+    cond = s->d_mask;
+    want = 1;
+  }
   if (s->world > 1) {
     int r = bt_localize(s, &g);
     if (r < 0) return r;
@@ -316,10 +323,11 @@ int bt_launch_gate_devmat(bt_sv* s, int k, const int* tb, const double2* d_mats)
   GateDesc g;
   g.k = k; g.nc = 0; g.diag = false;
   for (int i = 0; i < k; ++i) g.tb[i] = tb[i];
+  const int32_t* cond = s->mask_on ? s->d_mask : nullptr;
   switch (k) {
-    case 1: return launch_dense<1, 4>(s, g, d_mats, nullptr, 0);
-    case 2: return launch_dense<2, 2>(s, g, d_mats, nullptr, 0);
-    case 3: return launch_dense<3, 1>(s, g, d_mats, nullptr, 0);
+    case 1: return launch_dense<1, 4>(s, g, d_mats, cond, 1);
+    case 2: return launch_dense<2, 2>(s, g, d_mats, cond, 1);
+    case 3: return launch_dense<3, 1>(s, g, d_mats, cond, 1);
   }
   BT_FAIL(BT_ERR_ARG, "unsupported arity for per-trajectory matrices");
 }

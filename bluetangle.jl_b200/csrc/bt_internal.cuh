@@ -66,6 +66,9 @@ struct bt_sv {
   int32_t* d_err;     // device error flag
   int32_t* h_flag;    // pinned
   size_t traj_cap;
+  // trajectory mask (bt_sv_set_mask): gates, Kraus steps and measurements act only on trajectories with d_mask[t] != 0
+  int32_t* d_mask;
+  bool mask_on;
   // grow-only device scratch (sampling prefix sums, uniforms, results)
   void* d_scratch; size_t scratch_cap;
   // timing / accounting

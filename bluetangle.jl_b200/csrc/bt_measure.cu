@@ -12,10 +12,16 @@ int bt_prepare_local_bits(bt_sv* s, int n, const int* logical_bits);
 // ---- measurement ----------------------------------------------------------------------------------------------
 // res: n_batch x 4 packed 2x2 RDMs ([0] = p0, [3] = p1).  outcome = (u < p0) ? 0 : 1  (src/hilbert.jl:693)
 __global__ void k_decide_measure(const double* __restrict__ res, const double* __restrict__ u, int32_t* __restrict__ outcome,
-                                 double* __restrict__ scale, int64_t n_batch) {
+                                 double* __restrict__ scale, int64_t n_batch, const int32_t* __restrict__ mask) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_batch) return;
   double p0 = res[4 * t], p1 = res[4 * t + 3];
+  if (mask && !mask[t]) {  // trajectory not in the active branch: untouched, outcome -1
+    outcome[t] = -1;
+    scale[2 * t] = 1.0;
+    scale[2 * t + 1] = p0;
+    return;
+  }
   int ind = (u[t] < p0) ? 0 : 1;
   outcome[t] = ind;
   scale[2 * t] = 1.0 / sqrt(ind == 0 ? p0 : p1);  // normalize(P_ind * state): divide by the actual norm
@@ -34,6 +40,7 @@ __global__ void __launch_bounds__(256) k_collapse(double2* __restrict__ a, int n
     uint64_t i1 = i0 | (1ull << bit);
     int ind = outcome[t];
     double sc = scale[2 * t];
+    if (ind < 0) continue;
     if (ind == 0) {
       double2 x = a[i0];
       a[i0] = make_double2(x.x * sc, x.y * sc);
@@ -64,7 +71,7 @@ extern "C" int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* ou
     s->allreduce(s->allreduce_ctx, s->h_res, (int)(s->n_batch * 4));
     BT_CUDA(cudaMemcpyAsync(s->d_res, s->h_res, s->n_batch * 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   }
-  k_decide_measure<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(s->d_res, s->d_u, s->d_outcome, s->d_scale, s->n_batch);
+  k_decide_measure<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(s->d_res, s->d_u, s->d_outcome, s->d_scale, s->n_batch, s->mask_on ? s->d_mask : nullptr);
   BT_CHECK_LAUNCH(s);
   uint64_t npairs = s->len >> 1;
   unsigned grid = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 148ull * 32);
@@ -119,7 +126,11 @@ template <int D>
 __global__ void __launch_bounds__(64) k_decide_kraus(const double* __restrict__ res, const double* __restrict__ u,
                                                       const double2* __restrict__ K, int nK, int swap,
                                                       int32_t* __restrict__ chosen, double2* __restrict__ mats,
-                                                      double* __restrict__ probs_out, int32_t* __restrict__ err) {
+                                                      double* __restrict__ probs_out, int32_t* __restrict__ err, const int32_t* __restrict__ mask) {
+  if (mask && u && !mask[blockIdx.x]) {  // trajectory not in the active branch: no draw, no operator (the apply kernel skips it too)
+    if (threadIdx.x == 0) chosen[blockIdx.x] = -1;
+    return;
+  }
   __shared__ double2 rho[D * D];
   __shared__ double2 rho_s[D * D];
   __shared__ double probs[64];
@@ -225,9 +236,10 @@ static int kraus_common(bt_sv* s, int nq, int qubit, int target, const bt_c64* K
   double* d_probs = nullptr;
   if (probs_host) BT_CUDA(cudaMallocAsync(&d_probs, (size_t)s->n_batch * nK * sizeof(double), s->stream));
   const double* du = u ? s->d_u : nullptr;
-  if (nq == 1) k_decide_kraus<2><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err);
-  else if (nq == 2) k_decide_kraus<4><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, swap, s->d_outcome, s->d_mats, d_probs, s->d_err);
-  else k_decide_kraus<8><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err);
+  const int32_t* dmask = s->mask_on ? s->d_mask : nullptr;
+  if (nq == 1) k_decide_kraus<2><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err, dmask);
+  else if (nq == 2) k_decide_kraus<4><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, swap, s->d_outcome, s->d_mats, d_probs, s->d_err, dmask);
+  else k_decide_kraus<8><<<(unsigned)s->n_batch, 64, 0, s->stream>>>(s->d_res, du, d_K, nK, 0, s->d_outcome, s->d_mats, d_probs, s->d_err, dmask);
   BT_CHECK_LAUNCH(s);
   BT_CUDA(cudaFreeAsync(d_K, s->stream));
   if (u) BT_TRY(bt_launch_gate_devmat(s, nq, tb_apply, s->d_mats));

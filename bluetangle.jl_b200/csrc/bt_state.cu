@@ -106,6 +106,7 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
     BT_CUDA(cudaGetDevice(&dev));
     if (bt_sv* r = pool_take(n_qubits, n_local, n_batch, dev)) {
       r->launches = 0;
+      r->mask_on = false;
       for (int b = 0; b < 64; ++b) r->phys_of_bit[b] = b;
       k_set_basis<<<grid_for(r->len, 256), 256, 0, r->stream>>>(r->amp, 1ull << n_local, r->len, 0, 1);
       BT_CHECK_LAUNCH(r);
@@ -190,6 +191,7 @@ static void really_destroy(bt_sv* s) {
   if (s->d_outcome) cudaFree(s->d_outcome);
   if (s->d_mats) cudaFree(s->d_mats);
   if (s->d_scale) cudaFree(s->d_scale);
+  if (s->d_mask) cudaFree(s->d_mask);
   cudaFree(s->d_err);
   cudaFreeHost(s->h_flag);
   cudaEventDestroy(s->ev0);
@@ -207,6 +209,7 @@ int bt_ensure_traj(bt_sv* s) {
   BT_CUDA(cudaMemsetAsync(s->d_outcome, 0, nb * sizeof(int32_t), s->stream));
   BT_CUDA(cudaMalloc(&s->d_mats, nb * 64 * sizeof(double2)));
   BT_CUDA(cudaMalloc(&s->d_scale, nb * 2 * sizeof(double)));
+  BT_CUDA(cudaMalloc(&s->d_mask, nb * sizeof(int32_t)));
   s->traj_cap = nb;
   return BT_OK;
 }
@@ -250,6 +253,19 @@ extern "C" int bt_sv_set_basis(bt_sv* s, uint64_t index) {
   int hit = (int)((index >> s->n_local) == (uint64_t)s->rank);
   k_set_basis<<<grid_for(s->len, 256), 256, 0, s->stream>>>(s->amp, 1ull << s->n_local, s->len, local, hit);
   BT_CHECK_LAUNCH(s);
+  return BT_OK;
+}
+
+// Trajectory mask: while set, bt_sv_apply_1q/2q/3q, bt_sv_apply_circuit (unfused then), bt_sv_kraus and bt_sv_measure_z touch
+// only the trajectories with mask[t] != 0 -- the branch of an ifOp (src/struct.jl:587-590) on a batch whose trajectories
+// measured different outcomes.  Masked-out trajectories report outcome / chosen = -1.  NULL clears the mask.
+extern "C" int bt_sv_set_mask(bt_sv* s, const int32_t* mask) {
+  BT_TRY(bt_check_sv(s));
+  if (!mask) { s->mask_on = false; return BT_OK; }
+  BT_TRY(bt_ensure_traj(s));
+  BT_CUDA(cudaMemcpyAsync(s->d_mask, mask, s->n_batch * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));  // the caller's buffer may be pageable and short-lived
+  s->mask_on = true;
   return BT_OK;
 }
 

@@ -110,6 +110,7 @@ class CuState:
         self.h = h
         self.N = int(N)
         self.n_batch = int(n_batch)
+        self.mask: Optional[np.ndarray] = None  # batched states: trajectories the next ops act on (ifOp branches), None = all
 
     def __del__(self):
         try:
@@ -118,6 +119,20 @@ class CuState:
                 self.h = None
         except Exception:
             pass
+
+    def set_mask(self, mask: Optional[np.ndarray]) -> None:
+        """bt_sv_set_mask: gates, Kraus steps and measurements then touch only the trajectories with mask[t] true; draws of a
+        BatchDraws source are consumed for those trajectories only."""
+        if mask is None:
+            L.check(self.lib.bt_sv_set_mask(self.h, None))
+            self.mask = None
+            return
+        m = np.ascontiguousarray(np.asarray(mask).astype(bool))
+        if m.shape != (self.n_batch,):
+            raise ValueError("mask must have one entry per trajectory")
+        mi = m.astype(np.int32)
+        L.check(self.lib.bt_sv_set_mask(self.h, mi.ctypes.data_as(C.POINTER(C.c_int32))))
+        self.mask = m
 
     # transfers -------------------------------------------------------------------------------------------
     @staticmethod
@@ -489,7 +504,7 @@ def _kraus_probs(state: CuState, q: int, qubit: int, target: int, kraus) -> np.n
 
 def _uniforms(state: CuState, rng) -> np.ndarray:
     if isinstance(rng, BatchDraws):
-        return rng.take()
+        return rng.take(state.mask)
     r = _rng(rng)
     return np.array([r.uniform() for _ in range(state.n_batch)], dtype=np.float64)
 
@@ -590,16 +605,23 @@ def _ifop_apply(state: CuState, op: ifOp, noise, rng):
         for o in op.if01[0] if ind == 0 else op.if01[1]:
             apply(state, o, noise=noise, rng=rng)
     else:
-        # batched trajectories: both branches are issued, each masked by the per-trajectory outcome on the device
-        for want in (0, 1):
-            for o in op.if01[want]:
-                if not isinstance(o, Op) or o.ismeasure:
-                    raise NotImplementedError("batched ifOp branches support plain gates")
-                if isinstance(noise, NoiseModel) and o.noisy:
-                    raise NotImplementedError("batched ifOp branches with a NoiseModel")
-                if np.array_equal(o.mat, np.eye(1 << o.q)):
+        # batched trajectories: each branch runs under a trajectory mask (outcome == want, within the mask already active), so the
+        # branch ops are the general apply(state, ifop; noise=noise) of src/struct.jl:587-590 -- gates, the branch's own noise draws
+        # and nested measurements -- and a trajectory consumes draws only for the branch it took
+        outer = state.mask
+        ind = np.asarray(ind)
+        try:
+            for want in (0, 1):
+                branch = [o for o in op.if01[want] if not (isinstance(o, Op) and not o.ismeasure and not (isinstance(noise, NoiseModel) and o.noisy)
+                                                           and np.array_equal(o.mat, np.eye(1 << o.q)))]
+                sub = ind == want  # masked-out trajectories carry outcome -1
+                if not branch or not sub.any():
                     continue
-                _apply_matrix(state, o.q, o.mat, o.qubit, o.target_qubit, o.control, want=want)
+                state.set_mask(sub)
+                for o in branch:
+                    apply(state, o, noise=noise, rng=rng)
+        finally:
+            state.set_mask(outer)
     return state, ind
 
 

@@ -114,6 +114,11 @@ int bt_sv_probs(const bt_sv* s, double* host /* n_batch * 2^n : abs2.(state) src
  * outcome/p0 may be NULL (no host synchronisation then; outcomes stay in the device outcome buffer). */
 int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* outcome, double* p0, int reset);
 int bt_sv_outcomes(const bt_sv* s, int32_t* outcome /* n_batch: results of the last measure/kraus call */);
+/* Trajectory mask for batched states: while set, bt_sv_apply_1q/2q/3q, bt_sv_apply_circuit (gate by gate then), bt_sv_kraus and
+ * bt_sv_measure_z act only on trajectories with mask[t] != 0; the others are untouched, consume no draw and report outcome /
+ * chosen = -1.  This is how the branch op lists of an ifOp (src/struct.jl:587-590: apply(state, ifop; noise)) run on a batch whose
+ * trajectories measured different outcomes, incl. the branch's own noise draws and nested measurements.  mask = NULL clears it. */
+int bt_sv_set_mask(bt_sv* s, const int32_t* mask /* n_batch */);
 
 /* ---- Kraus trajectory step: __QuantumChannel_new_apply src/struct.jl:31-55, __calc_prob :9-29,
  * _weighted_sample src/hilbert.jl:810-819 (k = first i with u <= cumsum(p)[i]).

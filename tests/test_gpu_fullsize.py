@@ -117,10 +117,11 @@ def test_c4_20q_monitored_trajectories_batched(bt, orc):
     assert 0.2 < out.mean() < 0.8
     oops = wl.to_ops(orc, specs)
     ez = bt.expect(st, "Z")
-    for t in (0, 1, 255, 511):
+    S.use_all_cores()
+    for t in list(range(64)) + [255, 511]:  # every outcome vector of 66 trajectories against the sequential per-shot loop (src/ops.jl:671-676)
         sv, mo = S.SV(N).apply_ops(oops, draws=orc.ListDraws(U[t]), track_measurements=True)
-        assert list(out[t]) == mo                       # identical outcomes under shared uniform draws
-        assert np.max(np.abs(ez[t] - sv.expect_z_all())) < 1e-10
+        assert list(out[t]) == mo, t                    # identical outcomes under shared uniform draws
+        assert np.max(np.abs(ez[t] - sv.expect_z_all())) < 1e-10, t
 
 
 def test_specialised_passes_default_tiles_24q_vs_strided_oracle(bt, orc):
@@ -173,3 +174,30 @@ def test_specialised_passes_default_tiles_24q_vs_strided_oracle(bt, orc):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_c2_28q_amplitudes_vs_strided_oracle(bt, orc):
+    """configs[1] at its full size, amplitude by amplitude: the whole QFT(28) plus the first random layers (600 gates of C2's
+    4 556, non-adjacent CP pairs included) through the fused path as bench.py runs it, against the strided CPU oracle on all
+    host cores -- all 2^28 amplitudes within 1e-10 absolute (north star).  BT_FULLSIZE_GATES widens the prefix (4556 = whole circuit)."""
+    from oracle import strided as S
+
+    wl = mods()
+    L = bt._lib
+    N = 28
+    ngates = int(os.environ.get("BT_FULLSIZE_GATES", "600"))
+    specs = wl.c2_qft_layered(N, 100, 28)[:ngates]
+    arr = bt.pack_gates(wl.to_ops(bt, specs))
+    s = bt.zero_state(N)
+    L.check(s.lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1))
+    got = s.to_numpy()
+    del s
+    S.use_all_cores()
+    ref = S.SV(N)
+    ref.apply_ops(wl.to_ops(orc, specs))
+    worst = 0.0
+    step = 1 << 24
+    for i in range(0, 1 << N, step):
+        worst = max(worst, float(np.max(np.abs(got[i:i + step] - ref.v[i:i + step]))))
+    assert worst < 1e-10, worst
+    assert abs(float(np.vdot(got[:step], got[:step]).real) - float(np.vdot(ref.v[:step], ref.v[:step]).real)) < 1e-12

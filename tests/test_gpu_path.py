@@ -494,3 +494,40 @@ def test_opf_function_and_op_list_forms(bt, orc):
     ref2, mids_o = orc.apply_ops(v, ops_o, draws=orc.Draws(3), track_measurements=True)
     assert mids_d == mids_o
     assert np.max(np.abs(s2.to_numpy() - ref2)) < TOL
+
+
+def test_batched_ifop_branches_with_noise_and_nested_measurements(bt, orc):
+    """ifOp on a batch whose trajectories measure different outcomes (src/struct.jl:578-594): the branch op lists run under a
+    trajectory mask -- plain gates, a NoiseModel's Kraus draw after every noisy branch gate (apply(state, ifop; noise=noise), :587-590)
+    and a measurement Op inside a branch.  Every trajectory must equal the oracle's sequential per-shot loop fed that trajectory's
+    own uniform stream: a trajectory consumes draws only for the branch it took."""
+    N, T = 5, 24
+    noise_d, noise_o = bt.NoiseModel("amplitude_damping", 0.15), orc.NoiseModel.model("amplitude_damping", 0.15)
+
+    def build(m):
+        if0 = [m.Op("H", 3), m.Op("CX", 3, 4), m.Op("MX", 4)]
+        if1 = [m.Op("X", 2), m.Op("RY(0.7)", 5), m.Op("MZ", 1), m.Op("CZ", 1, 5)]
+        ops = [m.Op("H", q) for q in range(1, N + 1)] + [m.Op("CX", 1, 2), m.Op("RX(0.4)", 2), m.Op("FSIM(0.3,0.2)", 2, 3)]
+        ops.append(m.ifOp("MZ", 2, if0, if1))
+        ops += [m.Op("RY(1.1)", 4), m.Op("CX", 4, 5)]
+        ops.append(m.ifOp("MY", 4, [m.Op("I", 4)], [m.Op("Z", 1), m.Op("H", 2)]))
+        ops += [m.Op("MZ", 3), m.Op("T", 1)]
+        return ops
+
+    od, oo = build(bt), build(orc)
+    U = np.random.default_rng(17).random((T, 64))  # more draws than any trajectory needs
+    for noise_pair in ((False, False), (noise_d, noise_o)):
+        st = bt.zero_state(N, T)
+        _, mids = bt.apply(od, st, noise=noise_pair[0], rng=bt.BatchDraws(U), track_measurements=True)
+        out = np.stack([np.asarray(m) for m in mids], axis=1)
+        got = st.to_numpy()
+        used = set()
+        for t in range(T):
+            dr = orc.ListDraws(U[t])
+            so, mid_o = orc.apply_ops(orc.zero_state(N), oo, noise=noise_pair[1], draws=dr, track_measurements=True)
+            assert list(out[t]) == mid_o, (t, out[t], mid_o)
+            assert np.max(np.abs(got[t] - so)) < TOL, t
+            used.add(len(dr.log))
+        assert out.shape == (T, 3) and set(np.unique(out[:, 0])) == {0, 1}   # both branches were taken inside the batch
+        if noise_pair[0] is not False:
+            assert len(used) > 1  # the branches draw different numbers of uniforms: per-trajectory accounting matters
