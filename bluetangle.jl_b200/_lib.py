@@ -56,6 +56,7 @@ PROTOTYPES = {
     "bt_jit_stats": [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _pd],
     "bt_jit_selftest": [C.c_char_p, _u64],
     "bt_jit_wait": [C.POINTER(_u64)],
+    "bt_jit_selftest_workers": [_i],
     "bt_jit_cache_info": [C.POINTER(_u64), C.c_char_p, _u64],
     "bt_sv_create": [_i, _i64, C.POINTER(_vp)],
     "bt_sv_destroy": [_vp],

@@ -167,12 +167,15 @@ extern "C" int bt_sv_ipc_export(bt_sv* s, void* handles) {
   if (!s->alt) BT_FAIL(BT_ERR_ARG, "not a shard handle");
   static_assert(sizeof(cudaIpcMemHandle_t) <= BT_IPC_HANDLE_BYTES, "IPC handle size");
   if (s->amp != s->buf0) BT_FAIL(BT_ERR_ARG, "export the IPC handles before the first remap");
-  cudaIpcMemHandle_t h0, h1;
+  if (!s->flags) BT_FAIL(BT_ERR_ARG, "not a shard handle (no flag page)");
+  cudaIpcMemHandle_t h0, h1, h2;
   BT_CUDA(cudaIpcGetMemHandle(&h0, s->amp));
   BT_CUDA(cudaIpcGetMemHandle(&h1, s->alt));
-  memset(handles, 0, 2 * BT_IPC_HANDLE_BYTES);
+  BT_CUDA(cudaIpcGetMemHandle(&h2, s->flags));
+  memset(handles, 0, BT_IPC_HANDLES_PER_SHARD * BT_IPC_HANDLE_BYTES);
   memcpy(handles, &h0, sizeof(h0));
   memcpy((char*)handles + BT_IPC_HANDLE_BYTES, &h1, sizeof(h1));
+  memcpy((char*)handles + 2 * BT_IPC_HANDLE_BYTES, &h2, sizeof(h2));
   return BT_OK;
 }
 
@@ -181,16 +184,18 @@ extern "C" int bt_sv_ipc_attach(bt_sv* s, const void* all_handles) {
   if (!all_handles) BT_FAIL(BT_ERR_ARG, "null handles");
   for (int r = 0; r < s->world; ++r) {
     if (r == s->rank) continue;
-    cudaIpcMemHandle_t h0, h1;
-    memcpy(&h0, (const char*)all_handles + (size_t)r * 2 * BT_IPC_HANDLE_BYTES, sizeof(h0));
-    memcpy(&h1, (const char*)all_handles + (size_t)r * 2 * BT_IPC_HANDLE_BYTES + BT_IPC_HANDLE_BYTES, sizeof(h1));
-    void *p0 = nullptr, *p1 = nullptr;
+    cudaIpcMemHandle_t h0, h1, h2;
+    const char* base = (const char*)all_handles + (size_t)r * BT_IPC_HANDLES_PER_SHARD * BT_IPC_HANDLE_BYTES;
+    memcpy(&h0, base, sizeof(h0));
+    memcpy(&h1, base + BT_IPC_HANDLE_BYTES, sizeof(h1));
+    memcpy(&h2, base + 2 * BT_IPC_HANDLE_BYTES, sizeof(h2));
+    void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
     BT_CUDA(cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess));
     BT_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
+    BT_CUDA(cudaIpcOpenMemHandle(&p2, h2, cudaIpcMemLazyEnablePeerAccess));
     s->peer_amp[r] = (double2*)p0;
     s->peer_alt[r] = (double2*)p1;
-    // the peer's flag page sits behind the amplitudes of its first buffer (same shard size on every rank)
-    s->peer_flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p0) + s->len * sizeof(double2));
+    s->peer_flags[r] = (uint32_t*)p2;
   }
   s->ipc_opened = true;
   s->peers_attached = true;
@@ -319,7 +324,7 @@ static int remap_build(int n, int n_local, int rank, int world, const int* cur_p
   if (world > 1 && env_int("BT_REMAP_ORDER", 1) != 0) {
     for (int d = REMAP_KEEP; d < n_local && P->sel_n < 4; ++d)
       if (sigma[d] >= n_local) P->sel_pos[P->sel_n++] = d;
-    int lo = env_int("BT_REMAP_SEL_LO", 8);
+    int lo = env_int("BT_REMAP_SEL_LO", 16);
     lo = std::max(lo, REMAP_KEEP);
     lo = std::min(lo, n_local - P->sel_n);
     P->sel_lo = lo;

@@ -89,9 +89,9 @@ struct bt_sv {
   bt_barrier_fn barrier; void* barrier_ctx;
   bt_allreduce_fn allreduce; void* allreduce_ctx;
   uint64_t n_remaps, remap_bytes; float remap_ms;
-  // device-side remap synchronisation (multi-process shards): a 4 KB flag page behind the first buffer of every shard, mapped
-  // by the peers together with the buffer; peer r writes its epoch into slot r (ready: [0..15], done: [16..31])
-  double2* buf0;             // the allocation that carries the flag page (amp and alt swap roles, buf0 does not)
+  // device-side remap synchronisation (multi-process shards): a 4 KB flag page per shard (its own allocation and IPC handle),
+  // mapped by the peers; peer r writes its epoch into slot r (ready: [0..15], done: [16..31])
+  double2* buf0;             // the first buffer as allocated (amp and alt swap roles at every remap, buf0 does not)
   uint32_t* flags;           // own flag page, or nullptr
   uint32_t* peer_flags[16];  // every rank's flag page as seen from this device
   uint32_t remap_epoch;

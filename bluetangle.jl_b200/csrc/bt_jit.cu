@@ -486,12 +486,16 @@ struct Entry {
   std::vector<char> cubin;  // state 3 only
 };
 
-std::mutex g_mu;
-std::condition_variable g_cv_jobs, g_cv_idle;
-std::unordered_map<std::string, Entry> g_cache;  // node-based: Entry addresses are stable, the workers keep pointers
+// Never destroyed (references to leaked heap objects): the detached compile workers wait on the condition variable for the life of
+// the process, and destroying a condition variable that has waiters blocks in pthread_cond_destroy -- a static object here would hang
+// every process at exit once the workers exist.
+std::mutex& g_mu = *new std::mutex();
+std::condition_variable& g_cv_jobs = *new std::condition_variable();
+std::condition_variable& g_cv_idle = *new std::condition_variable();
+std::unordered_map<std::string, Entry>& g_cache = *new std::unordered_map<std::string, Entry>();  // node-based: Entry addresses are stable, the workers keep pointers
 uint64_t g_compiled = 0, g_launches = 0, g_failed = 0;
 double g_compile_seconds = 0.0;
-std::string g_last_log;
+std::string& g_last_log = *new std::string();
 
 // ---- optional on-disk cubin cache (BT_JIT_CACHE_DIR; off when unset) -----------------------------------------------------
 // A pass structure costs ~0.2 s of NVRTC time; a process that runs the same circuits as an earlier one (the next job of a
@@ -518,8 +522,8 @@ std::string cache_dir() {
   else if (const char* x = getenv("XDG_CACHE_HOME"); x && *x) d = std::string(x) + "/bluetangle_cuda";
   else if (const char* h = getenv("HOME"); h && *h) d = std::string(h) + "/.cache/bluetangle_cuda";
   if (d.empty()) return d;
-  static std::mutex mu;
-  static std::string made;
+  static std::mutex& mu = *new std::mutex();        // leaked on purpose: the compile workers may still be running at exit
+  static std::string& made = *new std::string();
   std::lock_guard<std::mutex> lk(mu);
   if (made != d) { mkdir_p(d); made = d; }
   return d;
@@ -733,9 +737,8 @@ extern "C" int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* fa
   return BT_OK;
 }
 
-// Host-only self test (no device needed): specialise a synthetic pass that uses every micro-op site kind and compile it with
-// NVRTC.  Returns 0 on success; `source` (optional) receives the generated text.
-extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
+// synthetic pass that uses every micro-op site kind, as CUDA text (host only)
+static bool selftest_source(std::string& src) {
   TileParams* Pp = new TileParams();
   TileParams& P = *Pp;
   memset(&P, 0, sizeof(P));
@@ -755,10 +758,17 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
   { double m; uint64_t em = 0, lm = 1ull << 8; emit(PROG_SITE_CPH1(2), 2); memcpy(&m, &em, 8); G.coef[kc++] = m; memcpy(&m, &lm, 8); G.coef[kc++] = m; }
   { double m; uint64_t em = 1ull << 22, lm = 0; emit(PROG_SITE_CCX1(1), 0); memcpy(&m, &em, 8); G.coef[kc++] = m; memcpy(&m, &lm, 8); G.coef[kc++] = m; }
   G.nops = (uint32_t)ko;
-  std::string src;
   Plan pl;
-  int rc = 0;
-  if (!make_plan(P, 1, pl) || !generate(P, pl, src)) rc = -1;
+  const bool ok = make_plan(P, 1, pl) && generate(P, pl, src);
+  delete Pp;
+  return ok;
+}
+
+// Host-only self test (no device needed): specialise a synthetic pass that uses every micro-op site kind and compile it with
+// NVRTC.  Returns 0 on success; `source` (optional) receives the generated text.
+extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
+  std::string src;
+  int rc = selftest_source(src) ? 0 : -1;
   if (rc == 0 && source && cap) { strncpy(source, src.c_str(), cap - 1); source[cap - 1] = 0; }
   if (rc == 0) {
     if (!nvrtc().ok) rc = -2;
@@ -779,6 +789,35 @@ extern "C" int bt_jit_selftest(char* source, uint64_t cap) {
       }
     }
   }
-  delete Pp;
   return rc;
+}
+
+// Host-only check of the compile workers: `jobs` variants of the synthetic pass go through the worker pool (disk cache or NVRTC),
+// bt_jit_wait() must see them all finish.  0 = ok, -2 = no libnvrtc.  tests/test_build_tools.py also checks that a process that has
+// started the workers still EXITS (the workers are detached and wait on a condition variable for the life of the process).
+extern "C" int bt_jit_selftest_workers(int jobs) {
+  std::string src;
+  if (!selftest_source(src)) return -1;
+  if (!nvrtc().ok) return -2;
+  std::vector<Entry*> es;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < jobs; ++i) {
+      char key[64];
+      snprintf(key, sizeof(key), "selftest-worker#%d#%p", i, (void*)&es);
+      Entry& e = g_cache[key];
+      es.push_back(&e);
+      char tag[64];
+      snprintf(tag, sizeof(tag), "\n// selftest variant %d\n", i);
+      enqueue_compile(src + tag, &e);
+    }
+  }
+  bt_jit_wait(nullptr);
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Entry* e : es) {
+    if (e->state != 3 || e->cubin.size() < 1000) { bt_set_error("%s", g_last_log.substr(0, 900).c_str()); return -4; }
+    std::vector<char>().swap(e->cubin);
+    e->state = -1;
+  }
+  return 0;
 }

@@ -123,8 +123,10 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
   s->len = (uint64_t)n_batch << n_local;
   s->rank = 0; s->world = 1; s->g = 0;
   for (int b = 0; b < 64; ++b) s->phys_of_bit[b] = b;
-  // shards: the first buffer carries a 4 KB flag page behind the amplitudes (bt_dist.cu: device-side remap synchronisation)
-  cudaError_t ea = cudaMalloc(&s->amp, s->len * sizeof(double2) + (want_alt ? BT_FLAG_PAGE_BYTES : 0));
+  // Both shard buffers are allocated with exactly the same power-of-two size.  (Round 1 put the 4 KB flag page of the device-side
+  // remap synchronisation behind the amplitudes of the first buffer; a 32 GiB + 4 KB allocation is mapped differently from a
+  // 32 GiB one, and every remap that read the odd-sized buffer ran 4-12x slower at 4 and 8 GPUs -- profiles/r2_remap_diag_n4.txt.)
+  cudaError_t ea = cudaMalloc(&s->amp, s->len * sizeof(double2));
   if (ea != cudaSuccess) { delete s; cudaGetLastError(); BT_FAIL(BT_ERR_ALLOC, "cudaMalloc of %llu bytes failed: %s", (unsigned long long)(s->len * sizeof(double2)), cudaGetErrorString(ea)); }
   if (want_alt) {
     ea = cudaMalloc(&s->alt, s->len * sizeof(double2));
@@ -132,8 +134,9 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
   }
   BT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   s->buf0 = s->amp;
-  if (want_alt) {
-    s->flags = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->amp) + s->len * sizeof(double2));
+  if (want_alt) {  // flag page of the device-side remap synchronisation (bt_dist.cu): its own small allocation, exported by its own IPC handle
+    // a whole 2 MiB granule: the IPC handle then names an allocation of its own, not a slice of a page shared with other small buffers
+    BT_CUDA(cudaMalloc(&s->flags, (size_t)2 << 20));
     BT_CUDA(cudaMemset(s->flags, 0, BT_FLAG_PAGE_BYTES));
   }
   BT_CUDA(cudaEventCreate(&s->ev0));
@@ -176,8 +179,10 @@ static void really_destroy(bt_sv* s) {
       if (r == s->rank) continue;
       if (s->peer_amp[r]) cudaIpcCloseMemHandle(s->peer_amp[r]);
       if (s->peer_alt[r]) cudaIpcCloseMemHandle(s->peer_alt[r]);
+      if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
     }
   }
+  if (s->flags) cudaFree(s->flags);
   if (s->remap_ev) { for (cudaEvent_t e : *s->remap_ev) cudaEventDestroy(e); delete s->remap_ev; }
   delete s->remap_log;
   if (s->d_remap_tab) cudaFree(s->d_remap_tab);

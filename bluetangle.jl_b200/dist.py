@@ -2,7 +2,7 @@
 
 The data path never goes through torch or NCCL: every rank maps its peers' shard buffers with CUDA IPC
 (bt_sv_ipc_export / bt_sv_ipc_attach) and the library's remap kernel pulls amplitudes straight over NVLink.
-torch.distributed supplies (i) the all-gather of the 128-byte IPC handles, (ii) the barrier that brackets a remap,
+torch.distributed supplies (i) the all-gather of the three 64-byte IPC handles, (ii) the barrier that brackets a remap,
 (iii) the all-reduce of a handful of doubles for reductions -- exactly the three callbacks of include/bluetangle_cuda.h.
 A Julia deployment would use MPI.jl for the same three calls.
 """
@@ -47,7 +47,7 @@ class ShardedState:
         L.check(self.lib.bt_sv_set_barrier(self.h, self._cb_barrier, None))
         L.check(self.lib.bt_sv_set_allreduce(self.h, self._cb_allreduce, None))
         if self.world > 1:
-            mine = np.zeros(2 * 64, dtype=np.uint8)
+            mine = np.zeros(3 * 64, dtype=np.uint8)  # BT_IPC_HANDLES_PER_SHARD x BT_IPC_HANDLE_BYTES: both buffers + the flag page
             L.check(self.lib.bt_sv_ipc_export(self.h, L.ptr(mine)))
             t = torch.from_numpy(mine).to(self.device)
             out = [torch.empty_like(t) for _ in range(self.world)]

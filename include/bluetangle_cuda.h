@@ -95,6 +95,7 @@ int bt_jit_selftest(char* source, uint64_t cap);
  * (*pending_before, optional: structures still compiling at the call).  bt_jit_cache_info: modules that came from the on-disk
  * cubin cache instead of NVRTC, and the cache directory in use (BT_JIT_CACHE_DIR; default ~/.cache/bluetangle_cuda; "" = off). */
 int bt_jit_wait(uint64_t* pending_before);
+int bt_jit_selftest_workers(int jobs); /* host-only: `jobs` synthetic passes through the compile workers; 0 = ok, -2 = no libnvrtc */
 int bt_jit_cache_info(uint64_t* disk_hits, char* dir, uint64_t cap);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
@@ -184,10 +185,11 @@ int bt_dm_sample(const bt_dm* d, const double* u, uint64_t shots, int64_t* out);
  * are diagonal or controls need no communication; others trigger a qubit-remap exchange in which every rank
  * pulls its new shard from its peers' memory over NVLink in one kernel (bit permutation fused in). */
 #define BT_IPC_HANDLE_BYTES 64
+#define BT_IPC_HANDLES_PER_SHARD 3 /* both amplitude buffers + the flag page of the device-side remap synchronisation */
 typedef void (*bt_barrier_fn)(void* ctx);
 int bt_sv_create_shard(int n_qubits_total, int rank, int world, bt_sv** out);
-int bt_sv_ipc_export(bt_sv* s, void* handles /* 2*BT_IPC_HANDLE_BYTES: both buffers */);
-int bt_sv_ipc_attach(bt_sv* s, const void* all_handles /* world x 2*BT_IPC_HANDLE_BYTES, rank order */);
+int bt_sv_ipc_export(bt_sv* s, void* handles /* BT_IPC_HANDLES_PER_SHARD * BT_IPC_HANDLE_BYTES */);
+int bt_sv_ipc_attach(bt_sv* s, const void* all_handles /* world x BT_IPC_HANDLES_PER_SHARD * BT_IPC_HANDLE_BYTES, rank order */);
 int bt_sv_attach_local_peers(bt_sv** shards, int world); /* single-process variant: all shards in this process */
 int bt_sv_set_barrier(bt_sv* s, bt_barrier_fn fn, void* ctx);
 int bt_sv_remap(bt_sv* s, const int* new_phys_of_logical_bit /* n_qubits_total entries */);

@@ -149,3 +149,21 @@ def test_pass_specialiser_disk_cache_round_trip(tmp_path, monkeypatch):
     # an unwritable directory: the self test reports that nothing came back (-5); the product path just compiles as usual
     monkeypatch.setenv("BT_JIT_CACHE_DIR", "/proc/nonexistent-dir")
     assert lib.bt_jit_selftest(None, 0) == -5
+
+
+def test_compile_workers_finish_their_jobs_and_the_process_still_exits(tmp_path):
+    """The pass specialiser's worker threads (csrc/bt_jit.cu) are detached and wait on a condition variable for the life of the
+    process.  A process that has used them must exit normally: a static std::condition_variable with waiters blocks forever in its
+    destructor at exit (seen on a 4-GPU box: every rank hung after its last line of output)."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import __graft_entry__ as ge\n"
+            "lib = ge.load_package()._lib.load()\n"
+            "rc = lib.bt_jit_selftest_workers(6)\n"
+            "print('workers rc', rc, flush=True)\n"
+            "sys.exit(0 if rc in (0, -2) else 1)\n") % ROOT
+    env = dict(os.environ, BT_JIT_CACHE_DIR=str(tmp_path), BT_JIT_THREADS="3")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    if "workers rc 0" in r.stdout:
+        assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == 6

@@ -74,16 +74,15 @@ def main():
     lay_b = (C.c_int * N)(*ident)
     variants = [
         ("linear walk, device flags", {"BT_REMAP_ORDER": 0}),
-        ("linear walk, host barriers", {"BT_REMAP_ORDER": 0, "BT_REMAP_DEVICE_SYNC": 0}),
-        ("interleaved sel_lo=8 rot, device flags", {"BT_REMAP_ORDER": 1}),
-        ("interleaved sel_lo=8 rot, host barriers", {"BT_REMAP_ORDER": 1, "BT_REMAP_DEVICE_SYNC": 0}),
-        ("interleaved sel_lo=5 rot", {"BT_REMAP_ORDER": 1, "BT_REMAP_SEL_LO": 5}),
-        ("interleaved sel_lo=8 no rot", {"BT_REMAP_ORDER": 1, "BT_REMAP_ROT": 0}),
-        ("interleaved sel_lo=12 rot", {"BT_REMAP_ORDER": 1, "BT_REMAP_SEL_LO": 12}),
-        ("interleaved sel_lo=16 rot", {"BT_REMAP_ORDER": 1, "BT_REMAP_SEL_LO": 16}),
-        ("interleaved sel_lo=8 rot, 4 CTAs/SM", {"BT_REMAP_ORDER": 1, "BT_REMAP_CTAS_PER_SM": 4}),
-        ("interleaved sel_lo=8 rot, 16 CTAs/SM", {"BT_REMAP_ORDER": 1, "BT_REMAP_CTAS_PER_SM": 16}),
+        ("interleaved sel_lo=8 rot, device flags", {"BT_REMAP_ORDER": 1, "BT_REMAP_SEL_LO": 8}),
+        ("interleaved sel_lo=16 rot (default)", {}),
+        ("interleaved sel_lo=16 rot, host barriers", {"BT_REMAP_DEVICE_SYNC": 0}),
+        ("interleaved sel_lo=16 no rot", {"BT_REMAP_ROT": 0}),
+        ("interleaved sel_lo=20 rot", {"BT_REMAP_SEL_LO": 20}),
+        ("interleaved sel_lo=16 rot, 4 CTAs/SM", {"BT_REMAP_CTAS_PER_SM": 4}),
     ]
+    if os.environ.get("DIAG_QUICK", "") not in ("", "0"):
+        variants = variants[:3]
     remote_gb = shard_gb * (1.0 - 2.0 ** -g)
     for name, kv in variants:
         set_knobs(kv)
@@ -91,13 +90,13 @@ def main():
         torch.cuda.synchronize()
         remap_log(st)
         t0 = time.perf_counter()
-        for k in range(6):
+        for k in range(4):
             L.check(lib.bt_sv_remap(st.h, lay_a if k % 2 == 0 else lay_b))
         st.sync()
         dt = time.perf_counter() - t0
         lg = remap_log(st)
         pulls = [p for (_, p, _) in lg]
-        say(f"[pull] {name:45s} wall {dt * 1e3 / 6:7.1f} ms/remap  pull ms {pulls}  -> {remote_gb / (np.median(pulls) / 1e3):6.0f} GB/s remote per rank (median)  (wait,pull,done) {lg}")
+        say(f"[pull] {name:45s} wall {dt * 1e3 / 4:7.1f} ms/remap  pull ms {pulls}  -> {remote_gb / (np.median(pulls) / 1e3):6.0f} GB/s remote per rank (median)  (wait,pull,done) {lg}")
 
     # ---- 2. the C5 step ------------------------------------------------------------------------------------------------
     specs = wl.c5_random(N, 20, 31)
@@ -122,14 +121,13 @@ def main():
     say(f"[step] warm-up: first step (interpreter, compile in the background) {t1 - t0:.2f} s, waiting for the compile workers {t2 - t1:.2f} s, 2 more steps {time.perf_counter() - t2:.2f} s")
     step_variants = [
         ("linear walk, device flags, profile on", {"BT_REMAP_ORDER": 0}, True, False),
-        ("linear walk, device flags, profile off", {"BT_REMAP_ORDER": 0}, False, False),
-        ("linear walk, device flags, barrier before every step", {"BT_REMAP_ORDER": 0}, False, True),
-        ("linear walk, host barriers", {"BT_REMAP_ORDER": 0, "BT_REMAP_DEVICE_SYNC": 0}, False, False),
-        ("interleaved, device flags, profile on", {"BT_REMAP_ORDER": 1}, True, False),
-        ("interleaved, device flags, profile off", {"BT_REMAP_ORDER": 1}, False, False),
-        ("interleaved, device flags, barrier before every step", {"BT_REMAP_ORDER": 1}, False, True),
-        ("interleaved, host barriers", {"BT_REMAP_ORDER": 1, "BT_REMAP_DEVICE_SYNC": 0}, False, False),
+        ("interleaved sel_lo=8, device flags, profile on", {"BT_REMAP_SEL_LO": 8}, True, False),
+        ("interleaved sel_lo=16 (default), device flags, profile on", {}, True, False),
+        ("interleaved sel_lo=16 (default), device flags, profile off", {}, False, False),
+        ("interleaved sel_lo=16, host barriers", {"BT_REMAP_DEVICE_SYNC": 0}, False, False),
     ]
+    if os.environ.get("DIAG_QUICK", "") not in ("", "0"):
+        step_variants = step_variants[:3]
     for name, kv, prof, barrier in step_variants:
         set_knobs(kv)
         dist.barrier()
