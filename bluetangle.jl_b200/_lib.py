@@ -83,6 +83,9 @@ PROTOTYPES = {
     "bt_sv_rdm2": [_vp, _i, _i, _vp],
     "bt_sv_rdm3": [_vp, _i, _vp],
     "bt_sv_rdm": [_vp, _i, C.POINTER(_i), _vp],
+    "bt_sv_schmidt_spectrum": [_vp, _i, _pd, C.POINTER(_i)],
+    "bt_jacobi_pairs_host": [_i, _i, C.POINTER(_i)],
+    "bt_sv_expect_op": [_vp, _i, _i, _i, _i, _vp, _pd],
     "bt_sv_norm2": [_vp, _pd],
     "bt_sv_inner": [_vp, _vp, _vp],
     "bt_sv_normalize": [_vp],
@@ -121,6 +124,9 @@ PROTOTYPES = {
     "bt_dm_expect_1q_all": [_vp, _vp, _pd],
     "bt_dm_expect_product": [_vp, _i, C.POINTER(_i), _vp, _pd],
     "bt_dm_sample": [_vp, _pd, _u64, _pi64],
+    "bt_dm_rdm": [_vp, _i, C.POINTER(_i), _vp],
+    "bt_dm_expect_op": [_vp, _i, _i, _i, _i, _vp, _pd],
+    "bt_dm_bipartition_spectrum": [_vp, _i, _pd, C.POINTER(_i)],
     "bt_sv_create_shard": [_i, _i, _i, C.POINTER(_vp)],
     "bt_sv_ipc_export": [_vp, _vp],
     "bt_sv_ipc_attach": [_vp, _vp],

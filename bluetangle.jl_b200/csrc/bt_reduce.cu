@@ -367,6 +367,7 @@ static int allreduce_host(const bt_sv* s, double* buf, int n) {
 }
 
 int bt_prepare_local_bits(bt_sv* s, int n, const int* logical_bits);  // bt_dist.cu
+int bt_reduce_rdm_gram(bt_sv* s, int k, const int* tb, bt_c64* out_host);  // bt_linalg.cu
 
 extern "C" int bt_sv_rdm1(const bt_sv* s, int qubit, bt_c64* out) {
   BT_TRY(bt_check_sv(s));
@@ -418,7 +419,19 @@ extern "C" int bt_sv_rdm3(const bt_sv* s, int first, bt_c64* out) {
 extern "C" int bt_sv_rdm(const bt_sv* s, int k, const int* qubits, bt_c64* out) {
   BT_TRY(bt_check_sv(s));
   if (!qubits || !out) BT_FAIL(BT_ERR_ARG, "null argument");
-  if (k < 1 || k > 3) BT_FAIL(BT_ERR_UNSUPPORTED, "device partial_trace keeps 1, 2 or 3 qubits");
+  if (k < 1 || k > 12 || k > s->n_qubits) BT_FAIL(BT_ERR_UNSUPPORTED, "device partial_trace keeps 1..12 qubits (asked for %d)", k);
+  if (k > 3) {  // tiled Gram kernel over the gathered 2^k x 2^(N-k) matrix (bt_linalg.cu)
+    if (s->world > 1) BT_FAIL(BT_ERR_UNSUPPORTED, "partial_trace keeping more than 3 qubits of a sharded state");
+    int qs[12], tbs[12];
+    for (int i = 0; i < k; ++i) {
+      qs[i] = qubits[i];
+      if (qs[i] < 1 || qs[i] > s->n_qubits) BT_FAIL(BT_ERR_ARG, "qubit %d out of range", qs[i]);
+    }
+    std::sort(qs, qs + k);
+    for (int i = 0; i + 1 < k; ++i) if (qs[i] == qs[i + 1]) BT_FAIL(BT_ERR_ARG, "repeated qubit %d", qs[i]);
+    for (int t = 0; t < k; ++t) tbs[t] = s->phys_of_bit[s->n_qubits - qs[k - 1 - t]];
+    return bt_reduce_rdm_gram(const_cast<bt_sv*>(s), k, tbs, out);
+  }
   int q[3];
   for (int i = 0; i < k; ++i) {
     q[i] = qubits[i];

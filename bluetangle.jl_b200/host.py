@@ -772,14 +772,27 @@ def partial_trace(state: CuState, *keep) -> np.ndarray:
         out = np.empty((state.n_batch, 4, 4), dtype=c128)
         L.check(lib.bt_sv_rdm2(state.h, qs[0], qs[1], L.ptr(out)))
         out = out.transpose(0, 2, 1)
-    elif len(qs) == 3 and general:
-        out = np.empty((state.n_batch, 8, 8), dtype=c128)
-        arr = (C.c_int * 3)(*qs)
-        L.check(lib.bt_sv_rdm(state.h, 3, arr, L.ptr(out)))
+    elif len(qs) >= 3 and general:
+        # any number of kept qubits (the library accepts up to 12): tiled Gram kernel over the gathered 2^k x 2^(N-k) matrix
+        D = 1 << len(qs)
+        out = np.empty((state.n_batch, D, D), dtype=c128)
+        arr = (C.c_int * len(qs))(*qs)
+        L.check(lib.bt_sv_rdm(state.h, len(qs), arr, L.ptr(out)))
         out = out.transpose(0, 2, 1)
     else:
-        raise NotImplementedError("device partial_trace keeps up to 3 qubits (the reference's general path is O(4^N))")
+        raise ValueError("partial_trace(state, q), (state, q1, q2) or (state, [q...])")
     return out[0] if state.n_batch == 1 else out
+
+
+def partial_trace_rho(rho: "CuRho", keep: Sequence[int]) -> np.ndarray:
+    """``partial_trace(rho, dims, trace_out)`` src/linalg.jl:88-140 for qubit registers, given the KEPT qubits (the reference
+    passes the traced-out ones: ``setdiff(1:N, keep)``); kept qubits in ascending label order."""
+    qs = sorted(set(int(q) for q in keep))
+    D = 1 << len(qs)
+    out = np.empty((D, D), dtype=c128)
+    arr = (C.c_int * max(1, len(qs)))(*qs)
+    L.check(rho.lib.bt_dm_rdm(rho.h, len(qs), arr, L.ptr(out)))
+    return out.T
 
 
 def norm2(state: CuState):
@@ -860,8 +873,16 @@ def expect(x: State, what):
         L.check(lib.bt_sv_expect_1q_all(x.h, L.ptr(m), L.pdouble(out)))
         return out[0] if x.n_batch == 1 else out
     if isinstance(what, Op):
-        if what.control != -2:
-            raise NotImplementedError("expectation of a controlled operator")
+        if what.control != -2 or (what.q == 2 and isinstance(x, CuRho)):
+            # controlled operators and 2-qubit operators on rho: trace against the reduced density matrix of the touched qubits
+            m = L.cmat(what.mat, 1 << what.q)
+            if isinstance(x, CuRho):
+                out = C.c_double()
+                L.check(lib.bt_dm_expect_op(x.h, what.q, what.qubit, what.target_qubit, what.control, L.ptr(m), C.byref(out)))
+                return float(out.value)
+            out = np.empty(x.n_batch, dtype=np.float64)
+            L.check(lib.bt_sv_expect_op(x.h, what.q, what.qubit, what.target_qubit, what.control, L.ptr(m), L.pdouble(out)))
+            return float(out[0]) if x.n_batch == 1 else out
         if what.q == 1:
             m = L.cmat(what.mat, 2)
             if isinstance(x, CuRho):
@@ -873,8 +894,6 @@ def expect(x: State, what):
             qs = (C.c_int * 1)(what.qubit)
             L.check(lib.bt_sv_expect_product(x.h, 1, qs, L.ptr(m), L.pdouble(out)))
             return float(out[0]) if x.n_batch == 1 else out
-        if isinstance(x, CuRho):
-            raise NotImplementedError("2-qubit operator expectation on a density matrix")
         out = np.empty(x.n_batch, dtype=np.float64)
         L.check(lib.bt_sv_expect_matrix2q(x.h, what.qubit, what.target_qubit, L.ptr(L.cmat(what.mat, 4)), L.pdouble(out)))
         return float(out[0]) if x.n_batch == 1 else out
@@ -1158,13 +1177,30 @@ def shadow(circuit, number_of_experiment: int, rng=None) -> np.ndarray:
     return rho
 
 
-def entanglement_entropy(state: CuState) -> float:
-    """src/func.jl:299-312: Schmidt spectrum across the cut between the first N - N/2 and the last N/2 qubits (Julia reshapes
-    column-major, so its rows are the LOW N/2 index bits).  The SVD runs on the host on a downloaded copy: a convenience for
-    small N ("next" row of SURVEY 8f), not part of the device hot path."""
-    N = state.N
+def entanglement_entropy(x, spectrum_bool: bool = False):
+    """src/func.jl:299-312 (state) and :323-328 (rho).  State: Schmidt spectrum across the cut between the first N - N/2 and
+    the last N/2 qubits (Julia reshapes column-major, so its rows are the LOW N/2 index bits), sum(-s log s) over the squared
+    singular values s > 0; with ``spectrum_bool`` also -log.(s).  rho: singular values of ``bipartition_trace(rho)`` (the last
+    N/2 qubits; N must be even like the reference's ``Int(N/2)``), returns (entropy, -log.(spec)) like the reference.
+    The spectrum comes from the device (one-sided Jacobi iteration, ``bt_sv_schmidt_spectrum`` / ``bt_dm_bipartition_spectrum``);
+    a batched state returns one entropy per trajectory."""
+    N = x.N
+    sweeps = C.c_int()
+    if isinstance(x, CuRho):
+        if N % 2:
+            raise ValueError("InexactError: Int(N/2)")  # src/linalg.jl:152
+        spec = np.empty(1 << (N // 2), dtype=np.float64)
+        L.check(x.lib.bt_dm_bipartition_spectrum(x.h, N // 2, L.pdouble(spec), C.byref(sweeps)))
+        spec = spec[spec > 0]
+        return float(np.sum(-spec * np.log(spec))), -np.log(spec)
     part_a = N // 2
-    v = state.to_numpy().reshape(1 << (N - part_a), 1 << part_a)
-    spec = np.linalg.svd(v, compute_uv=False) ** 2
-    spec = spec[spec > 0]
-    return float(np.sum(-spec * np.log(spec)))
+    spec = np.empty((x.n_batch, 1 << part_a), dtype=np.float64)
+    L.check(x.lib.bt_sv_schmidt_spectrum(x.h, part_a, L.pdouble(spec), C.byref(sweeps)))
+    ent, logs = [], []
+    for row in spec:
+        r = row[row > 0]
+        ent.append(float(np.sum(-r * np.log(r))))
+        logs.append(-np.log(r))
+    if x.n_batch == 1:
+        return (ent[0], logs[0]) if spectrum_bool else ent[0]
+    return (np.array(ent), logs) if spectrum_bool else np.array(ent)

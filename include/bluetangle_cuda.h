@@ -103,7 +103,16 @@ int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates 
 int bt_sv_rdm1(const bt_sv* s, int qubit, bt_c64* out /* n_batch x 4, column-major 2x2 each */);
 int bt_sv_rdm2(const bt_sv* s, int qubit_a, int qubit_b, bt_c64* out /* n_batch x 16; index 2*b_min + b_max */);
 int bt_sv_rdm3(const bt_sv* s, int first_qubit, bt_c64* out /* n_batch x 64; qubits first..first+2 */);
-int bt_sv_rdm(const bt_sv* s, int k, const int* qubits, bt_c64* out /* n_batch x 4^k */); /* partial_trace(state, keep) linalg.jl:83-86, k <= 3 arbitrary qubits, ascending-label order */
+int bt_sv_rdm(const bt_sv* s, int k, const int* qubits, bt_c64* out /* n_batch x 4^k */); /* partial_trace(state, keep) linalg.jl:83-86, k <= 12 arbitrary qubits, ascending-label order (k >= 4: tiled Gram kernel, unsharded states) */
+/* Squared singular values (descending) of the 2^n_low x 2^(N - n_low) column-major reshape of the state: the spectrum
+ * entanglement_entropy(psi) src/func.jl:299-312 sums over (n_low = N / 2).  One-sided Jacobi iteration on a scratch copy, on the
+ * device; spec: n_batch x 2^min(n_low, N - n_low); sweeps (optional): Jacobi sweeps used.  The long side may have up to 2^13 entries. */
+int bt_sv_schmidt_spectrum(const bt_sv* s, int n_low, double* spec, int* sweeps);
+/* pure host (no device needed): the disjoint vector pairs the Jacobi kernel rotates in round `round` (0..nvec-2) of a sweep */
+int bt_jacobi_pairs_host(int nvec, int round, int* pairs /* nvec/2 x 2 */);
+/* expect(state, op) src/func.jl:91 for any Op: 1- or 2-qubit matrix (column-major), optional control (-2 = none):
+ * real(state' * op.expand(N) * state) as a trace against the reduced density matrix of the qubits the op touches; out[n_batch] */
+int bt_sv_expect_op(const bt_sv* s, int nq, int qubit, int target, int control, const bt_c64* m, double* out);
 int bt_sv_norm2(const bt_sv* s, double* out /* n_batch: sum |a|^2 */);
 int bt_sv_inner(const bt_sv* a, const bt_sv* b, bt_c64* out /* n_batch: <a|b>, src/tensor.jl:199 */);
 int bt_sv_normalize(bt_sv* s);
@@ -178,6 +187,14 @@ int bt_dm_expect_pauli(const bt_dm* d, const char* paulis, double* out);        
 int bt_dm_expect_1q_all(const bt_dm* d, const bt_c64 m[4], double* out /* n */);        /* func.jl:98 */
 int bt_dm_expect_product(const bt_dm* d, int n_ops, const int* qubits, const bt_c64* mats, double* out);
 int bt_dm_sample(const bt_dm* d, const double* u, uint64_t shots, int64_t* out);
+/* partial_trace(rho, dims, trace_out) src/linalg.jl:88-140: reduced density matrix of the k kept qubits (ascending-label order,
+ * first = most significant index bit), column-major 2^k x 2^k; k <= 12 */
+int bt_dm_rdm(const bt_dm* d, int k, const int* qubits, bt_c64* out);
+/* expect(rho, op) src/func.jl:92 for any Op (2-qubit and controlled operators included): real(tr(rho * op.expand(N))) */
+int bt_dm_expect_op(const bt_dm* d, int nq, int qubit, int target, int control, const bt_c64* m, double* out);
+/* singular values (descending) of bipartition_trace(rho) src/linalg.jl:151-161 generalised to the last n_keep qubits: the spectrum
+ * entanglement_entropy(rho) src/func.jl:323-328 sums over (n_keep = N / 2); spec: 2^n_keep */
+int bt_dm_bipartition_spectrum(const bt_dm* d, int n_keep, double* spec, int* sweeps);
 
 /* ---- multi-GPU shards (no reference analogue).  One process per GPU: each rank creates its
  * shard, the host plumbing (torch.distributed / MPI) all-gathers the IPC handles and supplies a barrier.

@@ -1158,6 +1158,27 @@ def entanglement_entropy(psi: np.ndarray) -> float:
     return float(np.sum(-spec * np.log(spec)))
 
 
+def bipartition_trace(rho) -> np.ndarray:
+    """src/linalg.jl:151-161: ptr[i, j] = sum_k rho[i + k d, j + k d], d = 2^(N/2) (keeps the low half of the index = the last
+    N/2 qubits); ``Int(N/2)`` throws for odd N."""
+    rho = np.asarray(rho.todense()) if sp.issparse(rho) else np.asarray(rho)
+    N = get_N(rho)
+    if N % 2:
+        raise ValueError("InexactError: Int(N/2)")
+    d = 1 << (N // 2)
+    out = np.zeros((d, d), dtype=C)
+    for k in range(d):
+        out += rho[k * d:(k + 1) * d, k * d:(k + 1) * d]
+    return out
+
+
+def entanglement_entropy_rho(rho):
+    """src/func.jl:323-328: singular values (not squared) of the half-traced density matrix -> (entropy, -log.(spec))."""
+    spec = np.linalg.svd(bipartition_trace(rho), compute_uv=False)
+    spec = spec[spec > 0]
+    return float(np.sum(-spec * np.log(spec))), -np.log(spec)
+
+
 # ---- variational front end (callers of apply + expect): src/vqa.jl ---------------------------------------------
 GATES_WITH_PHASE = ["P", "RX", "RY", "RZ", "U1", "U2", "U3", "CP", "GIVENS", "FSIM", "SWAPA", "RXX", "RYY", "RZZ", "RXY"]  # src/gates.jl:361
 TWO_QUBIT_GATES = ["CX", "CNOT", "CY", "CZ", "CP", "RXX", "RYY", "RZZ", "RXY", "GIVENS", "FSIM", "SWAP", "ISWAP", "FSWAP", "SYC", "ECR"]  # src/gates.jl:65

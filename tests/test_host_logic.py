@@ -208,3 +208,23 @@ def test_remap_walk_is_a_bijection_and_reads_sigma_of_dest(bt, monkeypatch):
                         nsel = sum(1 for d in range(5, nl) if sigma[d] >= nl)
                         if nsel:
                             assert len(set(srcrank[: 1 << nsel, 0].tolist())) == 1 << nsel
+
+
+def test_jacobi_tournament_schedule_covers_every_pair_once(bt):
+    """bt_jacobi_pairs_host: the round-robin schedule the Schmidt-spectrum kernel (csrc/bt_linalg.cu) walks -- the pairs of a
+    round are disjoint (one CTA per pair may rotate in place) and a sweep meets every unordered pair exactly once."""
+    import ctypes as C
+
+    lib = bt._lib.load()
+    for n in (2, 4, 8, 32, 256):
+        seen = set()
+        for r in range(n - 1):
+            pairs = (C.c_int * n)()
+            bt._lib.check(lib.bt_jacobi_pairs_host(n, r, pairs))
+            flat = list(pairs)
+            assert sorted(flat) == list(range(n))
+            for k in range(n // 2):
+                p, q = flat[2 * k], flat[2 * k + 1]
+                seen.add((min(p, q), max(p, q)))
+        assert len(seen) == n * (n - 1) // 2
+    assert lib.bt_jacobi_pairs_host(3, 0, (C.c_int * 4)()) != 0
