@@ -1472,66 +1472,217 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   return flush();
 }
 
+// ---- pass scheduler ---------------------------------------------------------------------------------------------------------
+// A pass = the blocks one launch of the tile kernel carries + the index bits its tile needs beyond the fixed low bits.
+// Dependencies: a block may run once no earlier unfinished block touches one of its bits ("blocked" set while scanning).
+// Two policies (BT_FUSE_SCHED):
+//   0  first fit: scan in program order, a block that does not depend on a skipped one joins the pass if its non-diagonal bits
+//      still fit the tile -- the tile bits are whatever the first few blocks happen to need;
+//   1  (default) look-ahead: the tile bits are CHOSEN.  Starting from the fixed low bits, the scheduler repeatedly evaluates, for
+//      every candidate bit set (the missing bits of a block on the dependency frontier), how much work the pass would carry with
+//      the tile enlarged by it -- a full dry run of the scan restricted to that tile -- and keeps the best gain per added bit;
+//      brickwork / layered circuits then advance a deep light-cone on 12 chosen qubits instead of one layer on the first 12.
+struct PassPlan {
+  std::vector<int> blocks;     // indices into the block list, execution order
+  std::vector<int> tile_bits;  // beyond the fixed low bits
+  double cost = 0.0;
+  int end_reason = 0;          // statistics: 1 = cost cap reached, 2 = block cap, 0 = ran out of eligible blocks
+};
+
+struct SchedCfg { int n_local, T, lowb, window; double maxg; int policy; };
+
+static inline double block_cost(const Block& b) {
+  // cost units: a dense 4x4 block = 2.8 (the cap of 28 keeps ~10 of them per pass, the measured optimum for dense passes);
+  // a structured block pays per micro-op (dispatch) and per FP64 instruction
+  if (b.sok) return 0.15 * (double)b.prog.size() + 0.04 * b.scost;
+  return b.desc.diag ? 0.7 : (b.desc.k == 2 ? 2.8 : 1.7);
+}
+
+struct SchedBlock { uint64_t touch, need; double cost; int ngates; bool solo, scalar; };
+
+// dry run (out == nullptr) or commit of one pass restricted to the tile bit set `tile`; returns the gain (cost units carried)
+static double scan_pass(const std::vector<SchedBlock>& sb, const std::vector<char>& done, size_t first, const SchedCfg& cfg, uint64_t tile, PassPlan* out,
+                        uint64_t* frontier_need /* optional: per frontier block, the missing bits (appended) */, std::vector<uint64_t>* frontier) {
+  uint64_t blocked = 0;
+  const uint64_t all = cfg.n_local >= 64 ? ~0ull : ((1ull << cfg.n_local) - 1);
+  double cost = 0.0;
+  int cnt = 0, reason = 0;
+  size_t scanned = 0;
+  (void)frontier_need;
+  for (size_t i = first; i < sb.size() && scanned < (size_t)cfg.window && (blocked & all) != all; ++i) {
+    if (done[i]) continue;
+    scanned++;
+    const SchedBlock& b = sb[i];
+    bool ok = !(b.touch & blocked);
+    if (ok && b.solo) {
+      if (cnt == 0) { if (out) { out->blocks.push_back((int)i); out->cost = 0.0; } return 1e9; }  // runs alone, in order
+      ok = false;
+    }
+    if (ok) {
+      const uint64_t missing = b.need & ~tile;
+      if (missing) { ok = false; if (frontier) frontier->push_back(missing); }
+      else if (cnt >= 44) { ok = false; reason = 2; }
+      else if (cost + b.cost > cfg.maxg && cnt > 0) { ok = false; reason = 1; }
+      if (ok) {
+        cost += b.cost; cnt++;
+        if (out) out->blocks.push_back((int)i);
+        continue;
+      }
+    }
+    blocked |= b.touch;
+    if (b.scalar) break;  // a global scalar orders everything
+  }
+  if (out) { out->cost = cost; out->end_reason = reason; }
+  return cost;
+}
+
+static int plan_next_pass(const std::vector<SchedBlock>& sb, const std::vector<char>& done, size_t first, const SchedCfg& cfg, PassPlan& out) {
+  out = PassPlan();
+  const uint64_t low = (1ull << cfg.lowb) - 1;
+  uint64_t tile = low;
+  if (cfg.policy == 0) {
+    // first fit: tile bits are taken as the scan meets them
+    uint64_t blocked = 0;
+    const uint64_t all = cfg.n_local >= 64 ? ~0ull : ((1ull << cfg.n_local) - 1);
+    double cost = 0.0;
+    size_t scanned = 0;
+    for (size_t i = first; i < sb.size() && scanned < (size_t)cfg.window && (blocked & all) != all; ++i) {
+      if (done[i]) continue;
+      scanned++;
+      const SchedBlock& b = sb[i];
+      bool ok = !(b.touch & blocked);
+      if (ok && b.solo) {
+        if (out.blocks.empty()) { out.blocks.push_back((int)i); return BT_OK; }
+        ok = false;
+      }
+      if (ok) {
+        const int extra = __builtin_popcountll(b.need & ~tile);
+        if (__builtin_popcountll(tile) + extra > cfg.T || (int)out.blocks.size() >= 44 || (cost + b.cost > cfg.maxg && !out.blocks.empty())) ok = false;
+        if (ok) { tile |= b.need; out.blocks.push_back((int)i); cost += b.cost; continue; }
+      }
+      blocked |= b.touch;
+      if (b.scalar) break;
+    }
+    out.cost = cost;
+  } else {
+    std::vector<uint64_t> frontier;
+    double cur = scan_pass(sb, done, first, cfg, tile, nullptr, nullptr, &frontier);
+    if (cur < 1e8) {
+      while (__builtin_popcountll(tile) < cfg.T) {
+        // candidates: the distinct missing-bit sets of the blocks that were refused only for their bits
+        std::sort(frontier.begin(), frontier.end());
+        frontier.erase(std::unique(frontier.begin(), frontier.end()), frontier.end());
+        double best_rate = 0.0, best_gain = 0.0;
+        uint64_t best = 0;
+        const int room = cfg.T - __builtin_popcountll(tile);
+        for (uint64_t cand : frontier) {
+          const int add = __builtin_popcountll(cand);
+          if (add > room) continue;
+          const double g = scan_pass(sb, done, first, cfg, tile | cand, nullptr, nullptr, nullptr);
+          const double rate = (g - cur) / (double)add;
+          if (rate > best_rate + 1e-12 || (rate > best_rate - 1e-12 && best && cand < best && rate > 0)) { best_rate = rate; best = cand; best_gain = g; }
+        }
+        if (!best) break;
+        tile |= best;
+        cur = best_gain;
+        if (cur >= cfg.maxg - 0.15) break;  // the cost cap is reached: more bits cannot add work
+        frontier.clear();
+        scan_pass(sb, done, first, cfg, tile, nullptr, nullptr, &frontier);
+      }
+    }
+    scan_pass(sb, done, first, cfg, tile, &out, nullptr, nullptr);
+  }
+  if (out.blocks.empty()) BT_FAIL(BT_ERR_ARG, "internal: fusion scheduler made no progress");
+  uint64_t used = 0;
+  for (int bi : out.blocks) used |= sb[bi].need;
+  for (int b = cfg.lowb; b < cfg.n_local; ++b)
+    if (used >> b & 1) out.tile_bits.push_back(b);
+  return BT_OK;
+}
+
+static void sched_blocks(const std::vector<Block>& blocks, std::vector<SchedBlock>& sb) {
+  std::vector<int> need;
+  sb.resize(blocks.size());
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    const Block& b = blocks[i];
+    SchedBlock& o = sb[i];
+    o.touch = o.need = 0;
+    for (int t : b.touch) o.touch |= 1ull << t;
+    o.solo = b.opaque || b.desc.k > 2;
+    o.scalar = b.touch.empty();
+    o.ngates = b.ngates;
+    o.cost = 0.0;
+    if (!o.solo) {
+      needed_bits(b.desc, need);
+      if (b.sok) need = b.abits;  // structured blocks: the bits they act on non-diagonally must be program positions
+      for (int t : need) o.need |= 1ull << t;
+      o.cost = block_cost(b);
+    }
+  }
+}
+
+static SchedCfg sched_cfg(int n_local) {
+  SchedCfg c;
+  c.n_local = n_local;
+  c.T = std::min(n_local, env_int("BT_TILE_BITS", TILE_TDEF));
+  c.lowb = std::min(tile_lowb(), c.T);
+  c.maxg = (double)std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", 28)));  // cost units per pass (measured sweep: profiles/r1_fusion_sweep.txt)
+  c.window = env_int("BT_FUSE_WINDOW", 256);
+  c.policy = env_int("BT_FUSE_SCHED", 1);
+  return c;
+}
+
 int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
   std::vector<Block> blocks;
   fuse_blocks(gates, blocks);
-  const int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
-  const int lowb = std::min(tile_lowb(), T);
-  const int maxg = std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", 28)));  // cost units per pass (measured sweep: profiles/r1_fusion_sweep.txt)
-  const int window = env_int("BT_FUSE_WINDOW", 256);
+  std::vector<SchedBlock> sb;
+  sched_blocks(blocks, sb);
+  const SchedCfg cfg = sched_cfg(s->n_local);
   const size_t n = blocks.size();
   std::vector<char> done(n, 0);
   size_t first = 0;
-  std::vector<int> need;
+  PassPlan plan;
+  std::vector<const Block*> pass;
   while (first < n) {
     if (done[first]) { first++; continue; }
-    // opaque / scalar blocks run alone, in order
-    bool blocked[64] = {false};
-    bool in_tile[64] = {false};
-    for (int j = 0; j < lowb; ++j) in_tile[j] = true;
-    int tile_cnt = lowb;
-    std::vector<const Block*> pass;
-    std::vector<int> tile_bits;
-    double cost = 0.0;
-    int nblocked = 0;
-    size_t scanned = 0;
-    for (size_t i = first; i < n && scanned < (size_t)window && nblocked < s->n_local; ++i) {
-      if (done[i]) continue;
-      scanned++;
-      Block& b = blocks[i];
-      bool dep = false;
-      for (int t : b.touch) if (blocked[t]) dep = true;
-      bool ok = !dep;
-      if (ok && (b.opaque || b.desc.k > 2)) {
-        // runs through the direct kernels, alone: only as the first element of a pass
-        ok = pass.empty();
-        if (ok) {
-          pass.push_back(&b); done[i] = 1;
-          break;
-        }
-      }
-      if (ok) {
-        needed_bits(b.desc, need);
-        if (b.sok) need = b.abits;  // structured blocks: the bits they act on non-diagonally must be program positions
-        int extra = 0;
-        for (int t : need) if (!in_tile[t]) extra++;
-        // cost units: a dense 4x4 block = 2.8 (the cap of 28 keeps ~10 of them per pass, the measured optimum for dense passes);
-        // a structured block pays per micro-op (dispatch) and per FP64 instruction
-        double c = b.desc.diag ? 0.7 : (b.desc.k == 2 ? 2.8 : 1.7);
-        if (b.sok) c = 0.15 * (double)b.prog.size() + 0.04 * b.scost;
-        if (tile_cnt + extra > T || (int)pass.size() >= 44 || (cost + c > (double)maxg && !pass.empty())) ok = false;
-        if (ok) {
-          for (int t : need) if (!in_tile[t]) { in_tile[t] = true; tile_cnt++; tile_bits.push_back(t); }
-          pass.push_back(&b); done[i] = 1; cost += c;
-          continue;
-        }
-      }
-      for (int t : b.touch) if (!blocked[t]) { blocked[t] = true; nblocked++; }
-      if (b.touch.empty()) break;  // a global scalar orders everything
-    }
-    if (pass.empty()) BT_FAIL(BT_ERR_ARG, "internal: fusion scheduler made no progress");
-    BT_TRY(launch_pass(s, pass, tile_bits));
+    BT_TRY(plan_next_pass(sb, done, first, cfg, plan));
+    pass.clear();
+    for (int bi : plan.blocks) { pass.push_back(&blocks[bi]); done[bi] = 1; }
+    BT_TRY(launch_pass(s, pass, plan.tile_bits));
   }
+  return BT_OK;
+}
+
+// pure host (no device): the passes the scheduler forms for a gate list in physical-bit space on a register of n_local bits
+int bt_fusion_plan(const std::vector<GateDesc>& gates, int n_local, int* n_passes, int* n_blocks, int* gates_in_pass, int* tile_bits /* cap x 16 */, double* cost_in_pass,
+                   int* end_reason, int cap) {
+  std::vector<Block> blocks;
+  fuse_blocks(gates, blocks);
+  std::vector<SchedBlock> sb;
+  sched_blocks(blocks, sb);
+  const SchedCfg cfg = sched_cfg(n_local);
+  std::vector<char> done(blocks.size(), 0);
+  size_t first = 0;
+  int np = 0;
+  PassPlan plan;
+  while (first < blocks.size()) {
+    if (done[first]) { first++; continue; }
+    BT_TRY(plan_next_pass(sb, done, first, cfg, plan));
+    int ng = 0;
+    for (int bi : plan.blocks) { done[bi] = 1; ng += blocks[bi].ngates; }
+    if (np < cap) {
+      if (gates_in_pass) gates_in_pass[np] = ng;
+      if (cost_in_pass) cost_in_pass[np] = plan.cost;
+      if (end_reason) end_reason[np] = plan.end_reason;
+      if (tile_bits) {
+        for (int j = 0; j < 16; ++j) tile_bits[np * 16 + j] = -1;
+        for (size_t j = 0; j < plan.tile_bits.size() && j < 16; ++j) tile_bits[np * 16 + j] = plan.tile_bits[j];
+      }
+    }
+    np++;
+  }
+  if (n_passes) *n_passes = np;
+  if (n_blocks) *n_blocks = (int)blocks.size();
   return BT_OK;
 }
 
