@@ -51,7 +51,7 @@ PROTOTYPES = {
     "bt_set_device": [_i],
     "bt_set_strict": [_i],
     "bt_fp64_peak": [_pd, _pd, _i],
-    "bt_fusion_plan_host": [_i, _vp, _u64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _pd, C.POINTER(_i), _i],
+    "bt_fusion_plan_host": [_i, _vp, _u64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _pd, C.POINTER(_i), _i, C.POINTER(_i)],
     "bt_fusion_stats": [C.POINTER(_u64), C.POINTER(_u64)],
     "bt_fusion_flops": [_pd],
     "bt_jit_stats": [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _pd],

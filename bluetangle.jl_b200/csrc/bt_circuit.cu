@@ -231,16 +231,17 @@ extern "C" int bt_plan_circuit_host(int n_qubits, int world, const bt_gate* g, u
 }
 
 int bt_fusion_plan(const std::vector<GateDesc>& gates, int n_local, int* n_passes, int* n_blocks, int* gates_in_pass, int* tile_bits, double* cost_in_pass,
-                   int* end_reason, int cap);  // bt_tile.cu
+                   int* end_reason, int cap, int* dry_counts);  // bt_tile.cu
 
 // Pure host: the fused passes bt_sv_apply_circuit(fuse = 1) forms for this gate list on one unsharded GPU.
 extern "C" int bt_fusion_plan_host(int n_qubits, const bt_gate* g, uint64_t n, int* n_passes, int* n_blocks, int* gates_in_pass, int* tile_bits, double* cost_in_pass,
-                                   int* end_reason, int cap) {
+                                   int* end_reason, int cap, int* launch_counts) {
   if (n && !g) BT_FAIL(BT_ERR_ARG, "null gate list");
   if (n_qubits < 1 || n_qubits > 40) BT_FAIL(BT_ERR_ARG, "n_qubits out of range");
   std::vector<GateDesc> L;
   BT_TRY(build_logical(n_qubits, g, n, L));
-  return bt_fusion_plan(L, n_qubits, n_passes, n_blocks, gates_in_pass, tile_bits, cost_in_pass, end_reason, cap);
+  if (launch_counts) memset(launch_counts, 0, 4 * sizeof(int));
+  return bt_fusion_plan(L, n_qubits, n_passes, n_blocks, gates_in_pass, tile_bits, cost_in_pass, end_reason, cap, launch_counts);
 }
 
 extern "C" int bt_dm_apply_circuit(bt_dm* d, const bt_gate* g, uint64_t n, int fuse) {

@@ -113,8 +113,19 @@ __device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
   acc.y = fma(a.y, b.x, acc.y);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two neighbouring amplitudes in one request.  Used when index bit 0 is a
+// target: the two amplitudes of a pair are adjacent, and a warp-wide 16-byte load at a 32- or 64-byte stride would otherwise
+// fetch every sector twice through L1.
+__device__ __forceinline__ void ld256(const double2* p, double2& a, double2& b) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st256(double2* p, double2 a, double2 b) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
 // gshift = log2(groups per trajectory): G >> gshift is the trajectory a group belongs to.
-template <int K, int U, bool DEVMAT, bool COND>
+// T0 >= 0: matrix index bit T0 sits on physical bit 0 -> entries j and j | (1 << T0) are adjacent and move as one 256-bit access.
+template <int K, int U, bool DEVMAT, bool COND, int T0>
 __global__ void __launch_bounds__(256) k_dense(double2* __restrict__ a, uint64_t ngroups, int gshift,
                                                 const __grid_constant__ DenseParams<K> P,
                                                 const double2* __restrict__ dmats,
@@ -132,7 +143,10 @@ __global__ void __launch_bounds__(256) k_dense(double2* __restrict__ a, uint64_t
     base[u] = bt_expand(G, P.plan);
     if (ok[u]) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) x[u][j] = a[base[u] + P.off[j]];
+      for (int j = 0; j < D; ++j) {
+        if (T0 >= 0) { if (!((j >> (T0 >= 0 ? T0 : 0)) & 1)) ld256(a + base[u] + P.off[j], x[u][j], x[u][j | (1 << (T0 >= 0 ? T0 : 0))]); }
+        else x[u][j] = a[base[u] + P.off[j]];
+      }
     }
   }
 #pragma unroll
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(256) k_dense(double2* __restrict__ a, uint64_t
     if (!ok[u]) continue;
     const double2* mm = nullptr;
     if (DEVMAT) mm = dmats + (((g0 + (uint64_t)u * blockDim.x) >> gshift) << 6);
+    double2 y[D];
 #pragma unroll
     for (int r = 0; r < D; ++r) {
       double2 acc = make_double2(0.0, 0.0);
@@ -148,7 +163,12 @@ __global__ void __launch_bounds__(256) k_dense(double2* __restrict__ a, uint64_t
         double2 mv = DEVMAT ? __ldg(&mm[r * D + c]) : P.m[r * D + c];
         cfma(acc, mv, x[u][c]);
       }
-      a[base[u] + P.off[r]] = acc;
+      y[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      if (T0 >= 0) { if (!((r >> (T0 >= 0 ? T0 : 0)) & 1)) st256(a + base[u] + P.off[r], y[r], y[r | (1 << (T0 >= 0 ? T0 : 0))]); }
+      else a[base[u] + P.off[r]] = y[r];
     }
   }
 }
@@ -206,6 +226,14 @@ static int make_plan(const bt_sv* s, const GateDesc& g, IdxPlan* plan, uint64_t*
   return BT_OK;
 }
 
+template <int K, int U, int T0>
+static void launch_dense_t0(bt_sv* s, unsigned grid, uint64_t ngroups, int gshift, const DenseParams<K>& P, const double2* dmats, const int32_t* cond, int want) {
+  if (dmats && cond) k_dense<K, U, true, true, T0><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, cond, want);
+  else if (dmats) k_dense<K, U, true, false, T0><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, nullptr, 0);
+  else if (cond) k_dense<K, U, false, true, T0><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, cond, want);
+  else k_dense<K, U, false, false, T0><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0);
+}
+
 template <int K, int U>
 static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const int32_t* cond, int want) {
   DenseParams<K> P;
@@ -217,16 +245,17 @@ static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const
   uint64_t ngroups = (uint64_t)s->n_batch << gshift;
   uint64_t per_block = 256ull * U;
   unsigned grid = (unsigned)((ngroups + per_block - 1) / per_block);
+  // matrix bit that sits on index bit 0 (1- and 2-qubit gates): its pairs move as 256-bit accesses
+  int t0 = -1;
+  if (K <= 2)
+    for (int t = 0; t < K; ++t)
+      if (g.tb[t] == 0) t0 = t;
+  static const bool wide = []() { const char* v = getenv("BT_WIDE_LOADS"); return !(v && *v == '0'); }();
+  if (!wide) t0 = -1;
   bt_prof_begin(s, BT_CLS_DENSE);
-  if (dmats && cond) {
-    k_dense<K, U, true, true><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, cond, want);
-  } else if (dmats) {
-    k_dense<K, U, true, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, dmats, nullptr, 0);
-  } else if (cond) {
-    k_dense<K, U, false, true><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, cond, want);
-  } else {
-    k_dense<K, U, false, false><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0);
-  }
+  if (t0 == 0) launch_dense_t0<K, U, 0>(s, grid, ngroups, gshift, P, dmats, cond, want);
+  else if (t0 == 1 && K == 2) launch_dense_t0<K, U, (K == 2 ? 1 : -1)>(s, grid, ngroups, gshift, P, dmats, cond, want);
+  else launch_dense_t0<K, U, -1>(s, grid, ngroups, gshift, P, dmats, cond, want);
   bt_prof_end(s);
   BT_CHECK_LAUNCH(s);
   return BT_OK;

@@ -284,15 +284,19 @@ __device__ __forceinline__ double prob_at(const double2* __restrict__ a, uint64_
   return x.x * x.x + x.y * x.y;
 }
 
-__global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum) {
+// All three kernels take a batch of `ntraj` independent distributions of n entries each (trajectory t at a + t * n * stride-free
+// layout: consecutive state vectors); a single state is ntraj == 1.
+__global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum, uint64_t nb) {
   // one CTA per block of 2^SB entries; fixed-order tree => reproducible
   __shared__ double sm[8];
-  const uint64_t b0 = (uint64_t)blockIdx.x << SB;
+  const uint64_t traj = blockIdx.x / nb, blk = blockIdx.x % nb;
+  const double2* __restrict__ base = a + traj * n;
+  const uint64_t b0 = blk << SB;
   double acc = 0.0;
 #pragma unroll 8
   for (uint64_t k = threadIdx.x; k < (1ull << SB); k += 256) {
     uint64_t i = b0 + k;
-    if (i < n) acc += prob_at(a, i, dm_stride);
+    if (i < n) acc += prob_at(base, i, dm_stride);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -305,10 +309,11 @@ __global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ 
   }
 }
 
-// single-CTA inclusive scan (sequential carry over tiles of 1024)
-__global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ x, uint64_t n) {
+// inclusive scan of each trajectory's block sums: one CTA per trajectory (sequential carry over tiles of 1024)
+__global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ xs, uint64_t n) {
   __shared__ double warp_tot[32];
   __shared__ double carry_s;
+  double* __restrict__ x = xs + (uint64_t)blockIdx.x * n;
   if (threadIdx.x == 0) carry_s = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -341,25 +346,38 @@ __global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ x,
   }
 }
 
-// pre: prefix = inclusive scan of block sums (nb entries); total mass `lo..hi` window for sharded sampling:
-// a shot with target t (already scaled to the global total) is handled iff offset <= t' where t' = t - offset
-// falls in (.., local_total]; otherwise out = -1.
+// Sharded sampling: every rank holds the same inclusive prefix of the per-rank totals (same doubles, same order), so ownership of a
+// shot is decided identically everywhere: owner = first rank r with rank_prefix[r] >= target (the last rank takes what rounding
+// pushes past the end).  world == 0: unsharded, the target is u * local total.
+struct ShardCdf {
+  int world, rank;
+  double prefix[16];  // inclusive prefix of the rank totals, rank order = physical index order
+};
+
+// pre: prefix = inclusive scan of the block sums of each trajectory (nb entries each); one warp per shot: binary search over the
+// block prefix, then a warp scan inside the block.  out = -1 for a shot another rank owns.
 __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride,
-                                                 const double* __restrict__ prefix, uint64_t nb,
-                                                 const double* __restrict__ u, uint64_t shots, double total_global, double offset,
-                                                 int is_last_rank, int64_t* __restrict__ out) {
+                                                 const double* __restrict__ prefixes, uint64_t nb,
+                                                 const double* __restrict__ u, uint64_t shots_per_traj, uint64_t shots, const __grid_constant__ ShardCdf sh,
+                                                 int64_t* __restrict__ out) {
   const uint64_t shot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (shot >= shots) return;
+  const uint64_t traj = shot / shots_per_traj;
+  const double* __restrict__ prefix = prefixes + traj * nb;
+  const double2* __restrict__ base_a = a + traj * n;
   const double local_total = prefix[nb - 1];
-  double t = u[shot] * (total_global < 0.0 ? local_total : total_global) - offset;
-  // ownership: first index with global cumsum >= target
-  const bool is_first_rank = (is_last_rank & 2) != 0;
-  const bool last = (is_last_rank & 1) != 0;
-  // rank r owns the shot iff offset_r < target <= offset_r + total_r; target <= 0 goes to the first rank (u == 0 ->
-  // first entry with cumsum >= 0), anything past the end (rounding) to the last
-  bool mine = (t > 0.0 || is_first_rank) && (t <= local_total || last);
-  if (!mine) { if (lane == 0) out[shot] = -1; return; }
+  double t;
+  if (sh.world > 1) {
+    const double target = u[shot] * sh.prefix[sh.world - 1];
+    int owner = sh.world - 1;
+    for (int r = 0; r < sh.world - 1; ++r)
+      if (sh.prefix[r] >= target) { owner = r; break; }
+    if (owner != sh.rank) { if (lane == 0) out[shot] = -1; return; }
+    t = target - (owner > 0 ? sh.prefix[owner - 1] : 0.0);
+  } else {
+    t = u[shot] * local_total;
+  }
   // binary search: first block j with prefix[j] >= t
   uint64_t lo = 0, hi = nb - 1;
   while (lo < hi) {
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, u
   int64_t last_nz = -1;
   for (uint64_t base = b0; base < bend && found < 0; base += 32) {
     uint64_t i = base + lane;
-    double p = (i < bend) ? prob_at(a, i, dm_stride) : 0.0;
+    double p = (i < bend) ? prob_at(base_a, i, dm_stride) : 0.0;
     double v = p;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -394,38 +412,42 @@ __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, u
   if (lane == 0) out[shot] = found;
 }
 
-static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_stride, const double* u, uint64_t shots, int64_t* out) {
+// ntraj distributions of n entries (consecutive in memory), shots_per_traj uniforms each: three launches for the whole batch
+static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_stride, const double* u, uint64_t shots_per_traj, uint64_t ntraj, int64_t* out) {
   if (!u || !out) BT_FAIL(BT_ERR_ARG, "null argument");
+  const uint64_t shots = shots_per_traj * ntraj;
   if (shots == 0) return BT_OK;
-  uint64_t nb = (n + (1ull << SB) - 1) >> SB;
-  size_t off_u = ((nb * sizeof(double) + 255) / 256) * 256;
+  const uint64_t nb = (n + (1ull << SB) - 1) >> SB;
+  if (nb * ntraj >= (1ull << 31)) BT_FAIL(BT_ERR_UNSUPPORTED, "sampling: batch too large");
+  size_t off_u = ((nb * ntraj * sizeof(double) + 255) / 256) * 256;
   size_t off_o = off_u + ((shots * sizeof(double) + 255) / 256) * 256;
   BT_TRY(bt_ensure_scratch(s, off_o + shots * sizeof(int64_t)));
   double* d_prefix = (double*)s->d_scratch;
   double* d_u = (double*)((char*)s->d_scratch + off_u);
   int64_t* d_out = (int64_t*)((char*)s->d_scratch + off_o);
   BT_CUDA(cudaMemcpyAsync(d_u, u, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  k_block_sums<<<(unsigned)nb, 256, 0, s->stream>>>(base, n, dm_stride, d_prefix);
+  k_block_sums<<<(unsigned)(nb * ntraj), 256, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb);
   BT_CHECK_LAUNCH(s);
-  k_scan_inclusive<<<1, 1024, 0, s->stream>>>(d_prefix, nb);
+  k_scan_inclusive<<<(unsigned)ntraj, 1024, 0, s->stream>>>(d_prefix, nb);
   BT_CHECK_LAUNCH(s);
-  double total = -1.0, offset = 0.0;  // total < 0: the kernel uses the local total (unsharded: no host round trip)
-  int is_last = 3;
+  ShardCdf sh;
+  memset(&sh, 0, sizeof(sh));
   if (s->world > 1) {
+    if (ntraj != 1) BT_FAIL(BT_ERR_UNSUPPORTED, "batched sampling of a sharded state");
+    if (s->world > 16) BT_FAIL(BT_ERR_UNSUPPORTED, "sharded sampling supports up to 16 ranks");
     BT_CUDA(cudaMemcpyAsync(s->h_res, d_prefix + (nb - 1), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     BT_CUDA(cudaStreamSynchronize(s->stream));
     if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
-    // physical rank order is the order of the physical index; totals all-gathered through a sum
+    // the totals are all-gathered through a sum of one-hot vectors: every rank then holds the same doubles and forms the same prefix
     std::vector<double> tots(s->world, 0.0);
     tots[s->rank] = s->h_res[0];
     s->allreduce(s->allreduce_ctx, tots.data(), s->world);
-    total = 0.0;
-    for (int r = 0; r < s->world; ++r) { if (r == s->rank) offset = total; total += tots[r]; }
-    is_last = (s->rank == s->world - 1) ? 1 : 0;
-    if (s->rank == 0) is_last |= 2;
+    sh.world = s->world; sh.rank = s->rank;
+    double run = 0.0;
+    for (int r = 0; r < s->world; ++r) { run += tots[r]; sh.prefix[r] = run; }
   }
   uint64_t threads = shots * 32;
-  k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots, total, offset, is_last, d_out);
+  k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots_per_traj, shots, sh, d_out);
   BT_CHECK_LAUNCH(s);
   BT_CUDA(cudaMemcpyAsync(out, d_out, shots * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
   BT_CUDA(cudaStreamSynchronize(s->stream));
@@ -450,15 +472,18 @@ extern "C" int bt_sv_sample(const bt_sv* cs, const double* u, uint64_t shots, in
     for (int b = 0; b < 64; ++b) ident[b] = b;
     BT_TRY(bt_sv_remap(s, ident));
   }
-  BT_TRY(sample_impl(s, s->amp, 1ull << s->n_local, 0, u, shots, out));
+  BT_TRY(sample_impl(s, s->amp, 1ull << s->n_local, 0, u, shots, 1, out));
   if (s->world > 1) {
+    // exactly one rank owns a shot (ownership is computed from identical numbers everywhere): the owner contributes index + 1,
+    // the others 0; a sum of 0 means nobody claimed the shot -- an error, not index 0
     std::vector<double> buf(shots);
-    for (uint64_t i = 0; i < shots; ++i) {
-      if (out[i] >= 0) buf[i] = (double)phys_to_logical(s, ((uint64_t)s->rank << s->n_local) | (uint64_t)out[i]);
-      else buf[i] = 0.0;
-    }
+    for (uint64_t i = 0; i < shots; ++i)
+      buf[i] = out[i] >= 0 ? (double)(phys_to_logical(s, ((uint64_t)s->rank << s->n_local) | (uint64_t)out[i]) + 1) : 0.0;
     s->allreduce(s->allreduce_ctx, buf.data(), (int)shots);
-    for (uint64_t i = 0; i < shots; ++i) out[i] = (int64_t)buf[i];
+    for (uint64_t i = 0; i < shots; ++i) {
+      if (buf[i] < 1.0) BT_FAIL(BT_ERR_SAMPLE, "sharded sampling: no rank owned shot %llu", (unsigned long long)i);
+      out[i] = (int64_t)buf[i] - 1;
+    }
   }
   return BT_OK;
 }
@@ -467,11 +492,10 @@ extern "C" int bt_sv_sample_batched(const bt_sv* cs, const double* u, uint64_t s
   BT_TRY(bt_check_sv(cs));
   bt_sv* s = const_cast<bt_sv*>(cs);
   if (s->world > 1) BT_FAIL(BT_ERR_UNSUPPORTED, "batched sampling of a sharded state");
-  for (int64_t t = 0; t < s->n_batch; ++t)
-    BT_TRY(sample_impl(s, s->amp + ((uint64_t)t << s->n_local), 1ull << s->n_local, 0, u + t * shots_per_traj, shots_per_traj, out + t * shots_per_traj));
-  return BT_OK;
+  // one segmented launch set for the whole batch (block sums, per-trajectory scan, one warp per (trajectory, shot)): no host loop
+  return sample_impl(s, s->amp, 1ull << s->n_local, 0, u, shots_per_traj, (uint64_t)s->n_batch, out);
 }
 
 int bt_sample_diag(bt_sv* v, int n, const double* u, uint64_t shots, int64_t* out) {
-  return sample_impl(v, v->amp, 1ull << n, (1ull << n) + 1, u, shots, out);
+  return sample_impl(v, v->amp, 1ull << n, (1ull << n) + 1, u, shots, 1, out);
 }

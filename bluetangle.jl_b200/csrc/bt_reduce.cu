@@ -64,7 +64,12 @@ __device__ __forceinline__ uint64_t rdm_expand(uint64_t g, const RdmPlan& p) {
 }
 
 // rho[a][b] = sum x_a conj(x_b).  Stored as D*D doubles: [a*D+a] = diag (real); for a<b: [a*D+b] = Re, [b*D+a] = Im of rho[a][b].
-template <int K>
+__device__ __forceinline__ void ld256(const double2* p, double2& a, double2& b) {  // see bt_gates.cu
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+
+// T0 >= 0: matrix index bit T0 sits on physical bit 0 -> entries j and j | (1 << T0) are one 256-bit load
+template <int K, int T0>
 __global__ void __launch_bounds__(RB) k_rdm(const double2* __restrict__ a, int n_local, const __grid_constant__ RdmPlan P,
                                              double* __restrict__ part, int nblk) {
   constexpr int D = 1 << K;
@@ -79,7 +84,10 @@ __global__ void __launch_bounds__(RB) k_rdm(const double2* __restrict__ a, int n
     uint64_t i0 = rdm_expand(g, P);
     double2 x[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = base[i0 + P.off[j]];
+    for (int j = 0; j < D; ++j) {
+      if (T0 >= 0) { if (!((j >> (T0 >= 0 ? T0 : 0)) & 1)) ld256(base + i0 + P.off[j], x[j], x[j | (1 << (T0 >= 0 ? T0 : 0))]); }
+      else x[j] = base[i0 + P.off[j]];
+    }
 #pragma unroll
     for (int r = 0; r < D; ++r) {
       acc[r * D + r] += x[r].x * x[r].x + x[r].y * x[r].y;
@@ -325,9 +333,16 @@ int bt_reduce_rdm_at(const bt_sv* cs, int k, const int* tb, size_t res_off) {
   int nblk = pick_nblk(s, 1ull << (s->n_local - k));
   BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * nv));
   dim3 grid(nblk, (unsigned)s->n_batch);
-  if (k == 1) k_rdm<1><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
-  else if (k == 2) k_rdm<2><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
-  else k_rdm<3><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk);
+  int t0 = -1;  // matrix bit on index bit 0: its pairs are read as 256-bit loads
+  for (int t = 0; t < k; ++t)
+    if (tb[t] == 0) t0 = t;
+  static const bool wide = []() { const char* v = getenv("BT_WIDE_LOADS"); return !(v && *v == '0'); }();
+  if (!wide) t0 = -1;
+#define RDM_LAUNCH(K, T0) k_rdm<K, T0><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, s->d_part, nblk)
+  if (k == 1) { if (t0 == 0) RDM_LAUNCH(1, 0); else RDM_LAUNCH(1, -1); }
+  else if (k == 2) { if (t0 == 0) RDM_LAUNCH(2, 0); else if (t0 == 1) RDM_LAUNCH(2, 1); else RDM_LAUNCH(2, -1); }
+  else { if (t0 == 0) RDM_LAUNCH(3, 0); else if (t0 == 1) RDM_LAUNCH(3, 1); else if (t0 == 2) RDM_LAUNCH(3, 2); else RDM_LAUNCH(3, -1); }
+#undef RDM_LAUNCH
   BT_CHECK_LAUNCH(s);
   return finish(s, nblk, nv, res_off);
 }

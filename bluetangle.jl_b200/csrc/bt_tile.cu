@@ -1106,8 +1106,16 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
 
 int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, uint64_t ntiles, size_t tile_bytes, int np);  // bt_jit.cu
 
+// dry run (host-only planning, bt_fusion_plan): launch_pass forms slots and programs exactly as for a real launch but touches no
+// device; t_dry[0] counts kernel launches, [1] register programs, [2] other items, [3] single-gate passes
+static thread_local int* t_dry = nullptr;
+
 static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const std::vector<int>& tile_bits_in) {
-  if (pass_in.size() == 1) return bt_launch_gate(s, pass_in[0]->desc);
+  const bool dry = t_dry != nullptr;
+  if (pass_in.size() == 1) {
+    if (dry) { t_dry[0]++; t_dry[3]++; return BT_OK; }
+    return bt_launch_gate(s, pass_in[0]->desc);
+  }
   int T = std::min(s->n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   int lowb = std::min(tile_lowb(), T);
   const bool use_clusters = env_int("BT_TILE_CLUSTERS", 1) != 0 && T >= CL_BITS;
@@ -1124,7 +1132,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   memset(&P, 0, sizeof(P));
   P.T = T; P.lowb = lowb;
   alignas(64) CUtensorMap tmap;
-  const bool use_tma = env_int("BT_TILE_TMA", 1) != 0 && build_tensor_map(s, in, T, &tmap, P);
+  const bool use_tma = dry || (env_int("BT_TILE_TMA", 1) != 0 && build_tensor_map(s, in, T, &tmap, P));
   P.swz_mode = use_tma ? 0 : 1;
   int local_pos[64];
   for (int b = 0; b < 64; ++b) local_pos[b] = -1;
@@ -1149,7 +1157,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   uint64_t ntiles = s->len >> T;
   size_t smem = sizeof(double2) << T;
   static bool attr_set[64] = {false};  // the opt-in shared-memory size is a per-device function attribute
-  if (!attr_set[s->device & 63]) {
+  if (!dry && !attr_set[s->device & 63]) {
     BT_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << TILE_TMAX)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
     BT_CUDA(cudaFuncSetAttribute(k_tile_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(double2) << TILE_TMAX) + 1024 + 64)));
@@ -1158,9 +1166,14 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
     attr_set[s->device & 63] = true;
   }
   int nsm = 148;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+  if (!dry) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
   auto flush = [&]() -> int {
     if (nitems == 0) return BT_OK;
+    if (dry) {
+      t_dry[0]++; t_dry[1] += np; t_dry[2] += ng + nc + nd;
+      ng = nc = nd = np = nitems = 0;
+      return BT_OK;
+    }
       P.nitems = nitems;
     P.stagger_ns = env_int("BT_TILE_STAGGER_NS", 0);
     P.n_sm = nsm;
@@ -1655,7 +1668,7 @@ int bt_fuse_and_run(bt_sv* s, const std::vector<GateDesc>& gates) {
 
 // pure host (no device): the passes the scheduler forms for a gate list in physical-bit space on a register of n_local bits
 int bt_fusion_plan(const std::vector<GateDesc>& gates, int n_local, int* n_passes, int* n_blocks, int* gates_in_pass, int* tile_bits /* cap x 16 */, double* cost_in_pass,
-                   int* end_reason, int cap) {
+                   int* end_reason, int cap, int* dry_counts /* optional, 4 ints: launches, programs, other items, single-gate passes */) {
   std::vector<Block> blocks;
   fuse_blocks(gates, blocks);
   std::vector<SchedBlock> sb;
@@ -1670,6 +1683,19 @@ int bt_fusion_plan(const std::vector<GateDesc>& gates, int n_local, int* n_passe
     BT_TRY(plan_next_pass(sb, done, first, cfg, plan));
     int ng = 0;
     for (int bi : plan.blocks) { done[bi] = 1; ng += blocks[bi].ngates; }
+    if (dry_counts) {
+      std::vector<const Block*> pass;
+      for (int bi : plan.blocks) pass.push_back(&blocks[bi]);
+      bt_sv fake;
+      memset(&fake, 0, sizeof(fake));
+      fake.n_qubits = fake.n_local = n_local;
+      fake.n_batch = 1;
+      fake.len = 1ull << n_local;
+      t_dry = dry_counts;
+      int rc = launch_pass(&fake, pass, plan.tile_bits);
+      t_dry = nullptr;
+      BT_TRY(rc);
+    }
     if (np < cap) {
       if (gates_in_pass) gates_in_pass[np] = ng;
       if (cost_in_pass) cost_in_pass[np] = plan.cost;

@@ -5,6 +5,7 @@ This is product code: it does not import anything from ``oracle/``.
 """
 from __future__ import annotations
 
+import ast
 import math
 import re
 from typing import List
@@ -163,13 +164,57 @@ def is_measurement(name: str) -> bool:
     return name.upper() in {"MZ", "M(Z)", "MX", "M(X)", "MY", "M(Y)", "MR", "M(R)"}
 
 
+_BIN = {ast.Add: lambda a, b: a + b, ast.Sub: lambda a, b: a - b, ast.Mult: lambda a, b: a * b, ast.Div: lambda a, b: a / b}
+
+
+def _eval_node(n) -> float:
+    if isinstance(n, ast.Expression):
+        return _eval_node(n.body)
+    if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)) and not isinstance(n.value, bool):
+        return float(n.value)
+    if isinstance(n, ast.Name) and n.id == "pi":
+        return math.pi
+    if isinstance(n, ast.UnaryOp) and isinstance(n.op, (ast.UAdd, ast.USub)):
+        v = _eval_node(n.operand)
+        return -v if isinstance(n.op, ast.USub) else v
+    if isinstance(n, ast.BinOp) and type(n.op) in _BIN:
+        return _BIN[type(n.op)](_eval_node(n.left), _eval_node(n.right))
+    raise ValueError("unsupported expression")
+
+
 def parse_number(text: str) -> float:
-    """Numeric gate arguments as the reference writes them: ``0.37``, ``.1pi``, ``0.5π``, ``-pi/2``."""
+    """Numeric gate arguments as the reference writes them: ``0.37``, ``.1pi``, ``0.5π``, ``-pi/2``, ``(1+2)*pi/4``.
+    Evaluated by a small AST walker (numbers, pi, + - * /, unary minus, parentheses): no ``eval``, no powers, no names -- gate
+    arguments arrive from QASM files."""
     e = text.strip().replace("π", "pi")
     e = re.sub(r"(?<=[0-9\.])\s*pi", "*pi", e)
-    if re.fullmatch(r"[0-9eE\.\+\-\*/\(\) pi]+", e) is None:
+    if len(e) > 200 or re.fullmatch(r"[0-9eE\.\+\-\*/\(\) pi]+", e) is None or "**" in e:
         raise ValueError(f"cannot parse gate argument {text!r}")
-    return float(eval(e, {"__builtins__": {}}, {"pi": math.pi}))
+    try:
+        return float(_eval_node(ast.parse(e, mode="eval")))
+    except (SyntaxError, ValueError, ZeroDivisionError, RecursionError) as err:
+        raise ValueError(f"cannot parse gate argument {text!r}") from err
+
+
+def split_args(inner: str):
+    """split a gate argument list at top-level commas (arguments may contain parentheses)"""
+    out, depth, cur = [], 0, []
+    for ch in inner:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth < 0:
+                raise ValueError(f"unbalanced parentheses in {inner!r}")
+        if ch == "," and depth == 0:
+            out.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    if depth != 0:
+        raise ValueError(f"unbalanced parentheses in {inner!r}")
+    out.append("".join(cur))
+    return out
 
 
 def gates(op_name: str) -> np.ndarray:
@@ -179,7 +224,7 @@ def gates(op_name: str) -> np.ndarray:
     if cn in _functions:
         inner = op_name.split("(", 1)[1]
         inner = inner[: inner.rindex(")")]
-        return _functions[cn](*[parse_number(t) for t in inner.split(",")])
+        return _functions[cn](*[parse_number(t) for t in split_args(inner)])
     if un in ("M(Z)", "MZ", "M(R)", "MR", "RES"):
         return gate["I"]
     if un in ("M(X)", "MX"):

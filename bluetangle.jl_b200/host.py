@@ -915,6 +915,15 @@ def sample(x: State, shots: int, rng=None, uniforms: Optional[np.ndarray] = None
         r = _rng(rng)
         uniforms = np.array([r.uniform() for _ in range(shots)], dtype=np.float64)
     u = np.ascontiguousarray(uniforms, dtype=np.float64)
+    if isinstance(x, CuState) and x.n_batch > 1:
+        # batched trajectories: uniforms[t] are trajectory t's draws; one segmented launch set for the whole batch
+        if u.ndim == 1:
+            u = np.ascontiguousarray(u.reshape(x.n_batch, -1))
+        if u.shape[0] != x.n_batch:
+            raise ValueError("uniforms must have one row per trajectory")
+        out = np.empty(u.shape, dtype=np.int64)
+        L.check(x.lib.bt_sv_sample_batched(x.h, L.pdouble(u), u.shape[1], out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
     out = np.empty(len(u), dtype=np.int64)
     if isinstance(x, CuRho):
         L.check(x.lib.bt_dm_sample(x.h, L.pdouble(u), len(u), out.ctypes.data_as(C.POINTER(C.c_int64))))

@@ -6,10 +6,10 @@ from __future__ import annotations
 import re
 from typing import List
 
+from .gates import split_args
 from .host import Op
 
 _Q = r"([a-z_][a-z0-9_]*\[\d+\])"
-_ARGS = r"\(\s*(.+?)\s*\)"
 
 _ONE = {"x": "X", "y": "Y", "z": "Z", "h": "H", "s": "S", "sdg": "SD", "t": "T", "tdg": "TD", "sx": "XSQRT", "id": "I"}
 _ONE_PARAM = {"rx": "RX", "ry": "RY", "rz": "RZ", "u1": "U1", "p": "P", "u2": "U2", "u3": "U3", "u": "U3"}
@@ -44,12 +44,24 @@ def from_qasm(text: str) -> List:
         if m:
             ops.append(Op("RES", _label(m.group(1))))
             continue
-        m = re.fullmatch(rf"([a-z0-9]+)\s*(?:{_ARGS})?\s*(.+)", s)
+        m = re.fullmatch(r"([a-z0-9]+)\s*(.*)", s)
         if not m:
             raise ValueError(f"Unsupported or unrecognized statement: {raw.strip()};")
-        head, args, qs = m.group(1), m.group(2), [t.strip() for t in m.group(3).split(",")]
-        q = [_label(t) for t in qs]
-        arg_s = "(" + ",".join(a.strip() for a in args.split(",")) + ")" if args else ""
+        head, rest, args = m.group(1), m.group(2).strip(), None
+        if rest.startswith("("):  # argument list: up to the parenthesis that balances the first one
+            depth = 0
+            for k, ch in enumerate(rest):
+                depth += ch == "("
+                depth -= ch == ")"
+                if depth == 0:
+                    args, rest = rest[1:k].strip(), rest[k + 1:].strip()
+                    break
+            else:
+                raise ValueError(f"Unsupported or unrecognized statement: {raw.strip()};")
+        if not rest:
+            raise ValueError(f"Unsupported or unrecognized statement: {raw.strip()};")
+        q = [_label(t) for t in rest.split(",")]
+        arg_s = "(" + ",".join(a.strip() for a in split_args(args)) + ")" if args else ""
         if head in _ONE and len(q) == 1 and not args:
             ops.append(Op(_ONE[head], q[0]))
         elif head in _ONE_PARAM and len(q) == 1 and args:

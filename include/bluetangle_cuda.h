@@ -84,9 +84,11 @@ int bt_sv_apply_1q_if(bt_sv* s, int qubit, const bt_c64 m[4], int control, int w
 int bt_sv_apply_2q_if(bt_sv* s, int qubit, int target, const bt_c64 m[16], int control, int want);
 /* pure host (no device needed): the fused passes bt_sv_apply_circuit(fuse != 0) forms for this gate list on one unsharded GPU:
  * number of passes and fused blocks, and per pass (up to cap) the original gates it carries, the index bits its tile takes beyond the
- * fixed low bits (16 ints per pass, -1 padded), its cost units and why it ended (0 no eligible block left, 1 cost cap, 2 block cap) */
+ * fixed low bits (16 ints per pass, -1 padded), its cost units and why it ended (0 no eligible block left, 1 cost cap, 2 block cap);
+ * launch_counts (optional, 4 ints): kernel launches the passes need (a pass that overflows the slots of one launch is split),
+ * register programs, other items, single-gate passes */
 int bt_fusion_plan_host(int n_qubits, const bt_gate* g, uint64_t n, int* n_passes, int* n_blocks, int* gates_in_pass, int* tile_bits /* cap x 16 */,
-                        double* cost_in_pass, int* end_reason, int cap);
+                        double* cost_in_pass, int* end_reason, int cap, int* launch_counts);
 int bt_fusion_stats(uint64_t* passes, uint64_t* blocks); /* cumulative: fused tile-kernel launches and blocks they carried */
 int bt_fusion_flops(double* flops); /* cumulative FP64 flops issued by the fused passes (FMA = 2 flops) */
 /* Pass specialiser (csrc/bt_jit.cu): fused passes that recur are compiled once (NVRTC) into straight-line kernels.

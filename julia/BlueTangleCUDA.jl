@@ -198,7 +198,7 @@ function apply(ops::Vector{<:QuantumOps}, s::CuState; noise::Union{NoiseModel,Bo
             check(ccall((:bt_sv_apply_circuit, LIB), Cint, (Ptr{Cvoid}, Ptr{BtGate}, UInt64, Cint), s.h, g, length(g), 1))
             i = j + 1
         else
-            r = apply(s, ops[i]; noise=noise, track_measurements=track_measurements)
+            r = apply(s, ops[i]; noise=noise, track_measurements=track_measurements, kwargs...)   # kwargs forwarded like src/hilbert.jl:531-536 (pars of variational ops)
             track_measurements && append!(mids, r[2])
             i += 1
         end
@@ -216,10 +216,45 @@ function partial_trace(s::CuState, q1::Int, q2::Int)                            
     out = Matrix{ComplexF64}(undef, 4, 4)
     check(ccall((:bt_sv_rdm2, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}), s.h, q1, q2, out)); out
 end
-function partial_trace(s::CuState, keep::AbstractVector)                             # src/linalg.jl:83-86
-    length(keep) == 2 || throw(ArgumentError("device partial_trace keeps 1, 2 or 3 consecutive qubits"))
-    out = Matrix{ComplexF64}(undef, 4, 4)
-    check(ccall((:bt_sv_rdm2, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}), s.h, keep[1], keep[2], out)); out
+function partial_trace(s::CuState, keep::AbstractVector)                             # src/linalg.jl:83-86 (any number of kept qubits up to 12)
+    k = length(keep); d = 2^k
+    out = Matrix{ComplexF64}(undef, d, d)
+    check(ccall((:bt_sv_rdm, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{ComplexF64}), s.h, k, Cint.(keep), out)); out
+end
+function partial_trace(r::CuRho, dims::Vector, trace_out::Vector)                    # src/linalg.jl:88-140 (qubit registers: all dims == 2)
+    all(==(2), dims) || throw(ArgumentError("device density matrices are qubit registers"))
+    keep = setdiff(1:length(dims), trace_out); k = length(keep); d = 2^k
+    out = Matrix{ComplexF64}(undef, d, d)
+    check(ccall((:bt_dm_rdm, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{ComplexF64}), r.h, k, Cint.(keep), out)); out
+end
+bipartition_trace(r::CuRho) = partial_trace(r, fill(2, r.N), collect(1:Int(r.N / 2)))  # src/linalg.jl:151-161: keeps the last N/2 qubits
+
+# entanglement_entropy src/func.jl:299-312 / :323-328: the spectrum comes from the device (one-sided Jacobi iteration)
+function entanglement_entropy(s::CuState; spectrum_bool=false)
+    partA = s.N ÷ 2
+    spec = Vector{Float64}(undef, 2^partA * s.n_batch)
+    check(ccall((:bt_sv_schmidt_spectrum, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Cint}), s.h, partA, spec, C_NULL))
+    spec = spec[spec .> 0]
+    return spectrum_bool == false ? sum(-spec .* log.(spec)) : (sum(-spec .* log.(spec)), -log.(spec))
+end
+function entanglement_entropy(r::CuRho)
+    nk = Int(r.N / 2)
+    spec = Vector{Float64}(undef, 2^nk)
+    check(ccall((:bt_dm_bipartition_spectrum, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Cint}), r.h, nk, spec, C_NULL))
+    spec = spec[spec .> 0]
+    return sum(-spec .* log.(spec)), -log.(spec)
+end
+
+# expect(x, op) src/func.jl:91-92 for any Op (1- or 2-qubit, with or without a control)
+function expect(s::CuState, op::Op)
+    out = Vector{Float64}(undef, s.n_batch)
+    check(ccall((:bt_sv_expect_op, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{ComplexF64}, Ptr{Float64}), s.h, op.q, op.qubit, op.target_qubit, op.control, cmat(op.mat), out))
+    return s.n_batch == 1 ? out[1] : out
+end
+function expect(r::CuRho, op::Op)
+    out = Ref{Float64}(0.0)
+    check(ccall((:bt_dm_expect_op, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{Float64}), r.h, op.q, op.qubit, op.target_qubit, op.control, cmat(op.mat), out))
+    return out[]
 end
 
 function expect(s::CuState, op_str::String)                                          # src/func.jl:97

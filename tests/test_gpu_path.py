@@ -531,3 +531,24 @@ def test_batched_ifop_branches_with_noise_and_nested_measurements(bt, orc):
         assert out.shape == (T, 3) and set(np.unique(out[:, 0])) == {0, 1}   # both branches were taken inside the batch
         if noise_pair[0] is not False:
             assert len(used) > 1  # the branches draw different numbers of uniforms: per-trajectory accounting matters
+
+
+def test_batched_sampling_is_one_segmented_pass_per_trajectory_cdf(bt, orc):
+    """bt_sv_sample_batched: every trajectory's shots follow its own inverse CDF (src/ops.jl:46-62 per trajectory, the per-shot loop
+    of src/ops.jl:616-631 with shots = 1 included); three launches for the whole batch, whatever its size."""
+    rng = np.random.default_rng(77)
+    for N, nb, shots in ((3, 5, 7), (13, 9, 33), (14, 40, 1)):
+        v = rng.normal(size=(nb, 1 << N)) + 1j * rng.normal(size=(nb, 1 << N))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v[1] = 0
+        v[1, (1 << N) - 1] = 1.0  # a basis state: every draw returns the last index
+        s = bt.CuState.from_numpy(v)
+        us = rng.random((nb, shots))
+        us[0, 0] = 0.0
+        l0 = s.launch_count()
+        got = bt.sample(s, shots, uniforms=us)
+        assert s.launch_count() - l0 == 3
+        assert got.shape == (nb, shots)
+        for t in range(nb):
+            assert np.array_equal(got[t], orc.sample(v[t], us[t])), t
+        assert np.all(got[1] == (1 << N) - 1)

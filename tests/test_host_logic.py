@@ -129,6 +129,13 @@ def test_qasm_front_door(bt):
     assert np.allclose(ops[2].mat, bt.gates("RZ(0.25*pi)"))
     with pytest.raises(ValueError):
         bt.from_qasm("foo q[0];")
+    # arguments with nested parentheses split at top-level commas only; arithmetic is evaluated by an AST walker, not eval()
+    ops = bt.from_qasm("qreg q[2]; rz((1+2)*pi/4) q[0]; u3(pi/2, (0.1), -pi) q[1]; cu1(pi/(2)) q[0],q[1];")
+    assert np.allclose(ops[0].mat, bt.gates(f"RZ({3 * np.pi / 4!r})")) and np.allclose(ops[1].mat, bt.gates(f"U3({np.pi / 2!r},0.1,{-np.pi!r})"))
+    assert ops[2].control == 1 and np.allclose(ops[2].mat, bt.gates(f"U1({np.pi / 2!r})"))
+    for hostile in ("rz(9**9**9**9) q[0];", "rz(__import__('os').getpid()) q[0];", "rz(1/0) q[0];", "rz((1) q[0];"):
+        with pytest.raises(ValueError):
+            bt.from_qasm("qreg q[1]; " + hostile)
 
 
 def test_opf_dispatch_and_forms(bt, orc):
