@@ -286,25 +286,36 @@ __device__ __forceinline__ double prob_at(const double2* __restrict__ a, uint64_
 
 // All three kernels take a batch of `ntraj` independent distributions of n entries each (trajectory t at a + t * n * stride-free
 // layout: consecutive state vectors); a single state is ntraj == 1.
-__global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum, uint64_t nb) {
-  // one CTA per block of 2^SB entries; fixed-order tree => reproducible
-  __shared__ double sm[8];
+#define SUBS (1 << (SB - 8))  // sub-blocks of 256 entries per block
+__global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum, double* __restrict__ ssum,
+                                                     uint64_t nb) {
+  // one CTA per block of 2^SB entries; also the sums of its 16 sub-blocks of 256 entries (the in-block search of k_sample starts
+  // from them); fixed-order tree => reproducible
+  __shared__ double sm[SUBS][8];
+  __shared__ double sub[SUBS];
   const uint64_t traj = blockIdx.x / nb, blk = blockIdx.x % nb;
   const double2* __restrict__ base = a + traj * n;
   const uint64_t b0 = blk << SB;
-  double acc = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 8
-  for (uint64_t k = threadIdx.x; k < (1ull << SB); k += 256) {
-    uint64_t i = b0 + k;
-    if (i < n) acc += prob_at(base, i, dm_stride);
-  }
+  for (int it = 0; it < SUBS; ++it) {
+    uint64_t i = b0 + (uint64_t)it * 256 + threadIdx.x;
+    double acc = (i < n) ? prob_at(base, i, dm_stride) : 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) sm[it][warp] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < SUBS) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sm[threadIdx.x][w];
+    sub[threadIdx.x] = s;
+    ssum[(uint64_t)blockIdx.x * SUBS + threadIdx.x] = s;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += sm[w];
+    for (int k = 0; k < SUBS; ++k) s += sub[k];
     bsum[blockIdx.x] = s;
   }
 }
@@ -317,9 +328,13 @@ __global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ xs
   if (threadIdx.x == 0) carry_s = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint64_t base = 0; base < n; base += 1024) {
-    uint64_t i = base + threadIdx.x;
-    double v = (i < n) ? x[i] : 0.0;
+  for (uint64_t base = 0; base < n; base += 4096) {  // a thread owns 4 consecutive entries
+    const uint64_t i0 = base + (uint64_t)threadIdx.x * 4;
+    double e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = (i0 + k < n) ? x[i0 + k] : 0.0;
+    e[1] += e[0]; e[2] += e[1]; e[3] += e[2];
+    double v = e[3];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       double y = __shfl_up_sync(0xffffffffu, v, o);
@@ -337,11 +352,11 @@ __global__ void __launch_bounds__(1024) k_scan_inclusive(double* __restrict__ xs
       warp_tot[lane] = w;
     }
     __syncthreads();
-    double off = carry_s + (warp > 0 ? warp_tot[warp - 1] : 0.0);
-    v += off;
-    if (i < n) x[i] = v;
+    const double off = carry_s + (warp > 0 ? warp_tot[warp - 1] : 0.0) + (v - e[3]);  // everything before this thread's 4 entries
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k < n) x[i0 + k] = off + e[k];
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = v;
+    if (threadIdx.x == 1023) carry_s = off + e[3];
     __syncthreads();
   }
 }
@@ -357,7 +372,7 @@ struct ShardCdf {
 // pre: prefix = inclusive scan of the block sums of each trajectory (nb entries each); one warp per shot: binary search over the
 // block prefix, then a warp scan inside the block.  out = -1 for a shot another rank owns.
 __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride,
-                                                 const double* __restrict__ prefixes, uint64_t nb,
+                                                 const double* __restrict__ prefixes, const double* __restrict__ ssum, uint64_t nb,
                                                  const double* __restrict__ u, uint64_t shots_per_traj, uint64_t shots, const __grid_constant__ ShardCdf sh,
                                                  int64_t* __restrict__ out) {
   const uint64_t shot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -388,9 +403,24 @@ __global__ void __launch_bounds__(128) k_sample(const double2* __restrict__ a, u
   double carry = (j > 0) ? prefix[j - 1] : 0.0;
   const uint64_t b0 = j << SB;
   const uint64_t bend = (b0 + (1ull << SB) < n) ? b0 + (1ull << SB) : n;
+  // sub-block (256 entries) that holds the target: warp scan over the block's 16 sub-block sums; the entries before it are skipped
+  uint64_t start = b0;
+  {
+    double v = (lane < SUBS) ? ssum[(traj * nb + j) * SUBS + lane] : 0.0;
+#pragma unroll
+    for (int o = 1; o < SUBS; o <<= 1) {
+      double y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += y;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, lane < SUBS && carry + v >= t);
+    // the first sub-block whose inclusive sum reaches the target; none (rounding: the entry-level sums differ in the last bits): start at the last one
+    const int sb = hit ? (__ffs(hit) - 1) : (SUBS - 1);
+    const double before = __shfl_sync(0xffffffffu, v, sb > 0 ? sb - 1 : 0);
+    if (sb > 0) { carry += before; start = b0 + (uint64_t)sb * 256; }
+  }
   int64_t found = -1;
   int64_t last_nz = -1;
-  for (uint64_t base = b0; base < bend && found < 0; base += 32) {
+  for (uint64_t base = start; base < bend && found < 0; base += 32) {
     uint64_t i = base + lane;
     double p = (i < bend) ? prob_at(base_a, i, dm_stride) : 0.0;
     double v = p;
@@ -419,14 +449,16 @@ static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_st
   if (shots == 0) return BT_OK;
   const uint64_t nb = (n + (1ull << SB) - 1) >> SB;
   if (nb * ntraj >= (1ull << 31)) BT_FAIL(BT_ERR_UNSUPPORTED, "sampling: batch too large");
-  size_t off_u = ((nb * ntraj * sizeof(double) + 255) / 256) * 256;
+  size_t off_s = ((nb * ntraj * sizeof(double) + 255) / 256) * 256;
+  size_t off_u = off_s + ((nb * ntraj * SUBS * sizeof(double) + 255) / 256) * 256;
   size_t off_o = off_u + ((shots * sizeof(double) + 255) / 256) * 256;
   BT_TRY(bt_ensure_scratch(s, off_o + shots * sizeof(int64_t)));
   double* d_prefix = (double*)s->d_scratch;
+  double* d_sub = (double*)((char*)s->d_scratch + off_s);
   double* d_u = (double*)((char*)s->d_scratch + off_u);
   int64_t* d_out = (int64_t*)((char*)s->d_scratch + off_o);
   BT_CUDA(cudaMemcpyAsync(d_u, u, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  k_block_sums<<<(unsigned)(nb * ntraj), 256, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb);
+  k_block_sums<<<(unsigned)(nb * ntraj), 256, 0, s->stream>>>(base, n, dm_stride, d_prefix, d_sub, nb);
   BT_CHECK_LAUNCH(s);
   k_scan_inclusive<<<(unsigned)ntraj, 1024, 0, s->stream>>>(d_prefix, nb);
   BT_CHECK_LAUNCH(s);
@@ -447,7 +479,7 @@ static int sample_impl(bt_sv* s, const double2* base, uint64_t n, uint64_t dm_st
     for (int r = 0; r < s->world; ++r) { run += tots[r]; sh.prefix[r] = run; }
   }
   uint64_t threads = shots * 32;
-  k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, nb, d_u, shots_per_traj, shots, sh, d_out);
+  k_sample<<<(unsigned)((threads + 127) / 128), 128, 0, s->stream>>>(base, n, dm_stride, d_prefix, d_sub, nb, d_u, shots_per_traj, shots, sh, d_out);
   BT_CHECK_LAUNCH(s);
   BT_CUDA(cudaMemcpyAsync(out, d_out, shots * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
   BT_CUDA(cudaStreamSynchronize(s->stream));

@@ -303,6 +303,8 @@ extern "C" int bt_sv_copy(bt_sv* dst, const bt_sv* src) {
   if (!src || src->len != dst->len || src->n_qubits != dst->n_qubits) BT_FAIL(BT_ERR_ARG, "bt_sv_copy: shape mismatch");
   BT_CUDA(cudaStreamSynchronize(src->stream));
   BT_CUDA(cudaMemcpyAsync(dst->amp, src->amp, dst->len * sizeof(double2), cudaMemcpyDeviceToDevice, dst->stream));
+  // the copy runs on dst's stream: later work enqueued on src's stream (which may overwrite the source) must not overtake it
+  BT_CUDA(cudaStreamSynchronize(dst->stream));
   memcpy(dst->phys_of_bit, src->phys_of_bit, sizeof(dst->phys_of_bit));
   return BT_OK;
 }

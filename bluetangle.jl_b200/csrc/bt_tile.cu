@@ -806,7 +806,12 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-static int tile_lowb() { return std::max(TILE_LOWB_MIN, std::min(TILE_LOWB, env_int("BT_TILE_LOWB", TILE_LOWB))); }
+// fixed low bits of every tile: 3 (one 128-byte row of the tensor copy) with the look-ahead scheduler -- the 9 free bits buy deeper
+// passes (C2: 66 instead of 93 launches, 165 instead of 184 ms) --, 5 with first fit (round-1 behaviour); BT_TILE_LOWB overrides
+static int tile_lowb() {
+  const int dflt = env_int("BT_FUSE_SCHED", 1) != 0 ? TILE_LOWB_MIN : TILE_LOWB;
+  return std::max(TILE_LOWB_MIN, std::min(TILE_LOWB, env_int("BT_TILE_LOWB", dflt)));
+}
 
 static void fuse_blocks(const std::vector<GateDesc>& gates, std::vector<Block>& blocks) {
   std::vector<int> last(64, -1);  // last block index touching a physical bit
@@ -1639,9 +1644,10 @@ static SchedCfg sched_cfg(int n_local) {
   c.n_local = n_local;
   c.T = std::min(n_local, env_int("BT_TILE_BITS", TILE_TDEF));
   c.lowb = std::min(tile_lowb(), c.T);
-  c.maxg = (double)std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", 28)));  // cost units per pass (measured sweep: profiles/r1_fusion_sweep.txt)
-  c.window = env_int("BT_FUSE_WINDOW", 256);
   c.policy = env_int("BT_FUSE_SCHED", 1);
+  // cost units per pass (measured sweeps: profiles/r1_fusion_sweep.txt for first fit, profiles/r2_sched_sweep.txt for look-ahead)
+  c.maxg = (double)std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", c.policy != 0 ? 40 : 28)));
+  c.window = env_int("BT_FUSE_WINDOW", 256);
   return c;
 }
 
