@@ -88,6 +88,129 @@ extern "C" int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* ou
   return BT_OK;
 }
 
+// ---- several measurements in one read pass + one collapse pass -----------------------------------------------------------------
+int bt_reduce_joint_probs(const bt_sv* cs, int k, const int* tb);  // bt_reduce.cu
+
+// One thread per trajectory: the k outcomes in order.  Measurement j sees the state collapsed and renormalised by measurements
+// 0..j-1 (born_measure_Z normalises after every projection, src/hilbert.jl:694): p0 = mass(pattern so far, bit j = 0) / mass(pattern
+// so far); the first one uses the raw mass of the state as it is, like the single call.
+__global__ void k_decide_multi(const double* __restrict__ res, int k, const double* __restrict__ u, int32_t* __restrict__ pattern_out, int32_t* __restrict__ outcomes,
+                               double* __restrict__ scale, int64_t n_batch, const int32_t* __restrict__ mask) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_batch) return;
+  const int D = 1 << k;
+  const double* p = res + t * D;
+  if (mask && !mask[t]) {
+    pattern_out[t] = -1;
+    scale[2 * t] = 1.0; scale[2 * t + 1] = 0.0;
+    for (int j = 0; j < k; ++j) outcomes[t * k + j] = -1;
+    return;
+  }
+  int pattern = 0, decided = 0;
+  for (int j = 0; j < k; ++j) {
+    double tot = 0.0, m0 = 0.0;
+    for (int b = 0; b < D; ++b)
+      if ((b & decided) == pattern) {
+        tot += p[b];
+        if (!((b >> j) & 1)) m0 += p[b];
+      }
+    const double p0 = j == 0 ? m0 : m0 / tot;
+    const int ind = (u[t * k + j] < p0) ? 0 : 1;
+    outcomes[t * k + j] = ind;
+    pattern |= ind << j;
+    decided |= 1 << j;
+  }
+  pattern_out[t] = pattern;
+  scale[2 * t] = 1.0 / sqrt(p[pattern]);
+  scale[2 * t + 1] = p[pattern];
+}
+
+struct MultiPlan {
+  int k, ni;
+  int ins[4];
+  uint64_t off[16];
+  uint32_t reset_mask;  // bit j set: measurement j resets its qubit (|1> -> |0>)
+};
+
+// one thread per group of 2^k amplitudes: the member selected by the trajectory's outcome pattern survives (scaled), the others
+// become zero; reset bits move the survivor to the member with those bits cleared
+__global__ void __launch_bounds__(256) k_collapse_multi(double2* __restrict__ a, int n_local, uint64_t ngroups_total, const __grid_constant__ MultiPlan P,
+                                                         const int32_t* __restrict__ pattern, const double* __restrict__ scale) {
+  const int D = 1 << P.k;
+  const double2 zero = make_double2(0.0, 0.0);
+  for (uint64_t G = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; G < ngroups_total; G += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t t = G >> (n_local - P.k);
+    const int pat = pattern[t];
+    if (pat < 0) continue;
+    uint64_t g = G;
+    for (int i = 0; i < P.ni; ++i) {
+      const int b = P.ins[i];
+      g = ((g >> b) << (b + 1)) | (g & ((1ull << b) - 1));
+    }
+    const double sc = scale[2 * t];
+    double2 x = a[g + P.off[pat]];
+    x = make_double2(x.x * sc, x.y * sc);
+    const int dst = pat & ~(int)P.reset_mask;
+    for (int j = 0; j < D; ++j) a[g + P.off[j]] = (j == dst) ? x : zero;
+  }
+}
+
+extern "C" int bt_sv_measure_z_multi(bt_sv* s, int k, const int* qubits, const double* u, int32_t* outcomes, const int* reset) {
+  BT_TRY(bt_check_sv(s));
+  if (!u || !qubits) BT_FAIL(BT_ERR_ARG, "null argument");
+  if (k < 1 || k > 4) BT_FAIL(BT_ERR_ARG, "bt_sv_measure_z_multi takes 1..4 qubits per call");
+  int lbs[4];
+  for (int j = 0; j < k; ++j) {
+    if (qubits[j] < 1 || qubits[j] > s->n_qubits) BT_FAIL(BT_ERR_ARG, "N must be larger than qubit");
+    for (int i = 0; i < j; ++i)
+      if (qubits[i] == qubits[j]) BT_FAIL(BT_ERR_ARG, "repeated qubit %d: measure it in separate calls", qubits[j]);
+    lbs[j] = s->n_qubits - qubits[j];
+  }
+  BT_TRY(bt_ensure_traj(s));
+  if (s->world > 1) BT_TRY(bt_prepare_local_bits(s, k, lbs));
+  int tb[4];
+  for (int j = 0; j < k; ++j) tb[j] = s->phys_of_bit[lbs[j]];
+  const int D = 1 << k;
+  BT_TRY(bt_reduce_joint_probs(s, k, tb));  // may use the head of d_scratch (k == 4): the buffers below come after it
+  if (s->world > 1) {
+    BT_TRY(bt_results_to_host(s, (size_t)s->n_batch * D));
+    if (!s->allreduce) BT_FAIL(BT_ERR_ARG, "sharded state: set an all-reduce callback first");
+    s->allreduce(s->allreduce_ctx, s->h_res, (int)(s->n_batch * D));
+    BT_CUDA(cudaMemcpyAsync(s->d_res, s->h_res, s->n_batch * D * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  }
+  const size_t off_u = 256, off_o = off_u + (((size_t)s->n_batch * k * sizeof(double) + 255) / 256) * 256;
+  BT_TRY(bt_ensure_scratch(s, off_o + (size_t)s->n_batch * k * sizeof(int32_t)));
+  double* d_u = (double*)((char*)s->d_scratch + off_u);
+  int32_t* d_out = (int32_t*)((char*)s->d_scratch + off_o);
+  BT_CUDA(cudaMemcpyAsync(d_u, u, (size_t)s->n_batch * k * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  k_decide_multi<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(s->d_res, k, d_u, s->d_outcome, d_out, s->d_scale, s->n_batch, s->mask_on ? s->d_mask : nullptr);
+  BT_CHECK_LAUNCH(s);
+  MultiPlan P;
+  memset(&P, 0, sizeof(P));
+  P.k = k; P.ni = k;
+  int sorted[4];
+  for (int j = 0; j < k; ++j) sorted[j] = tb[j];
+  std::sort(sorted, sorted + k);
+  for (int j = 0; j < k; ++j) P.ins[j] = sorted[j];
+  for (int j = 0; j < D; ++j) {
+    uint64_t o = 0;
+    for (int i = 0; i < k; ++i)
+      if ((j >> i) & 1) o |= 1ull << tb[i];
+    P.off[j] = o;
+  }
+  for (int j = 0; j < k; ++j)
+    if (reset && reset[j]) P.reset_mask |= 1u << j;
+  const uint64_t ngroups = s->len >> k;
+  const unsigned grid = (unsigned)std::min<uint64_t>((ngroups + 255) / 256, 148ull * 32);
+  k_collapse_multi<<<grid, 256, 0, s->stream>>>(s->amp, s->n_local, ngroups, P, s->d_outcome, s->d_scale);
+  BT_CHECK_LAUNCH(s);
+  if (outcomes) {
+    BT_CUDA(cudaMemcpyAsync(outcomes, d_out, (size_t)s->n_batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    BT_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  return BT_OK;
+}
+
 extern "C" int bt_sv_outcomes(const bt_sv* s, int32_t* outcome) {
   BT_TRY(bt_check_sv(s));
   if (!outcome) BT_FAIL(BT_ERR_ARG, "null output");

@@ -349,6 +349,75 @@ int bt_reduce_rdm_at(const bt_sv* cs, int k, const int* tb, size_t res_off) {
 
 int bt_reduce_rdm(const bt_sv* s, int k, const int* tb) { return bt_reduce_rdm_at(s, k, tb, 0); }
 
+// joint distribution of K index bits: acc[j] = sum over the other bits of |a[.., bits = j, ..]|^2 (the diagonal of the K-bit RDM)
+template <int K>
+__global__ void __launch_bounds__(RB) k_joint_probs(const double2* __restrict__ a, int n_local, const __grid_constant__ RdmPlan P, const uint64_t* __restrict__ off16,
+                                                     double* __restrict__ part, int nblk) {
+  constexpr int D = 1 << K;
+  const int64_t traj = blockIdx.y;
+  const uint64_t ngroups = 1ull << (n_local - K);
+  const double2* base = a + ((uint64_t)traj << n_local);
+  uint64_t off[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) off[j] = K <= 3 ? P.off[j] : off16[j];
+  double acc[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) acc[i] = 0.0;
+#pragma unroll 2
+  for (uint64_t g = (uint64_t)blockIdx.x * RB + threadIdx.x; g < ngroups; g += (uint64_t)nblk * RB) {
+    const uint64_t i0 = rdm_expand(g, P);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double2 x = base[i0 + off[j]];
+      acc[j] = fma(x.x, x.x, fma(x.y, x.y, acc[j]));
+    }
+  }
+  block_reduce_store<D>(acc, part + ((size_t)traj * nblk + blockIdx.x) * D);
+}
+
+// results: s->d_res[t * 2^k + j], j's bit i <-> physical bit tb[i]; k <= 4
+int bt_reduce_joint_probs(const bt_sv* cs, int k, const int* tb) {
+  bt_sv* s = const_cast<bt_sv*>(cs);
+  BT_TRY(check_batch_grid(s));
+  if (k < 1 || k > 4 || s->n_local < k) BT_FAIL(BT_ERR_ARG, "joint distribution of %d bits unsupported", k);
+  RdmPlan P;
+  int sorted[4];
+  for (int i = 0; i < k; ++i) {
+    if (tb[i] < 0 || tb[i] >= s->n_local) BT_FAIL(BT_ERR_UNSUPPORTED, "measured qubit on a global bit needs a remap first");
+    sorted[i] = tb[i];
+  }
+  std::sort(sorted, sorted + k);
+  for (int i = 0; i + 1 < k; ++i)
+    if (sorted[i] == sorted[i + 1]) BT_FAIL(BT_ERR_ARG, "repeated qubit");
+  P.ni = k;
+  for (int i = 0; i < 4; ++i) P.ins[i] = i < k ? sorted[i] : 0;
+  uint64_t off[16];
+  for (int j = 0; j < (1 << k); ++j) {
+    uint64_t o = 0;
+    for (int t = 0; t < k; ++t)
+      if ((j >> t) & 1) o |= 1ull << tb[t];
+    off[j] = o;
+    if (j < 8) P.off[j] = o;
+  }
+  const int D = 1 << k;
+  const int nblk = pick_nblk(s, 1ull << (s->n_local - k));
+  BT_TRY(bt_ensure_partials(s, (size_t)s->n_batch * nblk * D));
+  if ((size_t)s->n_batch * D > s->res_cap) BT_FAIL(BT_ERR_ARG, "internal: result buffer overflow");
+  uint64_t* d_off = nullptr;
+  if (k == 4) {
+    BT_TRY(bt_ensure_scratch(s, sizeof(off)));
+    d_off = (uint64_t*)s->d_scratch;
+    BT_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, s->stream));
+  }
+  dim3 grid(nblk, (unsigned)s->n_batch);
+  if (k == 1) k_joint_probs<1><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, d_off, s->d_part, nblk);
+  else if (k == 2) k_joint_probs<2><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, d_off, s->d_part, nblk);
+  else if (k == 3) k_joint_probs<3><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, d_off, s->d_part, nblk);
+  else k_joint_probs<4><<<grid, RB, 0, s->stream>>>(s->amp, s->n_local, P, d_off, s->d_part, nblk);
+  BT_CHECK_LAUNCH(s);
+  return finish(s, nblk, D, 0);
+}
+
 int bt_reduce_norm2(const bt_sv* cs) {
   bt_sv* s = const_cast<bt_sv*>(cs);
   BT_TRY(check_batch_grid(s));

@@ -641,6 +641,11 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
             if isinstance(o, _GateRun):
                 o.run(x)
                 continue
+            if isinstance(o, _MeasureRun):
+                m = o.run(x, rng)
+                if track_measurements:
+                    mids.extend(m)
+                continue
             if track_measurements and isinstance(x, CuState):
                 x, m = apply(x, o, noise=noise, rng=rng, track_measurements=True)
                 mids.extend(m)
@@ -730,20 +735,75 @@ def pack_gates(ops: Sequence[Op]) -> np.ndarray:
     return arr
 
 
+class _MeasureRun:
+    """Consecutive Z-basis measurements / resets on distinct qubits: ONE read pass (joint distribution of the measured bits per
+    trajectory) and ONE collapse pass through ``bt_sv_measure_z_multi`` instead of one of each per measurement.  Outcomes are
+    decided in op order, each on the state collapsed by the previous ones, and the draws are consumed in the same order as by
+    the op-by-op loop (src/hilbert.jl:517-553 over born_measure_Z :682-696), so results and draw streams are unchanged."""
+
+    MAXK = 4
+
+    def __init__(self, ops):
+        self.ops = list(ops)
+
+    def run(self, x: "CuState", rng) -> List:
+        k = len(self.ops)
+        u = np.empty((x.n_batch, k), dtype=np.float64)
+        for j in range(k):
+            u[:, j] = _uniforms(x, rng)
+        out = np.empty((x.n_batch, k), dtype=np.int32)
+        qs = (C.c_int * k)(*[int(o.qubit) for o in self.ops])
+        rs = (C.c_int * k)(*[1 if isinstance(o, OpQC) else 0 for o in self.ops])
+        L.check(x.lib.bt_sv_measure_z_multi(x.h, k, qs, L.pdouble(u), out.ctypes.data_as(C.POINTER(C.c_int32)), rs))
+        # resets are channels (OpQC): they report no mid-circuit outcome (apply() only tracks type "🔬" ops)
+        return [(int(out[0, j]) if x.n_batch == 1 else out[:, j].copy()) for j in range(k) if not isinstance(self.ops[j], OpQC)]
+
+
+MEASURE_FUSE_DEFAULT = True
+
+
+def _z_measurement(o) -> bool:
+    """plain Z-basis measurement (no rotation, no random basis, no branches) or a reset channel"""
+    if isinstance(o, ifOp):
+        return False
+    if isinstance(o, OpQC):
+        return o.name.upper() in ("RES", "RESET")
+    return isinstance(o, Op) and o.ismeasure and o.name.upper() in ("MZ", "M(Z)")
+
+
 def _coalesce(ops, x, noise):
-    """Group maximal runs of plain gates (no noise attached, not measurements/channels) into single library calls."""
-    out, run = [], []
+    """Group maximal runs of plain gates (no noise attached, not measurements/channels) into single library calls, and runs of
+    Z-basis measurements / resets on distinct qubits of a state vector into single multi-measurement calls."""
+    out, run, mrun = [], [], []
     plain_ok = not isinstance(noise, NoiseModel)
+    fuse_meas = MEASURE_FUSE_DEFAULT and isinstance(x, CuState)
+
+    def flush_m():
+        nonlocal mrun
+        if len(mrun) == 1:
+            out.append(mrun[0])
+        elif mrun:
+            out.append(_MeasureRun(mrun))
+        mrun = []
+
     for o in ops:
         if isinstance(o, tuple):
             o = Op(*o)
         if plain_ok and isinstance(o, Op) and not o.ismeasure:
+            flush_m()
             run.append(o)
             continue
         if run:
             out.append(_GateRun(run, FUSE_DEFAULT))
             run = []
+        if fuse_meas and _z_measurement(o):
+            if len(mrun) == _MeasureRun.MAXK or any(m.qubit == o.qubit for m in mrun):
+                flush_m()
+            mrun.append(o)
+            continue
+        flush_m()
         out.append(o)
+    flush_m()
     if run:
         out.append(_GateRun(run, FUSE_DEFAULT))
     return out

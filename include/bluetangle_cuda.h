@@ -130,6 +130,12 @@ int bt_sv_probs(const bt_sv* s, double* host /* n_batch * 2^n : abs2.(state) src
  * u: n_batch uniforms; outcome = (u < p0) ? 0 : 1; the state is projected and renormalised by its own norm.
  * outcome/p0 may be NULL (no host synchronisation then; outcomes stay in the device outcome buffer). */
 int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* outcome, double* p0, int reset);
+/* k <= 4 consecutive born_measure_Z calls (src/hilbert.jl:682-696; _reset_Z :752-759 where reset[j] != 0) on DISTINCT qubits in one
+ * read pass + one collapse pass instead of k of each: the joint distribution of the k measured bits is reduced per trajectory, then
+ * the outcomes are decided in order -- measurement j sees the state collapsed and renormalised by measurements 0..j-1, exactly like
+ * the sequential calls (the per-shot loop of a monitored circuit, src/ops.jl:616-631).  u[t*k + j], outcomes[t*k + j] (may be NULL:
+ * no synchronisation); the handle's outcome record (bt_sv_outcomes) then holds the pattern sum_j outcome_j << j. */
+int bt_sv_measure_z_multi(bt_sv* s, int k, const int* qubits, const double* u, int32_t* outcomes, const int* reset /* k flags or NULL */);
 int bt_sv_outcomes(const bt_sv* s, int32_t* outcome /* n_batch: results of the last measure/kraus call */);
 /* Trajectory mask for batched states: while set, bt_sv_apply_1q/2q/3q, bt_sv_apply_circuit (gate by gate then), bt_sv_kraus and
  * bt_sv_measure_z act only on trajectories with mask[t] != 0; the others are untouched, consume no draw and report outcome /

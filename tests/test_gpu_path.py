@@ -552,3 +552,54 @@ def test_batched_sampling_is_one_segmented_pass_per_trajectory_cdf(bt, orc):
         for t in range(nb):
             assert np.array_equal(got[t], orc.sample(v[t], us[t])), t
         assert np.all(got[1] == (1 << N) - 1)
+
+
+def test_multi_measurement_equals_sequential_born_measurements(bt, orc):
+    """bt_sv_measure_z_multi: k measurements / resets in one read + one collapse pass give the outcomes, the collapsed state and
+    the draw consumption of k sequential born_measure_Z / _reset_Z calls (src/hilbert.jl:682-696, :752-759), on single states,
+    batches, under a trajectory mask, and through apply() on an op list (oracle fed the same draws)."""
+    import ctypes as C
+    L = bt._lib
+    rng = np.random.default_rng(2024)
+    for N, nb, qs, rs in ((5, 1, [3], [0]), (6, 1, [2, 5], [0, 0]), (7, 3, [7, 1, 4], [0, 1, 0]), (9, 4, [2, 9, 5, 1], [1, 0, 0, 1]), (4, 6, [4, 3, 2, 1], [0, 0, 0, 0])):
+        v = rng.normal(size=(nb, 1 << N)) + 1j * rng.normal(size=(nb, 1 << N))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        k = len(qs)
+        u = rng.random((nb, k))
+        a = bt.CuState.from_numpy(v if nb > 1 else v[0])
+        b = bt.CuState.from_numpy(v if nb > 1 else v[0])
+        out = np.empty((nb, k), dtype=np.int32)
+        L.check(a.lib.bt_sv_measure_z_multi(a.h, k, (C.c_int * k)(*qs), L.pdouble(np.ascontiguousarray(u)), out.ctypes.data_as(C.POINTER(C.c_int32)), (C.c_int * k)(*rs)))
+        seq = np.empty((nb, k), dtype=np.int32)
+        for j in range(k):
+            o = np.empty(nb, dtype=np.int32)
+            L.check(b.lib.bt_sv_measure_z(b.h, qs[j], L.pdouble(np.ascontiguousarray(u[:, j])), o.ctypes.data_as(C.POINTER(C.c_int32)), None, rs[j]))
+            seq[:, j] = o
+        assert np.array_equal(out, seq), (N, qs)
+        assert np.max(np.abs(a.to_numpy() - b.to_numpy())) < 1e-13
+        assert np.max(np.abs(np.atleast_1d(bt.norm2(a)) - 1)) < 1e-12
+    # under a mask: untouched trajectories, outcome -1
+    v = rng.normal(size=(4, 64)) + 1j * rng.normal(size=(4, 64))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    a = bt.CuState.from_numpy(v)
+    a.set_mask(np.array([True, False, True, False]))
+    out = np.empty((4, 2), dtype=np.int32)
+    L.check(a.lib.bt_sv_measure_z_multi(a.h, 2, (C.c_int * 2)(2, 6), L.pdouble(np.ascontiguousarray(rng.random((4, 2)))), out.ctypes.data_as(C.POINTER(C.c_int32)), None))
+    a.set_mask(None)
+    got = a.to_numpy()
+    assert np.all(out[[1, 3]] == -1) and np.all(out[[0, 2]] >= 0)
+    assert np.array_equal(got[1], v[1]) and np.array_equal(got[3], v[3])
+    # through apply(): a monitored layer with consecutive measurements and a reset, against the oracle's op-by-op loop
+    N = 7
+    names = [("H", 1), ("H", 4), ("CNOT", 1, 2), ("CNOT", 4, 5), ("RY(0.7)", 6), ("MZ", 2), ("MZ", 5), ("MZ", 6), ("MZ", 1), ("MZ", 7), ("H", 3), ("CNOT", 3, 2), ("MZ", 2), ("MZ", 3)]
+    od = [bt.Op(*t) for t in names]
+    oo = [orc.Op(*t) for t in names]
+    od.insert(10, bt.Op("RES", 4)); oo.insert(10, orc.RES(4))
+    for seed in range(6):
+        st, mid = bt.apply(od, bt.zero_state(N), rng=bt.Draws(seed), track_measurements=True)
+        ref, mid_o = orc.apply_ops(orc.zero_state(N), oo, draws=orc.Draws(seed), track_measurements=True)
+        assert mid == mid_o, (seed, mid, mid_o)
+        assert np.max(np.abs(st.to_numpy() - ref)) < 1e-12
+    import bluetangle_jl_b200.host as H
+    groups = H._coalesce(od, bt.zero_state(N), False)
+    assert sum(isinstance(g, H._MeasureRun) for g in groups) == 3  # [2,5,6,1] + [7,RES 4] + [2,3]
