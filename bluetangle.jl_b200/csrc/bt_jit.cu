@@ -54,6 +54,8 @@ struct Nvrtc {
   int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
   int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
   int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  int major = 0, minor = 0;
   bool ok = false;
 };
 
@@ -74,6 +76,8 @@ Nvrtc& nvrtc() {
   BT_NVRTC_SYM(CreateProgram) BT_NVRTC_SYM(CompileProgram) BT_NVRTC_SYM(GetCUBINSize) BT_NVRTC_SYM(GetCUBIN)
   BT_NVRTC_SYM(GetProgramLogSize) BT_NVRTC_SYM(GetProgramLog) BT_NVRTC_SYM(DestroyProgram)
 #undef BT_NVRTC_SYM
+  *(void**)(&n.Version) = dlsym(h, "nvrtcVersion");
+  if (n.Version) n.Version(&n.major, &n.minor);
   n.ok = true;
   return n;
 }
@@ -236,6 +240,24 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
   return true;
 }
 
+// Code shape of the generated kernels (BT_JIT_VARIANT; bit flags):
+//   0  a condition that depends on the thread (a control / phase bit inside the tile but outside the program) is a branch around the
+//      arithmetic -- the fastest form (C2: 160.6 ms per step);
+//   2  such a condition SELECTS the coefficient (identity when off) and the arithmetic runs unconditionally: no thread-dependent
+//      control flow is left inside the group loop (C2: 171.8 ms);
+//   1  the group loop is fully unrolled (179 ms); 4 select only for lane-dependent conditions; 16 opaque group index (experiments).
+// Default: 0 with NVRTC <= 12.8, 2 with anything newer or unknown.  Measured on B200 (profiles/r2_jit_nvrtc129.txt): the cubins NVRTC
+// 12.9.86 produces for form 0 drop individual conditional phases in QFT-like passes (dozens of thread-dependent branches inside the
+// two-iteration group loop; amplitudes off by 1e-4) -- the same text is correct when compiled by NVRTC 12.8, with -Xptxas=-O0, when
+// executed on the host (tests/test_jit_codegen_cpu.py), and in forms 1 and 2.  BT_JIT_VERIFY=1 cross-checks every launch on the device.
+int jit_variant() {
+  const char* v = getenv("BT_JIT_VARIANT");
+  if (v && *v) return atoi(v);
+  Nvrtc& n = nvrtc();
+  const bool known_good = n.ok && n.major > 0 && (n.major < 12 || (n.major == 12 && n.minor <= 8));
+  return known_good ? 0 : 2;
+}
+
 // structure key: everything the generator turns into literals or code shape (numeric coefficients excluded)
 void make_key(const TileParams& P, const Plan& pl, int device, std::string& key) {
   key.clear();
@@ -247,6 +269,8 @@ void make_key(const TileParams& P, const Plan& pl, int device, std::string& key)
   put(P.item, (size_t)P.nitems);
   const char cs = pl.complex_scale ? 1 : 0;
   put(&cs, 1);
+  const int variant = jit_variant();
+  put(&variant, 4);
   for (int it = 0; it < P.nitems; ++it) {
     const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
     put(G.lp, sizeof(int32_t) * PROG_BITS); put(G.bit_sw, sizeof(G.bit_sw)); put(&G.niter, 4);
@@ -287,8 +311,19 @@ std::string cond_open(const JOp& o) {
   return buf;
 }
 
+std::string cond_expr(const JOp& o) {
+  char buf[160];
+  snprintf(buf, sizeof(buf), "((base & 0x%llxull) == 0x%llxull && (gl & 0x%llxull) == 0x%llxull)", (unsigned long long)o.em, (unsigned long long)o.em, (unsigned long long)o.lm,
+           (unsigned long long)o.lm);
+  return buf;
+}
+
+// BT_JIT_VARIANT (bit flags, experiments): 1 = the group loop is fully unrolled, 2 = conditions that depend on the thread (a control bit
+// inside the tile) select the coefficient (identity when off) instead of branching around the arithmetic
+
 // Emits the kernel for the planned pass.
 bool generate(const TileParams& P, const Plan& pl, std::string& s) {
+  const int variant = jit_variant();
   const int T = P.T;
   const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
   std::string body;
@@ -299,6 +334,9 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
     for (const JOp& o : pl.prog[(size_t)it]) if (o.lm) need_gl = true;
     int perm[PROG_AMPS];  // logical amplitude (index bits = program positions) -> variable
     for (int j = 0; j < PROG_AMPS; ++j) perm[j] = j;
+    uint64_t lane_mask = 0;  // tile-local bits that vary across the lanes of a warp
+    for (int k = 0; k < 5; ++k) lane_mask |= G.bit_lin[k];
+    auto use_select = [&](const JOp& o) { return o.lm != 0 && ((variant & 2) || ((variant & 4) && (o.lm & lane_mask))); };
     std::string ops;
     auto X = [&](int logical, char part) { char b[24]; snprintf(b, sizeof(b), "x%c[%d]", part, perm[logical]); return std::string(b); };
     for (const JOp& o : pl.prog[(size_t)it]) {
@@ -341,12 +379,16 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
           ops += "        " + ar + " = ta; " + ai + " = tc; " + br + " = tb; " + bi + " = td; }\n";
         }
       } else if (o.kind == JK_PHASE || o.kind == JK_CPH1) {
-        if (o.kind == JK_CPH1) ops += cond_open(o);
+        const bool sel = o.kind == JK_CPH1 && use_select(o);
+        if (o.kind == JK_CPH1 && !sel) ops += cond_open(o);
+        if (sel) { char b2[320]; snprintf(b2, sizeof(b2), "      { const bool on = %s; const double cr = on ? C.c[%d] : 1.0, ci = on ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), k, k + 1); ops += b2; }
         const int half = o.kind == JK_CPH1 ? 1 : o.q;
         for (int j = 0; j < PROG_AMPS; ++j)
           if (((j >> o.p) & 1) == half) {
             const std::string r = X(j, 'r'), i = X(j, 'i');
             char buf[256];
+            if (sel) snprintf(buf, sizeof(buf), "      { const double tr = cr * %s - ci * %s, ti = cr * %s + ci * %s; %s = tr; %s = ti; }\n", r.c_str(), i.c_str(), i.c_str(), r.c_str(), r.c_str(), i.c_str());
+            else
             snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * %s - C.c[%d] * %s, ti = C.c[%d] * %s + C.c[%d] * %s; %s = tr; %s = ti; }\n", k, r.c_str(), k + 1, i.c_str(), k,
                      i.c_str(), k + 1, r.c_str(), r.c_str(), i.c_str());
             ops += buf;
@@ -367,20 +409,30 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
             ops += buf;
           }
       } else if (o.kind == JK_CSCALE) {
-        ops += cond_open(o);
+        const bool sel = use_select(o);
+        if (!sel) ops += cond_open(o);
+        else { char b2[320]; snprintf(b2, sizeof(b2), "      { const bool on = %s; const double cr = on ? C.c[%d] : 1.0, ci = on ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), k, k + 1); ops += b2; }
         for (int j = 0; j < PROG_AMPS; ++j) {
           char buf[256];
+          if (sel) snprintf(buf, sizeof(buf), "      { const double tr = cr * xr[%d] - ci * xi[%d], ti = cr * xi[%d] + ci * xr[%d]; xr[%d] = tr; xi[%d] = ti; }\n", j, j, j, j, j, j);
+          else
           snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * xr[%d] - C.c[%d] * xi[%d], ti = C.c[%d] * xi[%d] + C.c[%d] * xr[%d]; xr[%d] = tr; xi[%d] = ti; }\n", k, j, k + 1, j, k, j,
                    k + 1, j, j, j);
           ops += buf;
         }
         ops += "      }\n";
       } else if (o.kind == JK_CCX1) {
-        ops += cond_open(o);
+        const bool sel = use_select(o);
+        if (!sel) ops += cond_open(o);
+        else ops += "      { const bool on = " + cond_expr(o) + ";\n";
         for (int j = 0; j < PROG_AMPS; ++j)
           if (!((j >> o.p) & 1)) {
             const std::string ar = X(j, 'r'), ai = X(j, 'i'), br = X(j | (1 << o.p), 'r'), bi = X(j | (1 << o.p), 'i');
-            ops += "      { const double tr = " + ar + ", ti = " + ai + "; " + ar + " = " + br + "; " + ai + " = " + bi + "; " + br + " = tr; " + bi + " = ti; }\n";
+            if (sel)
+              ops += "      { const double tr = " + ar + ", ti = " + ai + "; " + ar + " = on ? " + br + " : tr; " + ai + " = on ? " + bi + " : ti; " + br + " = on ? tr : " + br + "; " + bi +
+                     " = on ? ti : " + bi + "; }\n";
+            else
+              ops += "      { const double tr = " + ar + ", ti = " + ai + "; " + ar + " = " + br + "; " + ai + " = " + bi + "; " + br + " = tr; " + bi + " = ti; }\n";
           }
         ops += "      }\n";
       }
@@ -409,12 +461,14 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
     }
     uint32_t o[PROG_BITS];
     for (int q = 0; q < PROG_BITS; ++q) { uint32_t c = 1u << G.lp[q]; o[q] = c ^ ((c >> 3) & 7u); }
-    appf(body, "#pragma unroll 1\n    for (uint32_t it = 0; it < %uu; ++it) {\n", G.niter);
+    appf(body, "%s\n    for (uint32_t it = 0; it < %uu; ++it) {\n", (variant & 1) ? "#pragma unroll" : "#pragma unroll 1", G.niter);
     body += "      uint32_t b = s0;\n";
     for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) b = s0 ^ %uu;\n", i, G.iter_sw[i]);
     if (need_gl) {
       body += "      uint64_t gl = g0;\n";
       for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) gl = g0 ^ %uu;\n", i, G.iter_lin[i]);
+      // variant 16: the group index is opaque to the compiler in every iteration, so no condition on it can be hoisted out of the loop
+      if (variant & 16) body += "      asm volatile(\"mov.b64 %0, %0;\" : \"+l\"(gl));\n";
     } else {
       body += "      const uint64_t gl = 0ull;\n";
     }
@@ -534,6 +588,7 @@ std::string cache_path(const std::string& src) {
   if (dir.empty()) return std::string();
   std::string salted = src;
   for (const char* o : kJitOptions) { salted += '\n'; salted += o; }
+  if (const char* x = getenv("BT_JIT_EXTRA_OPTS")) { salted += '\n'; salted += x; }
   char name[80];
   snprintf(name, sizeof(name), "/btjit_%016llx%016llx.cubin", (unsigned long long)fnv1a(salted, 14695981039346656037ull),
            (unsigned long long)fnv1a(salted, 0x9e3779b97f4a7c15ull));
@@ -584,7 +639,18 @@ bool nvrtc_to_cubin(const std::string& src, std::vector<char>& cubin, std::strin
   if (!n.ok) { log = "libnvrtc is not available"; return false; }
   nvrtcProgram prog = nullptr;
   if (n.CreateProgram(&prog, src.c_str(), "bt_jit_pass.cu", 0, nullptr, nullptr) != 0) return false;
-  const int rc = n.CompileProgram(prog, 3, kJitOptions);
+  // BT_JIT_EXTRA_OPTS: space-separated additional NVRTC options (experiments: --fmad=false, -Xptxas=-O0 ...)
+  std::vector<std::string> extra;
+  if (const char* x = getenv("BT_JIT_EXTRA_OPTS")) {
+    std::string cur;
+    for (const char* c = x;; ++c) {
+      if (*c == ' ' || *c == '\0') { if (!cur.empty()) extra.push_back(cur); cur.clear(); if (!*c) break; }
+      else cur += *c;
+    }
+  }
+  std::vector<const char*> opts(kJitOptions, kJitOptions + 3);
+  for (const std::string& e : extra) opts.push_back(e.c_str());
+  const int rc = n.CompileProgram(prog, (int)opts.size(), opts.data());
   if (rc != 0) {
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
@@ -612,6 +678,9 @@ bool obtain_cubin(const std::string& src, std::vector<char>& cubin, std::string&
   return true;
 }
 
+}  // namespace
+bool bt_jit_source_for(const TileParams& P, int np, std::string& src);
+namespace {
 // ---- compile workers -----------------------------------------------------------------------------------------------------
 struct Job { std::string src; Entry* e; };
 std::deque<Job>* g_jobs = nullptr;   // heap objects that are never destroyed: the detached workers may outlive static destructors
@@ -655,10 +724,27 @@ void enqueue_compile(std::string&& src, Entry* e) {
 
 }  // namespace
 
+// debugging aid: only the k-th eligible pass since the call (0-based) may run specialised, every other one stays on the interpreter
+// (k < 0: no filter); with dump != 0 the CUDA text of that pass goes to stderr
+static int g_only = -1, g_only_seq = 0, g_only_dump = 0;
+extern "C" int bt_jit_debug_only(int k, int dump) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_only = k; g_only_seq = 0; g_only_dump = dump;
+  return BT_OK;
+}
+
 // 1: the pass was launched as a specialised kernel; 0: not (the caller runs the interpreter).  Never fails the pass.
 int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, uint64_t ntiles, size_t tile_bytes, int np) {
   const int mode = env_i("BT_TILE_JIT", 1);
   if (mode == 0 || np <= 0 || P.nitems != np || P.swz_mode != 0) return 0;
+  if (g_only >= 0) {
+    const int seq = g_only_seq++;
+    if (seq != g_only) return 0;
+    if (g_only_dump) {
+      std::string src;
+      if (bt_jit_source_for(P, np, src)) fprintf(stderr, "// ===== specialised pass %d =====\n%s\n", seq, src.c_str());
+    }
+  }
   if (mode != 2 && s->len < (1ull << env_i("BT_TILE_JIT_MINBITS", 22))) return 0;
   Plan pl;
   if (!make_plan(P, np, pl)) return 0;
@@ -709,6 +795,26 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   }
   g_launches++;
   return 1;
+}
+
+// host-only debugging aid: the CUDA text the specialiser would compile for this pass (planning dry runs: BT_JIT_DUMP=1)
+bool bt_jit_source_for(const TileParams& P, int np, std::string& src) {
+  Plan pl;
+  if (!make_plan(P, np, pl)) return false;
+  if (!generate(P, pl, src)) return false;
+  char buf[64];
+  {
+    std::string key;
+    make_key(P, pl, 0, key);
+    unsigned long long h = 1469598103934665603ull;
+    for (unsigned char ch : key) { h ^= ch; h *= 1099511628211ull; }
+    snprintf(buf, sizeof(buf), "// key %016llx\n", h);
+    src += buf;
+  }
+  src += "// coefficients:";
+  for (size_t i = 0; i < pl.coef.size(); ++i) { snprintf(buf, sizeof(buf), " [%zu]=%.17g", i, pl.coef[i]); src += buf; }
+  src += "\n";
+  return true;
 }
 
 // blocks until the compile workers are idle; *pending_before = structures that were still being compiled at the call

@@ -1110,6 +1110,55 @@ static bool build_tensor_map(bt_sv* s, const bool* in, int T, CUtensorMap* map, 
 }
 
 int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, uint64_t ntiles, size_t tile_bytes, int np);  // bt_jit.cu
+bool bt_jit_source_for(const TileParams& P, int np, std::string& src);  // bt_jit.cu
+
+// ---- BT_JIT_VERIFY: max |amp - alt|^2 and max |alt|^2 over the state (positive doubles order like their bit patterns) ----------------
+__global__ void __launch_bounds__(256) k_verify_diff(const double2* __restrict__ a, const double2* __restrict__ b, uint64_t len, unsigned long long* __restrict__ out) {
+  double md = 0.0, mn = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2 x = a[i], y = b[i];
+    const double dx = x.x - y.x, dy = x.y - y.y;
+    const double d = dx * dx + dy * dy;
+    md = (d > md || d != d) ? (d != d ? 1e300 : d) : md;  // NaN counts as a disagreement
+    mn = fmax(mn, y.x * y.x + y.y * y.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o)); mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(md));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(mn));
+  }
+}
+
+static std::atomic<uint64_t> g_verify_checked{0}, g_verify_failed{0};
+
+// amp = specialised result, alt = interpreter result of the same pass
+static int verify_compare(bt_sv* s) {
+  BT_TRY(bt_ensure_scratch(s, 16));
+  unsigned long long* d = (unsigned long long*)s->d_scratch;
+  BT_CUDA(cudaMemsetAsync(d, 0, 16, s->stream));
+  k_verify_diff<<<148 * 8, 256, 0, s->stream>>>(s->amp, s->alt, s->len, d);
+  BT_CUDA(cudaPeekAtLastError());
+  unsigned long long h[2];
+  BT_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  double md, mn;
+  memcpy(&md, &h[0], 8); memcpy(&mn, &h[1], 8);
+  g_verify_checked++;
+  if (sqrt(md) > 1e-12 * std::max(1e-30, sqrt(mn)) + 1e-300) {
+    g_verify_failed++;
+    fprintf(stderr, "[bluetangle_cuda] BT_JIT_VERIFY: a specialised pass differs from the interpreter (max |diff| %.3e, max |amp| %.3e): keeping the interpreter's result\n", sqrt(md),
+            sqrt(mn));
+    BT_CUDA(cudaMemcpyAsync(s->amp, s->alt, s->len * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+  }
+  return BT_OK;
+}
+
+extern "C" int bt_jit_verify_stats(uint64_t* checked, uint64_t* failed) {
+  if (checked) *checked = g_verify_checked.load();
+  if (failed) *failed = g_verify_failed.load();
+  return BT_OK;
+}
 
 // dry run (host-only planning, bt_fusion_plan): launch_pass forms slots and programs exactly as for a real launch but touches no
 // device; t_dry[0] counts kernel launches, [1] register programs, [2] other items, [3] single-gate passes
@@ -1139,6 +1188,7 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   alignas(64) CUtensorMap tmap;
   const bool use_tma = dry || (env_int("BT_TILE_TMA", 1) != 0 && build_tensor_map(s, in, T, &tmap, P));
   P.swz_mode = use_tma ? 0 : 1;
+  if (dry) P.tma_ncopy = 1;
   int local_pos[64];
   for (int b = 0; b < 64; ++b) local_pos[b] = -1;
   int j = 0;
@@ -1175,6 +1225,11 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
   auto flush = [&]() -> int {
     if (nitems == 0) return BT_OK;
     if (dry) {
+      if (env_int("BT_JIT_DUMP", 0) && ng == 0 && nc == 0 && nd == 0 && np > 0) {
+        P.nitems = nitems;
+        std::string src;
+        if (bt_jit_source_for(P, np, src)) fprintf(stderr, "// ===== pass %d =====\n%s\n", t_dry[0], src.c_str());
+      }
       t_dry[0]++; t_dry[1] += np; t_dry[2] += ng + nc + nd;
       ng = nc = nd = np = nitems = 0;
       return BT_OK;
@@ -1188,9 +1243,27 @@ static int launch_pass(bt_sv* s, const std::vector<const Block*>& pass_in, const
       for (int q = 0; q < np; ++q) fprintf(stderr, " %u(%d,%d,%d,%d)", P.pr[q].nops, P.pr[q].lp[0], P.pr[q].lp[1], P.pr[q].lp[2], P.pr[q].lp[3]);
       fprintf(stderr, "\n");
     }
+    // BT_JIT_VERIFY=1: every specialised launch is cross-checked against the interpreter kernel on a copy of the state (results
+    // of a specialised pass must never depend on the run-time compiler); a disagreement is counted, reported on stderr, and the
+    // interpreter's result is kept.  bt_jit_verify_stats() returns the counts.
+    const bool jit_eligible = use_tma && ng == 0 && nc == 0 && nd == 0 && np > 0;
+    const bool verify = jit_eligible && env_int("BT_JIT_VERIFY", 0) != 0;
+    if (verify) {
+      BT_TRY(bt_ensure_alt(s));
+      BT_CUDA(cudaMemcpyAsync(s->alt, s->amp, s->len * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+    }
     bt_prof_begin(s, BT_CLS_TILE);
-    if (use_tma && ng == 0 && nc == 0 && nd == 0 && np > 0 && bt_jit_try_launch(s, P, tmap, ntiles, smem, np) == 1) {
+    if (jit_eligible && bt_jit_try_launch(s, P, tmap, ntiles, smem, np) == 1) {
       // launched as a specialised straight-line kernel (bt_jit.cu)
+      if (verify) {
+        std::swap(s->amp, s->alt);  // the interpreter runs on the copy
+        alignas(64) CUtensorMap tmap2;
+        TileParams P2 = P;
+        const bool ok2 = build_tensor_map(s, in, T, &tmap2, P2);
+        if (ok2) k_tile_tma<false><<<(unsigned)ntiles, TILE_THREADS, smem + 1024 + 64, s->stream>>>(tmap2, P2);
+        std::swap(s->amp, s->alt);
+        if (ok2) BT_TRY(verify_compare(s));
+      }
     } else if (use_tma) {
       const bool lite = ng == 0 && nc == 0 && env_int("BT_TILE_LITE", 1);
       int K = env_int("BT_TILE_PIPE", 0);
@@ -1507,7 +1580,7 @@ struct PassPlan {
   int end_reason = 0;          // statistics: 1 = cost cap reached, 2 = block cap, 0 = ran out of eligible blocks
 };
 
-struct SchedCfg { int n_local, T, lowb, window; double maxg; int policy; };
+struct SchedCfg { int n_local, T, lowb, window; double maxg; int policy; bool split_classes; };
 
 static inline double block_cost(const Block& b) {
   // cost units: a dense 4x4 block = 2.8 (the cap of 28 keeps ~10 of them per pass, the measured optimum for dense passes);
@@ -1516,7 +1589,7 @@ static inline double block_cost(const Block& b) {
   return b.desc.diag ? 0.7 : (b.desc.k == 2 ? 2.8 : 1.7);
 }
 
-struct SchedBlock { uint64_t touch, need; double cost; int ngates; bool solo, scalar; };
+struct SchedBlock { uint64_t touch, need; double cost; int ngates; bool solo, scalar, sok; };
 
 // dry run (out == nullptr) or commit of one pass restricted to the tile bit set `tile`; returns the gain (cost units carried)
 static double scan_pass(const std::vector<SchedBlock>& sb, const std::vector<char>& done, size_t first, const SchedCfg& cfg, uint64_t tile, PassPlan* out,
@@ -1525,6 +1598,9 @@ static double scan_pass(const std::vector<SchedBlock>& sb, const std::vector<cha
   const uint64_t all = cfg.n_local >= 64 ? ~0ull : ((1ull << cfg.n_local) - 1);
   double cost = 0.0;
   int cnt = 0, reason = 0;
+  int cls = -1;  // split_classes: the first block taken decides whether the pass carries structured (program) blocks or dense ones --
+                 // only a program-only pass can run as a specialised straight-line kernel, one dense block would put the whole pass
+                 // back on the interpreter
   size_t scanned = 0;
   (void)frontier_need;
   for (size_t i = first; i < sb.size() && scanned < (size_t)cfg.window && (blocked & all) != all; ++i) {
@@ -1536,6 +1612,7 @@ static double scan_pass(const std::vector<SchedBlock>& sb, const std::vector<cha
       if (cnt == 0) { if (out) { out->blocks.push_back((int)i); out->cost = 0.0; } return 1e9; }  // runs alone, in order
       ok = false;
     }
+    if (ok && cfg.split_classes && cls >= 0 && cls != (int)b.sok) ok = false;
     if (ok) {
       const uint64_t missing = b.need & ~tile;
       if (missing) { ok = false; if (frontier) frontier->push_back(missing); }
@@ -1543,6 +1620,7 @@ static double scan_pass(const std::vector<SchedBlock>& sb, const std::vector<cha
       else if (cost + b.cost > cfg.maxg && cnt > 0) { ok = false; reason = 1; }
       if (ok) {
         cost += b.cost; cnt++;
+        cls = (int)b.sok;
         if (out) out->blocks.push_back((int)i);
         continue;
       }
@@ -1629,6 +1707,7 @@ static void sched_blocks(const std::vector<Block>& blocks, std::vector<SchedBloc
     o.solo = b.opaque || b.desc.k > 2;
     o.scalar = b.touch.empty();
     o.ngates = b.ngates;
+    o.sok = b.sok;
     o.cost = 0.0;
     if (!o.solo) {
       needed_bits(b.desc, need);
@@ -1648,6 +1727,7 @@ static SchedCfg sched_cfg(int n_local) {
   // cost units per pass (measured sweeps: profiles/r1_fusion_sweep.txt for first fit, profiles/r2_sched_sweep.txt for look-ahead)
   c.maxg = (double)std::max(1, std::min(80, env_int("BT_FUSE_MAX_GATES", c.policy != 0 ? 40 : 28)));
   c.window = env_int("BT_FUSE_WINDOW", 256);
+  c.split_classes = env_int("BT_FUSE_SPLIT_CLASSES", env_int("BT_TILE_JIT", 1) != 0 ? 1 : 0) != 0;
   return c;
 }
 

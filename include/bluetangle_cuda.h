@@ -104,6 +104,12 @@ int bt_jit_selftest(char* source, uint64_t cap);
 int bt_jit_wait(uint64_t* pending_before);
 int bt_jit_selftest_workers(int jobs); /* host-only: `jobs` synthetic passes through the compile workers; 0 = ok, -2 = no libnvrtc */
 int bt_jit_cache_info(uint64_t* disk_hits, char* dir, uint64_t cap);
+/* BT_JIT_VERIFY=1 (environment): every specialised launch is cross-checked against the interpreter kernel on a copy of the state; a
+ * disagreement is counted and reported on stderr and the interpreter's result is kept.  Returns launches checked / disagreements. */
+int bt_jit_verify_stats(uint64_t* checked, uint64_t* failed);
+/* debugging aid: only the k-th eligible fused pass since this call (0-based) runs specialised, the others stay on the interpreter
+ * (k < 0 removes the filter); dump != 0 prints the generated CUDA text of that pass to stderr */
+int bt_jit_debug_only(int k, int dump);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */

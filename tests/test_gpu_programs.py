@@ -230,3 +230,44 @@ def test_tiles_with_many_runs_move_as_up_to_16_tensor_boxes(bt, orc, free_bits):
         lib.bt_jit_stats(C.byref(c1), C.byref(l1), C.byref(f1), None)
         if mode == 2 and c1.value > c0.value:
             assert l1.value >= l0.value + 1            # the specialiser only takes tensor-copy passes
+
+
+def test_specialised_qft_passes_are_cross_checked_on_the_device(bt, orc):
+    """QFT passes carry dozens of conditional phases per register program -- the shape for which NVRTC 12.9 miscompiled the branchy
+    form of the generated code (profiles/r2_jit_nvrtc129.txt).  With the default code shape for the run-time compiler found on this
+    box: (a) BT_JIT_VERIFY cross-checks every specialised launch against the interpreter kernel on the device: no disagreement;
+    (b) the final amplitudes equal the interpreter's to rounding and the strided oracle's within 1e-10."""
+    import ctypes as C
+    from importlib import import_module
+
+    import __graft_entry__ as ge
+    from oracle import strided as S
+
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    L = bt._lib
+    lib = L.load()
+    N = 20
+    specs = wl.qft(N)
+    arr = bt.pack_gates(wl.to_ops(bt, specs))
+    chk0, bad0 = C.c_uint64(), C.c_uint64()
+    lib.bt_jit_verify_stats(C.byref(chk0), C.byref(bad0))
+    outs = {}
+    for mode, verify in ((0, 0), (2, 1)):
+        with tile_env(BT_TILE_JIT=mode, BT_JIT_VERIFY=verify):
+            s = bt.zero_state(N)
+            L.check(lib.bt_sv_set_basis(s.h, 5))
+            L.check(lib.bt_sv_apply_circuit(s.h, L.ptr(arr), len(arr), 1))
+            outs[mode] = s.to_numpy()
+    chk1, bad1 = C.c_uint64(), C.c_uint64()
+    lib.bt_jit_verify_stats(C.byref(chk1), C.byref(bad1))
+    c, l, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.bt_jit_stats(C.byref(c), C.byref(l), C.byref(f), None)
+    if l.value == 0 and f.value > 0:
+        pytest.skip("NVRTC not available on this box: passes stay on the interpreter")
+    assert chk1.value > chk0.value and bad1.value == bad0.value
+    assert np.max(np.abs(outs[0] - outs[2])) < 1e-13
+    ref0 = np.zeros(1 << N, dtype=np.complex128)
+    ref0[5] = 1
+    sv = S.SV(N, ref0)
+    sv.apply_ops(wl.to_ops(orc, specs))
+    assert np.max(np.abs(outs[2] - sv.v)) < TOL

@@ -1,0 +1,99 @@
+"""The pass specialiser's generated CUDA text, executed on the HOST: the planner's dry run (bt_fusion_plan_host with BT_JIT_DUMP=1)
+prints the straight-line kernel of every fused pass; the program bodies are wrapped into plain C++ (threads become a loop, the tensor
+copy a gather with the 128-byte swizzle), compiled with g++ and applied tile by tile to a state vector, which must then equal the
+oracle's result of the same circuit.  This pins the code generator (op order, pivots, pass scalar, condition masks, CX renaming,
+shared-memory slots) without a GPU and independently of the run-time compiler -- a mismatch on the device that this test does not
+see is the compiler's (NVRTC 12.9 and BT_JIT_VARIANT)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DUMP = '''
+import sys, os, ctypes as C
+sys.path.insert(0, {root!r})
+os.environ["BT_JIT_DUMP"] = "1"
+import __graft_entry__ as ge
+bt = ge.load_package(); L = bt._lib
+from importlib import import_module
+wl = import_module(ge.PKG_NAME + ".workloads")
+specs = {specs}
+arr = bt.pack_gates(wl.to_ops(bt, specs))
+npass, nblk, lc = C.c_int(), C.c_int(), (C.c_int * 4)()
+L.check(L.load().bt_fusion_plan_host({N}, L.ptr(arr), len(arr), C.byref(npass), C.byref(nblk), None, None, None, None, 0, lc))
+print(npass.value, lc[0], lc[1], lc[2])
+'''
+
+
+def emulate(N, specs_expr, variant, tmp_path):
+    env = dict(os.environ, BT_JIT_VARIANT=str(variant))
+    r = subprocess.run([sys.executable, "-c", DUMP.format(root=ROOT, specs=specs_expr, N=N)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    npass, launches, progs, other = (int(x) for x in r.stdout.split())
+    passes = re.split(r"// ===== pass \d+ =====\n", r.stderr)[1:]
+    assert other == 0 and len(passes) == launches, "the circuit must plan into program-only passes for this test"
+    cpp = ["#include <stdint.h>\n#include <math.h>\nstruct double2 { double x, y; };\nstatic inline double2 make_double2(double a, double b) { double2 r = {a, b}; return r; }\n#define PROG_AMPS 16\n"]
+    meta = []
+    for pi, src in enumerate(passes):
+        ncoef = int(re.search(r"struct BtCoefs \{ double c\[(\d+)\]; \};", src).group(1))
+        coefs = [float(x) for x in re.findall(r"\[\d+\]=(\S+)", src.split("// coefficients:")[1])]
+        assert len(coefs) == ncoef
+        lowb = int(re.search(r"uint64_t base = \(uint64_t\)blockIdx.x << (\d+);", src).group(1))
+        tbits = list(range(lowb)) + [int(x) for x in re.findall(r"base = \(\(base >> (\d+)\) <<", src)]
+        body = src[src.index("  if (tid <"):src.index('  asm volatile("fence.proxy.async.shared::cta;"')]
+        body = body.replace("__syncthreads();", "").replace("#pragma unroll 1\n", "").replace("#pragma unroll\n", "")
+        body = re.sub(r'asm volatile\("mov\.b64 %0, %0;" : "\+l"\(gl\)\);', "", body)
+        body = re.sub(r"  if \(tid < (\d+)u\) \{", r"  for (uint32_t tid = 0; tid < 128u; ++tid) if (tid < \1u) {", body)
+        cpp.append(f'struct Coefs{pi} {{ double c[{ncoef}]; }};\nextern "C" void pass{pi}(double2* sm, uint64_t base, const Coefs{pi}* Cp) {{ const Coefs{pi}& C = *Cp;\n{body}\n}}\n')
+        meta.append((tbits, coefs))
+    src_path, so_path = tmp_path / "emul.cpp", tmp_path / "emul.so"
+    src_path.write_text("".join(cpp))
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-o", str(so_path), str(src_path)])
+    lib = C.CDLL(str(so_path))
+    state = np.zeros(1 << N, dtype=np.complex128)
+    state[5] = 1
+    for pi, (tbits, coefs) in enumerate(meta):
+        T = len(tbits)
+        loc = np.arange(1 << T, dtype=np.int64)
+        off = np.zeros(1 << T, dtype=np.int64)
+        for j, b in enumerate(tbits):
+            off |= ((loc >> j) & 1) << b
+        slot = loc ^ ((loc >> 3) & 7)  # CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk index XOR (128-byte row index mod 8)
+        other_bits = [b for b in range(N) if b not in tbits]
+        cf = (C.c_double * len(coefs))(*coefs)
+        f = getattr(lib, f"pass{pi}")
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        for t in range(1 << len(other_bits)):
+            base = 0
+            for j, b in enumerate(other_bits):
+                base |= ((t >> j) & 1) << b
+            tile = np.empty(1 << T, dtype=np.complex128)
+            tile[slot] = state[base + off]
+            f(tile.ctypes.data, base, C.addressof(cf))
+            state[base + off] = tile[slot]
+    return state, launches, progs
+
+
+@pytest.mark.parametrize("variant", [0, 2, 16])
+@pytest.mark.parametrize("N,specs_expr", [(13, "wl.qft(13)"), (13, "wl.layered(13, 5, 28)"), (12, "wl.qft(12) + wl.layered(12, 4, 3)")])
+def test_generated_pass_source_equals_the_oracle_on_the_host(bt, orc, tmp_path, N, specs_expr, variant):
+    from importlib import import_module
+
+    import __graft_entry__ as ge
+    from oracle import strided as S
+
+    got, launches, progs = emulate(N, specs_expr, variant, tmp_path)
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    ops = wl.to_ops(orc, eval(specs_expr, {"wl": wl}))
+    ref0 = np.zeros(1 << N, dtype=np.complex128)
+    ref0[5] = 1
+    sv = S.SV(N, ref0)
+    sv.apply_ops(ops)
+    assert launches >= 1 and progs >= launches
+    assert np.max(np.abs(got - sv.v)) < 1e-13
