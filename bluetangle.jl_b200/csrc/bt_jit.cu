@@ -339,7 +339,7 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
     auto use_select = [&](const JOp& o) { return o.lm != 0 && ((variant & 2) || ((variant & 4) && (o.lm & lane_mask))); };
     std::string ops;
     auto X = [&](int logical, char part) { char b[24]; snprintf(b, sizeof(b), "x%c[%d]", part, perm[logical]); return std::string(b); };
-    for (const JOp& o : pl.prog[(size_t)it]) {
+    auto emit_op = [&](const JOp& o) {
       int k = o.c0;
       if (o.kind == JK_LIN2) {
         int kk[4];
@@ -436,6 +436,51 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
           }
         ops += "      }\n";
       }
+    };
+    // Diagonal ops commute, so inside a maximal run of them (no 2x2 block, no CX in between) the conditional / unconditional factors
+    // that hit the SAME set of amplitudes are multiplied up per thread first -- one complex multiplication per op -- and applied
+    // once: all 16 amplitudes for conditional scalars (a phase whose bits all lie outside the program), the 8 amplitudes with
+    // position bit p set for phases on p.  A QFT pass carries runs of ~40 such factors (64 FP64 instructions each before).
+    {
+      const std::vector<JOp>& L = pl.prog[(size_t)it];
+      const bool merge = env_i("BT_JIT_MERGE_DIAG", 1) != 0;
+      auto is_diag = [](const JOp& o) { return o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE || o.kind == JK_CZ; };
+      size_t i = 0;
+      while (i < L.size()) {
+        if (!is_diag(L[i]) || !merge) { emit_op(L[i]); ++i; continue; }
+        size_t j = i;
+        while (j < L.size() && is_diag(L[j])) ++j;
+        std::vector<char> done(j - i, 0);
+        for (int cls = -1; cls < PROG_BITS; ++cls) {  // -1: all amplitudes (CSCALE); p >= 0: amplitudes with position bit p set
+          std::vector<size_t> mem;
+          for (size_t t = i; t < j; ++t) {
+            const JOp& o = L[t];
+            if (cls < 0 ? o.kind == JK_CSCALE : ((o.kind == JK_CPH1 && o.p == cls) || (o.kind == JK_PHASE && o.p == cls && o.q == 1))) mem.push_back(t);
+          }
+          if (mem.size() < 2) continue;
+          ops += "      { double fr = 1.0, fi = 0.0;\n";
+          for (size_t t : mem) {
+            const JOp& o = L[t];
+            char buf[512];
+            if (o.kind == JK_PHASE)
+              snprintf(buf, sizeof(buf), "        { const double t0 = fr * C.c[%d] - fi * C.c[%d]; fi = fr * C.c[%d] + fi * C.c[%d]; fr = t0; }\n", o.c0, o.c0 + 1, o.c0 + 1, o.c0);
+            else
+              snprintf(buf, sizeof(buf), "        { const bool on = %s; const double cr = on ? C.c[%d] : 1.0, ci = on ? C.c[%d] : 0.0; const double t0 = fr * cr - fi * ci; fi = fr * ci + fi * cr; fr = t0; }\n",
+                       cond_expr(o).c_str(), o.c0, o.c0 + 1);
+            ops += buf;
+            done[t - i] = 1;
+          }
+          for (int a = 0; a < PROG_AMPS; ++a)
+            if (cls < 0 || ((a >> cls) & 1)) {
+              const std::string r = X(a, 'r'), im = X(a, 'i');
+              ops += "        { const double tr = fr * " + r + " - fi * " + im + ", ti = fr * " + im + " + fi * " + r + "; " + r + " = tr; " + im + " = ti; }\n";
+            }
+          ops += "      }\n";
+        }
+        for (size_t t = i; t < j; ++t)
+          if (!done[t - i]) emit_op(L[t]);
+        i = j;
+      }
     }
     if (last) {  // the pass scalar: product of all pivots and unconditional scalars
       const int k = pl.scale_at;
@@ -472,11 +517,24 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
     } else {
       body += "      const uint64_t gl = 0ull;\n";
     }
+    // variant 32: the coefficient block is addressed through an offset the compiler cannot see through (always 0), fetched once per
+    // loop iteration: without it every coefficient load is hoisted out of the two-iteration group loop, the hundreds of live values
+    // overflow the uniform register file and come back through local memory and R2UR moves (30 % of the stall samples, ncu)
+    if (variant & 32) body += "      uint32_t zoff; asm volatile(\"mov.u32 %0, 0;\" : \"=r\"(zoff));\n      const double* __restrict__ CC = C.c + zoff;\n";
     body += "      double xr[PROG_AMPS], xi[PROG_AMPS];\n";
     for (int j = 0; j < PROG_AMPS; ++j) {
       uint32_t off = 0;
       for (int q = 0; q < PROG_BITS; ++q) if ((j >> q) & 1) off ^= o[q];
       appf(body, "      { const double2 v = sm[b ^ %uu]; xr[%d] = v.x; xi[%d] = v.y; }\n", off, j, j);
+    }
+    if (variant & 32) {
+      std::string o2;
+      o2.reserve(ops.size());
+      for (size_t q = 0; q < ops.size(); ++q) {
+        if (ops.compare(q, 4, "C.c[") == 0) { o2 += "CC["; q += 3; }
+        else o2 += ops[q];
+      }
+      ops.swap(o2);
     }
     body += ops;
     for (int j = 0; j < PROG_AMPS; ++j) {  // logical amplitude j lives in variable perm[j] (CX renamings)

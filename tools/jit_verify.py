@@ -18,7 +18,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 layers = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 os.environ.setdefault("BT_JIT_VERIFY", "1")
 os.environ["BT_TILE_JIT_AFTER"] = "1"
-arr = bt.pack_gates(wl.to_ops(bt, wl.qft(N) + wl.layered(N, layers, 28)))
+kind = sys.argv[3] if len(sys.argv) > 3 else "qft+layers"
+specs = wl.qft(N) if kind == "qft" else (wl.layered(N, layers, 28) if kind == "layers" else wl.qft(N) + wl.layered(N, layers, 28))
+arr = bt.pack_gates(wl.to_ops(bt, specs))
 s = bt.zero_state(N)
 for rep in range(2):
     L.check(s.lib.bt_sv_set_basis(s.h, 5))
@@ -29,4 +31,4 @@ chk, bad = C.c_uint64(), C.c_uint64()
 L.check(s.lib.bt_jit_verify_stats(C.byref(chk), C.byref(bad)))
 c, l, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
 s.lib.bt_jit_stats(C.byref(c), C.byref(l), C.byref(f), None)
-print(f"N={N} gates={len(arr)} variant={os.environ.get('BT_JIT_VARIANT', 'auto')}: modules {c.value}, specialised launches {l.value}, cross-checked {chk.value}, disagreements {bad.value}, norm2 {bt.norm2(s):.12f}")
+print(f"{kind} N={N} gates={len(arr)} variant={os.environ.get('BT_JIT_VARIANT', 'auto')}: modules {c.value}, specialised launches {l.value}, cross-checked {chk.value}, disagreements {bad.value}, norm2 {bt.norm2(s):.12f}")
