@@ -575,6 +575,23 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
          "    asm volatile(\"cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%%0], [%%1, {%%2, %%3, %%4, %%5, %%6}], [%%7];\" "
          "::\"r\"(dst + %uu), \"l\"(tm), \"r\"(0), \"r\"(c1), \"r\"(c2), \"r\"(c3), \"r\"(c4 + %d), \"r\"(mb) : \"memory\");\n",
          e * chunk, P.tma_c4add[e]);
+  if (variant & 64) {
+    // L2 prefetch of the tile a later CTA of this SM slot will load (blockIdx + BT_JIT_PREFETCH_DIST, default 3 CTAs x 148 SMs): the pass is
+    // compute-bound, 12 % of the warp samples wait for the tile load -- from L2 the wait is shorter than from HBM
+    const int dist = env_i("BT_JIT_PREFETCH_DIST", 444);
+    appf(s, "    if (blockIdx.x + %du < gridDim.x) {\n      uint64_t b2 = (uint64_t)(blockIdx.x + %du) << %d;\n", dist, dist, P.lowb);
+    for (int j = P.lowb; j < T; ++j) {
+      const int b = P.tbits[j];
+      appf(s, "      b2 = ((b2 >> %d) << %d) | (b2 & 0x%llxull);\n", b, b + 1, (unsigned long long)((1ull << b) - 1ull));
+    }
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      appf(s,
+           "      asm volatile(\"cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%%0, {%%1, %%2, %%3, %%4, %%5}];\" ::\"l\"(tm), \"r\"(0), \"r\"((int32_t)((b2 >> %d) & 0x%xu)), "
+           "\"r\"((int32_t)((b2 >> %d) & 0x%xu)), \"r\"((int32_t)((b2 >> %d) & 0x%xu)), \"r\"((int32_t)((b2 >> %d) & 0x%xu) + %d) : \"memory\");\n",
+           P.tma_coord_shift[1], P.tma_coord_mask[1], P.tma_coord_shift[2], P.tma_coord_mask[2], P.tma_coord_shift[3], P.tma_coord_mask[3], P.tma_coord_shift[4],
+           P.tma_coord_mask[4], P.tma_c4add[e]);
+    s += "    }\n";
+  }
   s += "  }\n  {\n    uint32_t done = 0;\n    for (uint32_t spin = 0; !done; ++spin) {\n"
        "      asm volatile(\"{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }\" : \"=r\"(done) : \"r\"(mb) : \"memory\");\n"
        "      if (spin > (1u << 22)) __trap();\n    }\n  }\n";
