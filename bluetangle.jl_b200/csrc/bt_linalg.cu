@@ -73,7 +73,8 @@ extern "C" int bt_jacobi_pairs_host(int nvec, int round, int* pairs /* nvec/2 x 
 // A pair is rotated iff |<y,x>| > tol * |x| |y|; the rotation makes the two vectors orthogonal (complex Hestenes step:
 // a phase on y makes the inner product real, then a real plane rotation).
 template <int EPT>
-__global__ void __launch_bounds__(512) k_jacobi_round(double2* __restrict__ R, int nvec, int len, int round, double tol, unsigned int* __restrict__ rotations) {
+__global__ void __launch_bounds__(512) k_jacobi_round(double2* __restrict__ R, int nvec, int len, int round, double tol, const double* __restrict__ frob2,
+                                                      unsigned int* __restrict__ rotations) {
   __shared__ double sm[32 * 4];
   int p, q;
   tournament_pair(nvec, round, blockIdx.x, &p, &q);
@@ -94,7 +95,11 @@ __global__ void __launch_bounds__(512) k_jacobi_round(double2* __restrict__ R, i
   }
   block_allreduce<4>(acc, sm);
   const double a = acc[0], b = acc[1], g2 = acc[2] * acc[2] + acc[3] * acc[3];
-  if (!(g2 > tol * tol * a * b)) return;  // uniform across the CTA (also covers zero vectors and NaN)
+  // relative criterion, plus an absolute floor at rounding level of the whole matrix (Frobenius norm^2 F of this trajectory): vectors that
+  // have been rotated down to rounding noise keep an O(1) relative overlap with each other for ever -- their inner products are
+  // below 1e-16 F and change no singular value at the 1e-16 level
+  const double fl = 1e-16 * frob2[blockIdx.y];
+  if (!(g2 > tol * tol * a * b && g2 > fl * fl)) return;  // uniform across the CTA (also covers zero vectors and NaN)
   if (threadIdx.x == 0) atomicAdd(rotations, 1u);
   const double gabs = sqrt(g2);
   const double pr = acc[2] / gabs, pi = acc[3] / gabs;  // e^{i phi} = g / |g|
@@ -122,16 +127,25 @@ __global__ void __launch_bounds__(256) k_vec_norm2(const double2* __restrict__ R
   if (threadIdx.x == 0) out[(uint64_t)blockIdx.y * nvec + blockIdx.x] = acc[0];
 }
 
-static int launch_round(bt_sv* s, double2* R, int nvec, int len, int round, double tol, unsigned int* d_rot) {
+// F[t] = sum of the squared norms of trajectory t's vectors (one thread per trajectory: nvec <= 8192 additions, once per call)
+__global__ void k_frob2(const double* __restrict__ norm2, int nvec, int64_t n_batch, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_batch) return;
+  double f = 0.0;
+  for (int i = 0; i < nvec; ++i) f += norm2[t * nvec + i];
+  out[t] = f;
+}
+
+static int launch_round(bt_sv* s, double2* R, int nvec, int len, int round, double tol, const double* d_frob, unsigned int* d_rot) {
   dim3 grid(nvec / 2, (unsigned)s->n_batch);
   int threads = len <= 256 ? std::max(32, len) : (len <= 4096 ? 256 : 512);
   int ept = (len + threads - 1) / threads;
   switch (ept) {
-    case 1: k_jacobi_round<1><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_rot); break;
-    case 2: k_jacobi_round<2><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_rot); break;
-    case 4: k_jacobi_round<4><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_rot); break;
-    case 8: k_jacobi_round<8><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_rot); break;
-    case 16: k_jacobi_round<16><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_rot); break;
+    case 1: k_jacobi_round<1><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
+    case 2: k_jacobi_round<2><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
+    case 4: k_jacobi_round<4><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
+    case 8: k_jacobi_round<8><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
+    case 16: k_jacobi_round<16><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
     default: BT_FAIL(BT_ERR_UNSUPPORTED, "internal: vector length %d", len);
   }
   BT_CHECK_LAUNCH(s);
@@ -144,16 +158,24 @@ static int jacobi_spectrum(bt_sv* s, double2* R, int nvec, int len, double* spec
   if (len > 8192) BT_FAIL(BT_ERR_UNSUPPORTED, "Schmidt spectrum: the long side of the cut has 2^%d > 2^13 entries", (int)log2((double)len));
   if (s->n_batch > 65535) BT_FAIL(BT_ERR_UNSUPPORTED, "n_batch > 65535");
   size_t nvals = (size_t)s->n_batch * nvec;
-  BT_TRY(bt_ensure_scratch(s, nvals * sizeof(double) + 64));
+  BT_TRY(bt_ensure_scratch(s, (nvals + (size_t)s->n_batch) * sizeof(double) + 64));
   double* d_norm = (double*)s->d_scratch;
-  unsigned int* d_rot = (unsigned int*)((char*)s->d_scratch + nvals * sizeof(double));
+  double* d_frob = d_norm + nvals;
+  unsigned int* d_rot = (unsigned int*)(d_frob + s->n_batch);
+  {
+    dim3 g0(nvec, (unsigned)s->n_batch);
+    k_vec_norm2<<<g0, std::min(256, std::max(32, len)), 0, s->stream>>>(R, nvec, len, d_norm);
+    BT_CHECK_LAUNCH(s);
+    k_frob2<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(d_norm, nvec, s->n_batch, d_frob);
+    BT_CHECK_LAUNCH(s);
+  }
   const double tol = 1e-15 * sqrt((double)len) + 1e-15;
   int sweeps = 0;
   const int max_sweeps = 60;
   if (nvec >= 2) {
     for (; sweeps < max_sweeps;) {
       BT_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(unsigned int), s->stream));
-      for (int r = 0; r < nvec - 1; ++r) BT_TRY(launch_round(s, R, nvec, len, r, tol, d_rot));
+      for (int r = 0; r < nvec - 1; ++r) BT_TRY(launch_round(s, R, nvec, len, r, tol, d_frob, d_rot));
       ++sweeps;
       BT_CUDA(cudaMemcpyAsync(s->h_flag, d_rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
       BT_CUDA(cudaStreamSynchronize(s->stream));
@@ -395,7 +417,7 @@ extern "C" int bt_dm_bipartition_spectrum(const bt_dm* d, int n_keep, double* sp
   for (int j = 0; j < P.nenv; ++j) P.eb[j] = n_keep + j;
   const uint64_t DD = 1ull << (2 * n_keep);
   // the reduced matrix lives behind the spectrum scratch (jacobi_spectrum uses the head of d_scratch)
-  const size_t head = ((size_t)(1 << n_keep) * sizeof(double) + 64 + 255) & ~(size_t)255;
+  const size_t head = ((size_t)((1 << n_keep) + 1) * sizeof(double) + 64 + 255) & ~(size_t)255;  // norms + Frobenius norm + rotation counter
   BT_TRY(bt_ensure_scratch(v, head + DD * sizeof(double2)));
   double2* M = (double2*)((char*)v->d_scratch + head);
   k_dm_rdm<<<(unsigned)((DD + 7) / 8), 256, 0, v->stream>>>(v->amp, n, P, M);

@@ -413,33 +413,32 @@ __device__ __forceinline__ double prob_at(const double2* __restrict__ a, uint64_
 __global__ void __launch_bounds__(256) k_block_sums(const double2* __restrict__ a, uint64_t n, uint64_t dm_stride, double* __restrict__ bsum, double* __restrict__ ssum,
                                                      uint64_t nb) {
   // one CTA per block of 2^SB entries; also the sums of its 16 sub-blocks of 256 entries (the in-block search of k_sample starts
-  // from them); fixed-order tree => reproducible
-  __shared__ double sm[SUBS][8];
+  // from them).  Warp w owns the 512 consecutive entries of sub-blocks 2w and 2w+1: 8 independent loads per lane and one shuffle
+  // tree per sub-block; fixed order => reproducible
   __shared__ double sub[SUBS];
   const uint64_t traj = blockIdx.x / nb, blk = blockIdx.x % nb;
   const double2* __restrict__ base = a + traj * n;
-  const uint64_t b0 = blk << SB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 8
-  for (int it = 0; it < SUBS; ++it) {
-    uint64_t i = b0 + (uint64_t)it * 256 + threadIdx.x;
-    double acc = (i < n) ? prob_at(base, i, dm_stride) : 0.0;
+  const uint64_t w0 = (blk << SB) + (uint64_t)warp * 512 + lane;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint64_t i = w0 + (uint64_t)h * 256 + (uint64_t)it * 32;
+      v[it] = (i < n) ? prob_at(base, i, dm_stride) : 0.0;
+    }
+    double acc = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) sm[it][warp] = acc;
+    if (lane == 0) sub[warp * 2 + h] = acc;
   }
   __syncthreads();
-  if (threadIdx.x < SUBS) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += sm[threadIdx.x][w];
-    sub[threadIdx.x] = s;
-    ssum[(uint64_t)blockIdx.x * SUBS + threadIdx.x] = s;
-  }
-  __syncthreads();
+  if (threadIdx.x < SUBS) ssum[(uint64_t)blockIdx.x * SUBS + threadIdx.x] = sub[threadIdx.x];
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int k = 0; k < SUBS; ++k) s += sub[k];
-    bsum[blockIdx.x] = s;
+    double t = 0.0;
+    for (int k = 0; k < SUBS; ++k) t += sub[k];
+    bsum[blockIdx.x] = t;
   }
 }
 
