@@ -49,6 +49,13 @@ def main():
         p0 = np.zeros(1)
         L.check(st.lib.bt_sv_measure_z(st.h, 2, L.pdouble(u), out.ctypes.data_as(C.POINTER(C.c_int32)), L.pdouble(p0), 0))
         after = st.gather_logical()
+        # three more measurements in ONE call (joint distribution reduced over the shards through the all-reduce callback), the first
+        # of them on qubit 1 = the top index bit, which lives on the rank id until the library remaps it
+        qs3 = (C.c_int * 3)(1, N, 5)
+        u3 = np.array([[0.81, 0.12, 0.55]])
+        out3 = np.zeros((1, 3), dtype=np.int32)
+        L.check(st.lib.bt_sv_measure_z_multi(st.h, 3, qs3, L.pdouble(u3), out3.ctypes.data_as(C.POINTER(C.c_int32)), None))
+        after3 = st.gather_logical()
         nrem = st.remap_stats()
         if rank == 0:
             ref = bt.basis_state(N, basis)
@@ -65,10 +72,16 @@ def main():
             p2 = np.zeros(1)
             L.check(ref.lib.bt_sv_measure_z(ref.h, 2, L.pdouble(u), o2.ctypes.data_as(C.POINTER(C.c_int32)), L.pdouble(p2), 0))
             e5 = float(np.max(np.abs(after - ref.to_numpy())))
-            good = e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12 and e4 < 1e-12 and same_samples and out[0] == o2[0] and e5 < 1e-12
+            o3 = np.zeros(3, dtype=np.int32)
+            for j in range(3):  # the reference: three sequential single-GPU measurements with the same draws
+                oj = np.zeros(1, dtype=np.int32)
+                L.check(ref.lib.bt_sv_measure_z(ref.h, int(qs3[j]), L.pdouble(np.array([u3[0, j]])), oj.ctypes.data_as(C.POINTER(C.c_int32)), None, 0))
+                o3[j] = oj[0]
+            e6 = float(np.max(np.abs(after3 - ref.to_numpy())))
+            good = e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12 and e4 < 1e-12 and same_samples and out[0] == o2[0] and e5 < 1e-12 and np.array_equal(out3[0], o3) and e6 < 1e-12
             ok = ok and good
             print(f"[mp_shard_check] {name} N={N} world={world}: amp={e1:.1e} expZ={e2:.1e} norm={e3:.1e} pauli={e4:.1e} samples={same_samples} "
-                  f"outcome={out[0]}=={o2[0]} p0={p0[0]:.6f} post={e5:.1e} remaps={nrem[0]} {'OK' if good else 'FAIL'}", flush=True)
+                  f"outcome={out[0]}=={o2[0]} p0={p0[0]:.6f} post={e5:.1e} multi={[int(v) for v in out3[0]]}=={[int(v) for v in o3]} post3={e6:.1e} remaps={nrem[0]} {'OK' if good else 'FAIL'}", flush=True)
         del st
         dist.barrier()
     # back-to-back steps without any host synchronisation in between (what bench.py's timed loop does): the remaps of
