@@ -322,8 +322,18 @@ std::string cond_expr(const JOp& o) {
 // inside the tile) select the coefficient (identity when off) instead of branching around the arithmetic
 
 // Emits the kernel for the planned pass.
+// variant 128 ("wide"): 256 threads per CTA, 2 CTAs per SM; the second iteration of the two-iteration group loop becomes thread bit 7,
+// so a program is one straight-line block without any loop (16 instead of 12 warps per SM, two tiles in flight instead of three)
+bool wide_ok(const TileParams& P) {
+  if (!(jit_variant() & 128)) return false;
+  for (int it = 0; it < P.nitems; ++it)
+    if (P.pr[(int)P.item[it] - TILE_PBASE].niter != 2) return false;
+  return true;
+}
+
 bool generate(const TileParams& P, const Plan& pl, std::string& s) {
   const int variant = jit_variant();
+  const bool wide = wide_ok(P);
   const int T = P.T;
   const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
   std::string body;
@@ -506,12 +516,18 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
     }
     uint32_t o[PROG_BITS];
     for (int q = 0; q < PROG_BITS; ++q) { uint32_t c = 1u << G.lp[q]; o[q] = c ^ ((c >> 3) & 7u); }
-    appf(body, "%s\n    for (uint32_t it = 0; it < %uu; ++it) {\n", (variant & 1) ? "#pragma unroll" : "#pragma unroll 1", G.niter);
+    if (wide) {
+      appf(body, "    if (tid & 128u) s0 ^= %uu;\n", G.iter_sw[1]);
+      if (need_gl) appf(body, "    if (tid & 128u) g0 ^= %uu;\n", G.iter_lin[1]);
+      body += "    {\n";
+    } else {
+      appf(body, "%s\n    for (uint32_t it = 0; it < %uu; ++it) {\n", (variant & 1) ? "#pragma unroll" : "#pragma unroll 1", G.niter);
+    }
     body += "      uint32_t b = s0;\n";
-    for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) b = s0 ^ %uu;\n", i, G.iter_sw[i]);
+    for (uint32_t i = 1; i < G.niter && !wide; ++i) appf(body, "      if (it == %uu) b = s0 ^ %uu;\n", i, G.iter_sw[i]);
     if (need_gl) {
       body += "      uint64_t gl = g0;\n";
-      for (uint32_t i = 1; i < G.niter; ++i) appf(body, "      if (it == %uu) gl = g0 ^ %uu;\n", i, G.iter_lin[i]);
+      for (uint32_t i = 1; i < G.niter && !wide; ++i) appf(body, "      if (it == %uu) gl = g0 ^ %uu;\n", i, G.iter_lin[i]);
       // variant 16: the group index is opaque to the compiler in every iteration, so no condition on it can be hoisted out of the loop
       if (variant & 16) body += "      asm volatile(\"mov.b64 %0, %0;\" : \"+l\"(gl));\n";
     } else {
@@ -554,8 +570,8 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
   s += "struct __align__(64) BtTensorMap { unsigned long long opaque[16]; };\n";
   appf(s, "struct BtCoefs { double c[%d]; };\n", ncoef);
   s += "__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }\n";
-  appf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) bt_jit_pass(const __grid_constant__ BtTensorMap tmap, const __grid_constant__ BtCoefs C) {\n", TILE_THREADS,
-       TILE_MINB);
+  appf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) bt_jit_pass(const __grid_constant__ BtTensorMap tmap, const __grid_constant__ BtCoefs C) {\n",
+       wide ? 2 * TILE_THREADS : TILE_THREADS, wide ? 2 : TILE_MINB);
   s += "  extern __shared__ unsigned char smem_raw[];\n  const uint32_t raw = smem_u32(smem_raw);\n  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;\n";
   s += "  double2* sm = reinterpret_cast<double2*>(smem_raw + pad);\n  const uint32_t tid = threadIdx.x;\n";
   appf(s, "  uint64_t base = (uint64_t)blockIdx.x << %d;\n", P.lowb);
@@ -612,6 +628,7 @@ struct Entry {
   CUfunction fn = nullptr;
   int ncoef = 0;
   int smem_bytes = 0;
+  int threads = TILE_THREADS;
   std::vector<char> cubin;  // state 3 only
 };
 
@@ -837,6 +854,7 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
     if (!generate(P, pl, src)) { e.state = -1; g_failed++; return 0; }
     e.ncoef = (int)pl.coef.size();
     e.smem_bytes = (int)(tile_bytes + 1024 + 64);
+    e.threads = wide_ok(P) ? 2 * TILE_THREADS : TILE_THREADS;
     if (mode != 2 && env_i("BT_TILE_JIT_ASYNC", 1) != 0) {
       enqueue_compile(std::move(src), &e);  // the interpreter runs this pass; the cubin is picked up at a later launch
       return 0;
@@ -864,7 +882,7 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   if ((int)pl.coef.size() != e.ncoef) return 0;
   std::vector<double>& coef = pl.coef;
   void* args[2] = {(void*)&tmap, (void*)coef.data()};
-  if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, TILE_THREADS, 1, 1, (unsigned)e.smem_bytes, (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
+  if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, (unsigned)e.threads, 1, 1, (unsigned)e.smem_bytes, (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
     e.state = -1;
     return 0;
   }

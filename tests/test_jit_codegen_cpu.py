@@ -50,7 +50,8 @@ def emulate(N, specs_expr, variant, tmp_path):
         body = body.replace("__syncthreads();", "").replace("#pragma unroll 1\n", "").replace("#pragma unroll\n", "")
         body = re.sub(r'asm volatile\("mov\.b64 %0, %0;" : "\+l"\(gl\)\);', "", body)
         body = body.replace('uint32_t zoff; asm volatile("mov.u32 %0, 0;" : "=r"(zoff));', "uint32_t zoff = 0;")
-        body = re.sub(r"  if \(tid < (\d+)u\) \{", r"  for (uint32_t tid = 0; tid < 128u; ++tid) if (tid < \1u) {", body)
+        nthreads = int(re.search(r"__launch_bounds__\((\d+),", src).group(1))
+        body = re.sub(r"  if \(tid < (\d+)u\) \{", rf"  for (uint32_t tid = 0; tid < {nthreads}u; ++tid) if (tid < \1u) {{", body)
         cpp.append(f'struct Coefs{pi} {{ double c[{ncoef}]; }};\nextern "C" void pass{pi}(double2* sm, uint64_t base, const Coefs{pi}* Cp) {{ const Coefs{pi}& C = *Cp;\n{body}\n}}\n')
         meta.append((tbits, coefs))
     src_path, so_path = tmp_path / "emul.cpp", tmp_path / "emul.so"
@@ -81,7 +82,7 @@ def emulate(N, specs_expr, variant, tmp_path):
     return state, launches, progs
 
 
-@pytest.mark.parametrize("variant", [0, 2, 34])
+@pytest.mark.parametrize("variant", [0, 2, 34, 128])
 @pytest.mark.parametrize("N,specs_expr", [(13, "wl.qft(13)"), (13, "wl.layered(13, 5, 28)"), (12, "wl.qft(12) + wl.layered(12, 4, 3)")])
 def test_generated_pass_source_equals_the_oracle_on_the_host(bt, orc, tmp_path, N, specs_expr, variant):
     from importlib import import_module
