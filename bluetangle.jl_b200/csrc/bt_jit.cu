@@ -250,6 +250,10 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
 // 12.9.86 produces for form 0 drop individual conditional phases in QFT-like passes (dozens of thread-dependent branches inside the
 // two-iteration group loop; amplitudes off by 1e-4) -- the same text is correct when compiled by NVRTC 12.8, with -Xptxas=-O0, when
 // executed on the host (tests/test_jit_codegen_cpu.py), and in forms 1 and 2.  BT_JIT_VERIFY=1 cross-checks every launch on the device.
+// resident CTAs per SM the register allocation aims at (BT_JIT_MINB; 3 = 168 registers, 4 = 128, 5 = 102): more CTAs need tiles of
+// <= 2^11 amplitudes (shared memory)
+int jit_minb() { return std::max(1, std::min(8, env_i("BT_JIT_MINB", TILE_MINB))); }
+
 int jit_variant() {
   const char* v = getenv("BT_JIT_VARIANT");
   if (v && *v) return atoi(v);
@@ -259,8 +263,9 @@ int jit_variant() {
 }
 
 // structure key: everything the generator turns into literals or code shape (numeric coefficients excluded)
-void make_key(const TileParams& P, const Plan& pl, int device, std::string& key) {
+void make_key(const TileParams& P, const Plan& pl, int device, std::string& key, int K = 1) {
   key.clear();
+  key.append((const char*)&K, 4);
   auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
   put(&device, 4); put(&P.T, 4); put(&P.lowb, 4); put(&P.nitems, 4); put(&P.swz_mode, 4);
   put(P.tma_coord_shift, sizeof(P.tma_coord_shift)); put(P.tma_coord_mask, sizeof(P.tma_coord_mask));
@@ -271,6 +276,8 @@ void make_key(const TileParams& P, const Plan& pl, int device, std::string& key)
   put(&cs, 1);
   const int variant = jit_variant();
   put(&variant, 4);
+  const int minb = jit_minb();
+  put(&minb, 4);
   for (int it = 0; it < P.nitems; ++it) {
     const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
     put(G.lp, sizeof(int32_t) * PROG_BITS); put(G.bit_sw, sizeof(G.bit_sw)); put(&G.niter, 4);
@@ -331,9 +338,9 @@ bool wide_ok(const TileParams& P) {
   return true;
 }
 
-bool generate(const TileParams& P, const Plan& pl, std::string& s) {
+bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
   const int variant = jit_variant();
-  const bool wide = wide_ok(P);
+  const bool wide = wide_ok(P) && K <= 1;
   const int T = P.T;
   const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
   std::string body;
@@ -570,8 +577,56 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s) {
   s += "struct __align__(64) BtTensorMap { unsigned long long opaque[16]; };\n";
   appf(s, "struct BtCoefs { double c[%d]; };\n", ncoef);
   s += "__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }\n";
+  if (K > 1) {
+    // ---- pipelined frame (BT_TILE_PIPE = K, tiles of <= 2^11 amplitudes): a CTA owns K consecutive tiles and two tile buffers; the load of
+    // tile i+1 is in flight while the programs of tile i run, the store of tile i drains while tile i+1 computes, and the buffer is
+    // refilled with tile i+2 as soon as the store has read it.  Same programs, emitted once inside the tile loop.
+    const unsigned tb = (unsigned)(sizeof(double2) << T), ch = tb / (unsigned)P.tma_ncopy;
+    s += "__device__ __forceinline__ uint64_t tile_base(uint64_t t) {\n";
+    appf(s, "  uint64_t base = t << %d;\n", P.lowb);
+    for (int j = P.lowb; j < T; ++j) {
+      const int b = P.tbits[j];
+      appf(s, "  base = ((base >> %d) << %d) | (base & 0x%llxull);\n", b, b + 1, (unsigned long long)((1ull << b) - 1ull));
+    }
+    s += "  return base;\n}\n";
+    s += "__device__ __forceinline__ void issue_load(uint64_t tm, uint32_t mb, uint32_t dst, uint64_t base) {\n";
+    for (int k = 1; k <= 4; ++k) appf(s, "  const int32_t c%d = (int32_t)((base >> %d) & 0x%xu);\n", k, P.tma_coord_shift[k], P.tma_coord_mask[k]);
+    appf(s, "  asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%%0], %%1;\" ::\"r\"(mb), \"r\"(%uu) : \"memory\");\n", tb);
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      appf(s,
+           "  asm volatile(\"cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%%0], [%%1, {%%2, %%3, %%4, %%5, %%6}], [%%7];\" "
+           "::\"r\"(dst + %uu), \"l\"(tm), \"r\"(0), \"r\"(c1), \"r\"(c2), \"r\"(c3), \"r\"(c4 + %d), \"r\"(mb) : \"memory\");\n",
+           e * ch, P.tma_c4add[e]);
+    s += "}\n";
+    appf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) bt_jit_pass(const __grid_constant__ BtTensorMap tmap, const __grid_constant__ BtCoefs C) {\n", TILE_THREADS,
+         jit_minb());
+    s += "  extern __shared__ unsigned char smem_raw[];\n  const uint32_t raw = smem_u32(smem_raw);\n  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;\n";
+    s += "  double2* buf0 = reinterpret_cast<double2*>(smem_raw + pad);\n  const uint32_t tid = threadIdx.x;\n";
+    appf(s, "  const uint32_t dst0 = smem_u32(buf0), mb0 = dst0 + %uu;\n  const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);\n", 2 * tb);
+    appf(s, "  const uint64_t t0 = (uint64_t)blockIdx.x * %du;\n", K);
+    s += "  if (tid == 0) {\n    asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(mb0));\n    asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(mb0 + 8u));\n"
+         "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n  }\n  __syncthreads();\n";
+    appf(s, "  if (tid == 0) {\n    issue_load(tm, mb0, dst0, tile_base(t0));\n    issue_load(tm, mb0 + 8u, dst0 + %uu, tile_base(t0 + 1));\n  }\n", tb);
+    appf(s, "#pragma unroll 1\n  for (uint32_t ti = 0; ti < %du; ++ti) {\n", K);
+    appf(s, "    const uint32_t mb = mb0 + 8u * (ti & 1u), dst = dst0 + (ti & 1u) * %uu;\n    double2* sm = buf0 + (ti & 1u) * %uu;\n    const uint64_t base = tile_base(t0 + ti);\n", tb, 1u << T);
+    s += "    {\n      const uint32_t parity = (ti >> 1) & 1u;\n      uint32_t done = 0;\n      for (uint32_t spin = 0; !done; ++spin) {\n"
+         "        asm volatile(\"{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\" : \"=r\"(done) : \"r\"(mb), \"r\"(parity) : \"memory\");\n"
+         "        if (spin > (1u << 22)) __trap();\n      }\n    }\n";
+    s += body;
+    s += "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n    __syncthreads();\n    if (tid == 0) {\n";
+    for (int k = 1; k <= 4; ++k) appf(s, "      const int32_t c%d = (int32_t)((base >> %d) & 0x%xu);\n", k, P.tma_coord_shift[k], P.tma_coord_mask[k]);
+    for (int e = 0; e < P.tma_ncopy; ++e)
+      appf(s,
+           "      asm volatile(\"cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%%0, {%%1, %%2, %%3, %%4, %%5}], [%%6];\" ::\"l\"(tm), \"r\"(0), \"r\"(c1), \"r\"(c2), "
+           "\"r\"(c3), \"r\"(c4 + %d), \"r\"(dst + %uu) : \"memory\");\n",
+           P.tma_c4add[e], e * ch);
+    s += "      asm volatile(\"cp.async.bulk.commit_group;\" ::: \"memory\");\n";
+    appf(s, "      if (ti + 2u < %du) {\n        asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n        issue_load(tm, mb, dst, tile_base(t0 + ti + 2u));\n      }\n    }\n  }\n", K);
+    s += "  if (tid == 0) asm volatile(\"cp.async.bulk.wait_group.read 0;\" ::: \"memory\");\n}\n";
+    return true;
+  }
   appf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) bt_jit_pass(const __grid_constant__ BtTensorMap tmap, const __grid_constant__ BtCoefs C) {\n",
-       wide ? 2 * TILE_THREADS : TILE_THREADS, wide ? 2 : TILE_MINB);
+       wide ? 2 * TILE_THREADS : TILE_THREADS, wide ? 2 : jit_minb());
   s += "  extern __shared__ unsigned char smem_raw[];\n  const uint32_t raw = smem_u32(smem_raw);\n  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;\n";
   s += "  double2* sm = reinterpret_cast<double2*>(smem_raw + pad);\n  const uint32_t tid = threadIdx.x;\n";
   appf(s, "  uint64_t base = (uint64_t)blockIdx.x << %d;\n", P.lowb);
@@ -629,6 +684,7 @@ struct Entry {
   int ncoef = 0;
   int smem_bytes = 0;
   int threads = TILE_THREADS;
+  int tiles_per_cta = 1;
   std::vector<char> cubin;  // state 3 only
 };
 
@@ -840,8 +896,12 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   if (mode != 2 && s->len < (1ull << env_i("BT_TILE_JIT_MINBITS", 22))) return 0;
   Plan pl;
   if (!make_plan(P, np, pl)) return 0;
+  // pipelined frame: K tiles per CTA with two tile buffers (tiles of <= 2^11 amplitudes: 2 x 32 KB, still three CTAs per SM)
+  int K = env_i("BT_TILE_PIPE", 0);
+  if (P.T > 11 || K < 2 || (K & (K - 1)) != 0) K = 1;
+  while (K > 1 && (ntiles % (uint64_t)K != 0 || ntiles / (uint64_t)K < 6ull * 148ull)) K >>= 1;
   std::string key;
-  make_key(P, pl, s->device, key);
+  make_key(P, pl, s->device, key, K);
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_cache.size() > 8192 && g_cache.find(key) == g_cache.end()) return 0;  // bounded: a long-running host with ever-new passes keeps interpreting
   Entry& e = g_cache[key];
@@ -851,10 +911,11 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
     if (mode != 2 && e.seen < env_i("BT_TILE_JIT_AFTER", 1)) return 0;
     if (!driver().ok || !nvrtc().ok) { e.state = -1; g_failed++; g_last_log = "NVRTC or the driver entry points are not available"; return 0; }
     std::string src;
-    if (!generate(P, pl, src)) { e.state = -1; g_failed++; return 0; }
+    if (!generate(P, pl, src, K)) { e.state = -1; g_failed++; return 0; }
     e.ncoef = (int)pl.coef.size();
-    e.smem_bytes = (int)(tile_bytes + 1024 + 64);
-    e.threads = wide_ok(P) ? 2 * TILE_THREADS : TILE_THREADS;
+    e.smem_bytes = (int)((K > 1 ? 2 : 1) * tile_bytes + 1024 + 64);
+    e.threads = (wide_ok(P) && K <= 1) ? 2 * TILE_THREADS : TILE_THREADS;
+    e.tiles_per_cta = K;
     if (mode != 2 && env_i("BT_TILE_JIT_ASYNC", 1) != 0) {
       enqueue_compile(std::move(src), &e);  // the interpreter runs this pass; the cubin is picked up at a later launch
       return 0;
@@ -882,7 +943,7 @@ int bt_jit_try_launch(bt_sv* s, const TileParams& P, const CUtensorMap& tmap, ui
   if ((int)pl.coef.size() != e.ncoef) return 0;
   std::vector<double>& coef = pl.coef;
   void* args[2] = {(void*)&tmap, (void*)coef.data()};
-  if (driver().LaunchKernel(e.fn, (unsigned)ntiles, 1, 1, (unsigned)e.threads, 1, 1, (unsigned)e.smem_bytes, (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
+  if (driver().LaunchKernel(e.fn, (unsigned)(ntiles / (uint64_t)e.tiles_per_cta), 1, 1, (unsigned)e.threads, 1, 1, (unsigned)e.smem_bytes, (CUstream)s->stream, args, nullptr) != CUDA_SUCCESS) {
     e.state = -1;
     return 0;
   }
@@ -958,7 +1019,7 @@ static bool selftest_source(std::string& src) {
   { double m; uint64_t em = 1ull << 22, lm = 0; emit(PROG_SITE_CCX1(1), 0); memcpy(&m, &em, 8); G.coef[kc++] = m; memcpy(&m, &lm, 8); G.coef[kc++] = m; }
   G.nops = (uint32_t)ko;
   Plan pl;
-  const bool ok = make_plan(P, 1, pl) && generate(P, pl, src);
+  const bool ok = make_plan(P, 1, pl) && generate(P, pl, src, std::max(1, env_i("BT_JIT_SELFTEST_PIPE", 1)));  // BT_JIT_SELFTEST_PIPE=K: the pipelined frame
   delete Pp;
   return ok;
 }
