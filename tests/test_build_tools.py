@@ -105,7 +105,7 @@ def test_pass_specialiser_generates_and_compiles_on_the_host():
         pytest.skip("libnvrtc not available")
     assert rc == 0, lib.bt_last_error().decode()
     src = buf.value.decode()
-    for needle in ("bt_jit_pass", "cp.async.bulk.tensor.5d", "mbarrier.try_wait", "fma(C.c[", "if ((base & 0x100000ull) == 0x100000ull", "make_double2("):
+    for needle in ("bt_jit_pass", "cp.async.bulk.tensor.5d", "mbarrier.try_wait", "fma(C.c[", "(base & 0x100000ull) == 0x100000ull", "make_double2("):  # the condition is a branch or a select (BT_JIT_VARIANT)
         assert needle in src
     # the CX of the synthetic pass is a renaming: amplitudes are stored from permuted variables, no swap code is emitted
     stores = [l for l in src.splitlines() if "make_double2(" in l]
