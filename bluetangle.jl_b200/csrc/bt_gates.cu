@@ -247,15 +247,26 @@ static int launch_dense(bt_sv* s, const GateDesc& g, const double2* dmats, const
   unsigned grid = (unsigned)((ngroups + per_block - 1) / per_block);
   // matrix bit that sits on index bit 0 (1- and 2-qubit gates): its pairs move as 256-bit accesses
   int t0 = -1;
-  if (K <= 2)
-    for (int t = 0; t < K; ++t)
-      if (g.tb[t] == 0) t0 = t;
+  for (int t = 0; t < K; ++t)
+    if (g.tb[t] == 0) t0 = t;
   static const bool wide = []() { const char* v = getenv("BT_WIDE_LOADS"); return !(v && *v == '0'); }();
   if (!wide) t0 = -1;
+  if (K >= 3 && (dmats || cond)) t0 = -1;  // 3- and 4-bit blocks (superoperators of 2-qubit gates / channels on rho): plain form only
   bt_prof_begin(s, BT_CLS_DENSE);
-  if (t0 == 0) launch_dense_t0<K, U, 0>(s, grid, ngroups, gshift, P, dmats, cond, want);
-  else if (t0 == 1 && K == 2) launch_dense_t0<K, U, (K == 2 ? 1 : -1)>(s, grid, ngroups, gshift, P, dmats, cond, want);
-  else launch_dense_t0<K, U, -1>(s, grid, ngroups, gshift, P, dmats, cond, want);
+  if (K <= 2) {
+    if (t0 == 0) launch_dense_t0<K, U, 0>(s, grid, ngroups, gshift, P, dmats, cond, want);
+    else if (t0 == 1 && K == 2) launch_dense_t0<K, U, (K == 2 ? 1 : -1)>(s, grid, ngroups, gshift, P, dmats, cond, want);
+    else launch_dense_t0<K, U, -1>(s, grid, ngroups, gshift, P, dmats, cond, want);
+  } else if (t0 < 0) {
+    launch_dense_t0<K, U, -1>(s, grid, ngroups, gshift, P, dmats, cond, want);
+  } else {
+    switch (t0) {
+      case 0: k_dense<K, U, false, false, 0><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0); break;
+      case 1: k_dense<K, U, false, false, (K >= 3 ? 1 : -1)><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0); break;
+      case 2: k_dense<K, U, false, false, (K >= 3 ? 2 : -1)><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0); break;
+      default: k_dense<K, U, false, false, (K >= 4 ? 3 : -1)><<<grid, 256, 0, s->stream>>>(s->amp, ngroups, gshift, P, nullptr, nullptr, 0); break;
+    }
+  }
   bt_prof_end(s);
   BT_CHECK_LAUNCH(s);
   return BT_OK;
