@@ -139,6 +139,9 @@ struct JOp {
   signed char pat[4] = {2, 2, 2, 2};  // LIN2 entries after the pivot division: 0 zero, +1 / -1 unit, 2 general (takes a coefficient)
   int c0 = 0;              // first coefficient of this op in the coefficient block
   uint64_t em = 0, lm = 0; // condition masks
+  int merged = 0;          // member of a merged run of diagonal factors (its complex factor is multiplied up per thread first)
+  int shear = 0;           // unit-modulus phase applied as three shears (3 FMAs instead of 2 MUL + 2 FMA): coefficients are
+                           // (t, s) = (-tan(theta/2), sin(theta)); 2: theta was reduced by pi, the result is negated
 };
 
 struct Plan {
@@ -172,6 +175,8 @@ double pivot_real(const double m[4], signed char pat[4], double out[4]) {
   }
   return m[best];
 }
+
+int jit_variant();
 
 bool make_plan(const TileParams& P, int np, Plan& pl) {
   if (P.swz_mode != 0 || np <= 0 || P.nitems != np) return false;
@@ -233,6 +238,53 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
       pl.prog[(size_t)it].push_back(o);
     }
   }
+  // Runs of diagonal ops: the factors of a run that hit the same amplitudes are merged when there are two or more of them
+  // (generate() multiplies them up per thread).  Every other phase with a unit-modulus factor becomes a rotation by three shears
+  //   r += t i;  i += s r;  r += t i      t = -tan(theta/2), s = sin(theta)
+  // (3 FMAs per amplitude instead of 2 MUL + 2 FMA; |theta| <= pi/2 after an optional reduction by pi, so |t| <= 1).  A factor whose
+  // modulus is not 1 to rounding (T is rounded to 10 digits in the reference's table) keeps the complex multiplication.
+  const bool merge = env_i("BT_JIT_MERGE_DIAG", 1) != 0, use_shear = env_i("BT_JIT_SHEAR", 1) != 0;
+  const int variant = jit_variant();
+  for (std::vector<JOp>& L : pl.prog) {
+    auto is_diag = [](const JOp& o) { return o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE || o.kind == JK_CZ; };
+    size_t i = 0;
+    while (i < L.size()) {
+      if (!is_diag(L[i])) { ++i; continue; }
+      size_t j = i;
+      while (j < L.size() && is_diag(L[j])) ++j;
+      if (merge)
+        for (int cls = -1; cls < PROG_BITS; ++cls) {
+          std::vector<size_t> mem;
+          for (size_t t = i; t < j; ++t) {
+            const JOp& o = L[t];
+            if (cls < 0 ? o.kind == JK_CSCALE : ((o.kind == JK_CPH1 && o.p == cls) || (o.kind == JK_PHASE && o.p == cls && o.q == 1))) mem.push_back(t);
+          }
+          if (mem.size() >= 2)
+            for (size_t t : mem) L[t].merged = 1;
+        }
+      i = j;
+    }
+    if (!use_shear) continue;
+    for (JOp& o : L) {
+      if (o.merged || !(o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE)) continue;
+      const bool conditional_select = (o.kind == JK_CPH1 || o.kind == JK_CSCALE) && o.lm != 0 && (variant & 2);
+      const bool conditional_branch = (o.kind == JK_CPH1 || o.kind == JK_CSCALE) && !conditional_select;
+      (void)conditional_branch;
+      double& cr = pl.coef[(size_t)o.c0];
+      double& ci = pl.coef[(size_t)o.c0 + 1];
+      if (fabs(cr * cr + ci * ci - 1.0) > 4.5e-16) continue;
+      double th = atan2(ci, cr);
+      int shape = 1;
+      if (fabs(th) > 1.5707963267948966) {
+        if (conditional_select) continue;  // a selected identity cannot carry the sign
+        th -= th > 0 ? 3.141592653589793 : -3.141592653589793;
+        shape = 2;
+      }
+      o.shear = shape;
+      cr = -tan(0.5 * th);
+      ci = sin(th);
+    }
+  }
   pl.scale_at = (int)pl.coef.size();
   pl.complex_scale = gs.imag() != 0.0;
   pl.coef.push_back(gs.real());
@@ -285,7 +337,7 @@ void make_key(const TileParams& P, const Plan& pl, int device, std::string& key,
     const uint32_t n = (uint32_t)pl.prog[(size_t)it].size();
     put(&n, 4);
     for (const JOp& o : pl.prog[(size_t)it]) {
-      const int32_t h[4] = {o.kind, o.p, o.q, o.rxl};
+      const int32_t h[6] = {o.kind, o.p, o.q, o.rxl, o.merged, o.shear};
       put(h, sizeof(h)); put(o.pat, 4); put(&o.em, 8); put(&o.lm, 8);
     }
   }
@@ -395,6 +447,29 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
           ops += buf;
           ops += "        " + ar + " = ta; " + ai + " = tc; " + br + " = tb; " + bi + " = td; }\n";
         }
+      } else if (o.shear && (o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE)) {
+        // unit-modulus phase as three shears; coefficients (t, s); a condition selects (t, s) or (0, 0) = identity, or branches
+        const bool cond = o.kind == JK_CPH1 || o.kind == JK_CSCALE;
+        const bool sel = cond && use_select(o);
+        if (cond && !sel) ops += cond_open(o);
+        else ops += "      {\n";
+        char hdr[320];
+        if (sel) snprintf(hdr, sizeof(hdr), "        const bool on = %s; const double st = on ? C.c[%d] : 0.0, ss = on ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), k, k + 1);
+        else snprintf(hdr, sizeof(hdr), "        const double st = C.c[%d], ss = C.c[%d];\n", k, k + 1);
+        ops += hdr;
+        for (int j = 0; j < PROG_AMPS; ++j) {
+          bool hit;
+          if (o.kind == JK_CSCALE) hit = true;
+          else if (o.kind == JK_CPHASE) hit = ((j >> o.p) & 1) && ((j >> o.q) & 1);
+          else hit = ((j >> o.p) & 1) == (o.kind == JK_CPH1 ? 1 : o.q);
+          if (!hit) continue;
+          const std::string r = X(j, 'r'), i = X(j, 'i');
+          if (o.shear == 2)
+            ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1 = fma(ss, r1, " + i + "); " + r + " = -fma(st, i1, r1); " + i + " = -i1; }\n";
+          else
+            ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1 = fma(ss, r1, " + i + "); " + r + " = fma(st, i1, r1); " + i + " = i1; }\n";
+        }
+        ops += "      }\n";
       } else if (o.kind == JK_PHASE || o.kind == JK_CPH1) {
         const bool sel = o.kind == JK_CPH1 && use_select(o);
         if (o.kind == JK_CPH1 && !sel) ops += cond_open(o);
@@ -472,9 +547,10 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
           std::vector<size_t> mem;
           for (size_t t = i; t < j; ++t) {
             const JOp& o = L[t];
+            if (!o.merged) continue;  // decided in make_plan (the coefficients of merged members stay complex factors)
             if (cls < 0 ? o.kind == JK_CSCALE : ((o.kind == JK_CPH1 && o.p == cls) || (o.kind == JK_PHASE && o.p == cls && o.q == 1))) mem.push_back(t);
           }
-          if (mem.size() < 2) continue;
+          if (mem.empty()) continue;
           ops += "      { double fr = 1.0, fi = 0.0;\n";
           for (size_t t : mem) {
             const JOp& o = L[t];
