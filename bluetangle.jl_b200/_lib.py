@@ -95,6 +95,8 @@ PROTOTYPES = {
     "bt_sv_probs": [_vp, _pd],
     "bt_sv_measure_z": [_vp, _i, _pd, _pi32, _pd, _i],
     "bt_sv_measure_z_multi": [_vp, _i, C.POINTER(_i), _pd, _pi32, C.POINTER(_i)],
+    "bt_sv_measure_log": [_vp, _i],
+    "bt_sv_measure_log_read": [_vp, _pi32, _u64, C.POINTER(_u64)],
     "bt_sv_outcomes": [_vp, _pi32],
     "bt_sv_set_mask": [_vp, _pi32],
     "bt_sv_kraus": [_vp, _i, _i, _i, _vp, _i, _pd, _pi32],

@@ -69,6 +69,9 @@ struct bt_sv {
   // trajectory mask (bt_sv_set_mask): gates, Kraus steps and measurements act only on trajectories with d_mask[t] != 0
   int32_t* d_mask;
   bool mask_on;
+  // deferred outcome log (bt_sv_measure_log): multi-measurement calls append their outcomes here instead of returning them, so a
+  // monitored circuit runs without a host synchronisation per measurement layer
+  int32_t* d_mlog; size_t mlog_cap, mlog_len; bool mlog_on;
   // grow-only device scratch (sampling prefix sums, uniforms, results)
   void* d_scratch; size_t scratch_cap;
   // timing / accounting

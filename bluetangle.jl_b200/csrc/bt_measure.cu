@@ -182,6 +182,23 @@ extern "C" int bt_sv_measure_z_multi(bt_sv* s, int k, const int* qubits, const d
   BT_TRY(bt_ensure_scratch(s, off_o + (size_t)s->n_batch * k * sizeof(int32_t)));
   double* d_u = (double*)((char*)s->d_scratch + off_u);
   int32_t* d_out = (int32_t*)((char*)s->d_scratch + off_o);
+  const bool to_log = s->mlog_on && !outcomes;
+  if (to_log) {  // the outcomes of this call are appended to the device-side log (read once at the end: bt_sv_measure_log_read)
+    const size_t need = s->mlog_len + (size_t)s->n_batch * k;
+    if (need > s->mlog_cap) {
+      size_t cap = std::max<size_t>(need * 2, (size_t)s->n_batch * 256);
+      int32_t* nl = nullptr;
+      BT_CUDA(cudaMalloc(&nl, cap * sizeof(int32_t)));
+      if (s->d_mlog) {
+        BT_CUDA(cudaMemcpyAsync(nl, s->d_mlog, s->mlog_len * sizeof(int32_t), cudaMemcpyDeviceToDevice, s->stream));
+        BT_CUDA(cudaStreamSynchronize(s->stream));
+        BT_CUDA(cudaFree(s->d_mlog));
+      }
+      s->d_mlog = nl; s->mlog_cap = cap;
+    }
+    d_out = s->d_mlog + s->mlog_len;
+    s->mlog_len = need;
+  }
   BT_CUDA(cudaMemcpyAsync(d_u, u, (size_t)s->n_batch * k * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   k_decide_multi<<<(unsigned)((s->n_batch + 127) / 128), 128, 0, s->stream>>>(s->d_res, k, d_u, s->d_outcome, d_out, s->d_scale, s->n_batch, s->mask_on ? s->d_mask : nullptr);
   BT_CHECK_LAUNCH(s);
@@ -208,6 +225,24 @@ extern "C" int bt_sv_measure_z_multi(bt_sv* s, int k, const int* qubits, const d
     BT_CUDA(cudaMemcpyAsync(outcomes, d_out, (size_t)s->n_batch * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
     BT_CUDA(cudaStreamSynchronize(s->stream));
   }
+  return BT_OK;
+}
+
+extern "C" int bt_sv_measure_log(bt_sv* s, int on) {
+  BT_TRY(bt_check_sv(s));
+  s->mlog_on = on != 0;
+  s->mlog_len = 0;
+  return BT_OK;
+}
+
+extern "C" int bt_sv_measure_log_read(bt_sv* s, int32_t* out, uint64_t cap, uint64_t* n) {
+  BT_TRY(bt_check_sv(s));
+  if (n) *n = (uint64_t)s->mlog_len;
+  if (s->mlog_len == 0) return BT_OK;
+  if (!out || cap < s->mlog_len) BT_FAIL(BT_ERR_ARG, "outcome log holds %llu entries", (unsigned long long)s->mlog_len);
+  BT_CUDA(cudaMemcpyAsync(out, s->d_mlog, s->mlog_len * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+  BT_CUDA(cudaStreamSynchronize(s->stream));
+  s->mlog_len = 0;
   return BT_OK;
 }
 

@@ -107,6 +107,7 @@ int bt_sv_create_internal(int n_qubits, int n_local, int64_t n_batch, bool want_
     if (bt_sv* r = pool_take(n_qubits, n_local, n_batch, dev)) {
       r->launches = 0;
       r->mask_on = false;
+      r->mlog_on = false; r->mlog_len = 0;
       for (int b = 0; b < 64; ++b) r->phys_of_bit[b] = b;
       k_set_basis<<<grid_for(r->len, 256), 256, 0, r->stream>>>(r->amp, 1ull << n_local, r->len, 0, 1);
       BT_CHECK_LAUNCH(r);
@@ -197,6 +198,7 @@ static void really_destroy(bt_sv* s) {
   if (s->d_mats) cudaFree(s->d_mats);
   if (s->d_scale) cudaFree(s->d_scale);
   if (s->d_mask) cudaFree(s->d_mask);
+  if (s->d_mlog) cudaFree(s->d_mlog);
   cudaFree(s->d_err);
   cudaFreeHost(s->h_flag);
   cudaEventDestroy(s->ev0);

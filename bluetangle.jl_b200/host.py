@@ -637,12 +637,19 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
             _dm_apply_ops(x, list(op), noise)
             return (x, []) if track_measurements else x
         mids: List = []
-        for o in _coalesce(op, x, noise):
+        groups = _coalesce(op, x, noise)
+        # every measurement of the list is a plain Z measurement / reset on a state vector: outcomes are logged on the device and
+        # read once at the end, so the host enqueues the whole monitored circuit without waiting for the GPU in between
+        deferred = (DEFER_OUTCOMES and isinstance(x, CuState) and any(isinstance(g, _MeasureRun) for g in groups)
+                    and not any(isinstance(g, (ifOp, OpF)) or (isinstance(g, Op) and g.ismeasure) or (isinstance(g, OpQC) and _z_measurement(g)) for g in groups))
+        if deferred:
+            L.check(x.lib.bt_sv_measure_log(x.h, 1))
+        for o in groups:
             if isinstance(o, _GateRun):
                 o.run(x)
                 continue
             if isinstance(o, _MeasureRun):
-                m = o.run(x, rng)
+                m = o.run(x, rng, deferred=deferred)
                 if track_measurements:
                     mids.extend(m)
                 continue
@@ -651,6 +658,24 @@ def apply(a, b, noise=False, rng=None, track_measurements: bool = False):
                 mids.extend(m)
             else:
                 x = apply(x, o, noise=noise, rng=rng)
+        if deferred and not track_measurements:
+            L.check(x.lib.bt_sv_measure_log(x.h, 0))  # nobody asked for the outcomes: no read, no synchronisation
+        elif deferred:
+            runs = [g for g in groups if isinstance(g, _MeasureRun)]
+            total = x.n_batch * sum(len(g.ops) for g in runs)
+            log = np.empty(total, dtype=np.int32)
+            n = C.c_uint64()
+            L.check(x.lib.bt_sv_measure_log_read(x.h, log.ctypes.data_as(C.POINTER(C.c_int32)), total, C.byref(n)))
+            L.check(x.lib.bt_sv_measure_log(x.h, 0))
+            if n.value != total:
+                raise RuntimeError(f"outcome log holds {n.value} entries, expected {total}")
+            if track_measurements:
+                pos = 0
+                for g in runs:
+                    k = len(g.ops)
+                    blk = log[pos:pos + x.n_batch * k].reshape(x.n_batch, k)
+                    pos += x.n_batch * k
+                    mids.extend((int(blk[0, j]) if x.n_batch == 1 else blk[:, j].copy()) for j in range(k) if not isinstance(g.ops[j], OpQC))
         return (x, mids) if track_measurements else x
     if isinstance(op, tuple):
         op = Op(*op)
@@ -746,20 +771,24 @@ class _MeasureRun:
     def __init__(self, ops):
         self.ops = list(ops)
 
-    def run(self, x: "CuState", rng) -> List:
+    def run(self, x: "CuState", rng, deferred: bool = False) -> List:
         k = len(self.ops)
         u = np.empty((x.n_batch, k), dtype=np.float64)
         for j in range(k):
             u[:, j] = _uniforms(x, rng)
-        out = np.empty((x.n_batch, k), dtype=np.int32)
         qs = (C.c_int * k)(*[int(o.qubit) for o in self.ops])
         rs = (C.c_int * k)(*[1 if isinstance(o, OpQC) else 0 for o in self.ops])
+        if deferred:  # outcomes go to the device-side log (bt_sv_measure_log): no host synchronisation here
+            L.check(x.lib.bt_sv_measure_z_multi(x.h, k, qs, L.pdouble(u), None, rs))
+            return []
+        out = np.empty((x.n_batch, k), dtype=np.int32)
         L.check(x.lib.bt_sv_measure_z_multi(x.h, k, qs, L.pdouble(u), out.ctypes.data_as(C.POINTER(C.c_int32)), rs))
         # resets are channels (OpQC): they report no mid-circuit outcome (apply() only tracks type "🔬" ops)
         return [(int(out[0, j]) if x.n_batch == 1 else out[:, j].copy()) for j in range(k) if not isinstance(self.ops[j], OpQC)]
 
 
 MEASURE_FUSE_DEFAULT = True
+DEFER_OUTCOMES = True
 
 
 def _z_measurement(o) -> bool:
@@ -780,9 +809,7 @@ def _coalesce(ops, x, noise):
 
     def flush_m():
         nonlocal mrun
-        if len(mrun) == 1:
-            out.append(mrun[0])
-        elif mrun:
+        if mrun:
             out.append(_MeasureRun(mrun))
         mrun = []
 

@@ -142,6 +142,11 @@ int bt_sv_measure_z(bt_sv* s, int qubit, const double* u, int32_t* outcome, doub
  * the sequential calls (the per-shot loop of a monitored circuit, src/ops.jl:616-631).  u[t*k + j], outcomes[t*k + j] (may be NULL:
  * no synchronisation); the handle's outcome record (bt_sv_outcomes) then holds the pattern sum_j outcome_j << j. */
 int bt_sv_measure_z_multi(bt_sv* s, int k, const int* qubits, const double* u, int32_t* outcomes, const int* reset /* k flags or NULL */);
+/* Deferred outcomes: while the log is on, bt_sv_measure_z_multi calls with outcomes == NULL append their n_batch x k outcomes to a
+ * device-side log (call after call) instead of returning them; bt_sv_measure_log_read copies the log to the host (one
+ * synchronisation for a whole monitored circuit, src/ops.jl:616-631) and empties it.  on != 0 also empties the log. */
+int bt_sv_measure_log(bt_sv* s, int on);
+int bt_sv_measure_log_read(bt_sv* s, int32_t* out, uint64_t cap, uint64_t* n);
 int bt_sv_outcomes(const bt_sv* s, int32_t* outcome /* n_batch: results of the last measure/kraus call */);
 /* Trajectory mask for batched states: while set, bt_sv_apply_1q/2q/3q, bt_sv_apply_circuit (gate by gate then), bt_sv_kraus and
  * bt_sv_measure_z act only on trajectories with mask[t] != 0; the others are untouched, consume no draw and report outcome /
