@@ -138,6 +138,37 @@ def kraus_block(bt, L, s, N, peak):
     return out
 
 
+def c4_block(bt, L, wl, n=20, trajectories=512, reps=3):
+    """Config C4 (BASELINE.json configs[3]) on this GPU: `trajectories` monitored 20-qubit brickwork trajectories as one batched state
+    (the per-shot loop of src/ops.jl:616-631, 671-676), per-trajectory draws from a host matrix, mid-circuit outcomes returned to
+    the host.  Replicas only: N GPUs run N such batches (tools/c4_multi.py is the multi-rank driver with the oracle comparison)."""
+    specs, M = wl.c4_monitored(n, 20, 20)
+    ops = wl.to_ops(bt, specs)
+    U = np.random.Generator(np.random.PCG64(20)).random((trajectories, M))
+    dev, host, table = [], [], None
+    for rep in range(reps + 1):  # first repetition = warm-up (specialised passes compile in the background)
+        t0 = time.perf_counter()
+        st = bt.zero_state(n, trajectories)
+        ms = C.c_float()
+        L.check(st.lib.bt_sv_timer_start(st.h))
+        _, mids = bt.apply(ops, st, rng=bt.BatchDraws(U), track_measurements=True)
+        L.check(st.lib.bt_sv_timer_stop(st.h, C.byref(ms)))
+        table = np.stack([np.asarray(m) for m in mids], axis=1)
+        dt = time.perf_counter() - t0
+        if rep == 0:
+            L.check(st.lib.bt_jit_wait(None))
+        else:
+            dev.append(ms.value)
+            host.append(dt)
+        nrm = bt.norm2(st)
+        del st
+    d, h = float(np.median(dev)), float(np.median(host))
+    return {"workload": f"C4: {trajectories} trajectories of a {n}-qubit monitored brickwork circuit (depth 20, {len(ops) - M} gates + {M} mid-circuit measurements) in one batched state "
+                        f"({16 * trajectories * 2 ** n / 2 ** 30:.1f} GiB)", "ms": d, "trajectories_per_s": trajectories / (d / 1e3), "e2e_trajectories_per_s": trajectories / h,
+            "outcome_table": list(table.shape), "mean_outcome": float(table.mean()), "max_norm_error": float(np.max(np.abs(nrm - 1))),
+            "note": "runs of measurements share one read + one collapse pass; outcomes are logged on the device and read once"}
+
+
 def dm14_block(bt, L, wl, peak, n=14, depth=20):
     """Config C3 (BASELINE.json configs[2]): n-qubit density matrix, depolarizing + amplitude damping after every gate
     (to_rho's loop, src/ops.jl:813-841 with apply(rho,op) src/hilbert.jl:655-656 and the channels of src/struct.jl:58-76),
@@ -388,13 +419,18 @@ def bench_single(args):
     except Exception as e:
         dm14, extra_err["dm14"] = None, repr(e)
 
+    try:
+        c4 = c4_block(bt, L, wl) if not args.no_blocks else None
+    except Exception as e:
+        c4, extra_err["c4"] = None, repr(e)
+
     cpu = cpu_baseline_port(N, specs, budget_s=args.cpu_budget) if not args.no_cpu else None
     out = {"metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (ComplexF64 amplitudes)", "data": "synthetic",
            "config": {"workload": f"C2: {N}-qubit state vector, QFT({N}) + {depth} random layers (H/RX/RY/RZ/T + CNOT/CZ/CP brickwork), {ngates} gates, seed 28",
                       "fusion": "host fusion pass + shared-memory tile kernel", "l2": f"inputs larger than L2 ({(16 << N) / 2**30:.1f} GiB state)", "parallelism": "1 GPU"},
            "clocks": clk, "e2e": e2e, "gpu_launches": int(n1 - n0), "roofline": roof, "kernels": per_cls, "unfused_gate_kernels": micro,
-           "interpreter": interp, "cold_first_step_s": cold_first_step_s, "kraus": kraus, "dm14": dm14,
+           "interpreter": interp, "cold_first_step_s": cold_first_step_s, "kraus": kraus, "dm14": dm14, "c4": c4,
            "cpu_baseline": cpu, "state_norm2": norm, "jit": jitst}
     if extra_err:
         out["block_errors"] = extra_err
