@@ -10,7 +10,7 @@
 //
 // Policy: a structure is handed to the compile workers the BT_TILE_JIT_AFTER-th time it is seen (default 1) on states of at
 // least 2^BT_TILE_JIT_MINBITS amplitudes (default 22).  Compilation never stalls the caller: NVRTC runs on a small pool of
-// worker threads (BT_JIT_THREADS, default min(8, cores)) while the pass keeps running on the interpreter; the cubin is loaded
+// worker threads (BT_JIT_THREADS, default min(8, cores / ranks on the node)) while the pass keeps running on the interpreter; the cubin is loaded
 // by the calling thread the next time the structure comes by.  Cubins are also kept on disk (BT_JIT_CACHE_DIR, default
 // $XDG_CACHE_HOME/bluetangle_cuda or ~/.cache/bluetangle_cuda; empty string = off), so a later process pays a file read
 // instead of 0.2 s of NVRTC per structure.  BT_TILE_JIT=0 switches the specialiser off, BT_TILE_JIT=2 compiles synchronously
@@ -938,7 +938,11 @@ void worker_main() {
 // g_mu held
 void enqueue_compile(std::string&& src, Entry* e) {
   if (!g_jobs) g_jobs = new std::deque<Job>();
-  const int want = std::max(1, std::min(env_i("BT_JIT_THREADS", 8), (int)std::max(1u, std::thread::hardware_concurrency())));
+  // default: min(8, cores / processes of this job on the node) -- eight ranks with eight compile threads each on a 16-core host starve
+  // the threads that enqueue the kernels (LOCAL_WORLD_SIZE is set by torchrun; MPI launchers set OMPI_COMM_WORLD_LOCAL_SIZE)
+  int local_world = std::max(1, std::max(env_i("LOCAL_WORLD_SIZE", 1), env_i("OMPI_COMM_WORLD_LOCAL_SIZE", 1)));
+  const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int want = std::max(1, std::min(env_i("BT_JIT_THREADS", 8), std::max(1, cores / local_world)));
   while (g_workers < want) { std::thread(worker_main).detach(); ++g_workers; }
   e->state = 2;
   g_pending++;
