@@ -201,6 +201,8 @@ extern "C" int bt_sv_schmidt_spectrum(const bt_sv* cs, int n_low, double* spec, 
   if (s->is_dm) BT_FAIL(BT_ERR_ARG, "Schmidt spectrum takes a state vector");
   const int N = s->n_local;
   if (n_low < 0 || n_low > N) BT_FAIL(BT_ERR_ARG, "cut position %d outside 0..%d", n_low, N);
+  if (std::max(n_low, N - n_low) > 13)
+    BT_FAIL(BT_ERR_UNSUPPORTED, "Schmidt spectrum: the long side of the cut has 2^%d > 2^13 entries (a vector pair must fit one CTA's registers)", std::max(n_low, N - n_low));
   BT_TRY(bt_ensure_alt(s));
   int nvec, len;
   if (n_low <= N - n_low) {  // the low side is the short one: its 2^n_low rows become contiguous vectors
