@@ -133,6 +133,7 @@ PROTOTYPES = {
     "bt_dm_rdm": [_vp, _i, C.POINTER(_i), _vp],
     "bt_dm_expect_op": [_vp, _i, _i, _i, _i, _vp, _pd],
     "bt_dm_bipartition_spectrum": [_vp, _i, _pd, C.POINTER(_i)],
+    "bt_dm_fidelity": [_vp, _vp, _pd],
     "bt_sv_create_shard": [_i, _i, _i, C.POINTER(_vp)],
     "bt_sv_ipc_export": [_vp, _vp],
     "bt_sv_ipc_attach": [_vp, _vp],

@@ -72,9 +72,11 @@ extern "C" int bt_jacobi_pairs_host(int nvec, int round, int* pairs /* nvec/2 x 
 // One round of the tournament: CTA k rotates the pair (p, q) of vectors of length len (EPT elements per thread).
 // A pair is rotated iff |<y,x>| > tol * |x| |y|; the rotation makes the two vectors orthogonal (complex Hestenes step:
 // a phase on y makes the inner product real, then a real plane rotation).
+// `acc` (optional): a companion matrix of nvec vectors of length acc_len that receives the same column rotations -- started as the
+// identity it accumulates the right singular vectors (eigenvectors, for a Hermitian input).
 template <int EPT>
 __global__ void __launch_bounds__(512) k_jacobi_round(double2* __restrict__ R, int nvec, int len, int round, double tol, const double* __restrict__ frob2,
-                                                      unsigned int* __restrict__ rotations) {
+                                                      unsigned int* __restrict__ rotations, double2* __restrict__ accm = nullptr, int acc_len = 0) {
   __shared__ double sm[32 * 4];
   int p, q;
   tournament_pair(nvec, round, blockIdx.x, &p, &q);
@@ -115,6 +117,16 @@ __global__ void __launch_bounds__(512) k_jacobi_round(double2* __restrict__ R, i
       y[i] = make_double2(sn * xv[j].x + c * yr, sn * xv[j].y + c * yi);
     }
   }
+  if (accm) {
+    double2* __restrict__ vx = accm + ((uint64_t)blockIdx.y * nvec + p) * (uint64_t)acc_len;
+    double2* __restrict__ vy = accm + ((uint64_t)blockIdx.y * nvec + q) * (uint64_t)acc_len;
+    for (int i = threadIdx.x; i < acc_len; i += blockDim.x) {
+      const double2 a2 = vx[i], b2 = vy[i];
+      const double yr = pr * b2.x - pi * b2.y, yi = pr * b2.y + pi * b2.x;
+      vx[i] = make_double2(c * a2.x - sn * yr, c * a2.y - sn * yi);
+      vy[i] = make_double2(sn * a2.x + c * yr, sn * a2.y + c * yi);
+    }
+  }
 }
 
 // squared norm of every vector: one CTA per (vector, trajectory)
@@ -136,16 +148,17 @@ __global__ void k_frob2(const double* __restrict__ norm2, int nvec, int64_t n_ba
   out[t] = f;
 }
 
-static int launch_round(bt_sv* s, double2* R, int nvec, int len, int round, double tol, const double* d_frob, unsigned int* d_rot) {
+static int launch_round(bt_sv* s, double2* R, int nvec, int len, int round, double tol, const double* d_frob, unsigned int* d_rot, double2* accm = nullptr,
+                        int acc_len = 0) {
   dim3 grid(nvec / 2, (unsigned)s->n_batch);
   int threads = len <= 256 ? std::max(32, len) : (len <= 4096 ? 256 : 512);
   int ept = (len + threads - 1) / threads;
   switch (ept) {
-    case 1: k_jacobi_round<1><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
-    case 2: k_jacobi_round<2><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
-    case 4: k_jacobi_round<4><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
-    case 8: k_jacobi_round<8><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
-    case 16: k_jacobi_round<16><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot); break;
+    case 1: k_jacobi_round<1><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot, accm, acc_len); break;
+    case 2: k_jacobi_round<2><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot, accm, acc_len); break;
+    case 4: k_jacobi_round<4><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot, accm, acc_len); break;
+    case 8: k_jacobi_round<8><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot, accm, acc_len); break;
+    case 16: k_jacobi_round<16><<<grid, threads, 0, s->stream>>>(R, nvec, len, round, tol, d_frob, d_rot, accm, acc_len); break;
     default: BT_FAIL(BT_ERR_UNSUPPORTED, "internal: vector length %d", len);
   }
   BT_CHECK_LAUNCH(s);
@@ -154,7 +167,7 @@ static int launch_round(bt_sv* s, double2* R, int nvec, int len, int round, doub
 
 // Jacobi sweeps over nvec vectors of length len per trajectory stored contiguously in R; the squared norms of the
 // converged vectors (descending) go to spec[n_batch][nvec].
-static int jacobi_spectrum(bt_sv* s, double2* R, int nvec, int len, double* spec, int* sweeps_out) {
+static int jacobi_spectrum(bt_sv* s, double2* R, int nvec, int len, double* spec, int* sweeps_out, double2* accm = nullptr, int acc_len = 0, bool sorted = true) {
   if (len > 8192) BT_FAIL(BT_ERR_UNSUPPORTED, "Schmidt spectrum: the long side of the cut has 2^%d > 2^13 entries", (int)log2((double)len));
   if (s->n_batch > 65535) BT_FAIL(BT_ERR_UNSUPPORTED, "n_batch > 65535");
   size_t nvals = (size_t)s->n_batch * nvec;
@@ -175,7 +188,7 @@ static int jacobi_spectrum(bt_sv* s, double2* R, int nvec, int len, double* spec
   if (nvec >= 2) {
     for (; sweeps < max_sweeps;) {
       BT_CUDA(cudaMemsetAsync(d_rot, 0, sizeof(unsigned int), s->stream));
-      for (int r = 0; r < nvec - 1; ++r) BT_TRY(launch_round(s, R, nvec, len, r, tol, d_frob, d_rot));
+      for (int r = 0; r < nvec - 1; ++r) BT_TRY(launch_round(s, R, nvec, len, r, tol, d_frob, d_rot, accm, acc_len));
       ++sweeps;
       BT_CUDA(cudaMemcpyAsync(s->h_flag, d_rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
       BT_CUDA(cudaStreamSynchronize(s->stream));
@@ -188,7 +201,8 @@ static int jacobi_spectrum(bt_sv* s, double2* R, int nvec, int len, double* spec
   BT_CHECK_LAUNCH(s);
   BT_CUDA(cudaMemcpyAsync(spec, d_norm, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   BT_CUDA(cudaStreamSynchronize(s->stream));
-  for (int64_t t = 0; t < s->n_batch; ++t) std::sort(spec + t * nvec, spec + (t + 1) * nvec, [](double u, double v) { return u > v; });
+  if (sorted)
+    for (int64_t t = 0; t < s->n_batch; ++t) std::sort(spec + t * nvec, spec + (t + 1) * nvec, [](double u, double v) { return u > v; });
   if (sweeps_out) *sweeps_out = sweeps;
   return BT_OK;
 }
@@ -510,4 +524,123 @@ extern "C" int bt_dm_expect_op(const bt_dm* d, int nq, int qubit, int target, in
   build_op_matrix(k, sorted, nq, qubit, target, control, m, O);
   *out = trace_against(rho, O, D);
   return BT_OK;
+}
+
+// ---- fidelity(rho, sigma) = (tr sqrt(sqrt(rho) sigma sqrt(rho)))^2  (src/tensor.jl:222-229) -------------------------------------------
+// rho = V L V^dagger by one-sided Jacobi on the columns of rho with the rotations accumulated in V (rho V = V L: the converged columns
+// have norms L and directions V); the eigenvalues of sqrt(rho) sigma sqrt(rho) are those of C = sqrt(L) (V^dagger sigma V) sqrt(L),
+// again by Jacobi.  Two tiled complex GEMMs in between.  Dense O(n^3) like the reference's sqrt(Matrix): registers of <= 11 qubits.
+
+// C = op(A) * B, column-major n x n; CONJA: op(A) = A^dagger.  16 x 16 threads, 2 x 2 outputs each, k-chunks of 32 through shared memory.
+template <bool CONJA>
+__global__ void __launch_bounds__(256) k_zgemm(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ Cm, int n) {
+  __shared__ double2 As[32][33], Bs[32][33];  // As[i][k] = op(A)(i0+i, k0+k), Bs[k][j] = B(k0+k, j0+j)
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double2 acc[2][2] = {{make_double2(0, 0), make_double2(0, 0)}, {make_double2(0, 0), make_double2(0, 0)}};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      const int a = e & 31, b = e >> 5;
+      double2 va = make_double2(0, 0), vb = make_double2(0, 0);
+      if (CONJA) {  // op(A)(i, k) = conj(A(k, i)): read A(k0+a, i0+b) (coalesced in a)
+        if (k0 + a < n && i0 + b < n) { va = A[(size_t)(k0 + a) + (size_t)(i0 + b) * n]; va.y = -va.y; }
+        As[b][a] = va;
+      } else {      // op(A)(i, k) = A(i0+a, k0+b)
+        if (i0 + a < n && k0 + b < n) va = A[(size_t)(i0 + a) + (size_t)(k0 + b) * n];
+        As[a][b] = va;
+      }
+      if (k0 + a < n && j0 + b < n) vb = B[(size_t)(k0 + a) + (size_t)(j0 + b) * n];
+      Bs[a][b] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      double2 av[2] = {As[ty][k], As[ty + 16][k]}, bv[2] = {Bs[k][tx], Bs[k][tx + 16]};
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          acc[u][v].x = fma(av[u].x, bv[v].x, fma(-av[u].y, bv[v].y, acc[u][v].x));
+          acc[u][v].y = fma(av[u].x, bv[v].y, fma(av[u].y, bv[v].x, acc[u][v].y));
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int i = i0 + ty + 16 * u, j = j0 + tx + 16 * v;
+      if (i < n && j < n) Cm[(size_t)i + (size_t)j * n] = acc[u][v];
+    }
+}
+
+__global__ void k_set_identity(double2* __restrict__ V, int n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * n; i += (size_t)gridDim.x * blockDim.x)
+    V[i] = make_double2((i % n) == (i / n) ? 1.0 : 0.0, 0.0);
+}
+
+// C(i, j) *= sqrt(max(l_i, 0)) * sqrt(max(l_j, 0))
+__global__ void k_scale_sqrt(double2* __restrict__ Cm, const double* __restrict__ lam, int n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * n; e += (size_t)gridDim.x * blockDim.x) {
+    const double f = sqrt(fmax(lam[e % n], 0.0)) * sqrt(fmax(lam[e / n], 0.0));
+    Cm[e].x *= f; Cm[e].y *= f;
+  }
+}
+
+// squared column norms -> norms (the eigenvalues of a positive semi-definite matrix after the Jacobi iteration on its columns)
+__global__ void k_sqrt_inplace(double* __restrict__ x, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = sqrt(fmax(x[i], 0.0));
+}
+
+extern "C" int bt_dm_fidelity(const bt_dm* rho, const bt_dm* sigma, double* out) {
+  if (!rho || !rho->v || !sigma || !sigma->v) BT_FAIL(BT_ERR_ARG, "null density matrix");
+  if (!out) BT_FAIL(BT_ERR_ARG, "null output");
+  if (rho->n != sigma->n) BT_FAIL(BT_ERR_ARG, "fidelity: registers of %d and %d qubits", rho->n, sigma->n);
+  if (rho->v->device != sigma->v->device) BT_FAIL(BT_ERR_ARG, "fidelity: the two density matrices live on different devices");
+  if (rho->n > 11) BT_FAIL(BT_ERR_UNSUPPORTED, "fidelity(rho, sigma) is dense O(8^N) linear algebra: up to 11 qubits on the device (asked for %d)", rho->n);
+  bt_sv* v = rho->v;
+  const int n = 1 << rho->n;
+  const size_t nn = (size_t)n * n;
+  BT_CUDA(cudaStreamSynchronize(sigma->v->stream));
+  double2* W = nullptr;  // A | V | T | C
+  BT_CUDA(cudaMalloc(&W, 4 * nn * sizeof(double2)));
+  double2 *A = W, *V = W + nn, *T = W + 2 * nn, *Cm = W + 3 * nn;
+  int rc = BT_OK;
+  int64_t nb = v->n_batch;
+  v->n_batch = 1;
+  std::vector<double> lam((size_t)n), mu((size_t)n);
+  do {
+    if (cudaMemcpyAsync(A, v->amp, nn * sizeof(double2), cudaMemcpyDeviceToDevice, v->stream) != cudaSuccess) { rc = BT_ERR_CUDA; break; }
+    k_set_identity<<<148 * 4, 256, 0, v->stream>>>(V, n);
+    // eigen-decomposition of rho: columns of A converge to l_p v_p, V accumulates the eigenvectors; spectrum unsorted (index-aligned with V)
+    if (n >= 2) rc = jacobi_spectrum(v, A, n, n, lam.data(), nullptr, V, n, false);
+    else { bt_c64 r00; rc = bt_dm_trace(rho, &r00); lam[0] = r00.re * r00.re; }
+    if (rc != BT_OK) break;
+    // lam holds squared column norms = l^2: the device copy in d_scratch (head) is reused as l after a square root
+    double* d_lam = (double*)v->d_scratch;
+    k_sqrt_inplace<<<(n + 127) / 128, 128, 0, v->stream>>>(d_lam, n);
+    const dim3 g((n + 31) / 32, (n + 31) / 32);
+    k_zgemm<false><<<g, 256, 0, v->stream>>>(sigma->v->amp, V, T, n);   // T = sigma V
+    k_zgemm<true><<<g, 256, 0, v->stream>>>(V, T, Cm, n);               // C = V^dagger sigma V
+    k_scale_sqrt<<<148 * 4, 256, 0, v->stream>>>(Cm, d_lam, n);         // C = sqrt(L) C sqrt(L)
+    if (cudaPeekAtLastError() != cudaSuccess) { rc = BT_ERR_CUDA; break; }
+    v->launches += 4;
+    if (n >= 2) rc = jacobi_spectrum(v, Cm, n, n, mu.data(), nullptr);
+    else {
+      double2 c00;
+      if (cudaMemcpyAsync(&c00, Cm, sizeof(double2), cudaMemcpyDeviceToHost, v->stream) != cudaSuccess || cudaStreamSynchronize(v->stream) != cudaSuccess) { rc = BT_ERR_CUDA; break; }
+      mu[0] = c00.x * c00.x;
+    }
+    if (rc != BT_OK) break;
+    double tr = 0.0;
+    for (int i = 0; i < n; ++i) tr += sqrt(sqrt(std::max(mu[(size_t)i], 0.0)));  // mu = squared singular values of C = eigenvalues^2; sqrt(eigenvalue)
+    *out = tr * tr;
+  } while (0);
+  v->n_batch = nb;
+  cudaStreamSynchronize(v->stream);
+  cudaFree(W);
+  if (rc == BT_ERR_CUDA) BT_FAIL(BT_ERR_CUDA, "CUDA error in bt_dm_fidelity: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }

@@ -900,8 +900,15 @@ def inner(a: CuState, b: CuState):
     return complex(out[0]) if a.n_batch == 1 else out
 
 
-def fidelity(a: CuState, b: CuState):
-    """|<a|b>|^2 (src/tensor.jl:219)."""
+def fidelity(a, b):
+    """``fidelity(psi, psi2)`` = |<a|b>|^2 (src/tensor.jl:219); ``fidelity(rho, sigma)`` = real(tr(sqrt(sqrt(rho) sigma sqrt(rho)))^2)
+    (src/tensor.jl:222-229) as dense linear algebra on the device (``bt_dm_fidelity``: up to 11 qubits)."""
+    if isinstance(a, CuRho) and isinstance(b, CuRho):
+        out = C.c_double()
+        L.check(a.lib.bt_dm_fidelity(a.h, b.h, C.byref(out)))
+        return float(out.value)
+    if isinstance(a, CuRho) or isinstance(b, CuRho):
+        raise TypeError("fidelity takes two state vectors or two density matrices (src/tensor.jl:219-229)")
     v = inner(a, b)
     return abs(v) ** 2
 

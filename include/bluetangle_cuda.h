@@ -219,6 +219,10 @@ int bt_dm_expect_op(const bt_dm* d, int nq, int qubit, int target, int control, 
 /* singular values (descending) of bipartition_trace(rho) src/linalg.jl:151-161 generalised to the last n_keep qubits: the spectrum
  * entanglement_entropy(rho) src/func.jl:323-328 sums over (n_keep = N / 2); spec: 2^n_keep */
 int bt_dm_bipartition_spectrum(const bt_dm* d, int n_keep, double* spec, int* sweeps);
+/* fidelity(rho, sigma) src/tensor.jl:222-229: real(tr(sqrt(sqrt(rho) * sigma * sqrt(rho)))^2), as dense linear algebra on the device
+ * (eigen-decomposition of rho by a Jacobi iteration with accumulated eigenvectors, two complex GEMMs, a second Jacobi iteration);
+ * O(8^N) like the reference's sqrt(Matrix(rho)): registers of up to 11 qubits. */
+int bt_dm_fidelity(const bt_dm* rho, const bt_dm* sigma, double* out);
 
 /* ---- multi-GPU shards (no reference analogue).  One process per GPU: each rank creates its
  * shard, the host plumbing (torch.distributed / MPI) all-gathers the IPC handles and supplies a barrier.

@@ -245,6 +245,11 @@ function entanglement_entropy(r::CuRho)
     return sum(-spec .* log.(spec)), -log.(spec)
 end
 
+function fidelity(r::CuRho, s::CuRho)                                                # src/tensor.jl:222-229
+    out = Ref{Float64}(0.0)
+    check(ccall((:bt_dm_fidelity, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}), r.h, s.h, out)); out[]
+end
+
 # expect(x, op) src/func.jl:91-92 for any Op (1- or 2-qubit, with or without a control)
 function expect(s::CuState, op::Op)
     out = Vector{Float64}(undef, s.n_batch)

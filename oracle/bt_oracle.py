@@ -1067,6 +1067,23 @@ def fidelity(a: np.ndarray, b: np.ndarray) -> float:
     return float(abs(np.vdot(a, b)) ** 2)
 
 
+def _sqrt_psd(m: np.ndarray) -> np.ndarray:
+    """Julia's ``sqrt(::Matrix)`` for a Hermitian positive semi-definite argument: eigen-decomposition, square roots of the
+    eigenvalues (tiny negative rounding values clipped)."""
+    m = np.asarray(m.todense()) if sp.issparse(m) else np.asarray(m)
+    w, v = np.linalg.eigh((m + m.conj().T) / 2)
+    return (v * np.sqrt(np.clip(w, 0, None))) @ v.conj().T
+
+
+def fidelity_rho(rho, sigma) -> float:
+    """src/tensor.jl:222-229: a = sqrt(rho) * sigma * sqrt(rho); b = sqrt(a); real(tr(b)^2)."""
+    sigma = np.asarray(sigma.todense()) if sp.issparse(sigma) else np.asarray(sigma)
+    r = _sqrt_psd(rho)
+    a = r @ sigma @ r
+    b = _sqrt_psd(a)
+    return float(np.real(np.trace(b) ** 2))
+
+
 # --------------------------------------------------------------------------------------------------
 # drivers -- src/ops.jl:599-692, :790-844 (no layout/compile: ops are applied raw, SURVEY App. A.8)
 # --------------------------------------------------------------------------------------------------

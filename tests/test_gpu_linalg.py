@@ -151,3 +151,41 @@ def test_density_matrix_partial_trace_and_entropy(bt, orc):
     assert abs(e0) < TOL
     with pytest.raises(ValueError):
         bt.entanglement_entropy(bt.CuRho(5))
+
+
+def test_fidelity_of_density_matrices(bt, orc):
+    """fidelity(rho, sigma) src/tensor.jl:222-229 on the device (Jacobi eigen-decomposition with accumulated eigenvectors + two GEMMs +
+    Jacobi): mixed-mixed against the oracle's restatement, and closed forms -- F(rho, rho) = 1, F(|a><a|, |b><b|) = |<a|b>|^2,
+    F(|a><a|, sigma) = <a|sigma|a>, symmetry, a noisy circuit against its ideal state.
+    Tolerance 1e-6: the formula takes square roots of eigenvalues that are zero up to rounding (rank-deficient rho, sigma), and
+    sqrt(1e-16) = 1e-8 per null direction enters tr sqrt(.) in the reference, the oracle and here alike."""
+    FT = 1e-6
+    rng = np.random.default_rng(12)
+
+    def mixed(N, k, seed):
+        ws = [rand_state(N, seed + i) for i in range(k)]
+        p = rng.random(k)
+        p /= p.sum()
+        return sum(pi * np.outer(w, w.conj()) for pi, w in zip(p, ws))
+
+    for N in (1, 2, 3, 5, 7):
+        r, s_ = mixed(N, 1 << min(N, 3), 300 + N), mixed(N, 3, 400 + N)
+        R, S = bt.CuRho.from_numpy(r), bt.CuRho.from_numpy(s_)
+        f = bt.fidelity(R, S)
+        assert abs(f - orc.fidelity_rho(r, s_)) < FT, N
+        assert abs(f - bt.fidelity(S, R)) < FT
+        assert abs(bt.fidelity(R, R) - 1) < FT
+        a, b = rand_state(N, 1), rand_state(N, 2)
+        Pa, Pb = np.outer(a, a.conj()), np.outer(b, b.conj())
+        assert abs(bt.fidelity(bt.CuRho.from_numpy(Pa), bt.CuRho.from_numpy(Pb)) - abs(np.vdot(a, b)) ** 2) < FT
+        assert abs(bt.fidelity(bt.CuRho.from_numpy(Pa), S) - np.real(np.vdot(a, s_ @ a))) < FT
+    # a noisy 6-qubit circuit against the ideal one (the use the reference documents: how far noise moved the state)
+    N = 6
+    ops = [bt.Op("H", 1)] + [bt.Op("CNOT", q, q + 1) for q in range(1, N)] + [bt.Op("RY(0.4)", 3)]
+    ideal = bt.apply(ops, bt.CuRho(N))
+    noisy = bt.apply(ops, bt.CuRho(N), noise=bt.NoiseModel("depolarizing", 0.02))
+    f = bt.fidelity(ideal, noisy)
+    fo = orc.fidelity_rho(ideal.to_numpy(), noisy.to_numpy())
+    assert abs(f - fo) < FT and 0.3 < f < 0.999
+    with pytest.raises(TypeError):
+        bt.fidelity(ideal, bt.zero_state(N))
