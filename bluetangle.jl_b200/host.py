@@ -1067,6 +1067,27 @@ def mag_moments(N: int, bitstr, sample_probs, moment_order: int) -> float:
     return float(np.sum(mag ** moment_order * np.asarray(sample_probs)))
 
 
+def cumulants_from_moments(moments: Sequence[float], n: Optional[int] = None):
+    """src/func.jl:241-253: cumulant_n = moment_n - sum_{m<n} C(n-1, m-1) cumulant_m moment_{n-m}; all of them when ``n`` is None."""
+    from math import comb
+
+    if n is None:
+        return [cumulants_from_moments(moments, k) for k in range(1, len(moments) + 1)]
+    c: List[float] = []
+    for k in range(1, n + 1):
+        v = moments[k - 1]
+        for m in range(1, k):
+            v -= comb(k - 1, m - 1) * c[m - 1] * moments[k - m - 1]
+        c.append(v)
+    return c[n - 1]
+
+
+def mag_cumulants(m: "Measurement", cumulant_order: Optional[int] = None, max_moment: int = 12):
+    """src/func.jl:255-258: cumulants of the magnetisation from a Measurement's sample distribution."""
+    moments = [mag_moments(m.number_of_qubits, m.bitstr, m.sample, i) for i in range(1, max_moment + 1)]
+    return cumulants_from_moments(moments, cumulant_order)
+
+
 class Measurement:
     """src/struct.jl:907-930 (fields the path fills)."""
 

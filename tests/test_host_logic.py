@@ -272,3 +272,13 @@ def test_fusion_scheduler_look_ahead_plans_fewer_passes(bt):
     p0, l0 = plan(28, wl.qft(28) + wl.layered(28, 100, 28), 0)
     p1, l1 = plan(28, wl.qft(28) + wl.layered(28, 100, 28), 1)
     assert p1 <= 0.67 * p0 and l1 <= 0.67 * l0, (p0, p1, l0, l1)
+
+
+def test_cumulants_from_moments_recursion(bt):
+    """src/func.jl:241-253 against the closed forms k1 = m1, k2 = m2 - m1^2, k3 = m3 - 3 m2 m1 + 2 m1^3, k4 = m4 - 4 m3 m1 - 3 m2^2 + 12 m2 m1^2 - 6 m1^4."""
+    m = [0.3, 1.7, -0.4, 5.2, 0.9]
+    k = bt.cumulants_from_moments(m)
+    assert abs(k[0] - m[0]) < 1e-14 and abs(k[1] - (m[1] - m[0] ** 2)) < 1e-14
+    assert abs(k[2] - (m[2] - 3 * m[1] * m[0] + 2 * m[0] ** 3)) < 1e-13
+    assert abs(k[3] - (m[3] - 4 * m[2] * m[0] - 3 * m[1] ** 2 + 12 * m[1] * m[0] ** 2 - 6 * m[0] ** 4)) < 1e-13
+    assert bt.cumulants_from_moments(m, 3) == k[2]
