@@ -913,6 +913,12 @@ def fidelity(a, b):
     return abs(v) ** 2
 
 
+def same_up_to_global_phase(psi: CuState, phi: CuState):
+    """src/linalg.jl:67-72: (abs(<phi|psi>) ≈ 1, angle(<phi|psi>)) -- one fused reduction on the device."""
+    v = inner(phi, psi)
+    return bool(np.isclose(abs(v), 1.0)), float(np.angle(v))
+
+
 def prob(state: CuState) -> np.ndarray:
     """abs2.(state) (src/tensor.jl:150-158 wrapper of the same quantity)."""
     out = np.empty((state.n_batch, 1 << state.N), dtype=np.float64)

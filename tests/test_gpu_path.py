@@ -603,3 +603,15 @@ def test_multi_measurement_equals_sequential_born_measurements(bt, orc):
     import bluetangle_jl_b200.host as H
     groups = H._coalesce(od, bt.zero_state(N), False)
     assert sum(isinstance(g, H._MeasureRun) for g in groups) == 3  # [2,5,6,1] + [7,RES 4] + [2,3]
+
+
+def test_same_up_to_global_phase(bt):
+    """src/linalg.jl:67-72 on device states."""
+    g = np.random.default_rng(4)
+    v = g.normal(size=256) + 1j * g.normal(size=256)
+    v /= np.linalg.norm(v)
+    a, b = bt.CuState.from_numpy(v), bt.CuState.from_numpy(np.exp(0.7j) * v)
+    same, ph = bt.same_up_to_global_phase(b, a)
+    assert same and abs(ph - 0.7) < 1e-12
+    w = g.normal(size=256) + 1j * g.normal(size=256)
+    assert not bt.same_up_to_global_phase(bt.CuState.from_numpy(w / np.linalg.norm(w)), a)[0]
