@@ -1162,6 +1162,34 @@ class Circuit:
         self.mid_measurement_count = sum(1 for o in self.ops if getattr(o, "type", "") == "🔬")
 
 
+def ishermitian(op) -> bool:
+    """src/linalg.jl:1-7."""
+    m = getattr(op, "mat", None)
+    return isinstance(m, np.ndarray) and bool(np.array_equal(m, m.conj().T))
+
+
+def adjoint(x):
+    """``adjoint(op)`` / ``adjoint(ops)`` / ``adjoint(circuit)`` -- src/linalg.jl:9-45: Hermitian ops, OpF and ifOp come back unchanged,
+    any other Op gets the conjugate-transposed matrix and a "†" appended to its name (removed again by a second adjoint); a list or
+    a circuit is reversed.  With it ``apply(adjoint(ops), apply(ops, state))`` returns the state (the encode -> decode round trip the
+    full-size tests use)."""
+    if isinstance(x, Circuit):
+        return Circuit(adjoint(x.ops), x.options, x.N)
+    if isinstance(x, (list, tuple)):
+        return [adjoint(o) for o in reversed(list(x))]
+    if isinstance(x, (OpF, ifOp)) or not isinstance(x, Op) or ishermitian(x):
+        return x
+    name = x.name[:-1] if x.name.endswith("†") else x.name + "†"
+    args = (x.qubit,) if x.q == 1 else (x.qubit, x.target_qubit)
+    return Op(name, x.mat.conj().T, *args, control=x.control, noisy=x.noisy, type=x.type)
+
+
+def isunitary(mat) -> bool:
+    """src/linalg.jl:51."""
+    m = np.asarray(mat)
+    return bool(np.allclose(m.conj().T @ m, np.eye(m.shape[0]), atol=1e-12, rtol=0))
+
+
 def compile(ops, options: Optional[Options] = None) -> Circuit:
     """src/ops.jl:421-445 without the layout pass (the device needs no SWAP routing)."""
     return Circuit(ops, options or Options(), get_N_ops(ops))

@@ -615,3 +615,22 @@ def test_same_up_to_global_phase(bt):
     assert same and abs(ph - 0.7) < 1e-12
     w = g.normal(size=256) + 1j * g.normal(size=256)
     assert not bt.same_up_to_global_phase(bt.CuState.from_numpy(w / np.linalg.norm(w)), a)[0]
+
+
+def test_adjoint_circuit_round_trip(bt):
+    """apply(adjoint(ops), apply(ops, state)) returns the state (src/linalg.jl:33-45), fused path at 16 qubits."""
+    N = 16
+    g = np.random.default_rng(8)
+    ops = []
+    for l in range(6):
+        for q in range(1, N + 1):
+            ops.append(bt.Op(["H", "T", f"RX({g.uniform(0, 6)!r})", f"RZ({g.uniform(0, 6)!r})", "S"][int(g.integers(5))], q))
+        for q in range(1 + l % 2, N, 2):
+            ops.append(bt.Op(["CNOT", "CZ", f"CP({g.uniform(0, 6)!r})", "ISWAP"][int(g.integers(4))], q, q + 1))
+    s = bt.basis_state(N, 12345)
+    bt.apply(ops, s)
+    assert abs(bt.expect(s, "Z")).max() < 0.9
+    bt.apply(bt.adjoint(ops), s)
+    v = s.to_numpy()
+    assert abs(abs(v[12345]) - 1) < 1e-7  # T is rounded to 10 digits in the reference's table: T T† differs from 1 by 1e-10 per pair
+    assert np.max(np.abs(np.delete(v, 12345))) < 1e-9

@@ -282,3 +282,22 @@ def test_cumulants_from_moments_recursion(bt):
     assert abs(k[2] - (m[2] - 3 * m[1] * m[0] + 2 * m[0] ** 3)) < 1e-13
     assert abs(k[3] - (m[3] - 4 * m[2] * m[0] - 3 * m[1] ** 2 + 12 * m[1] * m[0] ** 2 - 6 * m[0] ** 4)) < 1e-13
     assert bt.cumulants_from_moments(m, 3) == k[2]
+
+
+def test_adjoint_of_ops_lists_and_circuits(bt):
+    """src/linalg.jl:1-51: Hermitian ops come back as they are, others get the conjugate transpose and a dagger in the name (a second
+    adjoint removes it), controls / flags are kept, lists and circuits are reversed."""
+    o = bt.Op("RZ(0.3)", 2)
+    a = bt.adjoint(o)
+    assert a.name == "RZ(0.3)†" and np.allclose(a.mat, o.mat.conj().T) and bt.adjoint(a).name == "RZ(0.3)"
+    h = bt.Op("H", 1)
+    assert bt.adjoint(h) is h and bt.ishermitian(h) and not bt.ishermitian(o)
+    x = bt.Op("RY(0.2)", 3, control=1, noisy=False)
+    ax = bt.adjoint(x)
+    assert ax.control == 1 and ax.noisy is False and ax.qubit == 3
+    c = bt.Op("CP(0.4)", 2, 3)
+    names = [t.name for t in bt.adjoint([o, h, c])]
+    assert names == ["CP(0.4)†", "H", "RZ(0.3)†"]
+    circ = bt.compile([o, h, c])
+    assert [t.name for t in bt.adjoint(circ).ops] == names and bt.adjoint(circ).N == circ.N
+    assert bt.isunitary(o.mat) and not bt.isunitary(np.array([[1, 1], [0, 1]]))
