@@ -410,6 +410,9 @@ def bench_single(args):
     jitst = jit_stats(lib, warmup_seconds)
     hits, cdir = C.c_uint64(), C.create_string_buffer(512)
     L.check(lib.bt_jit_cache_info(C.byref(hits), cdir, 512))
+    cfg = [C.c_int() for _ in range(4)]
+    L.check(lib.bt_jit_config(*[C.byref(x) for x in cfg]))
+    jitst.update({"nvrtc": f"{cfg[0].value}.{cfg[1].value}", "code_shape_variant": cfg[2].value, "arith_opt": cfg[3].value})
     jitst.update({"cold_first_step_s": cold_first_step_s, "all_modules_ready_s": jit_ready_s, "structures_compiling_after_first_step": int(pend.value),
                   "disk_cache_hits": int(hits.value), "disk_cache_dir": cdir.value.decode(),
                   "note": "first execution runs on the interpreter while worker threads compile (or read the on-disk cubin cache); steady-state steps use the specialised kernels"})

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "bt_jit_selftest": [C.c_char_p, _u64],
     "bt_jit_debug_only": [_i, _i],
     "bt_jit_verify_stats": [C.POINTER(_u64), C.POINTER(_u64)],
+    "bt_jit_config": [_pi32, _pi32, _pi32, _pi32],
     "bt_jit_wait": [C.POINTER(_u64)],
     "bt_jit_selftest_workers": [_i],
     "bt_jit_cache_info": [C.POINTER(_u64), C.c_char_p, _u64],

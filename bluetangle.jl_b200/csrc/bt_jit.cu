@@ -142,6 +142,8 @@ struct JOp {
   int merged = 0;          // member of a merged run of diagonal factors (its complex factor is multiplied up per thread first)
   int shear = 0;           // unit-modulus phase applied as three shears (3 FMAs instead of 2 MUL + 2 FMA): coefficients are
                            // (t, s) = (-tan(theta/2), sin(theta)); 2: theta was reduced by pi, the result is negated
+  int deferred = 0;        // CSCALE whose factor joins the program's per-thread scalar (applied once, after the last op)
+  int sgn = 0;             // conditional factor -1: a sign-bit flip (integer pipe), no coefficients
 };
 
 struct Plan {
@@ -149,6 +151,7 @@ struct Plan {
   std::vector<double> coef;
   int scale_at = -1;                   // coefficient index of the pass scalar (re, im)
   bool complex_scale = false;
+  int scale_prog = -1;                 // the program that applies the pass scalar (the last one unless a per-thread scalar carries it)
 };
 
 typedef std::complex<double> cd;
@@ -177,6 +180,20 @@ double pivot_real(const double m[4], signed char pat[4], double out[4]) {
 }
 
 int jit_variant();
+
+// Arithmetic reshaping on top of the code shape (BT_JIT_OPT, bit flags; default 7, 0 = the round-2 generator text byte for byte).
+// The specialised passes are bound by the FP64 pipe (ncu: 77 % pipe activity), so every FP64 instruction that
+// becomes an integer instruction or disappears is time:
+//   1  per-thread scalars are deferred: a conditional scalar (a phase whose bits all lie outside the program -- T / RZ / CP on tile
+//      bits that are not program positions) multiplies ALL amplitudes a thread holds, so it commutes with every op of the program;
+//      the factors of a program are multiplied up per thread (4 instructions each) and applied once behind the last op (64), in
+//      the last program together with the pass scalar -- before: 48-64 instructions per factor or per run of factors;
+//   2  negations are sign-bit flips on the integer pipe (the compiler turns -x on a double into DADD -RZ, -x): CZ inside a program,
+//      lone -a terms of a 2x2, and the pi-reduced shear rotation folds its sign into the operand modifiers of its FMAs;
+//   4  a conditional factor -1 (CZ with one bit outside the program) flips the sign bit under a selected mask instead of a selected
+//      complex multiplication (4 FP64 instructions per amplitude).
+// Counted on the 65 passes of C2 (cuobjdump -sass, DFMA + DADD + DMUL): 119 278 -> see profiles/r2_jit_fp64_counts.txt.
+int jit_opt() { return env_i("BT_JIT_OPT", 7); }
 
 bool make_plan(const TileParams& P, int np, Plan& pl) {
   if (P.swz_mode != 0 || np <= 0 || P.nitems != np) return false;
@@ -229,7 +246,8 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
         o.p = site == PROG_SITE_CSCALE ? 0 : (int)site - 169;
         o.em = as_u64(c[2]); o.lm = as_u64(c[3]);
         if (o.kind == JK_CSCALE && o.em == 0 && o.lm == 0) { gs *= cd(c[0], c[1]); continue; }  // unconditional scalar: joins the pass scalar
-        pl.coef.push_back(c[0]); pl.coef.push_back(c[1]);
+        if ((jit_opt() & 4) && c[0] == -1.0 && c[1] == 0.0) o.sgn = 1;
+        else { pl.coef.push_back(c[0]); pl.coef.push_back(c[1]); }
       } else if (site >= 177 && site < 185) {
         o.kind = JK_CCX1; o.p = (int)site - 177; o.em = as_u64(c[0]); o.lm = as_u64(c[1]);
       } else {
@@ -245,6 +263,25 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
   // modulus is not 1 to rounding (T is rounded to 10 digits in the reference's table) keeps the complex multiplication.
   const bool merge = env_i("BT_JIT_MERGE_DIAG", 1) != 0, use_shear = env_i("BT_JIT_SHEAR", 1) != 0;
   const int variant = jit_variant();
+  pl.scale_prog = (int)pl.prog.size() - 1;
+  if (jit_opt() & 1) {
+    // deferred per-thread scalars: worth it when a program carries two or more factors, or in the program that applies the pass
+    // scalar -- the scalar commutes with everything, so it rides with the per-thread scalar of the program that has the most
+    // factors (a single factor elsewhere keeps its own form: three shears cost 48, the deferred application 64)
+    const int defer_min = std::max(1, env_i("BT_JIT_DEFER_MIN", 2));
+    int best = 0;
+    for (size_t it = 0; it < pl.prog.size(); ++it) {
+      int n = 0;
+      for (const JOp& o : pl.prog[it]) if (o.kind == JK_CSCALE) n++;
+      if (n > 0 && n >= best) { best = n; pl.scale_prog = (int)it; }
+    }
+    for (size_t it = 0; it < pl.prog.size(); ++it) {
+      int nfac = 0, nsgn = 0;
+      for (const JOp& o : pl.prog[it]) if (o.kind == JK_CSCALE) { if (o.sgn) nsgn++; else nfac++; }
+      if (nfac >= defer_min || (nfac + nsgn >= 1 && (int)it == pl.scale_prog))
+        for (JOp& o : pl.prog[it]) if (o.kind == JK_CSCALE) o.deferred = 1;
+    }
+  }
   for (std::vector<JOp>& L : pl.prog) {
     auto is_diag = [](const JOp& o) { return o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE || o.kind == JK_CZ; };
     size_t i = 0;
@@ -257,6 +294,7 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
           std::vector<size_t> mem;
           for (size_t t = i; t < j; ++t) {
             const JOp& o = L[t];
+            if (o.sgn || o.deferred) continue;
             if (cls < 0 ? o.kind == JK_CSCALE : ((o.kind == JK_CPH1 && o.p == cls) || (o.kind == JK_PHASE && o.p == cls && o.q == 1))) mem.push_back(t);
           }
           if (mem.size() >= 2)
@@ -266,7 +304,7 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
     }
     if (!use_shear) continue;
     for (JOp& o : L) {
-      if (o.merged || !(o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE)) continue;
+      if (o.merged || o.sgn || o.deferred || !(o.kind == JK_PHASE || o.kind == JK_CPH1 || o.kind == JK_CSCALE || o.kind == JK_CPHASE)) continue;
       const bool conditional_select = (o.kind == JK_CPH1 || o.kind == JK_CSCALE) && o.lm != 0 && (variant & 2);
       const bool conditional_branch = (o.kind == JK_CPH1 || o.kind == JK_CSCALE) && !conditional_select;
       (void)conditional_branch;
@@ -276,7 +314,7 @@ bool make_plan(const TileParams& P, int np, Plan& pl) {
       double th = atan2(ci, cr);
       int shape = 1;
       if (fabs(th) > 1.5707963267948966) {
-        if (conditional_select) continue;  // a selected identity cannot carry the sign
+        if (conditional_select && !(jit_opt() & 4)) continue;  // a selected identity cannot carry the sign (BT_JIT_OPT & 4: the sign is a selected mask)
         th -= th > 0 ? 3.141592653589793 : -3.141592653589793;
         shape = 2;
       }
@@ -326,10 +364,13 @@ void make_key(const TileParams& P, const Plan& pl, int device, std::string& key,
   put(P.item, (size_t)P.nitems);
   const char cs = pl.complex_scale ? 1 : 0;
   put(&cs, 1);
+  put(&pl.scale_prog, 4);
   const int variant = jit_variant();
   put(&variant, 4);
   const int minb = jit_minb();
   put(&minb, 4);
+  const int opt = jit_opt();
+  put(&opt, 4);
   for (int it = 0; it < P.nitems; ++it) {
     const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
     put(G.lp, sizeof(int32_t) * PROG_BITS); put(G.bit_sw, sizeof(G.bit_sw)); put(&G.niter, 4);
@@ -337,14 +378,14 @@ void make_key(const TileParams& P, const Plan& pl, int device, std::string& key,
     const uint32_t n = (uint32_t)pl.prog[(size_t)it].size();
     put(&n, 4);
     for (const JOp& o : pl.prog[(size_t)it]) {
-      const int32_t h[6] = {o.kind, o.p, o.q, o.rxl, o.merged, o.shear};
+      const int32_t h[8] = {o.kind, o.p, o.q, o.rxl, o.merged, o.shear, o.deferred, o.sgn};
       put(h, sizeof(h)); put(o.pat, 4); put(&o.em, 8); put(&o.lm, 8);
     }
   }
 }
 
 // "t = alpha * a + beta * b" with alpha, beta given as pattern + coefficient reference; sa / sb flip the sign of a term
-std::string lin(const char* out, signed char pa, int ka, bool na, const std::string& a, signed char pb, int kb, bool nb, const std::string& b) {
+std::string lin(const char* out, signed char pa, int ka, bool na, const std::string& a, signed char pb, int kb, bool nb, const std::string& b, bool xneg = false) {
   auto term_coef = [](signed char pat, int k, bool neg) {  // textual coefficient of a general term
     char buf[48];
     snprintf(buf, sizeof(buf), neg ? "(-C.c[%d])" : "C.c[%d]", k);
@@ -354,8 +395,8 @@ std::string lin(const char* out, signed char pa, int ka, bool na, const std::str
   std::string e;
   const bool za = pa == 0, zb = pb == 0, ua = pa == 1 || pa == -1, ub = pb == 1 || pb == -1;
   if (za && zb) e = "0.0";
-  else if (za) e = ub ? (unit_sign(pb, nb) ? b : "-" + b) : term_coef(pb, kb, nb) + " * " + b;
-  else if (zb) e = ua ? (unit_sign(pa, na) ? a : "-" + a) : term_coef(pa, ka, na) + " * " + a;
+  else if (za) e = ub ? (unit_sign(pb, nb) ? b : (xneg ? "bt_neg(" + b + ")" : "-" + b)) : term_coef(pb, kb, nb) + " * " + b;
+  else if (zb) e = ua ? (unit_sign(pa, na) ? a : (xneg ? "bt_neg(" + a + ")" : "-" + a)) : term_coef(pa, ka, na) + " * " + a;
   else if (ua && ub) e = std::string(unit_sign(pa, na) ? "" : "-") + a + (unit_sign(pb, nb) ? " + " : " - ") + b;
   else if (ua) e = "fma(" + term_coef(pb, kb, nb) + ", " + b + ", " + (unit_sign(pa, na) ? "" : "-") + a + ")";
   else if (ub) e = "fma(" + term_coef(pa, ka, na) + ", " + a + ", " + (unit_sign(pb, nb) ? "" : "-") + b + ")";
@@ -392,13 +433,15 @@ bool wide_ok(const TileParams& P) {
 
 bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
   const int variant = jit_variant();
+  const int opt = jit_opt();
+  const bool xneg = (opt & 2) != 0;
   const bool wide = wide_ok(P) && K <= 1;
   const int T = P.T;
   const uint32_t nloc = 1u << T, ng = nloc >> PROG_BITS;
   std::string body;
   for (int it = 0; it < P.nitems; ++it) {
     const TileProg& G = P.pr[(int)P.item[it] - TILE_PBASE];
-    const bool last = it == P.nitems - 1;
+    const bool last = it == pl.scale_prog;  // the program that applies the pass scalar
     bool need_gl = false;
     for (const JOp& o : pl.prog[(size_t)it]) if (o.lm) need_gl = true;
     int perm[PROG_AMPS];  // logical amplitude (index bits = program positions) -> variable
@@ -410,6 +453,21 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
     auto X = [&](int logical, char part) { char b[24]; snprintf(b, sizeof(b), "x%c[%d]", part, perm[logical]); return std::string(b); };
     auto emit_op = [&](const JOp& o) {
       int k = o.c0;
+      if (o.deferred) return;  // joins the per-thread scalar behind the last op
+      if (o.sgn) {
+        // conditional factor -1 on the amplitudes with position bit p set (CPH1) or on all of them (CSCALE): sign-bit flips
+        const bool sel = use_select(o);
+        if (sel) ops += "      { const uint32_t sm_ = " + cond_expr(o) + " ? 0x80000000u : 0u;\n";
+        else ops += cond_open(o);
+        for (int j = 0; j < PROG_AMPS; ++j) {
+          if (o.kind == JK_CPH1 && !((j >> o.p) & 1)) continue;
+          const std::string r = X(j, 'r'), i = X(j, 'i');
+          if (sel) ops += "        " + r + " = bt_xsign(" + r + ", sm_); " + i + " = bt_xsign(" + i + ", sm_);\n";
+          else ops += "        " + r + " = bt_neg(" + r + "); " + i + " = bt_neg(" + i + ");\n";
+        }
+        ops += "      }\n";
+        return;
+      }
       if (o.kind == JK_LIN2) {
         int kk[4];
         for (int i = 0; i < 4; ++i) kk[i] = o.pat[i] == 2 ? k++ : -1;
@@ -419,17 +477,17 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
           if (!o.rxl) {
             for (char part : {'r', 'i'}) {
               const std::string a = X(i0, part), b = X(i1, part);
-              ops += lin(part == 'r' ? "ta" : "tc", o.pat[0], kk[0], false, a, o.pat[1], kk[1], false, b) + " ";
-              ops += lin(part == 'r' ? "tb" : "td", o.pat[2], kk[2], false, a, o.pat[3], kk[3], false, b) + " ";
+              ops += lin(part == 'r' ? "ta" : "tc", o.pat[0], kk[0], false, a, o.pat[1], kk[1], false, b, xneg) + " ";
+              ops += lin(part == 'r' ? "tb" : "td", o.pat[2], kk[2], false, a, o.pat[3], kk[3], false, b, xneg) + " ";
             }
             ops += X(i0, 'r') + " = ta; " + X(i1, 'r') + " = tb; " + X(i0, 'i') + " = tc; " + X(i1, 'i') + " = td; }\n";
           } else {
             // a' = m0 a + i m1 b, b' = i m2 a + m3 b:  (ar, bi) <- [[m0, -m1], [m2, m3]],  (ai, br) <- [[m0, m1], [-m2, m3]]
             const std::string ar = X(i0, 'r'), ai = X(i0, 'i'), br = X(i1, 'r'), bi = X(i1, 'i');
-            ops += lin("ta", o.pat[0], kk[0], false, ar, o.pat[1], kk[1], true, bi) + " ";
-            ops += lin("tb", o.pat[2], kk[2], false, ar, o.pat[3], kk[3], false, bi) + " ";
-            ops += lin("tc", o.pat[0], kk[0], false, ai, o.pat[1], kk[1], false, br) + " ";
-            ops += lin("td", o.pat[2], kk[2], true, ai, o.pat[3], kk[3], false, br) + " ";
+            ops += lin("ta", o.pat[0], kk[0], false, ar, o.pat[1], kk[1], true, bi, xneg) + " ";
+            ops += lin("tb", o.pat[2], kk[2], false, ar, o.pat[3], kk[3], false, bi, xneg) + " ";
+            ops += lin("tc", o.pat[0], kk[0], false, ai, o.pat[1], kk[1], false, br, xneg) + " ";
+            ops += lin("td", o.pat[2], kk[2], true, ai, o.pat[3], kk[3], false, br, xneg) + " ";
             ops += ar + " = ta; " + bi + " = tb; " + ai + " = tc; " + br + " = td; }\n";
           }
         }
@@ -454,7 +512,9 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
         if (cond && !sel) ops += cond_open(o);
         else ops += "      {\n";
         char hdr[320];
-        if (sel) snprintf(hdr, sizeof(hdr), "        const bool on = %s; const double st = on ? C.c[%d] : 0.0, ss = on ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), k, k + 1);
+        if (sel && o.shear == 2)
+          snprintf(hdr, sizeof(hdr), "        const bool on = %s; const double st = on ? C.c[%d] : 0.0, ss = on ? C.c[%d] : 0.0; const uint32_t sm_ = on ? 0x80000000u : 0u;\n", cond_expr(o).c_str(), k, k + 1);
+        else if (sel) snprintf(hdr, sizeof(hdr), "        const bool on = %s; const double st = on ? C.c[%d] : 0.0, ss = on ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), k, k + 1);
         else snprintf(hdr, sizeof(hdr), "        const double st = C.c[%d], ss = C.c[%d];\n", k, k + 1);
         ops += hdr;
         for (int j = 0; j < PROG_AMPS; ++j) {
@@ -464,7 +524,11 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
           else hit = ((j >> o.p) & 1) == (o.kind == JK_CPH1 ? 1 : o.q);
           if (!hit) continue;
           const std::string r = X(j, 'r'), i = X(j, 'i');
-          if (o.shear == 2)
+          if (o.shear == 2 && sel)  // rotation by theta - pi, then the sign under the selected mask
+            ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1 = fma(ss, r1, " + i + "); " + r + " = bt_xsign(fma(st, i1, r1), sm_); " + i + " = bt_xsign(i1, sm_); }\n";
+          else if (o.shear == 2 && xneg)  // -(rotation): i1n = -i1 and r' = -(r1 + st i1) through the operand signs of the FMAs
+            ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1n = fma(-ss, r1, -" + i + "); " + r + " = fma(st, i1n, -r1); " + i + " = i1n; }\n";
+          else if (o.shear == 2)
             ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1 = fma(ss, r1, " + i + "); " + r + " = -fma(st, i1, r1); " + i + " = -i1; }\n";
           else
             ops += "        { const double r1 = fma(st, " + i + ", " + r + "), i1 = fma(ss, r1, " + i + "); " + r + " = fma(st, i1, r1); " + i + " = i1; }\n";
@@ -494,7 +558,8 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
           if (((j >> o.p) & 1) && ((j >> o.q) & 1)) {
             const std::string r = X(j, 'r'), i = X(j, 'i');
             char buf[256];
-            if (o.kind == JK_CZ) snprintf(buf, sizeof(buf), "      %s = -%s; %s = -%s;\n", r.c_str(), r.c_str(), i.c_str(), i.c_str());
+            if (o.kind == JK_CZ && xneg) snprintf(buf, sizeof(buf), "      %s = bt_neg(%s); %s = bt_neg(%s);\n", r.c_str(), r.c_str(), i.c_str(), i.c_str());
+            else if (o.kind == JK_CZ) snprintf(buf, sizeof(buf), "      %s = -%s; %s = -%s;\n", r.c_str(), r.c_str(), i.c_str(), i.c_str());
             else
               snprintf(buf, sizeof(buf), "      { const double tr = C.c[%d] * %s - C.c[%d] * %s, ti = C.c[%d] * %s + C.c[%d] * %s; %s = tr; %s = ti; }\n", k, r.c_str(), k + 1, i.c_str(), k,
                        i.c_str(), k + 1, r.c_str(), r.c_str(), i.c_str());
@@ -575,7 +640,44 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
         i = j;
       }
     }
-    if (last) {  // the pass scalar: product of all pivots and unconditional scalars
+    // the program's per-thread scalar: product of its deferred conditional factors (and, in the last program, of the pass scalar)
+    bool scalar_applied = false;
+    {
+      std::vector<const JOp*> dq;
+      for (const JOp& o : pl.prog[(size_t)it]) if (o.deferred) dq.push_back(&o);
+      if (!dq.empty()) {
+        ops += "      {\n";
+        bool have = false;
+        char buf[512];
+        if (last) {
+          if (pl.complex_scale) snprintf(buf, sizeof(buf), "        double fr = C.c[%d], fi = C.c[%d];\n", pl.scale_at, pl.scale_at + 1);
+          else snprintf(buf, sizeof(buf), "        double fr = C.c[%d], fi = 0.0;\n", pl.scale_at);
+          ops += buf;
+          have = true;
+          scalar_applied = true;
+        }
+        for (const JOp* o : dq) {
+          if (o->sgn) {
+            if (!have) { ops += "        double fr = 1.0, fi = 0.0;\n"; have = true; }
+            ops += "        { const uint32_t sm_ = " + cond_expr(*o) + " ? 0x80000000u : 0u; fr = bt_xsign(fr, sm_); fi = bt_xsign(fi, sm_); }\n";
+          } else if (!have) {
+            snprintf(buf, sizeof(buf), "        const bool on0 = %s; double fr = on0 ? C.c[%d] : 1.0, fi = on0 ? C.c[%d] : 0.0;\n", cond_expr(*o).c_str(), o->c0, o->c0 + 1);
+            ops += buf;
+            have = true;
+          } else {
+            snprintf(buf, sizeof(buf), "        { const bool on = %s; const double cr = on ? C.c[%d] : 1.0, ci = on ? C.c[%d] : 0.0; const double t0 = fr * cr - fi * ci; fi = fr * ci + fi * cr; fr = t0; }\n",
+                     cond_expr(*o).c_str(), o->c0, o->c0 + 1);
+            ops += buf;
+          }
+        }
+        for (int j = 0; j < PROG_AMPS; ++j) {
+          snprintf(buf, sizeof(buf), "        { const double tr = fr * xr[%d] - fi * xi[%d], ti = fr * xi[%d] + fi * xr[%d]; xr[%d] = tr; xi[%d] = ti; }\n", j, j, j, j, j, j);
+          ops += buf;
+        }
+        ops += "      }\n";
+      }
+    }
+    if (last && !scalar_applied) {  // the pass scalar: product of all pivots and unconditional scalars
       const int k = pl.scale_at;
       for (int j = 0; j < PROG_AMPS; ++j) {
         char buf[256];
@@ -653,6 +755,9 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
   s += "struct __align__(64) BtTensorMap { unsigned long long opaque[16]; };\n";
   appf(s, "struct BtCoefs { double c[%d]; };\n", ncoef);
   s += "__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }\n";
+  if (opt & 7)  // sign-bit flips on the integer pipe (the high word of the double XOR a mask)
+    s += "__device__ __forceinline__ double bt_xsign(double x, uint32_t m) { return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x)); }\n"
+         "__device__ __forceinline__ double bt_neg(double x) { return bt_xsign(x, 0x80000000u); }\n";
   if (K > 1) {
     // ---- pipelined frame (BT_TILE_PIPE = K, tiles of <= 2^11 amplitudes): a CTA owns K consecutive tiles and two tile buffers; the load of
     // tile i+1 is in flight while the programs of tile i run, the store of tile i drains while tile i+1 computes, and the buffer is
@@ -1074,6 +1179,15 @@ extern "C" int bt_jit_stats(uint64_t* compiled, uint64_t* launches, uint64_t* fa
   if (launches) *launches = g_launches;
   if (failed) *failed = g_failed;
   if (compile_seconds) *compile_seconds = g_compile_seconds;
+  return BT_OK;
+}
+
+extern "C" int bt_jit_config(int* nvrtc_major, int* nvrtc_minor, int* variant, int* opt) {
+  Nvrtc& n = nvrtc();
+  if (nvrtc_major) *nvrtc_major = n.ok ? n.major : 0;
+  if (nvrtc_minor) *nvrtc_minor = n.ok ? n.minor : 0;
+  if (variant) *variant = jit_variant();
+  if (opt) *opt = jit_opt();
   return BT_OK;
 }
 

@@ -110,6 +110,9 @@ int bt_jit_verify_stats(uint64_t* checked, uint64_t* failed);
 /* debugging aid: only the k-th eligible fused pass since this call (0-based) runs specialised, the others stay on the interpreter
  * (k < 0 removes the filter); dump != 0 prints the generated CUDA text of that pass to stderr */
 int bt_jit_debug_only(int k, int dump);
+/* what the specialiser will use in this process: version of the run-time compiler it loaded (0.0 = none), the code shape
+ * (BT_JIT_VARIANT, chosen by compiler version unless set) and the arithmetic reshaping flags (BT_JIT_OPT).  Host only. */
+int bt_jit_config(int* nvrtc_major, int* nvrtc_minor, int* variant, int* opt);
 int bt_set_strict(int strict); /* strict != 0: controlled non-adjacent 2q gates other than CX/CZ are rejected like hilbert.jl:58-64 */
 
 /* ---- reductions: partial_trace src/linalg.jl:167-230, :83-140 ---------------------------------------- */

@@ -31,14 +31,20 @@ print(npass.value, lc[0], lc[1], lc[2])
 '''
 
 
-def emulate(N, specs_expr, variant, tmp_path):
+def emulate(N, specs_expr, variant, tmp_path, opt=None, shapes=None):
     env = dict(os.environ, BT_JIT_VARIANT=str(variant))
+    if opt is not None:
+        env["BT_JIT_OPT"] = str(opt)
     r = subprocess.run([sys.executable, "-c", DUMP.format(root=ROOT, specs=specs_expr, N=N)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     npass, launches, progs, other = (int(x) for x in r.stdout.split())
+    if shapes is not None:
+        shapes.update({k: r.stderr.count(k) for k in shapes})
     passes = re.split(r"// ===== pass \d+ =====\n", r.stderr)[1:]
     assert other == 0 and len(passes) == launches, "the circuit must plan into program-only passes for this test"
-    cpp = ["#include <stdint.h>\n#include <math.h>\nstruct double2 { double x, y; };\nstatic inline double2 make_double2(double a, double b) { double2 r = {a, b}; return r; }\n#define PROG_AMPS 16\n"]
+    cpp = ["#include <stdint.h>\n#include <math.h>\nstruct double2 { double x, y; };\nstatic inline double2 make_double2(double a, double b) { double2 r = {a, b}; return r; }\n#define PROG_AMPS 16\n"
+           "#include <string.h>\nstatic inline double bt_xsign(double x, uint32_t m) { uint64_t u; memcpy(&u, &x, 8); u ^= (uint64_t)m << 32; memcpy(&x, &u, 8); return x; }\n"
+           "static inline double bt_neg(double x) { return bt_xsign(x, 0x80000000u); }\n"]
     meta = []
     for pi, src in enumerate(passes):
         ncoef = int(re.search(r"struct BtCoefs \{ double c\[(\d+)\]; \};", src).group(1))
@@ -99,3 +105,29 @@ def test_generated_pass_source_equals_the_oracle_on_the_host(bt, orc, tmp_path, 
     sv.apply_ops(ops)
     assert launches >= 1 and progs >= launches
     assert np.max(np.abs(got - sv.v)) < 1e-13
+
+
+def test_fp64_saving_code_shapes_are_generated_and_exact(bt, orc, tmp_path):
+    """BT_JIT_OPT (default 7): deferred per-thread scalars carrying the pass scalar, sign-bit flips for -1 factors / negations, the
+    pi-reduced shear under a selected sign mask.  The circuit is chosen so that every one of these shapes occurs; the same circuit
+    with BT_JIT_OPT=0 (the earlier generator text) must give the same state."""
+    from importlib import import_module
+
+    import __graft_entry__ as ge
+    from oracle import strided as S
+
+    N, expr = 13, "wl.layered(13, 5, 28)"
+    shapes = {"bt_xsign(fma(st": 0, "const uint32_t sm_ = ": 0, "double fr = on0": 0, "double fr = C.c": 0, "bt_neg(": 0, "i1n": 0}
+    (tmp_path / "new").mkdir()
+    (tmp_path / "old").mkdir()  # separate directories: dlopen caches a library by its path
+    got, _, _ = emulate(N, expr, 2, tmp_path / "new", opt=7, shapes=shapes)
+    assert all(v > 0 for v in shapes.values()), shapes
+    old_shapes = dict.fromkeys(shapes, 0)
+    old, _, _ = emulate(N, expr, 2, tmp_path / "old", opt=0, shapes=old_shapes)
+    assert not any(old_shapes.values()), old_shapes
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    ref0 = np.zeros(1 << N, dtype=np.complex128)
+    ref0[5] = 1
+    sv = S.SV(N, ref0)
+    sv.apply_ops(wl.to_ops(orc, eval(expr, {"wl": wl})))
+    assert np.max(np.abs(got - sv.v)) < 1e-13 and np.max(np.abs(old - sv.v)) < 1e-13
