@@ -616,10 +616,20 @@ bool generate(const TileParams& P, const Plan& pl, std::string& s, int K = 1) {
             if (cls < 0 ? o.kind == JK_CSCALE : ((o.kind == JK_CPH1 && o.p == cls) || (o.kind == JK_PHASE && o.p == cls && o.q == 1))) mem.push_back(t);
           }
           if (mem.empty()) continue;
-          ops += "      { double fr = 1.0, fi = 0.0;\n";
+          const bool assign_first = (opt & 1) != 0;  // the first factor is an assignment (1.0 * c - 0.0 * d does not fold without fast-math)
+          if (!assign_first) ops += "      { double fr = 1.0, fi = 0.0;\n";
+          bool first_member = true;
           for (size_t t : mem) {
             const JOp& o = L[t];
             char buf[512];
+            if (assign_first && first_member) {
+              if (o.kind == JK_PHASE) snprintf(buf, sizeof(buf), "      { double fr = C.c[%d], fi = C.c[%d];\n", o.c0, o.c0 + 1);
+              else snprintf(buf, sizeof(buf), "      { const bool on0 = %s; double fr = on0 ? C.c[%d] : 1.0, fi = on0 ? C.c[%d] : 0.0;\n", cond_expr(o).c_str(), o.c0, o.c0 + 1);
+              ops += buf;
+              done[t - i] = 1;
+              first_member = false;
+              continue;
+            }
             if (o.kind == JK_PHASE)
               snprintf(buf, sizeof(buf), "        { const double t0 = fr * C.c[%d] - fi * C.c[%d]; fi = fr * C.c[%d] + fi * C.c[%d]; fr = t0; }\n", o.c0, o.c0 + 1, o.c0 + 1, o.c0);
             else
