@@ -344,6 +344,22 @@ def bench_single(args):
             tf = (fl1.value - fl0.value) / (cms[0] / 1e3) / 1e12
             roof["fp64"] = {"achieved_tflops": tf, "peak_tflops_measured": fp64["tflops"], "frac": tf / fp64["tflops"], "peak": fp64,
                             "note": "useful FP64 flops of the structured micro-ops (real / RX-like / diagonal gates cost half of a dense 2x2, CX none)"}
+            # issued FP64 instructions: counted from the text the specialiser generates for exactly these passes (planner dry run in
+            # a subprocess with this process's code shape / reshaping flags; tools/jit_fp64_count.py, checked against cuobjdump -sass
+            # in profiles/r2_jit_fp64_counts.txt).  One DFMA / DADD / DMUL each takes one issue slot of the FP64 pipe: peak = TF/s / 2.
+            try:
+                if 2 * jit_timed >= counts[0]:
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    import jit_fp64_count as J
+                    jc = [C.c_int() for _ in range(4)]
+                    L.check(lib.bt_jit_config(*[C.byref(x) for x in jc]))
+                    est = J.source_estimate(f"{N}, wl.c2_qft_layered({N}, {depth}, 28)", {"BT_JIT_VARIANT": str(jc[2].value), "BT_JIT_OPT": str(jc[3].value)})
+                    issued = est["executed_per_amplitude"] * float(1 << N) * args.steps / (cms[0] / 1e3) / 1e12
+                    roof["fp64"]["issued"] = {"instr_per_amplitude_per_step": est["executed_per_amplitude"], "static_instr_per_amplitude_per_step": est["static_per_amplitude"],
+                                              "tera_instr_per_s": issued, "peak_tera_instr_per_s": fp64["tflops"] / 2.0, "frac": issued / (fp64["tflops"] / 2.0),
+                                              "note": "DFMA + DADD + DMUL the specialised passes execute (each one FP64-pipe issue slot) / fused-kernel time / (measured FMA peak / 2)"}
+            except Exception as e:  # a diagnostic: never at the expense of the line
+                roof["fp64"]["issued"] = {"error": repr(e)[:300]}
             roof["gates_per_launch"] = ngates * args.steps / max(1, int(counts[0]))
             # a fused pass carries tens of gates per HBM round trip, so it sits between the two roofs; the look-ahead scheduler (round 2)
             # deliberately trades HBM fraction for fewer passes: the step gets faster while bytes / launch-time drops

@@ -106,16 +106,32 @@ def sass_count(path):
     return {k: len(re.findall(r"\b" + k + r"\b", sass)) for k in ("DFMA", "DADD", "DMUL")}, int(reg.group(1)) if reg else -1, len(re.findall(r"\b(LDL|STL)\b", sass))
 
 
-def main():
-    args = [a for a in sys.argv[1:] if "=" not in a]
-    env = dict(os.environ, **dict(a.split("=", 1) for a in sys.argv[1:] if "=" in a))
-    work = args[0] if args else "c2"
-    r = subprocess.run([sys.executable, "-c", DUMP.format(root=ROOT, work=WORK[work])], capture_output=True, text=True, env=env)
+def dump_passes(work_expr, env=None):
+    """CUDA text of every specialised pass of a workload (planner dry run in a subprocess: the dump goes to the C stderr).
+    work_expr: Python expression giving (N, specs) with `wl` = the workloads module.  Returns (ngates, launches, programs, other, [text])."""
+    r = subprocess.run([sys.executable, "-c", DUMP.format(root=ROOT, work=work_expr)], capture_output=True, text=True, env=dict(os.environ, **(env or {})), timeout=600)
     if r.returncode:
-        sys.exit(r.stderr[-2000:])
+        raise RuntimeError(r.stderr[-2000:])
     ngates, npass, launches, progs, other = (int(x) for x in r.stdout.split())
-    passes = re.split(r"// ===== pass \d+ =====\n", r.stderr)[1:]
-    branchy = "if ((base &" in r.stderr
+    return ngates, launches, progs, other, re.split(r"// ===== pass \d+ =====\n", r.stderr)[1:]
+
+
+def source_estimate(work_expr, env=None):
+    """FP64 instructions per amplitude per step from the generated text alone (no compiler): `static` counts every instruction
+    once (agrees with the SASS count to 0.1 - 3 %, profiles/r2_jit_fp64_counts.txt), `executed` weights blocks behind a branch."""
+    ngates, launches, progs, other, passes = dump_passes(work_expr, env)
+    branchy = any("if ((base &" in p for p in passes)
+    return {"gates": ngates, "specialised_launches": launches, "programs": progs, "other_items": other,
+            "static_per_amplitude": sum(dynamic_estimate(p, False) for p in passes) / 16.0,
+            "executed_per_amplitude": sum(dynamic_estimate(p, branchy) for p in passes) / 16.0, "branches_weighted": branchy}
+
+
+def main():
+    args = [a for a in sys.argv[1:] if "=" not in a and not a.startswith("-")]
+    env = dict(a.split("=", 1) for a in sys.argv[1:] if "=" in a)
+    work = args[0] if args else "c2"
+    ngates, launches, progs, other, passes = dump_passes(WORK[work], env)
+    branchy = any("if ((base &" in p for p in passes)
     with tempfile.TemporaryDirectory() as d:
         paths = []
         for i, src in enumerate(passes):
