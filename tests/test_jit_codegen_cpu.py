@@ -131,3 +131,22 @@ def test_fp64_saving_code_shapes_are_generated_and_exact(bt, orc, tmp_path):
     sv = S.SV(N, ref0)
     sv.apply_ops(wl.to_ops(orc, eval(expr, {"wl": wl})))
     assert np.max(np.abs(got - sv.v)) < 1e-13 and np.max(np.abs(old - sv.v)) < 1e-13
+
+
+def test_fp64_instruction_estimate_of_the_generated_text():
+    """tools/jit_fp64_count.source_estimate (what bench.py's roofline.fp64.issued block calls): FP64 instructions per amplitude from
+    the generated text of a workload's passes.  The reshaped generator (BT_JIT_OPT=7) must issue fewer than the earlier text in both
+    code shapes, the executed count can only be below the static one, and an RX on every qubit costs exactly 2 FMAs per amplitude."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import jit_fp64_count as J
+
+    work = "13, wl.layered(13, 6, 28)"
+    for variant in ("0", "2"):
+        old = J.source_estimate(work, {"BT_JIT_VARIANT": variant, "BT_JIT_OPT": "0"})
+        new = J.source_estimate(work, {"BT_JIT_VARIANT": variant, "BT_JIT_OPT": "7"})
+        assert old["specialised_launches"] == new["specialised_launches"] >= 1 and new["other_items"] == 0
+        assert 0 < new["executed_per_amplitude"] <= new["static_per_amplitude"] < old["static_per_amplitude"]
+        assert new["executed_per_amplitude"] < old["executed_per_amplitude"]
+    rx = J.source_estimate("12, [('RX(0.3)', q, -1, -2) for q in range(1, 13)]", {"BT_JIT_VARIANT": "2"})
+    # one pass of three programs; a rotation [[1, -i t], [-i t, 1]] (after the pivot) = 2 FMAs per amplitude, + the real pass scalar (2 multiplications)
+    assert rx["specialised_launches"] == 1 and rx["programs"] == 3 and rx["static_per_amplitude"] == 12 * 2 + 2, rx
