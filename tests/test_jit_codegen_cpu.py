@@ -150,3 +150,33 @@ def test_fp64_instruction_estimate_of_the_generated_text():
     rx = J.source_estimate("12, [('RX(0.3)', q, -1, -2) for q in range(1, 13)]", {"BT_JIT_VARIANT": "2"})
     # one pass of three programs; a rotation [[1, -i t], [-i t, 1]] (after the pivot) = 2 FMAs per amplitude, + the real pass scalar (2 multiplications)
     assert rx["specialised_launches"] == 1 and rx["programs"] == 3 and rx["static_per_amplitude"] == 12 * 2 + 2, rx
+
+
+RANDOM_PAIRS = """(lambda g: [s for l in range({layers}) for s in (
+    [(["H", "RX(%r)" % g.uniform(0, 6.28), "RY(%r)" % g.uniform(0, 6.28), "RZ(%r)" % g.uniform(0, 6.28), "T", "S", "Z", "X"][int(g.integers(8))], q, -1, -2) for q in range(1, {N} + 1)]
+    + [((["CNOT", "CZ", "CP(%r)" % g.uniform(0, 6.28)][int(g.integers(3))],) + tuple(int(x) for x in g.choice({N}, 2, replace=False) + 1) + (-2,)) for _ in range({N} // 2)])])(
+    __import__("numpy").random.Generator(__import__("numpy").random.PCG64({seed})))"""
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("N,layers,seed", [(16, 6, 1), (15, 8, 2)])
+def test_generated_source_with_random_qubit_pairs_and_bits_outside_the_tile(bt, orc, tmp_path, N, layers, seed, variant):
+    """Two-qubit gates on random (non-adjacent) pairs of a register wider than the tile: controls and phase bits fall on tile bits
+    that are not program positions (thread-dependent conditions) and on bits outside the tile (conditions on the tile's base
+    index), in both code shapes; S / Z / X join the one-qubit mix.  Host execution of the generated text against the oracle."""
+    from importlib import import_module
+
+    import __graft_entry__ as ge
+    from oracle import strided as S
+
+    expr = RANDOM_PAIRS.format(N=N, layers=layers, seed=seed).replace("\n", " ")
+    shapes = {"(base & 0x0ull)": 0, "if ((base &": 0, "double fr = ": 0}
+    got, launches, progs = emulate(N, expr, variant, tmp_path, shapes=shapes)
+    wl = import_module(ge.PKG_NAME + ".workloads")
+    ops = wl.to_ops(orc, eval(expr, {"wl": wl}))
+    ref0 = np.zeros(1 << N, dtype=np.complex128)
+    ref0[5] = 1
+    sv = S.SV(N, ref0)
+    sv.apply_ops(ops)
+    assert shapes["double fr = "] > 0 and shapes["if ((base &"] > 0
+    assert np.max(np.abs(got - sv.v)) < 1e-13
