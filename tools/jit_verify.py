@@ -31,4 +31,6 @@ chk, bad = C.c_uint64(), C.c_uint64()
 L.check(s.lib.bt_jit_verify_stats(C.byref(chk), C.byref(bad)))
 c, l, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
 s.lib.bt_jit_stats(C.byref(c), C.byref(l), C.byref(f), None)
-print(f"{kind} N={N} gates={len(arr)} variant={os.environ.get('BT_JIT_VARIANT', 'auto')}: modules {c.value}, specialised launches {l.value}, cross-checked {chk.value}, disagreements {bad.value}, norm2 {bt.norm2(s):.12f}")
+cfg = [C.c_int() for _ in range(4)]
+L.check(s.lib.bt_jit_config(*[C.byref(x) for x in cfg]))
+print(f"{kind} N={N} gates={len(arr)} nvrtc {cfg[0].value}.{cfg[1].value} code shape {cfg[2].value} BT_JIT_OPT {cfg[3].value}: modules {c.value}, specialised launches {l.value}, cross-checked {chk.value}, disagreements {bad.value}, norm2 {bt.norm2(s):.12f}")
