@@ -43,6 +43,14 @@ def rep(path):
         if k in hdr:
             i = hdr.index(k)
             print(f"{k:78s} {units[i]:16s} {[r[i] for r in rows[2:]]}")
+    for i, h in enumerate(hdr):  # warps stalled per issue-active cycle, by reason (the full set reports ratios, not percentages)
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+            try:
+                v = [float((r[i] or "0").replace(",", "")) for r in rows[2:]]
+            except ValueError:
+                continue
+            if max(v) >= 0.1 and "selected_per" not in h.replace("not_selected", ""):
+                print(f"stalled warps per issue: {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):24s} {v}")
     for i, h in enumerate(hdr):
         if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
             v = [float(r[i] or 0) for r in rows[2:]]
