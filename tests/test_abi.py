@@ -126,3 +126,40 @@ def test_c_caller_runs_the_minimal_path_on_the_device(tmp_path):
 
     r = subprocess.run([_build_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "abi_smoke ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_julia_shim_blocks_and_brackets_balance():
+    """No Julia in this image: the least a text check can do for julia/BlueTangleCUDA.jl is to balance its block keywords against
+    `end` (keywords inside brackets are comprehensions / filters and open nothing) and its brackets."""
+    src = open(os.path.join(ROOT, "julia", "BlueTangleCUDA.jl")).read()
+    openers = {"function", "if", "for", "while", "let", "begin", "struct", "module", "try", "do", "quote", "macro"}
+    stack, bdepth = [], 0
+    for n, line in enumerate(src.split("\n"), 1):
+        i, tok, in_str, line = 0, "", False, line + " "
+        while i < len(line):
+            c = line[i]
+            if in_str:
+                i += 2 if c == "\\" else 1
+                in_str = c != '"'
+                continue
+            if c == '"':
+                in_str = True
+            elif c == "#":
+                break
+            elif c.isalnum() or c in "_!":
+                tok += c
+                i += 1
+                continue
+            if tok:
+                prev = line[:i - len(tok)].rstrip()
+                if tok == "end" and bdepth == 0:
+                    assert stack, f"line {n}: `end` without an open block"
+                    stack.pop()
+                elif tok in openers and bdepth == 0 and not prev.endswith((":", ".")):
+                    stack.append((tok, n))
+                tok = ""
+            bdepth += (c in "([{") - (c in ")]}")
+            assert bdepth >= 0, f"line {n}: closing bracket without an opening one"
+            i += 1
+        assert not in_str, f"line {n}: unterminated string"
+    assert not stack and bdepth == 0, (stack[-3:], bdepth)
