@@ -163,12 +163,16 @@ __global__ void __launch_bounds__(256) k_dense(double2* __restrict__ a, uint64_t
         double2 mv = DEVMAT ? __ldg(&mm[r * D + c]) : P.m[r * D + c];
         cfma(acc, mv, x[u][c]);
       }
-      y[r] = acc;
+      // plain form: every row is stored as soon as it is complete, so the stores drain while the FP64 pipe works on the next rows
+      // (16 x 16 superoperators sit at the FP64 ridge: holding all rows back for one burst of stores cost them 19 %, 1.24 -> 1.47 ms)
+      // (the masked per-trajectory-matrix form keeps the buffered stores it was validated with on the device)
+      if (T0 >= 0 || (DEVMAT && COND)) y[r] = acc;
+      else a[base[u] + P.off[r]] = acc;
     }
 #pragma unroll
     for (int r = 0; r < D; ++r) {
       if (T0 >= 0) { if (!((r >> (T0 >= 0 ? T0 : 0)) & 1)) st256(a + base[u] + P.off[r], y[r], y[r | (1 << (T0 >= 0 ? T0 : 0))]); }
-      else a[base[u] + P.off[r]] = y[r];
+      else if (DEVMAT && COND) a[base[u] + P.off[r]] = y[r];
     }
   }
 }
